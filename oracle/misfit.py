@@ -1,0 +1,48 @@
+"""TEST INFRASTRUCTURE ONLY (oracle).  CPU (torch) restatement of the reference's
+L2 and envelope misfits.  Never imported by the product path.
+
+Follows:
+  * seistorch/loss.py:409-421      L2  (MSELoss(reduction='sum') summed over shots)
+  * seistorch/loss.py:178-216      Envelope (method='square')
+  * seistorch/transform.py:24-66   envelope / hilbert (nfft = nt, scipy convention)
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def l2(syn, obs):
+    """loss.py:417-421."""
+    loss = 0.0
+    for x, y in zip(syn, obs):
+        loss = loss + torch.sum((x - y) ** 2)
+    return loss
+
+
+def hilbert(data):
+    """transform.py:27-66: analytic signal along dim 0 of (nt, ntraces, nchan)."""
+    nt = data.shape[0]
+    spec = torch.fft.fft(data, n=nt, dim=0)
+    hfilt = np.zeros(nt, dtype=np.float32)
+    if nt % 2 == 0:
+        hfilt[0] = hfilt[nt // 2] = 1
+        hfilt[1:nt // 2] = 2
+    else:
+        hfilt[0] = 1
+        hfilt[1:(nt + 1) // 2] = 2
+    hfilt = torch.from_numpy(hfilt).view(-1, 1, 1)
+    return torch.fft.ifft(spec * hfilt, dim=0)
+
+
+def envelope(d):
+    """transform.py:24-25."""
+    return torch.abs(hilbert(d))
+
+
+def envelope_loss(syn, obs):
+    """loss.py:201-216 with method='square':  sum_shots 0.5*sum((E(x)^2-E(y)^2)^2)."""
+    loss = 0.0
+    for x, y in zip(syn, obs):
+        loss = loss + 0.5 * torch.sum((envelope(x) ** 2 - envelope(y) ** 2) ** 2)
+    return loss
