@@ -1,0 +1,191 @@
+/* seistorch_b200 -- C ABI of the B200-native wave-propagation hot path.
+ *
+ * The reference (GeophyAI/seistorch) has no FFI: its plug-in surface is a Python
+ * naming convention.  This header is the boundary underneath our
+ * Python mirror of that surface; every entry point cites the reference code whose
+ * work it replaces (file:line relative to the reference tree).  INTEGRATION.md shows
+ * the ctypes binding (seistorch_b200/_lib.py) a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers owned by the
+ *     caller (torch allocations); the library never allocates or frees;
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), does
+ *     not synchronise, keeps no mutable global state and is re-entrant;
+ *   - return value 0 = ok, <0 = error (ST_ERR_*); st_last_error() gives the
+ *     thread-local message;
+ *   - fields are fp32, [channel][shot][row][pitch] with pitch (`ld`) a multiple of 4;
+ *     index arrays are int32 (the Python layer converts the reference's int64).
+ */
+#ifndef SEISTORCH_B200_H
+#define SEISTORCH_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ST_ABI_VERSION 1
+
+/* equation-variant flags of the 2D second-order family (st_wave2d_*) */
+#define ST_EQ_ISO   1   /* Cxx == Czz == r^2, taken from r                                  */
+#define ST_EQ_PML   2   /* damped update, equations2d/acoustic.py:73-86                      */
+#define ST_EQ_HABC  4   /* one-way blend,  equations2d/acoustic_habc.py:79-101,147-221       */
+#define ST_EQ_XZ    8   /* mixed derivative, equations2d/tti_habc.py:40-57                   */
+#define ST_EQ_G1   16   /* first-derivative terms, equations2d/acoustic_fwim_habc.py:38-60   */
+#define ST_EQ_BORN 32   /* background+scattered pair, equations2d/acoustic_*_lsrtm_habc.py   */
+/*   acoustic                 = ISO|PML          acoustic_habc            = ISO|HABC
+ *   vti_habc2                = HABC             tti_habc                 = HABC|XZ
+ *   acoustic_fwim_habc       = ISO|HABC|G1
+ *   acoustic_vti_lsrtm_habc  = HABC|BORN        acoustic_tti_lsrtm_habc  = HABC|XZ|BORN   */
+
+#define ST_ERR_BADARG      (-1)
+#define ST_ERR_UNSUPPORTED (-2)
+#define ST_ERR_CUDA        (-3)
+
+int st_version(void);
+const char* st_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * Acquisition shared by all propagators.
+ *   sources  : replaces WaveSource.forward2d/3d (seistorch/source.py:47-70) and the one-hot
+ *              mask built per call in rnn.py:160-166.  One entry per point source.
+ *   receivers: replaces WaveProbe.forward2d/3d (seistorch/probe.py:42-48).  Receivers are
+ *              sorted by (shot, row) and indexed by a CSR over rows; rec_orig maps back
+ *              to the reference's concatenated order (rnn.py:51-73).
+ * ---------------------------------------------------------------------------------- */
+typedef struct st_acquisition {
+    int32_t ns;                 /* number of point sources (all shots)                 */
+    const int32_t* src_b;       /* [ns] shot index                                     */
+    const int32_t* src_i0;      /* [ns] 3D: first tensor dim (x); 2D: unused           */
+    const int32_t* src_i1;      /* [ns] row   (2D: z "y" index; 3D: z)                 */
+    const int32_t* src_i2;      /* [ns] column (2D: x; 3D: y)                          */
+    const float* amp;           /* [nt][ns] amplitude added at step i (wavelet sample) */
+    float* gamp;                /* [nt][ns] out: d loss / d amp, or NULL               */
+    int32_t src_fmask;          /* bit f: inject into field channel f                  */
+    int32_t R;                  /* number of receivers (all shots)                     */
+    const int32_t* row_start;   /* [nrows+1] CSR over rows: 2D row = b*nz+z; 3D row = (b*n0+i0)*n1+i1 */
+    const int32_t* rec_col;     /* [R] column index (sorted order)                     */
+    const int32_t* rec_orig;    /* [R] position in the reference's receiver order      */
+    int32_t nchan;              /* receiver channels (len(receiver_type))              */
+    int32_t chan_f[4];          /* field channel sampled by each receiver channel      */
+    float* rec_out;             /* [nt][R][nchan] seismograms (forward), or NULL       */
+    const float* rec_adj;       /* [nt][R][nchan] d loss / d seismogram (adjoint)      */
+} st_acquisition;
+
+/* ------------------------------------------------------------------------------------
+ * 2D second-order family.  Replaces, for `nsteps` time steps per call,
+ *   seistorch/rnn.py:178-205 (time loop), seistorch/cell.py:50-76 (step dispatch),
+ *   the `_time_step` of equations2d/{acoustic,acoustic_habc,vti_habc2,tti_habc,
+ *   acoustic_fwim_habc,acoustic_vti_lsrtm_habc,acoustic_tti_lsrtm_habc}.py,
+ *   source.py:47-57 and probe.py:42-44;
+ * st_wave2d_adjoint replaces torch autograd-through-time / checkpoint_new.py:146-217 with
+ * the exact discrete adjoint (transposed stencil + imaging-condition accumulation).
+ *
+ * State S_j = field after step j (source added).  `u` holds `nslots` time slots of
+ * [NF][B][nz][ld]; slot indices are taken modulo nslots (3 slots = rolling buffer for
+ * pure forward modelling, K+2 slots = stored history of a K-step segment).
+ * ---------------------------------------------------------------------------------- */
+typedef struct st_wave2d_problem {
+    int32_t flags;              /* ST_EQ_* */
+    int32_t B, nz, nx, ld;      /* shots, padded grid, row pitch */
+    int32_t bw, multiple;       /* absorbing width (50), free-surface flag */
+    int32_t nt;
+    float dt;                   /* only used by ST_EQ_PML (b*dt) */
+    const float* coef[8];       /* r=vp*dt/h, b(damping d), cxx, czz, cxz, ax, az, m : [nz][ld] or NULL */
+    float* u;                   /* [nslots][NF][B][nz][ld] */
+    int32_t nslots;
+    float* lam;                 /* [3][NF][B][nz][ld] adjoint state, slot = i mod 3 (zero before the first adjoint call) */
+    float* gacc;                /* [nchunk][7][nz][ld] += coefficient gradients (r,cxx,czz,cxz,ax,az,m), or NULL */
+    int32_t bchunk;             /* shots per block in the adjoint kernel; nchunk = ceil(B/bchunk) */
+    st_acquisition acq;
+} st_wave2d_problem;
+
+/* advance steps i0 .. i0+nsteps-1; S_{i0-2} lives in slot `slot0`, S_{i0-1} in slot0+1,
+ * step i writes slot0+2+(i-i0).                                                         */
+int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream);
+/* compute Lam_i for i = i_hi .. i_hi-nsteps+1 (descending); S_{i_hi} lives in slot
+ * `slot_hi`, S_{i} in slot_hi-(i_hi-i).  Accumulates the gradient of steps i+1.          */
+int st_wave2d_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32_t nsteps, int32_t slot_hi, void* stream);
+
+/* per-equation aliases (same argument meaning; they check p->flags) */
+int st_acoustic2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream);
+int st_acoustic2d_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32_t nsteps, int32_t slot_hi, void* stream);
+int st_acoustic2d_habc_forward(const st_wave2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream);
+int st_acoustic2d_habc_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32_t nsteps, int32_t slot_hi, void* stream);
+int st_qp2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream);
+int st_qp2d_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32_t nsteps, int32_t slot_hi, void* stream);
+int st_fwim2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream);
+int st_fwim2d_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32_t nsteps, int32_t slot_hi, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 2D elastic velocity-stress (Virieux).  Replaces equations2d/elastic.py:7-37 +
+ * equations2d/utils.py:3-48 inside the same time loop; the adjoint replaces
+ * checkpoint.py:146-230 / autograd.  State S_j = (vx,vz,txx,tzz,txz) after step j.
+ * `u` holds nslots slots of [5][B][nz][ld].  Coefficient planes (all [nz][ld]):
+ *   0: ca  = (1-c)/(1+c), c = 0.5*dt*d      1: cl2m = (lambda+2mu)*dt/h/(1+c)
+ *   2: cl  = lambda*dt/h/(1+c)              3: cm   = mu*dt/h/(1+c)
+ *   4: cb  = dt/(rho*h)/(1+c)
+ * gacc: [nchunk][4][nz][ld] gradients w.r.t. (cl2m, cl, cm, cb).
+ * ---------------------------------------------------------------------------------- */
+typedef struct st_elastic2d_problem {
+    int32_t B, nz, nx, ld, nt;
+    const float* coef[5];
+    float* u;                   /* [nslots][5][B][nz][ld] */
+    int32_t nslots;
+    float* lam;                 /* [2][5][B][nz][ld] adjoint state, slot = i mod 2 */
+    float* gacc;                /* [nchunk][4][nz][ld] or NULL */
+    int32_t bchunk;
+    st_acquisition acq;
+} st_elastic2d_problem;
+
+/* advance steps i0..i0+nsteps-1; S_{i0-1} in slot0, step i writes slot0+1+(i-i0). */
+int st_elastic2d_forward(const st_elastic2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream);
+/* compute Lam_i for i = i_hi .. i_hi-nsteps+1; S_{i_hi+1} lives in slot `slot_hi1`
+ * (S_i in slot_hi1-1-(i_hi-i)); accumulates the gradient of steps i+1.
+ * Lam_{nt-1} (pure receiver term) is produced by calling with i_hi = nt-1 first: the
+ * library treats Lam_nt as zero.                                                        */
+int st_elastic2d_adjoint(const st_elastic2d_problem* p, int32_t i_hi, int32_t nsteps, int32_t slot_hi1, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * 3D acoustic (PML).  Replaces equations3d/acoustic.py:65-85, source.py:59-70,
+ * probe.py:46-48 inside the time loop; adjoint replaces checkpoint_new.py + the
+ * host-staged face copies of equations3d/utils.py:57-121.  Tensor layout (B, n0, n1, n2)
+ * = the reference's (B, x, z, y), n2 fastest with pitch ld.
+ * coef[0] = r = vp*dt/h, coef[1] = b (PML damping), each [n0][n1][ld].
+ * ---------------------------------------------------------------------------------- */
+typedef struct st_acoustic3d_problem {
+    int32_t B, n0, n1, n2, ld, nt;
+    float dt;
+    const float* coef[2];
+    float* u;                   /* [nslots][B][n0][n1][ld] */
+    int32_t nslots;
+    float* lam;                 /* [3][B][n0][n1][ld] */
+    float* gacc;                /* [nchunk][n0][n1][ld] += d loss / d r, or NULL */
+    int32_t bchunk;
+    st_acquisition acq;
+} st_acoustic3d_problem;
+
+int st_acoustic3d_forward(const st_acoustic3d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream);
+int st_acoustic3d_adjoint(const st_acoustic3d_problem* p, int32_t i_hi, int32_t nsteps, int32_t slot_hi, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Misfits and their adjoint sources, on seismograms laid out [nt][R][nchan] (all shots
+ * concatenated along R).  Replace seistorch/loss.py:409-421 (L2) and :178-216 (Envelope,
+ * method 'square') with transform.py:24-66 (Hilbert transform, nfft = nt).
+ *   loss   : [1] (double) += scale * sum over all samples (caller zeroes it)
+ *   adj    : [nt][R][nchan] d loss / d syn (scaled by `scale`), or NULL
+ * st_misfit_envelope needs `hker` [nt]: imaginary part of the analytic-signal impulse
+ * response (ifft of the one-sided filter), computed once on the host, and a workspace of
+ * 3*nt*ntraces floats.
+ * ---------------------------------------------------------------------------------- */
+int st_misfit_l2(const float* syn, const float* obs, int64_t n, float scale,
+                 double* loss, float* adj, void* stream);
+int st_misfit_envelope(const float* syn, const float* obs, int32_t nt, int32_t ntraces,
+                       const float* hker, float scale, double* loss, float* adj,
+                       float* workspace, void* stream);
+int64_t st_misfit_envelope_workspace(int32_t nt, int32_t ntraces);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEISTORCH_B200_H */

@@ -1,0 +1,132 @@
+"""ctypes binding of include/seistorch_b200.h (the C-ABI boundary).
+
+The library is loaded lazily; if it is missing the product path fails loudly --
+there is no CPU or PyTorch fallback (BASELINE north star).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libseistorch_b200.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_int_p = C.POINTER(C.c_int32)
+
+
+class StAcquisition(C.Structure):
+    _fields_ = [
+        ("ns", C.c_int32),
+        ("src_b", C.c_void_p), ("src_i0", C.c_void_p), ("src_i1", C.c_void_p), ("src_i2", C.c_void_p),
+        ("amp", C.c_void_p), ("gamp", C.c_void_p),
+        ("src_fmask", C.c_int32),
+        ("R", C.c_int32),
+        ("row_start", C.c_void_p), ("rec_col", C.c_void_p), ("rec_orig", C.c_void_p),
+        ("nchan", C.c_int32),
+        ("chan_f", C.c_int32 * 4),
+        ("rec_out", C.c_void_p), ("rec_adj", C.c_void_p),
+    ]
+
+
+class StWave2dProblem(C.Structure):
+    _fields_ = [
+        ("flags", C.c_int32),
+        ("B", C.c_int32), ("nz", C.c_int32), ("nx", C.c_int32), ("ld", C.c_int32),
+        ("bw", C.c_int32), ("multiple", C.c_int32),
+        ("nt", C.c_int32),
+        ("dt", C.c_float),
+        ("coef", C.c_void_p * 8),
+        ("u", C.c_void_p),
+        ("nslots", C.c_int32),
+        ("lam", C.c_void_p),
+        ("gacc", C.c_void_p),
+        ("bchunk", C.c_int32),
+        ("acq", StAcquisition),
+    ]
+
+
+class StElastic2dProblem(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("nz", C.c_int32), ("nx", C.c_int32), ("ld", C.c_int32), ("nt", C.c_int32),
+        ("coef", C.c_void_p * 5),
+        ("u", C.c_void_p),
+        ("nslots", C.c_int32),
+        ("lam", C.c_void_p),
+        ("gacc", C.c_void_p),
+        ("bchunk", C.c_int32),
+        ("acq", StAcquisition),
+    ]
+
+
+class StAcoustic3dProblem(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("n0", C.c_int32), ("n1", C.c_int32), ("n2", C.c_int32), ("ld", C.c_int32),
+        ("nt", C.c_int32),
+        ("dt", C.c_float),
+        ("coef", C.c_void_p * 2),
+        ("u", C.c_void_p),
+        ("nslots", C.c_int32),
+        ("lam", C.c_void_p),
+        ("gacc", C.c_void_p),
+        ("bchunk", C.c_int32),
+        ("acq", StAcquisition),
+    ]
+
+
+# every symbol include/seistorch_b200.h declares
+EXPORTS = [
+    "st_version", "st_last_error",
+    "st_wave2d_forward", "st_wave2d_adjoint",
+    "st_acoustic2d_forward", "st_acoustic2d_adjoint",
+    "st_acoustic2d_habc_forward", "st_acoustic2d_habc_adjoint",
+    "st_qp2d_forward", "st_qp2d_adjoint", "st_fwim2d_forward", "st_fwim2d_adjoint",
+    "st_elastic2d_forward", "st_elastic2d_adjoint",
+    "st_acoustic3d_forward", "st_acoustic3d_adjoint",
+    "st_misfit_l2", "st_misfit_envelope", "st_misfit_envelope_workspace",
+]
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libseistorch_b200.so (once).  Raises LibraryMissing with build instructions."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+            "`python -m seistorch_b200.build` (needs nvcc). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.st_version.restype = C.c_int
+    L.st_last_error.restype = C.c_char_p
+    step_args = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    for name in EXPORTS[2:16]:
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = step_args
+    L.st_misfit_l2.restype = C.c_int
+    L.st_misfit_l2.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.st_misfit_envelope.restype = C.c_int
+    L.st_misfit_envelope.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.st_misfit_envelope_workspace.restype = C.c_int64
+    L.st_misfit_envelope_workspace.argtypes = [C.c_int32, C.c_int32]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().st_last_error().decode(errors="replace")
+        raise RuntimeError(f"seistorch_b200 {what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None -> NULL)."""
+    return None if t is None else t.data_ptr()

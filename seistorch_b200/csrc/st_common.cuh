@@ -1,0 +1,31 @@
+// Common definitions for the seistorch_b200 CUDA kernels (sm_100a).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+
+#ifdef __CUDACC__
+#define ST_HD __host__ __device__ __forceinline__
+#else
+#define ST_HD inline
+#endif
+
+// ---- equation-variant flags of the 2D second-order family ---------------------------
+// (which reference plugin maps to which flag set is listed in include/seistorch_b200.h)
+enum : int {
+    ST_F_ISO  = 1,    // Cxx == Czz == r^2 (acoustic-type Laplacian); coefficient derived from r in-kernel
+    ST_F_PML  = 2,    // damped update  y = h1 + a2 (h1-h2) + a3 lap(h1)      (equations2d/acoustic.py:73-86)
+    ST_F_HABC = 4,    // undamped update followed by the Higdon one-way blend   (equations2d/acoustic_habc.py:147-221)
+    ST_F_XZ   = 8,    // mixed-derivative term (TTI)                            (equations2d/tti_habc.py:40-57)
+    ST_F_G1   = 16,   // first-derivative terms (joint FWI-LSRTM "FWIM")        (equations2d/acoustic_fwim_habc.py:38-60)
+    ST_F_BORN = 32,   // background + scattered pair coupled through m          (equations2d/acoustic_*_lsrtm_habc.py)
+};
+
+// error codes returned by every C-ABI entry point
+#define ST_OK 0
+#ifndef ST_ERR_BADARG
+#define ST_ERR_BADARG (-1)
+#define ST_ERR_UNSUPPORTED (-2)
+#define ST_ERR_CUDA (-3)
+#endif
+
+void st_set_error(const char* fmt, ...);

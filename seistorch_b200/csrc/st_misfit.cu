@@ -1,0 +1,130 @@
+// Misfit + adjoint-source kernels (include/seistorch_b200.h: st_misfit_*).
+//   L2        : seistorch/loss.py:409-421   sum (syn-obs)^2           adj = 2 (syn-obs)
+//   Envelope  : seistorch/loss.py:178-216 (method 'square') with the Hilbert transform of
+//               seistorch/transform.py:27-66 (nfft = nt) restated as a circular
+//               convolution with the fixed kernel hker = Im ifft(one-sided filter):
+//                 E^2 = x^2 + (hker (*) x)^2,  loss = 0.5 sum (Es^2 - Eo^2)^2,
+//                 adj = 2 r x + H^T (2 r Hx),  r = Es^2 - Eo^2.
+// Seismograms are [nt][ntraces] (ntraces = receivers x channels, fastest).
+#include <cuda_runtime.h>
+
+#include "../../include/seistorch_b200.h"
+#include "st_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+    if (w == 0)
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) l2_kernel(const float* __restrict__ syn, const float* __restrict__ obs,
+                                                 long long n, float scale, double* loss, float* adj) {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float d = syn[i] - obs[i];
+        acc += (double)d * (double)d;
+        if (adj) adj[i] = 2.f * scale * d;
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * (double)scale);
+}
+
+constexpr int CT = 32;      // tile: 32 output samples x 32 traces, 32 taps per stage
+
+// out[n][tr] = sum_m k[(n-m) mod nt] x[m][tr]      (transpose == false)
+// out[n][tr] = sum_m k[(m-n) mod nt] x[m][tr]      (transpose == true)
+__global__ void __launch_bounds__(CT * CT) circ_conv_kernel(const float* __restrict__ x, const float* __restrict__ ker,
+                                                            float* __restrict__ out, int nt, int ntr, bool transpose) {
+    __shared__ float xs[CT][CT + 1];
+    __shared__ float ks[2 * CT];
+    const int tt = threadIdx.x, tn = threadIdx.y;
+    const int tr = blockIdx.x * CT + tt, n = blockIdx.y * CT + tn;
+    const int n0 = blockIdx.y * CT;
+    float acc = 0.f;
+    for (int m0 = 0; m0 < nt; m0 += CT) {
+        __syncthreads();
+        const int m = m0 + tn;
+        xs[tn][tt] = (m < nt && tr < ntr) ? __ldg(x + (long long)m * ntr + tr) : 0.f;
+        // taps needed: d = (n - m) for n in [n0,n0+CT), m in [m0,m0+CT)  ->  d - (n0-m0) in (-CT, CT)
+        const int tid = tn * CT + tt;
+        if (tid < 2 * CT) {
+            int d = (n0 - m0) + (tid - (CT - 1));
+            if (transpose) d = -d;
+            d %= nt;
+            if (d < 0) d += nt;
+            ks[tid] = __ldg(ker + d);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int mm = 0; mm < CT; ++mm) acc += ks[tn - mm + (CT - 1)] * xs[mm][tt];
+    }
+    if (n < nt && tr < ntr) out[(long long)n * ntr + tr] = acc;
+}
+
+// r = Es^2 - Eo^2; loss += 0.5 r^2; v = 2 r hs (in place over hs); base = 2 r xs -> adj
+__global__ void __launch_bounds__(256) env_residual_kernel(const float* __restrict__ syn, const float* __restrict__ obs,
+                                                           float* hs, const float* __restrict__ ho, long long n,
+                                                           float scale, double* loss, float* adj) {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float xs = syn[i], xo = obs[i], a = hs[i], b = ho[i];
+        const float r = (xs * xs + a * a) - (xo * xo + b * b);
+        acc += 0.5 * (double)r * (double)r;
+        if (adj) adj[i] = 2.f * r * xs;
+        hs[i] = 2.f * r * a;
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * (double)scale);
+}
+
+__global__ void __launch_bounds__(256) env_combine_kernel(float* adj, const float* __restrict__ t, long long n, float scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        adj[i] = scale * (adj[i] + t[i]);
+}
+
+inline int nblocks(long long n) {
+    long long b = (n + 255) / 256;
+    return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
+}  // namespace
+
+extern "C" int st_misfit_l2(const float* syn, const float* obs, int64_t n, float scale, double* loss, float* adj, void* stream) {
+    if (!syn || !obs || n < 0) { st_set_error("misfit_l2: bad arguments"); return ST_ERR_BADARG; }
+    if (n == 0) return ST_OK;
+    l2_kernel<<<nblocks(n), 256, 0, (cudaStream_t)stream>>>(syn, obs, n, scale, loss, adj);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_l2: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}
+
+extern "C" int64_t st_misfit_envelope_workspace(int32_t nt, int32_t ntraces) { return 3LL * nt * ntraces; }
+
+extern "C" int st_misfit_envelope(const float* syn, const float* obs, int32_t nt, int32_t ntraces, const float* hker,
+                                  float scale, double* loss, float* adj, float* workspace, void* stream) {
+    if (!syn || !obs || !hker || !workspace || nt <= 0 || ntraces < 0) { st_set_error("misfit_envelope: bad arguments"); return ST_ERR_BADARG; }
+    if (ntraces == 0) return ST_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)nt * ntraces;
+    float* hs = workspace;
+    float* ho = workspace + n;
+    float* tmp = workspace + 2 * n;
+    dim3 grid((ntraces + CT - 1) / CT, (nt + CT - 1) / CT), block(CT, CT);
+    circ_conv_kernel<<<grid, block, 0, st>>>(syn, hker, hs, nt, ntraces, false);
+    circ_conv_kernel<<<grid, block, 0, st>>>(obs, hker, ho, nt, ntraces, false);
+    env_residual_kernel<<<nblocks(n), 256, 0, st>>>(syn, obs, hs, ho, n, scale, loss, adj);
+    if (adj) {
+        circ_conv_kernel<<<grid, block, 0, st>>>(hs, hker, tmp, nt, ntraces, true);
+        env_combine_kernel<<<nblocks(n), 256, 0, st>>>(adj, tmp, n, scale);
+    }
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_envelope: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}

@@ -1,0 +1,306 @@
+// Per-cell arithmetic of the 2D second-order wave-equation family.
+//
+// One set of __host__ __device__ functions serves the sm_100a kernels
+// (st_wave2d.cu) and the host-side emulation used by the CPU unit tests
+// (tests/hostcheck), so the adjoint algebra is checked on CPU against the
+// oracle before it ever runs on a GPU.
+//
+// Reference behaviour restated here (file:line relative to the reference tree):
+//   equations2d/acoustic.py:73-86              damped (PML) update
+//   equations2d/acoustic_habc.py:79-101,147-221 one-way blend + side assignment
+//   seistorch/habc.py:4-40                     side masks
+//   equations2d/vti_habc2.py:25-60, tti_habc.py:25-62   anisotropic Laplacian
+//   equations2d/acoustic_fwim_habc.py:31-67    first-derivative terms
+//   equations2d/acoustic_{vti,tti}_lsrtm_habc.py  Born pair
+//
+// Formulation (see DESIGN.md "numerics"): fields are advanced in increment form
+//   y = h1 + alpha*(h1 - h2) + A[h1]
+// which is algebraically identical to the reference's expression but carries
+// ~15x less fp32 rounding noise.  Coefficients are dimensionless:
+//   r = vp*dt/h,  cxx/czz/cxz/ax/az precomputed per call from the model parameters.
+#pragma once
+#include "st_common.cuh"
+
+struct W2Geom {
+    int nz, nx, ld;     // grid and row pitch (floats)
+    int bw;             // absorbing frame width (50)
+    int multiple;       // free surface on top (no top frame)
+};
+
+struct W2Coef {         // per-cell coefficient values
+    float r, b, cxx, czz, cxz, ax, az, m;
+};
+
+// ----------------------------------------------------------------- HABC geometry
+ST_HD bool w2_in_frame(int z, int x, const W2Geom& g) {
+    return (x < g.bw) || (x >= g.nx - g.bw) || (z >= g.nz - g.bw) || (!g.multiple && z < g.bw);
+}
+
+// weight of each side's one-way blend (0:top 1:bottom 2:left 3:right) in the final
+// value of cell (z,x): closed form of the masks (habc.py:4-40) and of the assignment
+// order top,bottom,left,right followed by the four corner-block main diagonals
+// (acoustic_habc.py:165-202).
+ST_HD void w2_side_weights(int z, int x, const W2Geom& g, float f[4]) {
+    const int w = g.bw, nz = g.nz, nx = g.nx;
+    f[0] = f[1] = f[2] = f[3] = 0.f;
+    const int zb = nz - 1 - z, xr = nx - 1 - x;
+    if (!g.multiple && z < w && z <= x && x <= nx - 1 - z) f[0] = 1.f;
+    if (zb < w && zb <= x && x <= nx - 1 - zb) { f[0] = 0.f; f[1] = 1.f; }
+    const bool tri = (g.multiple && z < w);
+    if (x < w && ((x <= z && x <= nz - 1 - z) || tri)) { f[0] = f[1] = 0.f; f[2] = 1.f; }
+    if (xr < w && ((xr <= z && xr <= nz - 1 - z) || tri)) { f[0] = f[1] = f[2] = 0.f; f[3] = 1.f; }
+    if (!g.multiple && z < w) {
+        if (x == z) { f[0] = 0.5f; f[2] = 0.5f; f[1] = f[3] = 0.f; }
+        if (x == nx - w + z) { f[0] = 0.5f; f[3] = 0.5f; f[1] = f[2] = 0.f; }
+    }
+    const int i = z - (nz - w);
+    if (i >= 0) {
+        if (x == i) { f[1] = 0.5f; f[2] = 0.5f; f[0] = f[3] = 0.f; }
+        if (x == nx - w + i) { f[1] = 0.5f; f[3] = 0.5f; f[0] = f[2] = 0.f; }
+    }
+}
+
+ST_HD int w2_depth(int s, int z, int x, const W2Geom& g) {
+    return s == 0 ? z : (s == 1 ? g.nz - 1 - z : (s == 2 ? x : g.nx - 1 - x));
+}
+
+// coordinates of the cell at depth j from side s, same lateral position as (z,x)
+ST_HD void w2_at_depth(int s, int j, int z, int x, const W2Geom& g, int& zz, int& xx) {
+    zz = z; xx = x;
+    if (s == 0) zz = j;
+    else if (s == 1) zz = g.nz - 1 - j;
+    else if (s == 2) xx = j;
+    else xx = g.nx - 1 - j;
+}
+
+// one-way (Higdon) extrapolation differences of side s at (z,x):
+//   one = 2h1_j - h2_j + lam*Dlam + mu*Dmu,  lam = 2r, mu = r^2   (acoustic_habc.py:89-98)
+// neighbours j+1, j+2 live inside the (bw+1)-deep strip with wrap-around (torch.roll on
+// the cut strip); only depth bw-1 wraps (to depth 0).
+template <class F1, class F2>
+ST_HD void w2_oneway_diffs(int s, int z, int x, const W2Geom& g, F1 h1, F2 h2,
+                           float& base, float& dlam, float& dmu) {
+    const int j = w2_depth(s, z, x, g);
+    int z1, x1, z2, x2;
+    w2_at_depth(s, (j + 1) % (g.bw + 1), z, x, g, z1, x1);
+    w2_at_depth(s, (j + 2) % (g.bw + 1), z, x, g, z2, x2);
+    const float a0 = h1(z, x), a1 = h1(z1, x1), a2 = h1(z2, x2);
+    const float p0 = h2(z, x), p1 = h2(z1, x1);
+    base = a0 + (a0 - p0);
+    dlam = (a1 - a0) - (p1 - p0);
+    dmu = (a1 - a0) - (a2 - a1);
+}
+
+template <class F1, class F2>
+ST_HD float w2_habc_blend(float y, int z, int x, const W2Geom& g, float r, float b, F1 h1, F2 h2) {
+    float f[4];
+    w2_side_weights(z, x, g, f);
+    const float lam = 2.f * r, mu = r * r;
+    float acc = 0.f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (f[s] != 0.f) {
+            float base, dlam, dmu;
+            w2_oneway_diffs(s, z, x, g, h1, h2, base, dlam, dmu);
+            const float one = base + lam * dlam + mu * dmu;
+            acc += f[s] * (one - y);
+        }
+    }
+    return y + b * acc;
+}
+
+// ----------------------------------------------------------------- spatial operator
+template <int FL, class F1>
+ST_HD float w2_stencil(int z, int x, const W2Coef& c, float ciso, F1 u) {
+    const float C = u(z, x), N = u(z - 1, x), S = u(z + 1, x), W = u(z, x - 1), E = u(z, x + 1);
+    float A;
+    if (FL & ST_F_ISO) A = ciso * (((N - C) + (S - C)) + ((E - C) + (W - C)));
+    else A = c.cxx * ((E - C) + (W - C)) + c.czz * ((N - C) + (S - C));
+    if (FL & ST_F_XZ) A += c.cxz * ((u(z + 1, x + 1) - u(z + 1, x - 1)) - (u(z - 1, x + 1) - u(z - 1, x - 1)));
+    if (FL & ST_F_G1) A += c.ax * (E - W) + c.az * (S - N);
+    return A;
+}
+
+// Forward update of all field channels of one cell.
+//   H1(f,z,x), H2(f,z,x): current / previous field, zero outside the domain.
+//   out[f]: new value (before source injection).
+template <int FL, class FH1, class FH2>
+ST_HD void w2_forward_cell(int z, int x, const W2Geom& g, const W2Coef& c, float dt,
+                           FH1 H1, FH2 H2, float out[2]) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    float alpha = 1.f, ciso = c.r * c.r;
+    if (FL & ST_F_PML) {
+        const float bd = c.b * dt;
+        const float inv = 1.f / (1.f + bd);
+        alpha = (1.f - bd) * inv;
+        ciso *= inv;
+    }
+    float A0 = 0.f;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        auto h1 = [&](int zz, int xx) { return H1(f, zz, xx); };
+        auto h2 = [&](int zz, int xx) { return H2(f, zz, xx); };
+        const float u1 = h1(z, x), u2 = h2(z, x);
+        float A = w2_stencil<FL>(z, x, c, ciso, h1);
+        if (f == 0) A0 = A;
+        else A += c.m * A0;
+        float y = u1 + alpha * (u1 - u2) + A;
+        if ((FL & ST_F_HABC) && w2_in_frame(z, x, g)) y = w2_habc_blend(y, z, x, g, c.r, c.b, h1, h2);
+        out[f] = y;
+    }
+}
+
+// ----------------------------------------------------------------- adjoint
+// Computes, for cell p=(z,x), the cotangent Lam_i(f,p) of the field state S_i given
+//   L1 = Lam_{i+1}, L2 = Lam_{i+2}   (zero outside the domain)
+// and the contribution of forward step i+1 (which maps S_i, S_{i-1} -> S_{i+1}) to the
+// coefficient gradients at p:   S1 = S_i, S2 = S_{i-1}.
+//   CF(z,x) returns the W2Coef of an arbitrary in-domain cell.
+// grad[] layout: 0:r 1:cxx 2:czz 3:cxz 4:ax 5:az 6:m   (accumulated, +=)
+//
+// Transpose algebra (DESIGN.md "adjoint"):  forward  Y = (1-b*M) y + b*sum_s f_s one_s,
+//   y = h1 + alpha (h1-h2) + A[h1]  =>
+//   Lam_i = (1+alpha) l1' + A^T[l1'] + Ha^T[L1] - alpha l2' + Hb^T[L2],   l' = (1-b*M) L.
+template <int FL, class FL1, class FL2, class FS1, class FS2, class FC>
+ST_HD void w2_adjoint_cell(int z, int x, const W2Geom& g, float dt,
+                           FL1 L1, FL2 L2, FS1 S1, FS2 S2, FC CF,
+                           float out[2], float grad[7], bool want_grad) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    const bool habc = (FL & ST_F_HABC) != 0;
+    auto inside = [&](int zz, int xx) { return zz >= 0 && zz < g.nz && xx >= 0 && xx < g.nx; };
+    // pre-blend cotangent factor (1 - b*M) at q
+    auto pre = [&](int zz, int xx, const W2Coef& c) {
+        if (!habc) return 1.f;
+        return w2_in_frame(zz, xx, g) ? (1.f - c.b) : 1.f;
+    };
+    // Note: inside the frame sum_s f_s == 1 except where no side owns the cell, which
+    // cannot happen for frame cells (habc.py masks tile the frame), so M == in_frame.
+    auto iso_coef = [&](const W2Coef& c) {
+        float ci = c.r * c.r;
+        if (FL & ST_F_PML) ci *= 1.f / (1.f + c.b * dt);
+        return ci;
+    };
+    // effective cotangent that multiplies the spatial operator of field f at q
+    auto leff = [&](int f, int zz, int xx, const W2Coef& c) {
+        float v = pre(zz, xx, c) * L1(f, zz, xx);
+        if ((FL & ST_F_BORN) && f == 0) v += c.m * (pre(zz, xx, c) * L1(1, zz, xx));
+        return v;
+    };
+    const W2Coef cp = CF(z, x);
+    float alpha = 1.f;
+    if (FL & ST_F_PML) { const float bd = cp.b * dt; alpha = (1.f - bd) / (1.f + bd); }
+    const float prep = pre(z, x, cp);
+
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        // ---- pointwise terms
+        float acc = (1.f + alpha) * (prep * L1(f, z, x)) - alpha * (prep * L2(f, z, x));
+        // ---- transposed spatial operator: stencil applied to the products C(q)*leff(q)
+        auto wk = [&](int kind, int zz, int xx) -> float {
+            if (!inside(zz, xx)) return 0.f;
+            const W2Coef c = CF(zz, xx);
+            const float l = leff(f, zz, xx, c);
+            float cf;
+            if (kind == 0) cf = (FL & ST_F_ISO) ? iso_coef(c) : c.cxx;
+            else if (kind == 1) cf = c.czz;
+            else if (kind == 2) cf = c.cxz;
+            else if (kind == 3) cf = c.ax;
+            else cf = c.az;
+            return cf * l;
+        };
+        if (FL & ST_F_ISO) {
+            const float wc = wk(0, z, x);
+            acc += ((wk(0, z - 1, x) - wc) + (wk(0, z + 1, x) - wc)) + ((wk(0, z, x - 1) - wc) + (wk(0, z, x + 1) - wc));
+        } else {
+            const float wx = wk(0, z, x), wz = wk(1, z, x);
+            acc += ((wk(0, z, x - 1) - wx) + (wk(0, z, x + 1) - wx)) + ((wk(1, z - 1, x) - wz) + (wk(1, z + 1, x) - wz));
+        }
+        if (FL & ST_F_XZ)
+            acc += (wk(2, z - 1, x - 1) - wk(2, z - 1, x + 1)) - (wk(2, z + 1, x - 1) - wk(2, z + 1, x + 1));
+        if (FL & ST_F_G1)
+            acc += (wk(3, z, x - 1) - wk(3, z, x + 1)) + (wk(4, z - 1, x) - wk(4, z + 1, x));
+        // ---- transposed one-way blend: gather over the cells q whose extrapolation reads p
+        if (habc) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int jp = w2_depth(s, z, x, g);
+                if (jp > g.bw) continue;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {       // k==3 encodes the wrap (depth bw-1 reads depth 0 as j+2)
+                    int jq, kk;
+                    if (k < 3) { jq = jp - k; kk = k; if (jq < 0 || jq > g.bw - 1 || jq + kk > g.bw) continue; }
+                    else { if (jp != 0) continue; jq = g.bw - 1; kk = 2; }
+                    int zq, xq;
+                    w2_at_depth(s, jq, z, x, g, zq, xq);
+                    if (!inside(zq, xq)) continue;
+                    float fq[4];
+                    w2_side_weights(zq, xq, g, fq);
+                    if (fq[s] == 0.f) continue;
+                    const W2Coef cq = CF(zq, xq);
+                    const float lam = 2.f * cq.r, mu = cq.r * cq.r;
+                    const float wgt = cq.b * fq[s];
+                    const float a = kk == 0 ? (2.f - lam - mu) : (kk == 1 ? (lam + 2.f * mu) : -mu);
+                    acc += wgt * a * L1(f, zq, xq);
+                    if (kk <= 1) {
+                        const float bt = kk == 0 ? (lam - 1.f) : -lam;
+                        acc += wgt * bt * L2(f, zq, xq);
+                    }
+                }
+            }
+        }
+        out[f] = acc;
+    }
+
+    if (!want_grad) return;
+    // ---- coefficient gradients of forward step i+1 at p
+    {
+        const float ci = iso_coef(cp);
+        float A0 = 0.f;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            auto s1 = [&](int zz, int xx) { return S1(f, zz, xx); };
+            auto s2 = [&](int zz, int xx) { return S2(f, zz, xx); };
+            const float lraw = L1(f, z, x);
+            const float lpre = prep * lraw;
+            float le = lpre;
+            if ((FL & ST_F_BORN) && f == 0) le += cp.m * (prep * L1(1, z, x));
+            const float C = s1(z, x), N = s1(z - 1, x), S = s1(z + 1, x), W = s1(z, x - 1), E = s1(z, x + 1);
+            if (FL & ST_F_ISO) {
+                const float lap = ((N - C) + (S - C)) + ((E - C) + (W - C));
+                float dci = 2.f * cp.r;                 // d(r^2)/dr
+                if (FL & ST_F_PML) dci *= 1.f / (1.f + cp.b * dt);
+                grad[0] += le * dci * lap;
+            } else {
+                grad[1] += le * ((E - C) + (W - C));
+                grad[2] += le * ((N - C) + (S - C));
+            }
+            float cross = 0.f;
+            if (FL & ST_F_XZ) {
+                cross = (s1(z + 1, x + 1) - s1(z + 1, x - 1)) - (s1(z - 1, x + 1) - s1(z - 1, x - 1));
+                grad[3] += le * cross;
+            }
+            if (FL & ST_F_G1) {
+                grad[4] += le * (E - W);
+                grad[5] += le * (S - N);
+            }
+            if (FL & ST_F_BORN) {
+                if (f == 0) A0 = w2_stencil<FL>(z, x, cp, ci, s1);
+                else grad[6] += lpre * A0;
+            }
+            if (habc && w2_in_frame(z, x, g)) {
+                float fq[4];
+                w2_side_weights(z, x, g, fq);
+                float dsum = 0.f;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    if (fq[s] != 0.f) {
+                        float base, dlam, dmu;
+                        w2_oneway_diffs(s, z, x, g, s1, s2, base, dlam, dmu);
+                        dsum += fq[s] * (2.f * dlam + 2.f * cp.r * dmu);
+                    }
+                }
+                grad[0] += lraw * cp.b * dsum;
+            }
+        }
+    }
+}

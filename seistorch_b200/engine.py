@@ -1,0 +1,408 @@
+"""Whole-time-loop propagators on top of the C ABI (include/seistorch_b200.h).
+
+This is the host side of the hot path: it replaces the Python time loop of
+``WaveRNN.forward`` (seistorch/rnn.py:178-205), the per-step dispatch of
+``WaveCell.forward`` (seistorch/cell.py:50-76) and torch autograd-through-time /
+``CheckpointFunction`` (seistorch/checkpoint_new.py:109-217, checkpoint.py:108-230)
+with ONE ``torch.autograd.Function`` per forward call:
+
+  forward : nt fused step launches (stencil + boundary + source add + receiver gather)
+  backward: exact discrete adjoint (transposed stencil + imaging condition), fed either
+            by the stored wavefield history (when it fits the memory budget) or by
+            K-step checkpoints + recomputation (memory O(nt/K + K) states).
+
+PyTorch is used for device memory, streams and autograd plumbing only; all per-step
+arithmetic is in the sm_100a kernels.  There is no CPU fallback: a missing library or a
+CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+# equation-variant flags (include/seistorch_b200.h)
+EQ_ISO, EQ_PML, EQ_HABC, EQ_XZ, EQ_G1, EQ_BORN = 1, 2, 4, 8, 16, 32
+
+# (family, flags, field names in channel order, coefficient slots used -> gradient slot)
+# wave2d coefficient order: r, b, cxx, czz, cxz, ax, az, m ; gradient order r,cxx,czz,cxz,ax,az,m
+_W2_GRAD_OF_COEF = {0: 0, 2: 1, 3: 2, 4: 3, 5: 4, 6: 5, 7: 6}
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"seistorch_b200: {what} must be a CUDA tensor (no CPU fallback); got {t.device}")
+
+
+# ======================================================================== acquisition
+class Acquisition:
+    """Device-side source / receiver index tables (int32) in the layout of
+    ``st_acquisition``.  Mirrors the index semantics of WaveSource / WaveProbe
+    (source.py:47-70, probe.py:42-48): tensor-dimension order, one source row per point
+    source, receivers of all shots concatenated (rnn.py:51-73)."""
+
+    def __init__(self, shape: Sequence[int], B: int, src_b, src_idx, rec_b, rec_idx, device):
+        self.shape = tuple(int(s) for s in shape)
+        self.ndim = len(self.shape)
+        self.B = int(B)
+        dev = torch.device(device)
+        src_b = torch.as_tensor(src_b, dtype=torch.int64, device=dev).reshape(-1)
+        src_idx = torch.as_tensor(src_idx, dtype=torch.int64, device=dev).reshape(-1, self.ndim)
+        rec_b = torch.as_tensor(rec_b, dtype=torch.int64, device=dev).reshape(-1)
+        rec_idx = torch.as_tensor(rec_idx, dtype=torch.int64, device=dev).reshape(-1, self.ndim)
+        self.ns = int(src_b.numel())
+        self.R = int(rec_b.numel())
+        lim = torch.tensor(self.shape, dtype=torch.int64, device=dev)
+        bad = False
+        if self.ns:
+            bad |= bool(((src_idx < 0) | (src_idx >= lim)).any() or (src_b < 0).any() or (src_b >= B).any())
+        if self.R:
+            bad |= bool(((rec_idx < 0) | (rec_idx >= lim)).any() or (rec_b < 0).any() or (rec_b >= B).any())
+        if bad:
+            raise IndexError("seistorch_b200: source/receiver index outside the padded domain")
+        self.src_b = src_b.to(torch.int32).contiguous()
+        self.src_i = [src_idx[:, k].to(torch.int32).contiguous() for k in range(self.ndim)]
+        # receivers: sort by row key, CSR over rows
+        rows_per_shot = 1
+        for s in self.shape[:-1]:
+            rows_per_shot *= s
+        nrows = self.B * rows_per_shot
+        if nrows + 1 >= 2 ** 31:
+            raise ValueError("seistorch_b200: too many rows for int32 receiver index")
+        if self.R:
+            key = rec_b
+            for k in range(self.ndim - 1):
+                key = key * self.shape[k] + rec_idx[:, k]
+            order = torch.argsort(key, stable=True)
+            counts = torch.bincount(key, minlength=nrows)
+            self.rec_col = rec_idx[order, self.ndim - 1].to(torch.int32).contiguous()
+            self.rec_orig = order.to(torch.int32).contiguous()
+        else:
+            counts = torch.zeros(nrows, dtype=torch.int64, device=dev)
+            self.rec_col = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.rec_orig = torch.zeros(1, dtype=torch.int32, device=dev)
+        rs = torch.zeros(nrows + 1, dtype=torch.int64, device=dev)
+        rs[1:] = torch.cumsum(counts, 0)
+        self.row_start = rs.to(torch.int32).contiguous()
+
+    def fill(self, q: _lib.StAcquisition, amp, gamp, src_fmask, chan_f, rec_out, rec_adj):
+        q.ns = self.ns
+        q.src_b = _lib.ptr(self.src_b)
+        if self.ndim == 3:
+            q.src_i0, q.src_i1, q.src_i2 = (_lib.ptr(t) for t in self.src_i)
+        else:
+            q.src_i0 = None
+            q.src_i1, q.src_i2 = (_lib.ptr(t) for t in self.src_i)
+        q.amp = _lib.ptr(amp)
+        q.gamp = _lib.ptr(gamp)
+        q.src_fmask = int(src_fmask)
+        q.R = self.R
+        q.row_start = _lib.ptr(self.row_start)
+        q.rec_col = _lib.ptr(self.rec_col)
+        q.rec_orig = _lib.ptr(self.rec_orig)
+        q.nchan = len(chan_f)
+        for k in range(4):
+            q.chan_f[k] = int(chan_f[k]) if k < len(chan_f) else 0
+        q.rec_out = _lib.ptr(rec_out)
+        q.rec_adj = _lib.ptr(rec_adj)
+
+
+# ======================================================================== plan
+@dataclass
+class Spec:
+    """Static description of one propagation call."""
+    family: str                     # 'wave2d' | 'elastic2d' | 'acoustic3d'
+    flags: int
+    shape: tuple                    # padded domain (nz,nx) or (n0,n1,n2)
+    B: int
+    nt: int
+    dt: float
+    bw: int = 50
+    multiple: bool = False
+    src_fmask: int = 1
+    chan_f: tuple = (0,)
+    coef_slots: tuple = ()          # for wave2d: slot index (0..7) of every coefficient tensor passed
+    history_budget_bytes: Optional[int] = None     # None: derive from free memory
+    segment: Optional[int] = None                  # force a checkpoint segment length (tests)
+
+    @property
+    def nf(self):
+        if self.family == "wave2d":
+            return 2 if self.flags & EQ_BORN else 1
+        return 5 if self.family == "elastic2d" else 1
+
+    @property
+    def order(self):
+        return 1 if self.family == "elastic2d" else 2
+
+    @property
+    def nlam(self):
+        return 2 if self.family == "elastic2d" else 3
+
+    @property
+    def ngrad(self):
+        return {"wave2d": 7, "elastic2d": 4, "acoustic3d": 1}[self.family]
+
+    @property
+    def ld(self):
+        return _round_up(self.shape[-1], 4)
+
+    @property
+    def plane(self):
+        n = self.ld
+        for s in self.shape[:-1]:
+            n *= s
+        return n
+
+    @property
+    def slot_elems(self):
+        return self.nf * self.B * self.plane
+
+
+def _choose_bchunk(spec: Spec) -> int:
+    """Shots handled by one adjoint block (gradient accumulated in registers across
+    them); keep at least ~4 blocks per SM."""
+    if spec.family == "acoustic3d":
+        tiles = math.ceil(spec.shape[2] / 64) * math.ceil(spec.shape[1] / 8) * math.ceil(spec.shape[0] / 16)
+    else:
+        tiles = math.ceil(spec.shape[1] / 64) * math.ceil(spec.shape[0] / 32)
+    best = 1
+    for c in range(1, spec.B + 1):
+        if spec.B % c == 0 and tiles * (spec.B // c) >= 592:
+            best = c
+    return best
+
+
+class _Problem:
+    """Owns the ctypes problem struct + the torch buffers it points to."""
+
+    def __init__(self, spec: Spec, coefp: torch.Tensor, acq: Acquisition, amp: torch.Tensor, nslots: int,
+                 u: Optional[torch.Tensor] = None):
+        self.spec = spec
+        self.acq = acq
+        self.coefp = coefp            # [ncoef, plane]  pitched coefficient planes
+        self.amp = amp                # [nt, ns] fp32 contiguous
+        dev = coefp.device
+        self.nslots = nslots
+        self.u = u if u is not None else torch.zeros(nslots * spec.slot_elems, dtype=torch.float32, device=dev)
+        self.lam = None
+        self.gacc = None
+        self.bchunk = 1
+        self.rec_out = None
+        self.rec_adj = None
+        self.gamp = None
+        L = _lib.lib()
+        fam = spec.family
+        if fam == "wave2d":
+            self.p = _lib.StWave2dProblem()
+            self.fwd, self.adj = L.st_wave2d_forward, L.st_wave2d_adjoint
+        elif fam == "elastic2d":
+            self.p = _lib.StElastic2dProblem()
+            self.fwd, self.adj = L.st_elastic2d_forward, L.st_elastic2d_adjoint
+        elif fam == "acoustic3d":
+            self.p = _lib.StAcoustic3dProblem()
+            self.fwd, self.adj = L.st_acoustic3d_forward, L.st_acoustic3d_adjoint
+        else:
+            raise ValueError(fam)
+
+    def _sync_struct(self):
+        s, p = self.spec, self.p
+        if s.family == "wave2d":
+            p.flags = s.flags
+            p.B, p.nz, p.nx, p.ld = s.B, s.shape[0], s.shape[1], s.ld
+            p.bw, p.multiple = s.bw, int(s.multiple)
+            p.nt, p.dt = s.nt, float(s.dt)
+            for k in range(8):
+                p.coef[k] = None
+            for row, slot in enumerate(s.coef_slots):
+                p.coef[slot] = self.coefp[row].data_ptr()
+        elif s.family == "elastic2d":
+            p.B, p.nz, p.nx, p.ld, p.nt = s.B, s.shape[0], s.shape[1], s.ld, s.nt
+            for k in range(5):
+                p.coef[k] = self.coefp[k].data_ptr()
+        else:
+            p.B, p.n0, p.n1, p.n2, p.ld, p.nt = s.B, s.shape[0], s.shape[1], s.shape[2], s.ld, s.nt
+            p.dt = float(s.dt)
+            p.coef[0] = self.coefp[0].data_ptr()
+            p.coef[1] = self.coefp[1].data_ptr()
+        p.u = self.u.data_ptr()
+        p.nslots = self.nslots
+        p.lam = _lib.ptr(self.lam)
+        p.gacc = _lib.ptr(self.gacc)
+        p.bchunk = self.bchunk
+        self.acq.fill(p.acq, self.amp, self.gamp, s.src_fmask, s.chan_f, self.rec_out, self.rec_adj)
+
+    def forward(self, i0, nsteps, slot0, record=True):
+        keep = self.rec_out
+        if not record:
+            self.rec_out = None
+        self._sync_struct()
+        self.rec_out = keep
+        _lib.check(self.fwd(C.byref(self.p), i0, nsteps, slot0 % self.nslots, _stream_ptr()), f"{self.spec.family}_forward")
+
+    def adjoint(self, i_hi, nsteps, slot_hi):
+        self._sync_struct()
+        _lib.check(self.adj(C.byref(self.p), i_hi, nsteps, slot_hi % self.nslots, _stream_ptr()), f"{self.spec.family}_adjoint")
+
+    def slot_view(self, slot, count=1):
+        e = self.spec.slot_elems
+        slot %= self.nslots
+        return self.u[slot * e:(slot + count) * e]
+
+
+def _pack_coefs(spec: Spec, coefs: Sequence[torch.Tensor]) -> torch.Tensor:
+    """[ncoef, *shape] fp32 -> pitched planes [ncoef, plane]."""
+    dev = coefs[0].device
+    nx, ld = spec.shape[-1], spec.ld
+    out = torch.zeros((len(coefs),) + tuple(spec.shape[:-1]) + (ld,), dtype=torch.float32, device=dev)
+    for k, c in enumerate(coefs):
+        if tuple(c.shape) != tuple(spec.shape):
+            raise ValueError(f"coefficient {k} has shape {tuple(c.shape)}, expected {spec.shape}")
+        out[k, ..., :nx] = c.detach().to(torch.float32)
+    return out.reshape(len(coefs), -1)
+
+
+def _history_plan(spec: Spec, dev) -> tuple:
+    """Return (K, nseg): K-step segments with stored history inside a segment.
+    K == nt means the whole history is stored in the forward pass (no recomputation)."""
+    nt, p = spec.nt, spec.order
+    if spec.segment is not None:
+        K = max(1, min(int(spec.segment), nt))
+        return K, math.ceil(nt / K)
+    slot_bytes = spec.slot_elems * 4
+    if spec.history_budget_bytes is not None:
+        budget = int(spec.history_budget_bytes)
+    else:
+        env = os.environ.get("SEISTORCH_B200_HISTORY_GB")
+        if env:
+            budget = int(float(env) * 2 ** 30)
+        else:
+            free, _total = torch.cuda.mem_get_info(dev)
+            reserve = (spec.nlam + 2) * slot_bytes + spec.ngrad * spec.plane * 4 * spec.B + (1 << 30)
+            budget = int(0.85 * free) - reserve
+    nslots_max = max(budget // slot_bytes, p + 2)
+    if nt + p <= nslots_max:
+        return nt, 1
+    best = None
+    for K in range(1, nt + 1):
+        need = K + p + p * math.ceil(nt / K)
+        if need <= nslots_max:
+            best = K
+    if best is None:
+        raise RuntimeError(
+            f"seistorch_b200: wavefield history does not fit: one state slot is {slot_bytes / 2**20:.1f} MiB and "
+            f"the budget allows {nslots_max} slots; reduce the number of shots per call")
+    return best, math.ceil(nt / best)
+
+
+class _Propagate(torch.autograd.Function):
+    """records[nt, R, nchan] = F(amp[nt, ns], *coefs)."""
+
+    @staticmethod
+    def forward(ctx, spec: Spec, acq: Acquisition, amp: torch.Tensor, *coefs: torch.Tensor):
+        dev = coefs[0].device
+        for c in coefs:
+            _require_cuda(c, "model coefficient")
+        _require_cuda(amp, "wavelet")
+        amp32 = amp.detach().to(torch.float32).contiguous()
+        if tuple(amp32.shape) != (spec.nt, acq.ns):
+            raise ValueError(f"amp has shape {tuple(amp32.shape)}, expected {(spec.nt, acq.ns)}")
+        coefp = _pack_coefs(spec, coefs)
+        nchan = len(spec.chan_f)
+        rec = torch.zeros((spec.nt, acq.R, nchan), dtype=torch.float32, device=dev)
+        need_grad = any(ctx.needs_input_grad[2:])
+        p = spec.order
+        if not need_grad:
+            prob = _Problem(spec, coefp, acq, amp32, p + 1)
+            prob.rec_out = rec
+            prob.forward(0, spec.nt, 0)
+            return rec
+        K, nseg = _history_plan(spec, dev)
+        prob = _Problem(spec, coefp, acq, amp32, K + p)
+        prob.rec_out = rec
+        ckpts = []
+        slot0_last = 0
+        for s in range(nseg):
+            a, b = s * K, min((s + 1) * K, spec.nt)
+            slot0 = a % prob.nslots
+            if nseg > 1 and s < nseg - 1:
+                ckpts.append((prob.slot_view(slot0, 1).clone(), prob.slot_view(slot0 + 1, 1).clone() if p == 2 else None))
+            prob.forward(a, b - a, slot0)
+            slot0_last = slot0
+        ctx.spec, ctx.acq, ctx.prob = spec, acq, prob
+        ctx.K, ctx.nseg, ctx.ckpts, ctx.slot0_last = K, nseg, ckpts, slot0_last
+        ctx.ncoef = len(coefs)
+        ctx.coef_dtypes = [c.dtype for c in coefs]
+        ctx.amp_dtype = amp.dtype
+        return rec
+
+    @staticmethod
+    def backward(ctx, grad_rec):
+        spec, acq, prob = ctx.spec, ctx.acq, ctx.prob
+        dev = prob.u.device
+        p = spec.order
+        K, nseg = ctx.K, ctx.nseg
+        prob.rec_adj = grad_rec.detach().to(torch.float32).contiguous()
+        prob.lam = torch.zeros(spec.nlam * spec.slot_elems, dtype=torch.float32, device=dev)
+        prob.bchunk = _choose_bchunk(spec)
+        nchunk = math.ceil(spec.B / prob.bchunk)
+        prob.gacc = torch.zeros(nchunk * spec.ngrad * spec.plane, dtype=torch.float32, device=dev)
+        want_gamp = ctx.needs_input_grad[2]
+        prob.gamp = torch.zeros((spec.nt, acq.ns), dtype=torch.float32, device=dev) if want_gamp else None
+        for s in reversed(range(nseg)):
+            a, b = s * K, min((s + 1) * K, spec.nt)
+            if s == nseg - 1:
+                slot0 = ctx.slot0_last           # history of the last segment is still in place
+            else:
+                slot0 = 0
+                c0, c1 = ctx.ckpts[s]
+                prob.slot_view(0, 1).copy_(c0)
+                if p == 2:
+                    prob.slot_view(1, 1).copy_(c1)
+                prob.forward(a, b - a, 0, record=False)
+            if p == 2:
+                # Lam_i for i = b-1 .. a ; S_i sits in slot slot0 + 2 + (i - a)
+                prob.adjoint(b - 1, b - a, slot0 + 2 + (b - 1 - a))
+            else:
+                # first-order: Lam_i for i = i_hi .. max(a-1,0); S_{i+1} in slot slot0 + 1 + (i+1-a)
+                i_hi = b - 1 if s == nseg - 1 else b - 2
+                i_lo = max(a - 1, 0)
+                if i_hi >= i_lo:
+                    prob.adjoint(i_hi, i_hi - i_lo + 1, slot0 + 1 + (i_hi + 1 - a))
+        g = prob.gacc.view(nchunk, spec.ngrad, *spec.shape[:-1], spec.ld).sum(0)[..., :spec.shape[-1]]
+        grads = []
+        for k in range(ctx.ncoef):
+            if not ctx.needs_input_grad[3 + k]:
+                grads.append(None)
+                continue
+            if spec.family == "wave2d":
+                slot = spec.coef_slots[k]
+                gi = _W2_GRAD_OF_COEF.get(slot)
+                grads.append(None if gi is None else g[gi].to(ctx.coef_dtypes[k]))
+            elif spec.family == "elastic2d":
+                grads.append(None if k == 0 else g[k - 1].to(ctx.coef_dtypes[k]))
+            else:
+                grads.append(g[0].to(ctx.coef_dtypes[k]) if k == 0 else None)
+        gamp = prob.gamp.to(ctx.amp_dtype) if want_gamp else None
+        # free the big buffers eagerly
+        ctx.prob = None
+        return (None, None, gamp, *grads)
+
+
+def propagate(spec: Spec, acq: Acquisition, amp: torch.Tensor, coefs: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Run nt steps; returns seismograms [nt, R, nchan] (differentiable w.r.t. amp, coefs)."""
+    return _Propagate.apply(spec, acq, amp, *coefs)

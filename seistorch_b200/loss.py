@@ -1,0 +1,131 @@
+"""L2 and envelope misfits with fused adjoint-source kernels -- same class surface as
+seistorch/loss.py (Loss wrapper :23-50, L2 :409-421, Envelope :178-216).
+
+The forward value and d loss / d syn come from csrc/st_misfit.cu in one pass; inputs are
+stacked records [B, nt, nrec, nchan] (``TensorList.stack()``) or lists of per-shot
+records, like the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import _require_cuda, _stream_ptr
+
+_HKER = {}
+
+
+def hilbert_kernel(nt: int, device) -> torch.Tensor:
+    """Imaginary part of ifft(h), h = one-sided spectrum filter of transform.py:46-53
+    (scipy convention, nfft = nt): the analytic signal is x + i (hker (*) x)."""
+    key = (nt, str(device))
+    if key not in _HKER:
+        h = np.zeros(nt, dtype=np.float64)
+        if nt % 2 == 0:
+            h[0] = h[nt // 2] = 1
+            h[1:nt // 2] = 2
+        else:
+            h[0] = 1
+            h[1:(nt + 1) // 2] = 2
+        _HKER[key] = torch.from_numpy(np.fft.ifft(h).imag.astype(np.float32)).to(device)
+    return _HKER[key]
+
+
+class _Misfit(torch.autograd.Function):
+    """loss = misfit(syn, obs) on [nt, ntraces] data; saves d loss / d syn."""
+
+    @staticmethod
+    def forward(ctx, kind, syn, obs):
+        _require_cuda(syn, "synthetic record")
+        s = syn.detach().to(torch.float32).contiguous()
+        o = obs.detach().to(device=s.device, dtype=torch.float32).contiguous()
+        if s.shape != o.shape:
+            raise ValueError(f"syn {tuple(s.shape)} and obs {tuple(o.shape)} differ in shape")
+        loss = torch.zeros(1, dtype=torch.float64, device=s.device)
+        adj = torch.empty_like(s)
+        L = _lib.lib()
+        nt = s.shape[0]
+        ntr = s.numel() // max(nt, 1)
+        if kind == "l2":
+            _lib.check(L.st_misfit_l2(s.data_ptr(), o.data_ptr(), s.numel(), 1.0, loss.data_ptr(), adj.data_ptr(),
+                                      _stream_ptr()), "misfit_l2")
+        else:
+            ws = torch.empty(L.st_misfit_envelope_workspace(nt, ntr), dtype=torch.float32, device=s.device)
+            hk = hilbert_kernel(nt, s.device)
+            _lib.check(L.st_misfit_envelope(s.data_ptr(), o.data_ptr(), nt, ntr, hk.data_ptr(), 1.0, loss.data_ptr(),
+                                            adj.data_ptr(), ws.data_ptr(), _stream_ptr()), "misfit_envelope")
+        ctx.save_for_backward(adj)
+        ctx.dtype = syn.dtype
+        return loss[0].to(syn.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        (adj,) = ctx.saved_tensors
+        return None, (adj * g).to(ctx.dtype), None
+
+
+def _per_shot(kind, x, y):
+    """Sum of the misfit over shots; each shot record is (nt, nrec, nchan)."""
+    if isinstance(x, torch.Tensor) and x.ndim == 4 and isinstance(y, torch.Tensor):
+        # stacked [B, nt, nrec, nchan] -> one launch over [nt, B*nrec*nchan]
+        B, nt = x.shape[0], x.shape[1]
+        xs = x.permute(1, 0, 2, 3).reshape(nt, -1)
+        ys = y.permute(1, 0, 2, 3).reshape(nt, -1)
+        return _Misfit.apply(kind, xs, ys)
+    loss = 0.0
+    for _x, _y in zip(x, y):
+        loss = loss + _Misfit.apply(kind, _x.reshape(_x.shape[0], -1), torch.as_tensor(_y).reshape(_x.shape[0], -1))
+    return loss
+
+
+class L2(torch.nn.Module):
+    """loss.py:409-421: sum over shots of MSELoss(reduction='sum')."""
+
+    @property
+    def name(self):
+        return "l2"
+
+    def forward(self, x, y):
+        return _per_shot("l2", x, y)
+
+
+class Envelope(torch.nn.Module):
+    """loss.py:178-216 with method='square' (the only working method there):
+    sum over shots of 0.5 * sum((E(x)^2 - E(y)^2)^2), E = |analytic signal| along time."""
+
+    def __init__(self, method="square"):
+        super().__init__()
+        if method != "square":
+            raise NotImplementedError("seistorch_b200: only the 'square' envelope misfit is accelerated")
+        self.method = method
+
+    @property
+    def name(self):
+        return "envelope"
+
+    def forward(self, x, y):
+        return _per_shot("envelope", x, y)
+
+
+class Loss:
+    """loss.py:23-50: look a misfit up by its ``name`` property."""
+
+    def __init__(self, loss="l2"):
+        self.loss_name = loss
+
+    def __repr__(self):
+        return f"Loss(loss={self.loss_name})"
+
+    def __call__(self, *args, **kwargs):
+        return self.loss(*args, **kwargs)
+
+    def loss(self, cfg=None, *args, **kwargs):
+        for cls in (L2, Envelope):
+            if cls().name == self.loss_name:
+                obj = cls(**kwargs)
+                obj.cfg = cfg
+                return obj
+        raise ValueError(f"Cannot find loss named {self.loss_name}")
