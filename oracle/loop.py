@@ -110,7 +110,10 @@ def simulate(case, dtype=torch.float32, requires_grad=(), wavelet=None):
     fields = [torch.zeros((B,) + shape, dtype=dtype) for _ in wf_names]
     dt = torch.tensor(float(case["dt"]), dtype=dtype)   # cell.py:18 0-dim tensor
     h = torch.tensor(float(case["h"]), dtype=dtype)     # geom.py:32
-    x = torch.as_tensor(np.asarray(case["wavelet"] if wavelet is None else wavelet), dtype=dtype)
+    if isinstance(wavelet, torch.Tensor):
+        x = wavelet.to(dtype)
+    else:
+        x = torch.as_tensor(np.asarray(case["wavelet"] if wavelet is None else wavelet), dtype=dtype)
     nt = int(case["nt"])
     # one-hot source mask, rnn.py:160-166
     smask = torch.zeros((B,) + shape, dtype=dtype)

@@ -50,7 +50,8 @@ static int w2_check(const st_wave2d_problem* p) {
     ST_REQUIRE(p->ld >= p->nx && p->ld % 4 == 0, "wave2d: row pitch %d must be >= nx and a multiple of 4", p->ld);
     ST_REQUIRE(p->coef[0] && p->coef[1], "wave2d: coef r and b are required");
     if (p->flags & ST_EQ_HABC) {
-        ST_REQUIRE(p->bw > 0 && p->nz > 2 * p->bw && p->nx > 2 * p->bw, "wave2d: HABC needs nz,nx > 2*bw");
+        ST_REQUIRE(p->bw > 0 && p->nx > 2 * p->bw && p->nz > (p->multiple ? 1 : 2) * p->bw,
+                   "wave2d: HABC needs nx > 2*bw and nz > 2*bw (nz > bw with a free surface)");
     }
     if (!(p->flags & ST_EQ_ISO)) ST_REQUIRE(p->coef[2] && p->coef[3], "wave2d: cxx/czz required");
     if (p->flags & ST_EQ_XZ) ST_REQUIRE(p->coef[4] != nullptr, "wave2d: cxz required");

@@ -35,6 +35,10 @@ EQ_ISO, EQ_PML, EQ_HABC, EQ_XZ, EQ_G1, EQ_BORN = 1, 2, 4, 8, 16, 32
 _W2_GRAD_OF_COEF = {0: 0, 2: 1, 3: 2, 4: 3, 5: 4, 6: 5, 7: 6}
 
 
+# number of sm_100a kernel launches issued through the C ABI (bench.py reports it)
+LAUNCHES = {"forward": 0, "adjoint": 0, "misfit": 0}
+
+
 def _round_up(n, m):
     return (n + m - 1) // m * m
 
@@ -253,10 +257,12 @@ class _Problem:
         self._sync_struct()
         self.rec_out = keep
         _lib.check(self.fwd(C.byref(self.p), i0, nsteps, slot0 % self.nslots, _stream_ptr()), f"{self.spec.family}_forward")
+        LAUNCHES["forward"] += nsteps
 
     def adjoint(self, i_hi, nsteps, slot_hi):
         self._sync_struct()
         _lib.check(self.adj(C.byref(self.p), i_hi, nsteps, slot_hi % self.nslots, _stream_ptr()), f"{self.spec.family}_adjoint")
+        LAUNCHES["adjoint"] += nsteps
 
     def slot_view(self, slot, count=1):
         e = self.spec.slot_elems

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import _require_cuda, _stream_ptr
+from .engine import LAUNCHES, _require_cuda, _stream_ptr
 
 _HKER = {}
 
@@ -52,11 +52,13 @@ class _Misfit(torch.autograd.Function):
         if kind == "l2":
             _lib.check(L.st_misfit_l2(s.data_ptr(), o.data_ptr(), s.numel(), 1.0, loss.data_ptr(), adj.data_ptr(),
                                       _stream_ptr()), "misfit_l2")
+            LAUNCHES["misfit"] += 1
         else:
             ws = torch.empty(L.st_misfit_envelope_workspace(nt, ntr), dtype=torch.float32, device=s.device)
             hk = hilbert_kernel(nt, s.device)
             _lib.check(L.st_misfit_envelope(s.data_ptr(), o.data_ptr(), nt, ntr, hk.data_ptr(), 1.0, loss.data_ptr(),
                                             adj.data_ptr(), ws.data_ptr(), _stream_ptr()), "misfit_envelope")
+            LAUNCHES["misfit"] += 5
         ctx.save_for_backward(adj)
         ctx.dtype = syn.dtype
         return loss[0].to(syn.dtype)
