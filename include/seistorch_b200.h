@@ -91,11 +91,12 @@ typedef struct st_wave2d_problem {
     int32_t bw, multiple;       /* absorbing width (50), free-surface flag */
     int32_t nt;
     float dt;                   /* only used by ST_EQ_PML (b*dt) */
-    const float* coef[8];       /* r=vp*dt/h, b(damping d), cxx, czz, cxz, ax, az, m : [nz][ld] or NULL */
+    const float* coef[8];       /* r=vp*dt/h, b(damping d), cxx, czz, cxz, ax, az, m : [nz][ld] or NULL.
+                                   ISO equations: cxx = r^2 (HABC) or r^2/(1+b dt) (PML), czz = (1-b dt)/(1+b dt) (PML) */
     float* u;                   /* [nslots][NF][B][nz][ld] */
     int32_t nslots;
     float* lam;                 /* [3][NF][B][nz][ld] adjoint state, slot = i mod 3 (zero before the first adjoint call) */
-    float* gacc;                /* [nchunk][7][nz][ld] += coefficient gradients (r,cxx,czz,cxz,ax,az,m), or NULL */
+    float* gacc;                /* [nchunk][7][nz][ld] += coefficient gradients (r [one-way blend terms only],cxx,czz,cxz,ax,az,m), or NULL */
     int32_t bchunk;             /* shots per block in the adjoint kernel; nchunk = ceil(B/bchunk) */
     st_acquisition acq;
 } st_wave2d_problem;

@@ -59,13 +59,17 @@ def _ddz(v, h):
 
 def wave2d_coefficients(equation, params, dt, h, d):
     """Returns (coef tensors fp32, coef slots) for the 2D second-order family.
-    Slots: 0 r, 1 b, 2 cxx, 3 czz, 4 cxz, 5 ax, 6 az, 7 m."""
+    Slots: 0 r, 1 b, 2 cxx (ciso for ISO equations), 3 czz (alpha for PML), 4 cxz, 5 ax, 6 az, 7 m."""
     dt, h = float(dt), float(h)
     vp = _f64(params[0])
     r = vp * (dt / h)
     out = {0: r, 1: _f64(d)}
-    if equation in ("acoustic", "acoustic_habc"):
-        pass
+    if equation == "acoustic":
+        bd = _f64(d) * dt
+        out[2] = r * r / (1 + bd)              # ciso
+        out[3] = (1 - bd) / (1 + bd)           # alpha
+    elif equation == "acoustic_habc":
+        out[2] = r * r
     elif equation in ("vti_habc2", "acoustic_vti_lsrtm_habc"):
         eps, delta = _f64(params[1]), _f64(params[2])
         kx, kz = _kgrid(vp.shape, h, vp.device)
@@ -96,6 +100,7 @@ def wave2d_coefficients(equation, params, dt, h, d):
             out[7] = _f64(params[4])
     elif equation == "acoustic_fwim_habc":
         rx, rz = _f64(params[1]), _f64(params[2])
+        out[2] = r * r
         v_x, v_z = _ddx(vp, h), _ddz(vp, h)
         # term2 - term3 with p_x = (E-W)/(2h):   coefficient of (E-W) and (S-N)
         out[5] = (vp * dt ** 2 * v_x - 2 * vp ** 2 * dt ** 2 * rx) / (2 * h)

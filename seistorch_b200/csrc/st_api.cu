@@ -53,7 +53,9 @@ static int w2_check(const st_wave2d_problem* p) {
         ST_REQUIRE(p->bw > 0 && p->nx > 2 * p->bw && p->nz > (p->multiple ? 1 : 2) * p->bw,
                    "wave2d: HABC needs nx > 2*bw and nz > 2*bw (nz > bw with a free surface)");
     }
-    if (!(p->flags & ST_EQ_ISO)) ST_REQUIRE(p->coef[2] && p->coef[3], "wave2d: cxx/czz required");
+    ST_REQUIRE((long long)p->nz * p->ld < (1LL << 31), "wave2d: plane too large for 32-bit offsets");
+    ST_REQUIRE(p->coef[2] != nullptr, "wave2d: cxx (ciso for ISO equations) required");
+    if (!(p->flags & ST_EQ_ISO) || (p->flags & ST_EQ_PML)) ST_REQUIRE(p->coef[3] != nullptr, "wave2d: czz (alpha for PML) required");
     if (p->flags & ST_EQ_XZ) ST_REQUIRE(p->coef[4] != nullptr, "wave2d: cxz required");
     if (p->flags & ST_EQ_G1) ST_REQUIRE(p->coef[5] && p->coef[6], "wave2d: ax/az required");
     if (p->flags & ST_EQ_BORN) ST_REQUIRE(p->coef[7] != nullptr, "wave2d: m required");

@@ -5,33 +5,33 @@
 // One launch = one time step of every shot in the batch, with the source add and the
 // receiver gather fused in (reference: ~30-190 ATen launches per step).
 //
-// Data layout in HBM: fields [NF][B][nz][ld] fp32, row pitch ld a multiple of 4 so
-// that every row starts 16-byte aligned; coefficient planes [nz][ld] shared by all
-// shots (they stay L2-resident: <= 8 MB each at the BASELINE sizes vs 126 MB of L2).
+// Two kinds of thread blocks share a launch:
+//   * FAST blocks stream the non-frame cells: a warp owns a 128-column x 8-row tile, every
+//     lane 4 consecutive cells; rows are loaded once as 128-bit vectors and marched through
+//     a 3-row register pipeline, left/right neighbours come from warp shuffles (plus one
+//     predicated halo load per edge lane), no shared memory.
+//   * FRAME blocks evaluate the absorbing frame (one-way blend, side ownership, wrap-around
+//     strip neighbours) cell by cell from a shared-memory tile with a 2-cell halo.
+// The two block kinds write disjoint cells; whoever stores a cell also applies the source
+// add / receiver gather for it, so no inter-block ordering is needed.
+//
+// Data layout in HBM: fields [NF][B][nz][ld] fp32, row pitch ld a multiple of 4 so that
+// every row starts 16-byte aligned and columns [nx, ld) stay zero; coefficient planes
+// [nz][ld] shared by all shots (L2-resident: <= 8 MB each at the BASELINE sizes).
 #include "st_wave2d.cuh"
 
 namespace {
 
-constexpr int TX = 64;          // tile width  (x, fastest)
-constexpr int TZ = 32;          // tile height (z)
-constexpr int HALO = 2;         // the one-way blend reads j+1, j+2 along the normal
-constexpr int SW = TX + 2 * HALO;
-constexpr int SH = TZ + 2 * HALO;
-constexpr int NTX = 64, NTY = 4;            // 256 threads; each owns TZ/NTY = 8 rows of one column
-constexpr int RPT = TZ / NTY;
-
-__device__ __forceinline__ W2Coef load_coef(const W2Args& a, long long idx) {
-    W2Coef c;
-    c.r = a.coef[0] ? __ldg(a.coef[0] + idx) : 0.f;
-    c.b = a.coef[1] ? __ldg(a.coef[1] + idx) : 0.f;
-    c.cxx = a.coef[2] ? __ldg(a.coef[2] + idx) : 0.f;
-    c.czz = a.coef[3] ? __ldg(a.coef[3] + idx) : 0.f;
-    c.cxz = a.coef[4] ? __ldg(a.coef[4] + idx) : 0.f;
-    c.ax = a.coef[5] ? __ldg(a.coef[5] + idx) : 0.f;
-    c.az = a.coef[6] ? __ldg(a.coef[6] + idx) : 0.f;
-    c.m = a.coef[7] ? __ldg(a.coef[7] + idx) : 0.f;
-    return c;
-}
+constexpr int NT = 256;                     // threads per block (both block kinds)
+// ---- frame (general) tiles
+constexpr int TX = 64, TZ = 32, HALO = 2;
+constexpr int SW = TX + 2 * HALO, SH = TZ + 2 * HALO;
+constexpr int NTX = 64, NTY = 4, RPT = TZ / NTY;
+// ---- fast tiles
+constexpr int FW = 128;                     // columns per warp (32 lanes x float4)
+constexpr int FRZ = 8;                      // rows per warp
+constexpr int NWARP = NT / 32;
+constexpr int FH = FRZ * NWARP;             // rows per fast block (64)
 
 template <int FL>
 __device__ __forceinline__ W2Coef load_coef_fl(const W2Args& a, long long idx) {
@@ -39,17 +39,17 @@ __device__ __forceinline__ W2Coef load_coef_fl(const W2Args& a, long long idx) {
     c.r = __ldg(a.coef[0] + idx);
     c.b = __ldg(a.coef[1] + idx);
     c.cxx = c.czz = c.cxz = c.ax = c.az = c.m = 0.f;
-    if (!(FL & ST_F_ISO)) { c.cxx = __ldg(a.coef[2] + idx); c.czz = __ldg(a.coef[3] + idx); }
+    c.cxx = __ldg(a.coef[2] + idx);
+    if (!(FL & ST_F_ISO) || (FL & ST_F_PML)) c.czz = __ldg(a.coef[3] + idx);
     if (FL & ST_F_XZ) c.cxz = __ldg(a.coef[4] + idx);
     if (FL & ST_F_G1) { c.ax = __ldg(a.coef[5] + idx); c.az = __ldg(a.coef[6] + idx); }
     if (FL & ST_F_BORN) c.m = __ldg(a.coef[7] + idx);
     return c;
 }
 
-// cooperative load of a (TZ+4)x(TX+4) tile (zero outside the domain)
 __device__ __forceinline__ void load_tile(float (*s)[SW], const float* __restrict__ src,
                                           int z0, int x0, const W2Geom& g, int tid) {
-    for (int i = tid; i < SH * SW; i += NTX * NTY) {
+    for (int i = tid; i < SH * SW; i += NT) {
         const int lz = i / SW, lx = i - lz * SW;
         const int z = z0 - HALO + lz, x = x0 - HALO + lx;
         float v = 0.f;
@@ -58,26 +58,220 @@ __device__ __forceinline__ void load_tile(float (*s)[SW], const float* __restric
     }
 }
 
+// distance to the nearest absorbing edge (the free surface of `multiple` is not one)
+__device__ __forceinline__ int edge_depth(int z, int x, const W2Geom& g) {
+    int d = min(min(x, g.nx - 1 - x), g.nz - 1 - z);
+    if (!g.multiple) d = min(d, z);
+    return d;
+}
+
+// ---- enumeration of the TX x TZ tiles that touch the band of `band` cells along the
+//      absorbing edges (band = bw for the forward frame, bw+1 for the adjoint)
+struct BandTiles {
+    int nxt, nzt, rows_top, rows_bot, cols_l, cols_r, count;
+};
+__host__ __device__ inline BandTiles band_tiles(const W2Geom& g, int band) {
+    BandTiles t;
+    t.nxt = (g.nx + TX - 1) / TX;
+    t.nzt = (g.nz + TZ - 1) / TZ;
+    const int n_top = g.multiple ? 0 : (band + TZ - 1) / TZ;
+    const int n_bot = t.nzt - max(g.nz - band, 0) / TZ;
+    const int n_l = (band + TX - 1) / TX;
+    const int n_r = t.nxt - max(g.nx - band, 0) / TX;
+    t.rows_top = min(n_top, t.nzt);
+    t.rows_bot = min(n_bot, t.nzt - t.rows_top);
+    t.cols_l = min(n_l, t.nxt);
+    t.cols_r = min(n_r, t.nxt - t.cols_l);
+    const int mid = t.nzt - t.rows_top - t.rows_bot;
+    t.count = (t.rows_top + t.rows_bot) * t.nxt + mid * (t.cols_l + t.cols_r);
+    return t;
+}
+__device__ __forceinline__ void band_tile_decode(const BandTiles& t, int id, int& tz, int& tx) {
+    const int nb = (t.rows_top + t.rows_bot) * t.nxt;
+    if (id < nb) {
+        const int r = id / t.nxt;
+        tx = id - r * t.nxt;
+        tz = r < t.rows_top ? r : t.nzt - t.rows_bot + (r - t.rows_top);
+    } else {
+        const int j = id - nb, w = t.cols_l + t.cols_r;
+        const int r = j / w, c = j - r * w;
+        tz = t.rows_top + r;
+        tx = c < t.cols_l ? c : t.nxt - t.cols_r + (c - t.cols_l);
+    }
+}
+
+// ---- small float4 helpers
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float f4get(const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void f4set(float4& v, int e, float s) { if (e == 0) v.x = s; else if (e == 1) v.y = s; else if (e == 2) v.z = s; else v.w = s; }
+
+// one row of a field as a float4 per lane (zero outside the domain / pitch)
+__device__ __forceinline__ float4 ldrow(const float* __restrict__ base, int z, int x, const W2Geom& g) {
+    if (z < 0 || z >= g.nz || x >= g.ld) return f4zero();
+    return __ldg(reinterpret_cast<const float4*>(base + (z * g.ld + x)));
+}
+// left / right neighbours of the lane's 4 cells: shuffles + predicated halo loads at the warp edges
+__device__ __forceinline__ void row_halo(const float4& c, const float* __restrict__ base, int z, int x0, int lane,
+                                         const W2Geom& g, float& left, float& right) {
+    left = __shfl_up_sync(0xffffffffu, c.w, 1);
+    right = __shfl_down_sync(0xffffffffu, c.x, 1);
+    const bool zin = z >= 0 && z < g.nz;
+    if (lane == 0) left = (zin && x0 > 0) ? __ldg(base + (z * g.ld + x0 - 1)) : 0.f;
+    if (lane == 31) right = (zin && x0 + FW < g.nx) ? __ldg(base + (z * g.ld + x0 + FW)) : 0.f;
+}
+
+// source add + receiver gather for the cells this block stored
+template <int NF, class Own>
+__device__ __forceinline__ void forward_tail(const W2Args& a, int b, int z0, int zn, int x0, int xn, int tid, Own owns) {
+    const W2Geom& g = a.g;
+    const long long boff = (long long)b * a.fs;
+    __syncthreads();
+    for (int s = tid; s < a.ns; s += NT) {
+        if (a.src_b[s] != b) continue;
+        const int sz = a.src_z[s], sx = a.src_x[s];
+        if (sz >= z0 && sz < zn && sx >= x0 && sx < xn && owns(sz, sx)) {
+            const float v = a.amp[s];
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+                if (a.src_fmask >> f & 1) atomicAdd(a.next + f * a.cs + boff + (long long)sz * g.ld + sx, v);
+        }
+    }
+    if (!a.rec_out) return;
+    __syncthreads();
+    const int zend = min(zn, g.nz);
+    for (int z = z0; z < zend; ++z) {
+        const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
+        for (int r = lo + tid; r < hi; r += NT) {
+            const int rx = a.rec_x[r];
+            if (rx >= x0 && rx < xn && owns(z, rx)) {
+                const long long o = (long long)a.rec_orig[r] * a.nchan;
+                for (int ch = 0; ch < a.nchan; ++ch)
+                    a.rec_out[o + ch] = a.next[a.chan_f[ch] * a.cs + boff + (long long)z * g.ld + rx];
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ forward
 template <int FL>
-__global__ void __launch_bounds__(NTX * NTY) wave2d_forward_kernel(const W2Args a) {
+__device__ __forceinline__ void forward_fast_block(const W2Args& a, int bid, int nfx, int b, int tid) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
-    __shared__ float s1[NF][SH][SW];
+    constexpr bool HABC = (FL & ST_F_HABC) != 0;
     const W2Geom g = a.g;
-    const int tid = threadIdx.y * NTX + threadIdx.x;
-    const int x0 = blockIdx.x * TX, z0 = blockIdx.y * TZ, b = blockIdx.z;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int fz = bid / nfx, fx = bid - fz * nfx;
+    const int x0 = fx * FW, zb0 = fz * FH;
+    const int z0 = zb0 + warp * FRZ;
+    const int x = x0 + 4 * lane;
     const long long boff = (long long)b * a.fs;
 
+    if (z0 < g.nz) {
+        const int zn = min(z0 + FRZ, g.nz);
+        // warp tile completely inside the frame-free region -> unpredicated vector stores
+        bool clean = x0 + FW <= g.nx;
+        if (HABC) clean = clean && edge_depth(z0, x0, g) >= g.bw && edge_depth(zn - 1, x0 + FW - 1, g) >= g.bw &&
+                          edge_depth(z0, x0 + FW - 1, g) >= g.bw && edge_depth(zn - 1, x0, g) >= g.bw;
+        const float* cur[NF];
+        const float* prv[NF];
+        float* nxt[NF];
+        float4 U[NF], Cc[NF], D[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            cur[f] = a.cur + f * a.cs + boff;
+            prv[f] = a.prev + f * a.cs + boff;
+            nxt[f] = a.next + f * a.cs + boff;
+            U[f] = ldrow(cur[f], z0 - 1, x, g);
+            Cc[f] = ldrow(cur[f], z0, x, g);
+        }
+#pragma unroll
+        for (int k = 0; k < FRZ; ++k) {
+            const int z = z0 + k;
+            if (z < zn) {
+                const int ro = z * g.ld + x;
+                float4 P[NF];
+                float lc[NF], rc[NF], lu[NF], ru[NF], ldn[NF], rdn[NF];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    D[f] = ldrow(cur[f], z + 1, x, g);
+                    P[f] = ldrow(prv[f], z, x, g);
+                    row_halo(Cc[f], cur[f], z, x0, lane, g, lc[f], rc[f]);
+                    if (FL & ST_F_XZ) {
+                        row_halo(U[f], cur[f], z - 1, x0, lane, g, lu[f], ru[f]);
+                        row_halo(D[f], cur[f], z + 1, x0, lane, g, ldn[f], rdn[f]);
+                    }
+                }
+                float4 CXX = f4zero(), CZZ = f4zero(), CXZ = f4zero(), AX = f4zero(), AZ = f4zero(), M = f4zero();
+                if (x < g.ld) {
+                    CXX = __ldg(reinterpret_cast<const float4*>(a.coef[2] + ro));          // ciso for ISO
+                    if (!(FL & ST_F_ISO) || (FL & ST_F_PML))
+                        CZZ = __ldg(reinterpret_cast<const float4*>(a.coef[3] + ro));      // alpha for ISO|PML
+                    if (FL & ST_F_XZ) CXZ = __ldg(reinterpret_cast<const float4*>(a.coef[4] + ro));
+                    if (FL & ST_F_G1) {
+                        AX = __ldg(reinterpret_cast<const float4*>(a.coef[5] + ro));
+                        AZ = __ldg(reinterpret_cast<const float4*>(a.coef[6] + ro));
+                    }
+                    if (FL & ST_F_BORN) M = __ldg(reinterpret_cast<const float4*>(a.coef[7] + ro));
+                }
+                float4 Y[NF];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float alpha = (FL & ST_F_PML) ? f4get(CZZ, e) : 1.f;
+                    float A0 = 0.f;
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) {
+                        const float c = f4get(Cc[f], e), n = f4get(U[f], e), s = f4get(D[f], e);
+                        const float w = e == 0 ? lc[f] : f4get(Cc[f], e - 1);
+                        const float ea = e == 3 ? rc[f] : f4get(Cc[f], e + 1);
+                        float A;
+                        if (FL & ST_F_ISO) A = f4get(CXX, e) * (((n - c) + (s - c)) + ((ea - c) + (w - c)));
+                        else A = f4get(CXX, e) * ((ea - c) + (w - c)) + f4get(CZZ, e) * ((n - c) + (s - c));
+                        if (FL & ST_F_XZ) {
+                            const float nw = e == 0 ? lu[f] : f4get(U[f], e - 1), ne = e == 3 ? ru[f] : f4get(U[f], e + 1);
+                            const float sw = e == 0 ? ldn[f] : f4get(D[f], e - 1), se = e == 3 ? rdn[f] : f4get(D[f], e + 1);
+                            A += f4get(CXZ, e) * ((se - sw) - (ne - nw));
+                        }
+                        if (FL & ST_F_G1) A += f4get(AX, e) * (ea - w) + f4get(AZ, e) * (s - n);
+                        if (f == 0) A0 = A;
+                        else A += f4get(M, e) * A0;
+                        f4set(Y[f], e, c + alpha * (c - f4get(P[f], e)) + A);
+                    }
+                }
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    float* o = nxt[f] + ro;
+                    if (clean) {
+                        *reinterpret_cast<float4*>(o) = Y[f];
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (x + e < g.nx && (!HABC || !w2_in_frame(z, x + e, g))) o[e] = f4get(Y[f], e);
+                    }
+                    U[f] = Cc[f];
+                    Cc[f] = D[f];
+                }
+            }
+        }
+    }
+    forward_tail<NF>(a, b, zb0, zb0 + FH, x0, x0 + FW, tid,
+                     [&](int z, int xx) { return !HABC || !w2_in_frame(z, xx, g); });
+}
+
+template <int FL>
+__device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int tx, int b, int tid, float (*s1)[SH][SW]) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    const W2Geom g = a.g;
+    const int x0 = tx * TX, z0 = tz * TZ;
+    const long long boff = (long long)b * a.fs;
 #pragma unroll
     for (int f = 0; f < NF; ++f) load_tile(s1[f], a.cur + f * a.cs + boff, z0, x0, g, tid);
     __syncthreads();
-
-    const int x = x0 + threadIdx.x;
+    const int x = x0 + (tid & (NTX - 1)), ty = tid / NTX;
     if (x < g.nx) {
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < RPT; ++k) {
-            const int z = z0 + threadIdx.y + k * NTY;
+            const int z = z0 + ty + k * NTY;
             if (z >= g.nz) break;
+            if (!w2_in_frame(z, x, g)) continue;
             const long long idx = (long long)z * g.ld + x;
             const W2Coef c = load_coef_fl<FL>(a, idx);
             // current field: smem tile with global fallback (only the wrapped one-way
@@ -98,32 +292,22 @@ __global__ void __launch_bounds__(NTX * NTY) wave2d_forward_kernel(const W2Args 
             for (int f = 0; f < NF; ++f) a.next[f * a.cs + boff + idx] = out[f];
         }
     }
-    __syncthreads();
-    // ---- fused source add (source.py:47-57: added to the new field after the step)
-    for (int s = tid; s < a.ns; s += NTX * NTY) {
-        if (a.src_b[s] != b) continue;
-        const int sz = a.src_z[s], sx = a.src_x[s];
-        if (sz >= z0 && sz < z0 + TZ && sx >= x0 && sx < x0 + TX) {
-            const float v = a.amp[s];
-#pragma unroll
-            for (int f = 0; f < NF; ++f)
-                if (a.src_fmask >> f & 1) atomicAdd(a.next + f * a.cs + boff + (long long)sz * g.ld + sx, v);
-        }
-    }
-    __syncthreads();
-    // ---- fused receiver gather (probe.py:42-44: sampled after the source add)
-    if (a.rec_out) {
-        const int zend = min(z0 + TZ, g.nz);
-        for (int z = z0; z < zend; ++z) {
-            const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
-            for (int r = lo + tid; r < hi; r += NTX * NTY) {
-                const int rx = a.rec_x[r];
-                if (rx >= x0 && rx < x0 + TX) {
-                    const long long o = (long long)a.rec_orig[r] * a.nchan;
-                    for (int ch = 0; ch < a.nchan; ++ch)
-                        a.rec_out[o + ch] = a.next[a.chan_f[ch] * a.cs + boff + (long long)z * g.ld + rx];
-                }
-            }
+    forward_tail<NF>(a, b, z0, z0 + TZ, x0, x0 + TX, tid, [&](int z, int xx) { return w2_in_frame(z, xx, g); });
+}
+
+template <int FL>
+__global__ void __launch_bounds__(NT, 4) wave2d_forward_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    constexpr bool HABC = (FL & ST_F_HABC) != 0;
+    __shared__ float s1[HABC ? NF : 1][HABC ? SH : 1][SW];
+    const int bid = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (bid < nfast) {
+        forward_fast_block<FL>(a, bid, nfx, b, tid);
+    } else {
+        if constexpr (HABC) {
+            int tz, tx;
+            band_tile_decode(bt, bid - nfast, tz, tx);
+            forward_frame_block<FL>(a, tz, tx, b, tid, reinterpret_cast<float (*)[SH][SW]>(s1));
         }
     }
 }
@@ -132,32 +316,194 @@ __global__ void __launch_bounds__(NTX * NTY) wave2d_forward_kernel(const W2Args 
 // which of the 7 gradient accumulators (r,cxx,czz,cxz,ax,az,m) a flag set touches
 template <int FL>
 __host__ __device__ constexpr bool grad_used(int q) {
-    return q == 0 ? ((FL & ST_F_ISO) || (FL & ST_F_HABC))
-         : (q == 1 || q == 2) ? !(FL & ST_F_ISO)
+    return q == 0 ? (FL & ST_F_HABC) != 0
+         : q == 1 ? true
+         : q == 2 ? !(FL & ST_F_ISO)
          : q == 3 ? (FL & ST_F_XZ) != 0
          : (q == 4 || q == 5) ? (FL & ST_F_G1) != 0
          : (FL & ST_F_BORN) != 0;
 }
-
+// flag sets with a vectorised adjoint fast path (the acoustic flagship equations)
 template <int FL>
-__global__ void __launch_bounds__(NTX * NTY) wave2d_adjoint_kernel(const W2Args a) {
-    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
-    __shared__ float sl[NF][SH][SW];     // Lam_{i+1}
-    __shared__ float ss[NF][SH][SW];     // S_i
+__host__ __device__ constexpr bool adj_fast() { return FL == (ST_F_ISO | ST_F_PML) || FL == (ST_F_ISO | ST_F_HABC); }
+
+// receiver-adjoint scatter + source-amplitude gradient for the cells this block stored
+template <int NF, class Own>
+__device__ __forceinline__ void adjoint_tail(const W2Args& a, int b, int z0, int zn, int x0, int xn, int tid, Own owns) {
+    const W2Geom& g = a.g;
+    const long long boff = (long long)b * a.fs;
+    __syncthreads();
+    if (a.rec_adj) {
+        const int zend = min(zn, g.nz);
+        for (int z = z0; z < zend; ++z) {
+            const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
+            for (int r = lo + tid; r < hi; r += NT) {
+                const int rx = a.rec_x[r];
+                if (rx >= x0 && rx < xn && owns(z, rx)) {
+                    const long long o = (long long)a.rec_orig[r] * a.nchan;
+                    for (int ch = 0; ch < a.nchan; ++ch)
+                        atomicAdd(a.lam0 + a.chan_f[ch] * a.cs + boff + (long long)z * g.ld + rx, a.rec_adj[o + ch]);
+                }
+            }
+        }
+    }
+    if (a.gamp) {
+        __syncthreads();
+        for (int s = tid; s < a.ns; s += NT) {
+            if (a.src_b[s] != b) continue;
+            const int sz = a.src_z[s], sx = a.src_x[s];
+            if (sz >= z0 && sz < zn && sx >= x0 && sx < xn && owns(sz, sx)) {
+                float v = 0.f;
+#pragma unroll
+                for (int f = 0; f < NF; ++f)
+                    if (a.src_fmask >> f & 1) v += a.lam0[f * a.cs + boff + (long long)sz * g.ld + sx];
+                a.gamp[s] = v;
+            }
+        }
+    }
+}
+
+// ISO fast path: Lam_i = (1+alpha) L1 + lap(ciso L1) - alpha L2 ; g_ciso += L1 * lap(S_i).
+// Gradient partial sums of the block's shots live in shared memory (one float4 per lane and
+// row, conflict-free) so the register budget stays small and HBM sees one read-modify-write
+// of the gradient plane per `bchunk` shots.
+template <int FL>
+__device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int nfx, int chunk, int tid,
+                                                   float (*gsm)[FRZ][FW]) {
+    constexpr bool HABC = (FL & ST_F_HABC) != 0;
+    constexpr bool PML = (FL & ST_F_PML) != 0;
     const W2Geom g = a.g;
-    const int tid = threadIdx.y * NTX + threadIdx.x;
-    const int x0 = blockIdx.x * TX, z0 = blockIdx.y * TZ;
-    const int x = x0 + threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int fz = bid / nfx, fx = bid - fz * nfx;
+    const int x0 = fx * FW, zb0 = fz * FH;
+    const int z0 = zb0 + warp * FRZ;
+    const int x = x0 + 4 * lane;
+    const int band = g.bw + 1;               // cells this deep or deeper are untouched by the frame
     const bool want_grad = a.gacc != nullptr;
-
-    float gsum[RPT][7];
+    const bool rows = z0 < g.nz;
+    const int zn = min(z0 + FRZ, g.nz);
+    bool clean = x0 + FW <= g.nx;
+    if (HABC && rows) clean = clean && edge_depth(z0, x0, g) >= band && edge_depth(zn - 1, x0 + FW - 1, g) >= band &&
+                              edge_depth(z0, x0 + FW - 1, g) >= band && edge_depth(zn - 1, x0, g) >= band;
+    auto owns = [&](int z, int xx) { return !HABC || edge_depth(z, xx, g) >= band; };
+    const float* ciso = a.coef[2];
+    // product row  w = ciso * L1  (the pre-blend factor is 1 in the fast region and next to it)
+    auto wrow = [&](const float* l1, int z, float4& lraw) -> float4 {
+        lraw = ldrow(l1, z, x, g);
+        const float4 c = ldrow(ciso, z, x, g);
+        return make_float4(c.x * lraw.x, c.y * lraw.y, c.z * lraw.z, c.w * lraw.w);
+    };
+    auto whalo = [&](const float* l1, int z, const float4& w, float& left, float& right) {
+        left = __shfl_up_sync(0xffffffffu, w.w, 1);
+        right = __shfl_down_sync(0xffffffffu, w.x, 1);
+        if (lane == 0 || lane == 31) {
+            const int xx = lane == 0 ? x0 - 1 : x0 + FW;
+            float v = 0.f;
+            if (z >= 0 && z < g.nz && xx >= 0 && xx < g.nx) {
+                const int o = z * g.ld + xx;
+                v = __ldg(ciso + o) * __ldg(l1 + o);
+            }
+            if (lane == 0) left = v; else right = v;
+        }
+    };
+    float4* gsl = reinterpret_cast<float4*>(&gsm[warp][0][4 * lane]);      // stride FW/4 float4 per row
+    if (want_grad) {
 #pragma unroll
-    for (int k = 0; k < RPT; ++k)
-#pragma unroll
-        for (int q = 0; q < 7; ++q) gsum[k][q] = 0.f;
+        for (int k = 0; k < FRZ; ++k) gsl[k * (FW / 4)] = f4zero();
+    }
 
-    const int b_lo = blockIdx.z * a.bchunk;
-    const int b_hi = min(b_lo + a.bchunk, a.B);
+    const int b_lo = chunk * a.bchunk, b_hi = min(b_lo + a.bchunk, a.B);
+    for (int b = b_lo; b < b_hi; ++b) {
+        const long long boff = (long long)b * a.fs;
+        if (rows) {
+            const float* l1 = a.lam1 + boff;
+            const float* l2 = a.lam2 + boff;
+            const float* S = a.s1 + boff;
+            float* l0 = a.lam0 + boff;
+            float4 lC, lD;
+            float4 wU = wrow(l1, z0 - 1, lC);
+            float4 wC = wrow(l1, z0, lC);
+            float4 sU = ldrow(S, z0 - 1, x, g), sC = ldrow(S, z0, x, g);
+#pragma unroll
+            for (int k = 0; k < FRZ; ++k) {
+                const int z = z0 + k;
+                if (z < zn) {
+                    const float4 wD = wrow(l1, z + 1, lD);
+                    const float4 sD = ldrow(S, z + 1, x, g);
+                    const float4 p2 = ldrow(l2, z, x, g);
+                    float4 al = f4zero();
+                    if (PML) al = ldrow(a.coef[3], z, x, g);
+                    float wl, wr, sl, sr;
+                    whalo(l1, z, wC, wl, wr);
+                    row_halo(sC, S, z, x0, lane, g, sl, sr);
+                    float4 out, gq;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float c = f4get(wC, e);
+                        const float w = e == 0 ? wl : f4get(wC, e - 1), ea = e == 3 ? wr : f4get(wC, e + 1);
+                        const float lapw = ((f4get(wU, e) - c) + (f4get(wD, e) - c)) + ((ea - c) + (w - c));
+                        const float alpha = PML ? f4get(al, e) : 1.f;
+                        const float l1c = f4get(lC, e);
+                        f4set(out, e, (1.f + alpha) * l1c + lapw - alpha * f4get(p2, e));
+                        const float sc = f4get(sC, e);
+                        const float sw_ = e == 0 ? sl : f4get(sC, e - 1), se_ = e == 3 ? sr : f4get(sC, e + 1);
+                        const float laps = ((f4get(sU, e) - sc) + (f4get(sD, e) - sc)) + ((se_ - sc) + (sw_ - sc));
+                        f4set(gq, e, l1c * laps);
+                    }
+                    float* o = l0 + (z * g.ld + x);
+                    if (clean) {
+                        *reinterpret_cast<float4*>(o) = out;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (x + e < g.nx && owns(z, x + e)) o[e] = f4get(out, e);
+                    }
+                    if (want_grad) {
+                        float4 acc = gsl[k * (FW / 4)];
+                        acc.x += gq.x; acc.y += gq.y; acc.z += gq.z; acc.w += gq.w;
+                        gsl[k * (FW / 4)] = acc;
+                    }
+                    wU = wC; wC = wD; sU = sC; sC = sD; lC = lD;
+                }
+            }
+        }
+        adjoint_tail<1>(a, b, zb0, zb0 + FH, x0, x0 + FW, tid, owns);
+    }
+    if (want_grad && rows && x < g.ld) {
+        float* gb = a.gacc + ((long long)chunk * 7 + 1) * ((long long)g.nz * g.ld);       // slot 1: d/d ciso
+#pragma unroll
+        for (int k = 0; k < FRZ; ++k) {
+            const int z = z0 + k;
+            if (z < zn) {
+                float* o = gb + (z * g.ld + x);
+                const float4 acc = gsl[k * (FW / 4)];
+                if (clean) {
+                    float4 v = *reinterpret_cast<float4*>(o);
+                    v.x += acc.x; v.y += acc.y; v.z += acc.z; v.w += acc.w;
+                    *reinterpret_cast<float4*>(o) = v;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (x + e < g.nx && owns(z, x + e)) o[e] += f4get(acc, e);
+                }
+            }
+        }
+    }
+}
+
+// general cell-by-cell adjoint of one TX x TZ tile; `band` < 0: every cell, else only the
+// cells closer than `band` to an absorbing edge
+template <int FL>
+__device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, int tx, int chunk, int tid, int band,
+                                                      float (*sl)[SH][SW], float (*ss)[SH][SW]) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    const W2Geom g = a.g;
+    const int x0 = tx * TX, z0 = tz * TZ;
+    const int x = x0 + (tid & (NTX - 1)), ty = tid / NTX;
+    const bool want_grad = a.gacc != nullptr;
+    const long long plane = (long long)g.nz * g.ld;
+    auto owns = [&](int z, int xx) { return band < 0 || edge_depth(z, xx, g) < band; };
+    const int b_lo = chunk * a.bchunk, b_hi = min(b_lo + a.bchunk, a.B);
     for (int b = b_lo; b < b_hi; ++b) {
         const long long boff = (long long)b * a.fs;
         __syncthreads();
@@ -168,10 +514,11 @@ __global__ void __launch_bounds__(NTX * NTY) wave2d_adjoint_kernel(const W2Args 
         }
         __syncthreads();
         if (x < g.nx) {
-#pragma unroll
+#pragma unroll 1
             for (int k = 0; k < RPT; ++k) {
-                const int z = z0 + threadIdx.y + k * NTY;
+                const int z = z0 + ty + k * NTY;
                 if (z >= g.nz) break;
+                if (!owns(z, x)) continue;
                 const long long idx = (long long)z * g.ld + x;
                 auto inb = [&](int zz, int xx) { return zz >= 0 && zz < g.nz && xx >= 0 && xx < g.nx; };
                 auto L1 = [&](int f, int zz, int xx) -> float {
@@ -195,55 +542,50 @@ __global__ void __launch_bounds__(NTX * NTY) wave2d_adjoint_kernel(const W2Args 
                     return __ldg(a.s2 + f * a.cs + boff + (long long)zz * g.ld + xx);
                 };
                 auto CF = [&](int zz, int xx) -> W2Coef { return load_coef_fl<FL>(a, (long long)zz * g.ld + xx); };
-                float out[2];
-                w2_adjoint_cell<FL>(z, x, g, a.dt, L1, L2, S1, S2, CF, out, gsum[k], want_grad);
+                float out[2], gr[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                w2_adjoint_cell<FL>(z, x, g, a.dt, L1, L2, S1, S2, CF, out, gr, want_grad);
 #pragma unroll
                 for (int f = 0; f < NF; ++f) a.lam0[f * a.cs + boff + idx] = out[f];
-            }
-        }
-        __syncthreads();
-        // ---- adjoint of the receiver gather: scatter-add d loss / d sample into Lam_i
-        if (a.rec_adj) {
-            const int zend = min(z0 + TZ, g.nz);
-            for (int z = z0; z < zend; ++z) {
-                const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
-                for (int r = lo + tid; r < hi; r += NTX * NTY) {
-                    const int rx = a.rec_x[r];
-                    if (rx >= x0 && rx < x0 + TX) {
-                        const long long o = (long long)a.rec_orig[r] * a.nchan;
-                        for (int ch = 0; ch < a.nchan; ++ch)
-                            atomicAdd(a.lam0 + a.chan_f[ch] * a.cs + boff + (long long)z * g.ld + rx, a.rec_adj[o + ch]);
-                    }
-                }
-            }
-        }
-        // ---- adjoint of the source add: d loss / d amplitude = Lam_i at the source cell
-        if (a.gamp) {
-            __syncthreads();
-            for (int s = tid; s < a.ns; s += NTX * NTY) {
-                if (a.src_b[s] != b) continue;
-                const int sz = a.src_z[s], sx = a.src_x[s];
-                if (sz >= z0 && sz < z0 + TZ && sx >= x0 && sx < x0 + TX) {
-                    float v = 0.f;
+                if (want_grad) {
+                    float* gb = a.gacc + (long long)chunk * 7 * plane + idx;
 #pragma unroll
-                    for (int f = 0; f < NF; ++f)
-                        if (a.src_fmask >> f & 1) v += a.lam0[f * a.cs + boff + (long long)sz * g.ld + sx];
-                    a.gamp[s] = v;
+                    for (int q = 0; q < 7; ++q)
+                        if (grad_used<FL>(q)) gb[q * plane] += gr[q];
                 }
             }
+        }
+        adjoint_tail<NF>(a, b, z0, z0 + TZ, x0, x0 + TX, tid, owns);
+    }
+}
+
+template <int FL>
+__global__ void __launch_bounds__(NT, 3) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    constexpr bool NEED_GEN = !adj_fast<FL>() || (FL & ST_F_HABC);
+    constexpr int GEN_FLOATS = NEED_GEN ? 2 * NF * SH * SW : 1;
+    constexpr int FAST_FLOATS = adj_fast<FL>() ? NWARP * FRZ * FW : 1;
+    __shared__ __align__(16) float smem[GEN_FLOATS > FAST_FLOATS ? GEN_FLOATS : FAST_FLOATS];
+    const int bid = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+    bool fast = false;
+    if constexpr (adj_fast<FL>()) {
+        if (bid < nfast) {
+            fast = true;
+            adjoint_fast_block<FL>(a, bid, nfx, chunk, tid, reinterpret_cast<float (*)[FRZ][FW]>(smem));
         }
     }
-    if (want_grad && x < g.nx) {
-        const long long plane = (long long)g.nz * g.ld;
-        float* gb = a.gacc + (long long)blockIdx.z * 7 * plane;
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-            const int z = z0 + threadIdx.y + k * NTY;
-            if (z >= g.nz) break;
-            const long long idx = (long long)z * g.ld + x;
-#pragma unroll
-            for (int q = 0; q < 7; ++q)
-                if (grad_used<FL>(q)) gb[q * plane + idx] += gsum[k][q];
+    if constexpr (NEED_GEN) {
+        if (!fast) {
+            int tz, tx, band;
+            if (adj_fast<FL>()) {
+                band_tile_decode(bt, bid - nfast, tz, tx);
+                band = a.g.bw + 1;
+            } else {
+                tz = bid / bt.nxt;
+                tx = bid - tz * bt.nxt;
+                band = -1;
+            }
+            adjoint_general_block<FL>(a, tz, tx, chunk, tid, band, reinterpret_cast<float (*)[SH][SW]>(smem),
+                                      reinterpret_cast<float (*)[SH][SW]>(smem + NF * SH * SW));
         }
     }
 }
@@ -258,18 +600,30 @@ int st_w2_launch_adj(const W2Args& a, cudaStream_t st);
 #ifndef ST_W2_DISPATCH_ONLY
 template <int FL>
 int st_w2_launch_fwd(const W2Args& a, cudaStream_t st) {
-    dim3 grid((a.g.nx + TX - 1) / TX, (a.g.nz + TZ - 1) / TZ, a.B), block(NTX, NTY);
-    wave2d_forward_kernel<FL><<<grid, block, 0, st>>>(a);
+    const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
+    const int nfast = nfx * nfz;
+    BandTiles bt = band_tiles(a.g, a.g.bw);
+    if (!(FL & ST_F_HABC)) bt.count = 0;
+    dim3 grid(nfast + bt.count, a.B);
+    wave2d_forward_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
 template <int FL>
 int st_w2_launch_adj(const W2Args& a, cudaStream_t st) {
     const int nchunk = (a.B + a.bchunk - 1) / a.bchunk;
-    dim3 grid((a.g.nx + TX - 1) / TX, (a.g.nz + TZ - 1) / TZ, nchunk), block(NTX, NTY);
-    wave2d_adjoint_kernel<FL><<<grid, block, 0, st>>>(a);
+    const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
+    int nfast = 0, ngen;
+    BandTiles bt = band_tiles(a.g, a.g.bw + 1);
+    if (adj_fast<FL>()) {
+        nfast = nfx * nfz;
+        ngen = (FL & ST_F_HABC) ? bt.count : 0;
+    } else {
+        ngen = bt.nxt * bt.nzt;
+    }
+    dim3 grid(nfast + ngen, nchunk);
+    wave2d_adjoint_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
-
 #ifdef ST_W2_INSTANCE
 template int st_w2_launch_fwd<ST_W2_INSTANCE>(const W2Args&, cudaStream_t);
 template int st_w2_launch_adj<ST_W2_INSTANCE>(const W2Args&, cudaStream_t);

@@ -16,8 +16,12 @@
 // Formulation (see DESIGN.md "numerics"): fields are advanced in increment form
 //   y = h1 + alpha*(h1 - h2) + A[h1]
 // which is algebraically identical to the reference's expression but carries
-// ~15x less fp32 rounding noise.  Coefficients are dimensionless:
-//   r = vp*dt/h,  cxx/czz/cxz/ax/az precomputed per call from the model parameters.
+// ~15x less fp32 rounding noise.  Coefficients are dimensionless and
+// precomputed once per call from the model parameters (seistorch_b200/coefficients.py):
+//   r = vp*dt/h (one-way blend: lam = 2r, mu = r^2), b = blend weight / damping,
+//   cxx, czz, cxz, ax, az = spatial-operator coefficients, m = reflectivity.
+// ISO flag sets share one Laplacian coefficient: cxx holds  ciso = r^2  (HABC) or
+// r^2/(1+b dt) (PML), and for PML czz holds  alpha = (1-b dt)/(1+b dt).
 #pragma once
 #include "st_common.cuh"
 
@@ -82,8 +86,11 @@ ST_HD void w2_oneway_diffs(int s, int z, int x, const W2Geom& g, F1 h1, F2 h2,
                            float& base, float& dlam, float& dmu) {
     const int j = w2_depth(s, z, x, g);
     int z1, x1, z2, x2;
-    w2_at_depth(s, (j + 1) % (g.bw + 1), z, x, g, z1, x1);
-    w2_at_depth(s, (j + 2) % (g.bw + 1), z, x, g, z2, x2);
+    int j1 = j + 1, j2 = j + 2;              // wrap inside the (bw+1)-deep strip
+    if (j1 > g.bw) j1 -= g.bw + 1;
+    if (j2 > g.bw) j2 -= g.bw + 1;
+    w2_at_depth(s, j1, z, x, g, z1, x1);
+    w2_at_depth(s, j2, z, x, g, z2, x2);
     const float a0 = h1(z, x), a1 = h1(z1, x1), a2 = h1(z2, x2);
     const float p0 = h2(z, x), p1 = h2(z1, x1);
     base = a0 + (a0 - p0);
@@ -128,13 +135,8 @@ template <int FL, class FH1, class FH2>
 ST_HD void w2_forward_cell(int z, int x, const W2Geom& g, const W2Coef& c, float dt,
                            FH1 H1, FH2 H2, float out[2]) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
-    float alpha = 1.f, ciso = c.r * c.r;
-    if (FL & ST_F_PML) {
-        const float bd = c.b * dt;
-        const float inv = 1.f / (1.f + bd);
-        alpha = (1.f - bd) * inv;
-        ciso *= inv;
-    }
+    const float alpha = (FL & ST_F_PML) ? c.czz : 1.f;
+    const float ciso = c.cxx;
     float A0 = 0.f;
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
@@ -156,7 +158,7 @@ ST_HD void w2_forward_cell(int z, int x, const W2Geom& g, const W2Coef& c, float
 // and the contribution of forward step i+1 (which maps S_i, S_{i-1} -> S_{i+1}) to the
 // coefficient gradients at p:   S1 = S_i, S2 = S_{i-1}.
 //   CF(z,x) returns the W2Coef of an arbitrary in-domain cell.
-// grad[] layout: 0:r 1:cxx 2:czz 3:cxz 4:ax 5:az 6:m   (accumulated, +=)
+// grad[] layout: 0:r (one-way blend only) 1:cxx (= ciso for ISO) 2:czz 3:cxz 4:ax 5:az 6:m   (accumulated, +=)
 //
 // Transpose algebra (DESIGN.md "adjoint"):  forward  Y = (1-b*M) y + b*sum_s f_s one_s,
 //   y = h1 + alpha (h1-h2) + A[h1]  =>
@@ -175,11 +177,7 @@ ST_HD void w2_adjoint_cell(int z, int x, const W2Geom& g, float dt,
     };
     // Note: inside the frame sum_s f_s == 1 except where no side owns the cell, which
     // cannot happen for frame cells (habc.py masks tile the frame), so M == in_frame.
-    auto iso_coef = [&](const W2Coef& c) {
-        float ci = c.r * c.r;
-        if (FL & ST_F_PML) ci *= 1.f / (1.f + c.b * dt);
-        return ci;
-    };
+    auto iso_coef = [&](const W2Coef& c) { return c.cxx; };
     // effective cotangent that multiplies the spatial operator of field f at q
     auto leff = [&](int f, int zz, int xx, const W2Coef& c) {
         float v = pre(zz, xx, c) * L1(f, zz, xx);
@@ -187,8 +185,7 @@ ST_HD void w2_adjoint_cell(int z, int x, const W2Geom& g, float dt,
         return v;
     };
     const W2Coef cp = CF(z, x);
-    float alpha = 1.f;
-    if (FL & ST_F_PML) { const float bd = cp.b * dt; alpha = (1.f - bd) / (1.f + bd); }
+    const float alpha = (FL & ST_F_PML) ? cp.czz : 1.f;
     const float prep = pre(z, x, cp);
 
 #pragma unroll
@@ -201,7 +198,7 @@ ST_HD void w2_adjoint_cell(int z, int x, const W2Geom& g, float dt,
             const W2Coef c = CF(zz, xx);
             const float l = leff(f, zz, xx, c);
             float cf;
-            if (kind == 0) cf = (FL & ST_F_ISO) ? iso_coef(c) : c.cxx;
+            if (kind == 0) cf = c.cxx;
             else if (kind == 1) cf = c.czz;
             else if (kind == 2) cf = c.cxz;
             else if (kind == 3) cf = c.ax;
@@ -266,10 +263,7 @@ ST_HD void w2_adjoint_cell(int z, int x, const W2Geom& g, float dt,
             if ((FL & ST_F_BORN) && f == 0) le += cp.m * (prep * L1(1, z, x));
             const float C = s1(z, x), N = s1(z - 1, x), S = s1(z + 1, x), W = s1(z, x - 1), E = s1(z, x + 1);
             if (FL & ST_F_ISO) {
-                const float lap = ((N - C) + (S - C)) + ((E - C) + (W - C));
-                float dci = 2.f * cp.r;                 // d(r^2)/dr
-                if (FL & ST_F_PML) dci *= 1.f / (1.f + cp.b * dt);
-                grad[0] += le * dci * lap;
+                grad[1] += le * (((N - C) + (S - C)) + ((E - C) + (W - C)));       // d/d ciso
             } else {
                 grad[1] += le * ((E - C) + (W - C));
                 grad[2] += le * ((N - C) + (S - C));
