@@ -96,7 +96,8 @@ typedef struct st_wave2d_problem {
     float* u;                   /* [nslots][NF][B][nz][ld] */
     int32_t nslots;
     float* lam;                 /* [3][NF][B][nz][ld] adjoint state, slot = i mod 3 (zero before the first adjoint call) */
-    float* gacc;                /* [nchunk][7][nz][ld] += coefficient gradients (r [one-way blend terms only],cxx,czz,cxz,ax,az,m), or NULL */
+    float* gacc;                /* [max(nchunk,B)][7][nz][ld] += coefficient gradients (r [one-way blend terms only],cxx,czz,
+                                   cxz,ax,az,m), or NULL; the caller sums the planes */
     int32_t bchunk;             /* shots per block in the adjoint kernel; nchunk = ceil(B/bchunk) */
     st_acquisition acq;
 } st_wave2d_problem;

@@ -137,9 +137,20 @@ __device__ __forceinline__ void forward_tail(const W2Args& a, int b, int z0, int
         }
     }
     if (!a.rec_out) return;
+    // rows of this tile that hold receivers (usually none or one): found by one thread per
+    // row, then served by the whole block
+    __shared__ int s_cnt, s_rows[FH];
+    if (tid == 0) s_cnt = 0;
     __syncthreads();
-    const int zend = min(zn, g.nz);
-    for (int z = z0; z < zend; ++z) {
+    const int nrow = min(zn, g.nz) - z0;
+    if (tid < nrow) {
+        const int row = b * g.nz + z0 + tid;
+        if (a.row_start[row + 1] > a.row_start[row]) s_rows[atomicAdd(&s_cnt, 1)] = z0 + tid;
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    for (int i = 0; i < cnt; ++i) {
+        const int z = s_rows[i];
         const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
         for (int r = lo + tid; r < hi; r += NT) {
             const int rx = a.rec_x[r];
@@ -153,6 +164,136 @@ __device__ __forceinline__ void forward_tail(const W2Args& a, int b, int z0, int
 }
 
 // ------------------------------------------------------------------------------ forward
+// rows of one warp tile.  SAFE: every load of the tile (rows z0-1..z0+FRZ, columns x0-1..x0+FW)
+// is inside the domain, so no bounds predicate is needed and pointers are simply advanced by
+// the row pitch; otherwise the checked loaders are used (domain-edge tiles only).
+template <int FL, bool SAFE>
+__device__ __forceinline__ void forward_fast_rows(const W2Args& a, const W2Geom& g, int b, int x0, int z0, int zn,
+                                                  int lane, bool clean) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    constexpr bool HABC = (FL & ST_F_HABC) != 0;
+    const int x = x0 + 4 * lane;
+    const int ld = g.ld;
+    const long long boff = (long long)b * a.fs;
+    const float* cur[NF];
+    const float* prv[NF];
+    float* nxt[NF];
+    float4 U[NF], Cc[NF], D[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        cur[f] = a.cur + f * a.cs + boff;
+        prv[f] = a.prev + f * a.cs + boff;
+        nxt[f] = a.next + f * a.cs + boff;
+        if (SAFE) {
+            U[f] = __ldg(reinterpret_cast<const float4*>(cur[f] + ((z0 - 1) * ld + x)));
+            Cc[f] = __ldg(reinterpret_cast<const float4*>(cur[f] + (z0 * ld + x)));
+        } else {
+            U[f] = ldrow(cur[f], z0 - 1, x, g);
+            Cc[f] = ldrow(cur[f], z0, x, g);
+        }
+    }
+    const float* c2 = a.coef[2];
+    const float* c3 = a.coef[3];
+    const float* c4 = a.coef[4];
+    const float* c5 = a.coef[5];
+    const float* c6 = a.coef[6];
+    const float* c7 = a.coef[7];
+    const bool edge = lane == 0 || lane == 31;
+    const int xh = lane == 0 ? x0 - 1 : x0 + FW;          // halo column of the edge lanes
+    int ro = z0 * ld + x;                                  // offset of row z, this lane
+#pragma unroll
+    for (int k = 0; k < FRZ; ++k, ro += ld) {
+        const int z = z0 + k;
+        if (SAFE || z < zn) {
+            float4 P[NF];
+            float lc[NF], rc[NF], lu[NF], ru[NF], ldn[NF], rdn[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                if (SAFE) {
+                    D[f] = __ldg(reinterpret_cast<const float4*>(cur[f] + (ro + ld)));
+                    P[f] = __ldg(reinterpret_cast<const float4*>(prv[f] + ro));
+                    float hv = 0.f, hu = 0.f, hd = 0.f;
+                    if (edge) {
+                        const int ho = ro - x + xh;
+                        hv = __ldg(cur[f] + ho);
+                        if (FL & ST_F_XZ) { hu = __ldg(cur[f] + (ho - ld)); hd = __ldg(cur[f] + (ho + ld)); }
+                    }
+                    lc[f] = __shfl_up_sync(0xffffffffu, Cc[f].w, 1);
+                    rc[f] = __shfl_down_sync(0xffffffffu, Cc[f].x, 1);
+                    lc[f] = lane == 0 ? hv : lc[f];
+                    rc[f] = lane == 31 ? hv : rc[f];
+                    if (FL & ST_F_XZ) {
+                        lu[f] = __shfl_up_sync(0xffffffffu, U[f].w, 1);
+                        ru[f] = __shfl_down_sync(0xffffffffu, U[f].x, 1);
+                        ldn[f] = __shfl_up_sync(0xffffffffu, D[f].w, 1);
+                        rdn[f] = __shfl_down_sync(0xffffffffu, D[f].x, 1);
+                        lu[f] = lane == 0 ? hu : lu[f];
+                        ru[f] = lane == 31 ? hu : ru[f];
+                        ldn[f] = lane == 0 ? hd : ldn[f];
+                        rdn[f] = lane == 31 ? hd : rdn[f];
+                    }
+                } else {
+                    D[f] = ldrow(cur[f], z + 1, x, g);
+                    P[f] = ldrow(prv[f], z, x, g);
+                    row_halo(Cc[f], cur[f], z, x0, lane, g, lc[f], rc[f]);
+                    if (FL & ST_F_XZ) {
+                        row_halo(U[f], cur[f], z - 1, x0, lane, g, lu[f], ru[f]);
+                        row_halo(D[f], cur[f], z + 1, x0, lane, g, ldn[f], rdn[f]);
+                    }
+                }
+            }
+            float4 CXX = f4zero(), CZZ = f4zero(), CXZ = f4zero(), AX = f4zero(), AZ = f4zero(), M = f4zero();
+            if (SAFE || x < ld) {
+                CXX = __ldg(reinterpret_cast<const float4*>(c2 + ro));                              // ciso for ISO
+                if (!(FL & ST_F_ISO) || (FL & ST_F_PML)) CZZ = __ldg(reinterpret_cast<const float4*>(c3 + ro));   // alpha for ISO|PML
+                if (FL & ST_F_XZ) CXZ = __ldg(reinterpret_cast<const float4*>(c4 + ro));
+                if (FL & ST_F_G1) {
+                    AX = __ldg(reinterpret_cast<const float4*>(c5 + ro));
+                    AZ = __ldg(reinterpret_cast<const float4*>(c6 + ro));
+                }
+                if (FL & ST_F_BORN) M = __ldg(reinterpret_cast<const float4*>(c7 + ro));
+            }
+            float4 Y[NF];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float alpha = (FL & ST_F_PML) ? f4get(CZZ, e) : 1.f;
+                float A0 = 0.f;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const float c = f4get(Cc[f], e), n = f4get(U[f], e), s_ = f4get(D[f], e);
+                    const float w = e == 0 ? lc[f] : f4get(Cc[f], e - 1);
+                    const float ea = e == 3 ? rc[f] : f4get(Cc[f], e + 1);
+                    float A;
+                    if (FL & ST_F_ISO) A = f4get(CXX, e) * (((n - c) + (s_ - c)) + ((ea - c) + (w - c)));
+                    else A = f4get(CXX, e) * ((ea - c) + (w - c)) + f4get(CZZ, e) * ((n - c) + (s_ - c));
+                    if (FL & ST_F_XZ) {
+                        const float nw = e == 0 ? lu[f] : f4get(U[f], e - 1), ne = e == 3 ? ru[f] : f4get(U[f], e + 1);
+                        const float sw = e == 0 ? ldn[f] : f4get(D[f], e - 1), se = e == 3 ? rdn[f] : f4get(D[f], e + 1);
+                        A += f4get(CXZ, e) * ((se - sw) - (ne - nw));
+                    }
+                    if (FL & ST_F_G1) A += f4get(AX, e) * (ea - w) + f4get(AZ, e) * (s_ - n);
+                    if (f == 0) A0 = A;
+                    else A += f4get(M, e) * A0;
+                    f4set(Y[f], e, c + alpha * (c - f4get(P[f], e)) + A);
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                float* o = nxt[f] + ro;
+                if (clean) {
+                    *reinterpret_cast<float4*>(o) = Y[f];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (x + e < g.nx && (!HABC || !w2_in_frame(z, x + e, g))) o[e] = f4get(Y[f], e);
+                }
+                U[f] = Cc[f];
+                Cc[f] = D[f];
+            }
+        }
+    }
+}
+
 template <int FL>
 __device__ __forceinline__ void forward_fast_block(const W2Args& a, int bid, int nfx, int b, int tid) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
@@ -162,94 +303,18 @@ __device__ __forceinline__ void forward_fast_block(const W2Args& a, int bid, int
     const int fz = bid / nfx, fx = bid - fz * nfx;
     const int x0 = fx * FW, zb0 = fz * FH;
     const int z0 = zb0 + warp * FRZ;
-    const int x = x0 + 4 * lane;
-    const long long boff = (long long)b * a.fs;
-
     if (z0 < g.nz) {
         const int zn = min(z0 + FRZ, g.nz);
         // warp tile completely inside the frame-free region -> unpredicated vector stores
         bool clean = x0 + FW <= g.nx;
         if (HABC) clean = clean && edge_depth(z0, x0, g) >= g.bw && edge_depth(zn - 1, x0 + FW - 1, g) >= g.bw &&
                           edge_depth(z0, x0 + FW - 1, g) >= g.bw && edge_depth(zn - 1, x0, g) >= g.bw;
-        const float* cur[NF];
-        const float* prv[NF];
-        float* nxt[NF];
-        float4 U[NF], Cc[NF], D[NF];
-#pragma unroll
-        for (int f = 0; f < NF; ++f) {
-            cur[f] = a.cur + f * a.cs + boff;
-            prv[f] = a.prev + f * a.cs + boff;
-            nxt[f] = a.next + f * a.cs + boff;
-            U[f] = ldrow(cur[f], z0 - 1, x, g);
-            Cc[f] = ldrow(cur[f], z0, x, g);
-        }
-#pragma unroll
-        for (int k = 0; k < FRZ; ++k) {
-            const int z = z0 + k;
-            if (z < zn) {
-                const int ro = z * g.ld + x;
-                float4 P[NF];
-                float lc[NF], rc[NF], lu[NF], ru[NF], ldn[NF], rdn[NF];
-#pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    D[f] = ldrow(cur[f], z + 1, x, g);
-                    P[f] = ldrow(prv[f], z, x, g);
-                    row_halo(Cc[f], cur[f], z, x0, lane, g, lc[f], rc[f]);
-                    if (FL & ST_F_XZ) {
-                        row_halo(U[f], cur[f], z - 1, x0, lane, g, lu[f], ru[f]);
-                        row_halo(D[f], cur[f], z + 1, x0, lane, g, ldn[f], rdn[f]);
-                    }
-                }
-                float4 CXX = f4zero(), CZZ = f4zero(), CXZ = f4zero(), AX = f4zero(), AZ = f4zero(), M = f4zero();
-                if (x < g.ld) {
-                    CXX = __ldg(reinterpret_cast<const float4*>(a.coef[2] + ro));          // ciso for ISO
-                    if (!(FL & ST_F_ISO) || (FL & ST_F_PML))
-                        CZZ = __ldg(reinterpret_cast<const float4*>(a.coef[3] + ro));      // alpha for ISO|PML
-                    if (FL & ST_F_XZ) CXZ = __ldg(reinterpret_cast<const float4*>(a.coef[4] + ro));
-                    if (FL & ST_F_G1) {
-                        AX = __ldg(reinterpret_cast<const float4*>(a.coef[5] + ro));
-                        AZ = __ldg(reinterpret_cast<const float4*>(a.coef[6] + ro));
-                    }
-                    if (FL & ST_F_BORN) M = __ldg(reinterpret_cast<const float4*>(a.coef[7] + ro));
-                }
-                float4 Y[NF];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float alpha = (FL & ST_F_PML) ? f4get(CZZ, e) : 1.f;
-                    float A0 = 0.f;
-#pragma unroll
-                    for (int f = 0; f < NF; ++f) {
-                        const float c = f4get(Cc[f], e), n = f4get(U[f], e), s = f4get(D[f], e);
-                        const float w = e == 0 ? lc[f] : f4get(Cc[f], e - 1);
-                        const float ea = e == 3 ? rc[f] : f4get(Cc[f], e + 1);
-                        float A;
-                        if (FL & ST_F_ISO) A = f4get(CXX, e) * (((n - c) + (s - c)) + ((ea - c) + (w - c)));
-                        else A = f4get(CXX, e) * ((ea - c) + (w - c)) + f4get(CZZ, e) * ((n - c) + (s - c));
-                        if (FL & ST_F_XZ) {
-                            const float nw = e == 0 ? lu[f] : f4get(U[f], e - 1), ne = e == 3 ? ru[f] : f4get(U[f], e + 1);
-                            const float sw = e == 0 ? ldn[f] : f4get(D[f], e - 1), se = e == 3 ? rdn[f] : f4get(D[f], e + 1);
-                            A += f4get(CXZ, e) * ((se - sw) - (ne - nw));
-                        }
-                        if (FL & ST_F_G1) A += f4get(AX, e) * (ea - w) + f4get(AZ, e) * (s - n);
-                        if (f == 0) A0 = A;
-                        else A += f4get(M, e) * A0;
-                        f4set(Y[f], e, c + alpha * (c - f4get(P[f], e)) + A);
-                    }
-                }
-#pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    float* o = nxt[f] + ro;
-                    if (clean) {
-                        *reinterpret_cast<float4*>(o) = Y[f];
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (x + e < g.nx && (!HABC || !w2_in_frame(z, x + e, g))) o[e] = f4get(Y[f], e);
-                    }
-                    U[f] = Cc[f];
-                    Cc[f] = D[f];
-                }
-            }
+        // a tile lying entirely inside the frame has nothing to store
+        const bool dead = HABC && (zn <= (g.multiple ? 0 : g.bw) || z0 >= g.nz - g.bw || x0 + FW <= g.bw || x0 >= g.nx - g.bw);
+        const bool safe = z0 >= 1 && z0 + FRZ + 1 <= g.nz && x0 >= 1 && x0 + FW + 1 <= g.nx;
+        if (!dead) {
+            if (safe) forward_fast_rows<FL, true>(a, g, b, x0, z0, zn, lane, clean);
+            else forward_fast_rows<FL, false>(a, g, b, x0, z0, zn, lane, clean);
         }
     }
     forward_tail<NF>(a, b, zb0, zb0 + FH, x0, x0 + FW, tid,
@@ -301,12 +366,14 @@ __global__ void __launch_bounds__(NT, 4) wave2d_forward_kernel(const W2Args a, i
     constexpr bool HABC = (FL & ST_F_HABC) != 0;
     __shared__ float s1[HABC ? NF : 1][HABC ? SH : 1][SW];
     const int bid = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    if (bid < nfast) {
-        forward_fast_block<FL>(a, bid, nfx, b, tid);
+    // the (slower) frame blocks get the low block ids so they are scheduled first
+    const int nframe = HABC ? bt.count : 0;
+    if (bid >= nframe) {
+        forward_fast_block<FL>(a, bid - nframe, nfx, b, tid);
     } else {
         if constexpr (HABC) {
             int tz, tx;
-            band_tile_decode(bt, bid - nfast, tz, tx);
+            band_tile_decode(bt, bid, tz, tx);
             forward_frame_block<FL>(a, tz, tx, b, tid, reinterpret_cast<float (*)[SH][SW]>(s1));
         }
     }
@@ -332,10 +399,20 @@ template <int NF, class Own>
 __device__ __forceinline__ void adjoint_tail(const W2Args& a, int b, int z0, int zn, int x0, int xn, int tid, Own owns) {
     const W2Geom& g = a.g;
     const long long boff = (long long)b * a.fs;
+    __shared__ int s_cnt, s_rows[FH];
     __syncthreads();
     if (a.rec_adj) {
-        const int zend = min(zn, g.nz);
-        for (int z = z0; z < zend; ++z) {
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        const int nrow = min(zn, g.nz) - z0;
+        if (tid < nrow) {
+            const int row = b * g.nz + z0 + tid;
+            if (a.row_start[row + 1] > a.row_start[row]) s_rows[atomicAdd(&s_cnt, 1)] = z0 + tid;
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        for (int i = 0; i < cnt; ++i) {
+            const int z = s_rows[i];
             const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
             for (int r = lo + tid; r < hi; r += NT) {
                 const int rx = a.rec_x[r];
@@ -367,11 +444,93 @@ __device__ __forceinline__ void adjoint_tail(const W2Args& a, int b, int z0, int
 // Gradient partial sums of the block's shots live in shared memory (one float4 per lane and
 // row, conflict-free) so the register budget stays small and HBM sees one read-modify-write
 // of the gradient plane per `bchunk` shots.
+template <int FL, bool SAFE, class Own>
+__device__ __forceinline__ void adjoint_fast_rows(const W2Args& a, const W2Geom& g, int b, int x0, int z0, int zn,
+                                                  int lane, bool clean, bool want_grad, float4* gsl, Own owns) {
+    constexpr bool PML = (FL & ST_F_PML) != 0;
+    const int x = x0 + 4 * lane;
+    const int ld = g.ld;
+    const long long boff = (long long)b * a.fs;
+    const float* l1 = a.lam1 + boff;
+    const float* l2 = a.lam2 + boff;
+    const float* S = a.s1 + boff;
+    float* l0 = a.lam0 + boff;
+    const float* ciso = a.coef[2];
+    const float* alp = a.coef[3];
+    const bool edge = lane == 0 || lane == 31;
+    const int xh = lane == 0 ? x0 - 1 : x0 + FW;
+    auto ld4 = [&](const float* p, int z, int off) -> float4 {
+        if (SAFE) return __ldg(reinterpret_cast<const float4*>(p + off));
+        return ldrow(p, z, x, g);
+    };
+    auto ld1 = [&](const float* p, int z, int off) -> float {        // halo column of an edge lane
+        if (SAFE) return __ldg(p + off);
+        return (z >= 0 && z < g.nz && xh >= 0 && xh < g.nx) ? __ldg(p + off) : 0.f;
+    };
+    auto mul4 = [](const float4& u, const float4& v) { return make_float4(u.x * v.x, u.y * v.y, u.z * v.z, u.w * v.w); };
+    int ro = z0 * ld + x;
+    float4 lC = ld4(l1, z0, ro), lD;
+    float4 wU = mul4(ld4(ciso, z0 - 1, ro - ld), ld4(l1, z0 - 1, ro - ld));
+    float4 wC = mul4(ld4(ciso, z0, ro), lC);
+    float4 sU = ld4(S, z0 - 1, ro - ld), sC = ld4(S, z0, ro);
+#pragma unroll
+    for (int k = 0; k < FRZ; ++k, ro += ld) {
+        const int z = z0 + k;
+        if (SAFE || z < zn) {
+            lD = ld4(l1, z + 1, ro + ld);
+            const float4 wD = mul4(ld4(ciso, z + 1, ro + ld), lD);
+            const float4 sD = ld4(S, z + 1, ro + ld);
+            const float4 p2 = ld4(l2, z, ro);
+            float4 al = f4zero();
+            if (PML) al = ld4(alp, z, ro);
+            float hw = 0.f, hs = 0.f;
+            if (edge) {
+                const int ho = ro - x + xh;
+                hw = ld1(ciso, z, ho) * ld1(l1, z, ho);
+                hs = ld1(S, z, ho);
+            }
+            float wl = __shfl_up_sync(0xffffffffu, wC.w, 1), wr = __shfl_down_sync(0xffffffffu, wC.x, 1);
+            float sl = __shfl_up_sync(0xffffffffu, sC.w, 1), sr = __shfl_down_sync(0xffffffffu, sC.x, 1);
+            wl = lane == 0 ? hw : wl;
+            wr = lane == 31 ? hw : wr;
+            sl = lane == 0 ? hs : sl;
+            sr = lane == 31 ? hs : sr;
+            float4 out, gq;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float c = f4get(wC, e);
+                const float w = e == 0 ? wl : f4get(wC, e - 1), ea = e == 3 ? wr : f4get(wC, e + 1);
+                const float lapw = ((f4get(wU, e) - c) + (f4get(wD, e) - c)) + ((ea - c) + (w - c));
+                const float alpha = PML ? f4get(al, e) : 1.f;
+                const float l1c = f4get(lC, e);
+                f4set(out, e, (1.f + alpha) * l1c + lapw - alpha * f4get(p2, e));
+                const float sc = f4get(sC, e);
+                const float sw_ = e == 0 ? sl : f4get(sC, e - 1), se_ = e == 3 ? sr : f4get(sC, e + 1);
+                const float laps = ((f4get(sU, e) - sc) + (f4get(sD, e) - sc)) + ((se_ - sc) + (sw_ - sc));
+                f4set(gq, e, l1c * laps);
+            }
+            float* o = l0 + ro;
+            if (clean) {
+                *reinterpret_cast<float4*>(o) = out;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (x + e < g.nx && owns(z, x + e)) o[e] = f4get(out, e);
+            }
+            if (want_grad) {
+                float4 acc = gsl[k * (FW / 4)];
+                acc.x += gq.x; acc.y += gq.y; acc.z += gq.z; acc.w += gq.w;
+                gsl[k * (FW / 4)] = acc;
+            }
+            wU = wC; wC = wD; sU = sC; sC = sD; lC = lD;
+        }
+    }
+}
+
 template <int FL>
 __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int nfx, int chunk, int tid,
                                                    float (*gsm)[FRZ][FW]) {
     constexpr bool HABC = (FL & ST_F_HABC) != 0;
-    constexpr bool PML = (FL & ST_F_PML) != 0;
     const W2Geom g = a.g;
     const int warp = tid >> 5, lane = tid & 31;
     const int fz = bid / nfx, fx = bid - fz * nfx;
@@ -380,92 +539,27 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
     const int x = x0 + 4 * lane;
     const int band = g.bw + 1;               // cells this deep or deeper are untouched by the frame
     const bool want_grad = a.gacc != nullptr;
-    const bool rows = z0 < g.nz;
     const int zn = min(z0 + FRZ, g.nz);
+    bool rows = z0 < g.nz;
     bool clean = x0 + FW <= g.nx;
-    if (HABC && rows) clean = clean && edge_depth(z0, x0, g) >= band && edge_depth(zn - 1, x0 + FW - 1, g) >= band &&
-                              edge_depth(z0, x0 + FW - 1, g) >= band && edge_depth(zn - 1, x0, g) >= band;
+    if (HABC && rows) {
+        clean = clean && edge_depth(z0, x0, g) >= band && edge_depth(zn - 1, x0 + FW - 1, g) >= band &&
+                edge_depth(z0, x0 + FW - 1, g) >= band && edge_depth(zn - 1, x0, g) >= band;
+        // tile entirely inside the band: nothing to do here (the band blocks own it)
+        if (zn <= (g.multiple ? 0 : band) || z0 >= g.nz - band || x0 + FW <= band || x0 >= g.nx - band) rows = false;
+    }
+    const bool safe = z0 >= 1 && z0 + FRZ + 1 <= g.nz && x0 >= 1 && x0 + FW + 1 <= g.nx;
     auto owns = [&](int z, int xx) { return !HABC || edge_depth(z, xx, g) >= band; };
-    const float* ciso = a.coef[2];
-    // product row  w = ciso * L1  (the pre-blend factor is 1 in the fast region and next to it)
-    auto wrow = [&](const float* l1, int z, float4& lraw) -> float4 {
-        lraw = ldrow(l1, z, x, g);
-        const float4 c = ldrow(ciso, z, x, g);
-        return make_float4(c.x * lraw.x, c.y * lraw.y, c.z * lraw.z, c.w * lraw.w);
-    };
-    auto whalo = [&](const float* l1, int z, const float4& w, float& left, float& right) {
-        left = __shfl_up_sync(0xffffffffu, w.w, 1);
-        right = __shfl_down_sync(0xffffffffu, w.x, 1);
-        if (lane == 0 || lane == 31) {
-            const int xx = lane == 0 ? x0 - 1 : x0 + FW;
-            float v = 0.f;
-            if (z >= 0 && z < g.nz && xx >= 0 && xx < g.nx) {
-                const int o = z * g.ld + xx;
-                v = __ldg(ciso + o) * __ldg(l1 + o);
-            }
-            if (lane == 0) left = v; else right = v;
-        }
-    };
     float4* gsl = reinterpret_cast<float4*>(&gsm[warp][0][4 * lane]);      // stride FW/4 float4 per row
     if (want_grad) {
 #pragma unroll
         for (int k = 0; k < FRZ; ++k) gsl[k * (FW / 4)] = f4zero();
     }
-
     const int b_lo = chunk * a.bchunk, b_hi = min(b_lo + a.bchunk, a.B);
     for (int b = b_lo; b < b_hi; ++b) {
-        const long long boff = (long long)b * a.fs;
         if (rows) {
-            const float* l1 = a.lam1 + boff;
-            const float* l2 = a.lam2 + boff;
-            const float* S = a.s1 + boff;
-            float* l0 = a.lam0 + boff;
-            float4 lC, lD;
-            float4 wU = wrow(l1, z0 - 1, lC);
-            float4 wC = wrow(l1, z0, lC);
-            float4 sU = ldrow(S, z0 - 1, x, g), sC = ldrow(S, z0, x, g);
-#pragma unroll
-            for (int k = 0; k < FRZ; ++k) {
-                const int z = z0 + k;
-                if (z < zn) {
-                    const float4 wD = wrow(l1, z + 1, lD);
-                    const float4 sD = ldrow(S, z + 1, x, g);
-                    const float4 p2 = ldrow(l2, z, x, g);
-                    float4 al = f4zero();
-                    if (PML) al = ldrow(a.coef[3], z, x, g);
-                    float wl, wr, sl, sr;
-                    whalo(l1, z, wC, wl, wr);
-                    row_halo(sC, S, z, x0, lane, g, sl, sr);
-                    float4 out, gq;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float c = f4get(wC, e);
-                        const float w = e == 0 ? wl : f4get(wC, e - 1), ea = e == 3 ? wr : f4get(wC, e + 1);
-                        const float lapw = ((f4get(wU, e) - c) + (f4get(wD, e) - c)) + ((ea - c) + (w - c));
-                        const float alpha = PML ? f4get(al, e) : 1.f;
-                        const float l1c = f4get(lC, e);
-                        f4set(out, e, (1.f + alpha) * l1c + lapw - alpha * f4get(p2, e));
-                        const float sc = f4get(sC, e);
-                        const float sw_ = e == 0 ? sl : f4get(sC, e - 1), se_ = e == 3 ? sr : f4get(sC, e + 1);
-                        const float laps = ((f4get(sU, e) - sc) + (f4get(sD, e) - sc)) + ((se_ - sc) + (sw_ - sc));
-                        f4set(gq, e, l1c * laps);
-                    }
-                    float* o = l0 + (z * g.ld + x);
-                    if (clean) {
-                        *reinterpret_cast<float4*>(o) = out;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (x + e < g.nx && owns(z, x + e)) o[e] = f4get(out, e);
-                    }
-                    if (want_grad) {
-                        float4 acc = gsl[k * (FW / 4)];
-                        acc.x += gq.x; acc.y += gq.y; acc.z += gq.z; acc.w += gq.w;
-                        gsl[k * (FW / 4)] = acc;
-                    }
-                    wU = wC; wC = wD; sU = sC; sC = sD; lC = lD;
-                }
-            }
+            if (safe) adjoint_fast_rows<FL, true>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
+            else adjoint_fast_rows<FL, false>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
         }
         adjoint_tail<1>(a, b, zb0, zb0 + FH, x0, x0 + FW, tid, owns);
     }
@@ -493,9 +587,10 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
 
 // general cell-by-cell adjoint of one TX x TZ tile; `band` < 0: every cell, else only the
 // cells closer than `band` to an absorbing edge
+// Shots b_lo..b_hi-1 are processed in turn; gradient contributions go to plane `gplane`.
 template <int FL>
-__device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, int tx, int chunk, int tid, int band,
-                                                      float (*sl)[SH][SW], float (*ss)[SH][SW]) {
+__device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, int tx, int b_lo, int b_hi, int gplane,
+                                                      int tid, int band, float (*sl)[SH][SW], float (*ss)[SH][SW]) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     const W2Geom g = a.g;
     const int x0 = tx * TX, z0 = tz * TZ;
@@ -503,7 +598,6 @@ __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, i
     const bool want_grad = a.gacc != nullptr;
     const long long plane = (long long)g.nz * g.ld;
     auto owns = [&](int z, int xx) { return band < 0 || edge_depth(z, xx, g) < band; };
-    const int b_lo = chunk * a.bchunk, b_hi = min(b_lo + a.bchunk, a.B);
     for (int b = b_lo; b < b_hi; ++b) {
         const long long boff = (long long)b * a.fs;
         __syncthreads();
@@ -547,7 +641,7 @@ __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, i
 #pragma unroll
                 for (int f = 0; f < NF; ++f) a.lam0[f * a.cs + boff + idx] = out[f];
                 if (want_grad) {
-                    float* gb = a.gacc + (long long)chunk * 7 * plane + idx;
+                    float* gb = a.gacc + (long long)gplane * 7 * plane + idx;
 #pragma unroll
                     for (int q = 0; q < 7; ++q)
                         if (grad_used<FL>(q)) gb[q * plane] += gr[q];
@@ -565,28 +659,31 @@ __global__ void __launch_bounds__(NT, 3) wave2d_adjoint_kernel(const W2Args a, i
     constexpr int GEN_FLOATS = NEED_GEN ? 2 * NF * SH * SW : 1;
     constexpr int FAST_FLOATS = adj_fast<FL>() ? NWARP * FRZ * FW : 1;
     __shared__ __align__(16) float smem[GEN_FLOATS > FAST_FLOATS ? GEN_FLOATS : FAST_FLOATS];
-    const int bid = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
-    bool fast = false;
+    const int bid = blockIdx.x, tid = threadIdx.x;
+    // grid.x = [band blocks: one per (tile, shot)] ++ [fast blocks: one per (fast tile, shot chunk)]
+    // for the fast-path equations, else one general block per (tile, shot chunk).
     if constexpr (adj_fast<FL>()) {
-        if (bid < nfast) {
-            fast = true;
-            adjoint_fast_block<FL>(a, bid, nfx, chunk, tid, reinterpret_cast<float (*)[FRZ][FW]>(smem));
-        }
-    }
-    if constexpr (NEED_GEN) {
-        if (!fast) {
-            int tz, tx, band;
-            if (adj_fast<FL>()) {
-                band_tile_decode(bt, bid - nfast, tz, tx);
-                band = a.g.bw + 1;
-            } else {
-                tz = bid / bt.nxt;
-                tx = bid - tz * bt.nxt;
-                band = -1;
+        const int nband = (FL & ST_F_HABC) ? bt.count * a.B : 0;
+        if (bid >= nband) {
+            const int q = bid - nband;
+            adjoint_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid, reinterpret_cast<float (*)[FRZ][FW]>(smem));
+        } else {
+            if constexpr (NEED_GEN) {
+                int tz, tx;
+                const int b = bid / bt.count;
+                band_tile_decode(bt, bid - b * bt.count, tz, tx);
+                // band gradients of shot b accumulate in gradient plane b (see nchunk in the launcher)
+                adjoint_general_block<FL>(a, tz, tx, b, b + 1, b, tid, a.g.bw + 1, reinterpret_cast<float (*)[SH][SW]>(smem),
+                                          reinterpret_cast<float (*)[SH][SW]>(smem + NF * SH * SW));
             }
-            adjoint_general_block<FL>(a, tz, tx, chunk, tid, band, reinterpret_cast<float (*)[SH][SW]>(smem),
-                                      reinterpret_cast<float (*)[SH][SW]>(smem + NF * SH * SW));
         }
+    } else {
+        const int ntile = bt.nxt * bt.nzt;
+        const int chunk = bid / ntile, t = bid - chunk * ntile;
+        const int tz = t / bt.nxt, tx = t - tz * bt.nxt;
+        const int b_lo = chunk * a.bchunk, b_hi = min(b_lo + a.bchunk, a.B);
+        adjoint_general_block<FL>(a, tz, tx, b_lo, b_hi, chunk, tid, -1, reinterpret_cast<float (*)[SH][SW]>(smem),
+                                  reinterpret_cast<float (*)[SH][SW]>(smem + NF * SH * SW));
     }
 }
 
@@ -612,15 +709,12 @@ template <int FL>
 int st_w2_launch_adj(const W2Args& a, cudaStream_t st) {
     const int nchunk = (a.B + a.bchunk - 1) / a.bchunk;
     const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
-    int nfast = 0, ngen;
+    const int nfast = nfx * nfz;
     BandTiles bt = band_tiles(a.g, a.g.bw + 1);
-    if (adj_fast<FL>()) {
-        nfast = nfx * nfz;
-        ngen = (FL & ST_F_HABC) ? bt.count : 0;
-    } else {
-        ngen = bt.nxt * bt.nzt;
-    }
-    dim3 grid(nfast + ngen, nchunk);
+    long long nblocks;
+    if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)bt.count * a.B : 0);
+    else nblocks = (long long)bt.nxt * bt.nzt * nchunk;
+    dim3 grid((unsigned)nblocks);
     wave2d_adjoint_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }

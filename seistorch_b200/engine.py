@@ -366,6 +366,8 @@ class _Propagate(torch.autograd.Function):
         prob.lam = torch.zeros(spec.nlam * spec.slot_elems, dtype=torch.float32, device=dev)
         prob.bchunk = _choose_bchunk(spec)
         nchunk = math.ceil(spec.B / prob.bchunk)
+        if spec.family == "wave2d":
+            nchunk = max(nchunk, spec.B)      # frame blocks accumulate per shot (include/seistorch_b200.h)
         prob.gacc = torch.zeros(nchunk * spec.ngrad * spec.plane, dtype=torch.float32, device=dev)
         want_gamp = ctx.needs_input_grad[2]
         prob.gamp = torch.zeros((spec.nt, acq.ns), dtype=torch.float32, device=dev) if want_gamp else None

@@ -71,7 +71,8 @@ class _Step(torch.autograd.Function):
         nx, e = spec.shape[-1], spec.slot_elems
         gouts = [torch.zeros((spec.B,) + tuple(spec.shape), device=dev) if g is None else g for g in gouts]
         prob.bchunk = spec.B
-        prob.gacc = torch.zeros(spec.ngrad * spec.plane, dtype=torch.float32, device=dev)
+        nplanes = spec.B if spec.family == "wave2d" else 1     # frame blocks accumulate per shot
+        prob.gacc = torch.zeros(nplanes * spec.ngrad * spec.plane, dtype=torch.float32, device=dev)
         unpad = lambda buf: buf.view(spec.nf, spec.B, *spec.shape[:-1], spec.ld)[..., :nx]
         if spec.order == 2:
             gy = _to_slots(gouts[0::2], spec).reshape(-1)
@@ -90,7 +91,7 @@ class _Step(torch.autograd.Function):
             gfields = []
             for k in range(spec.nf):
                 gfields += [g_cur[k] + gouts[2 * k + 1], g_prev[k]]
-            g = prob.gacc.view(spec.ngrad, *spec.shape[:-1], spec.ld)[..., :nx]
+            g = prob.gacc.view(nplanes, spec.ngrad, *spec.shape[:-1], spec.ld).sum(0)[..., :nx]
             from .engine import _W2_GRAD_OF_COEF
             gcoefs = []
             for k in range(ncoef):
