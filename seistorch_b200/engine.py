@@ -180,13 +180,18 @@ class Spec:
 def _choose_bchunk(spec: Spec) -> int:
     """Shots handled by one adjoint block (gradient accumulated in registers across
     them); keep at least ~4 blocks per SM."""
+    env = os.environ.get("SEISTORCH_B200_BCHUNK")
+    if env:
+        return max(1, min(int(env), spec.B))
     if spec.family == "acoustic3d":
         tiles = math.ceil(spec.shape[2] / 64) * math.ceil(spec.shape[1] / 8) * math.ceil(spec.shape[0] / 16)
+    elif spec.family == "wave2d":
+        tiles = math.ceil(spec.shape[1] / 128) * math.ceil(spec.shape[0] / 64)     # fast tiles (256 threads)
     else:
         tiles = math.ceil(spec.shape[1] / 64) * math.ceil(spec.shape[0] / 32)
     best = 1
     for c in range(1, spec.B + 1):
-        if spec.B % c == 0 and tiles * (spec.B // c) >= 592:
+        if spec.B % c == 0 and tiles * (spec.B // c) >= 888:      # >= 2 waves of 3 blocks/SM on 148 SMs
             best = c
     return best
 
