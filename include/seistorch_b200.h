@@ -93,6 +93,9 @@ typedef struct st_wave2d_problem {
     float dt;                   /* only used by ST_EQ_PML (b*dt) */
     const float* coef[8];       /* r=vp*dt/h, b(damping d), cxx, czz, cxz, ax, az, m : [nz][ld] or NULL.
                                    ISO equations: cxx = r^2 (HABC) or r^2/(1+b dt) (PML), czz = (1-b dt)/(1+b dt) (PML) */
+    float* taps;                /* optional workspace of st_wave2d_taps_floats() floats, filled by st_wave2d_prepare():
+                                   precomputed absorbing-frame taps (ST_EQ_ISO|ST_EQ_HABC only); NULL = evaluate
+                                   the one-way blend cell by cell */
     float* u;                   /* [nslots][NF][B][nz][ld] */
     int32_t nslots;
     float* lam;                 /* [3][NF][B][nz][ld] adjoint state, slot = i mod 3 (zero before the first adjoint call) */
@@ -101,6 +104,11 @@ typedef struct st_wave2d_problem {
     int32_t bchunk;             /* shots per block in the adjoint kernel; nchunk = ceil(B/bchunk) */
     st_acquisition acq;
 } st_wave2d_problem;
+
+/* size (floats) of the `taps` workspace, 0 if the flag set / grid does not use one */
+int64_t st_wave2d_taps_floats(const st_wave2d_problem* p);
+/* fill p->taps from the coefficient planes (once per call, before forward/adjoint) */
+int st_wave2d_prepare(const st_wave2d_problem* p, void* stream);
 
 /* advance steps i0 .. i0+nsteps-1; S_{i0-2} lives in slot `slot0`, S_{i0-1} in slot0+1,
  * step i writes slot0+2+(i-i0).                                                         */

@@ -37,6 +37,7 @@ class StWave2dProblem(C.Structure):
         ("nt", C.c_int32),
         ("dt", C.c_float),
         ("coef", C.c_void_p * 8),
+        ("taps", C.c_void_p),
         ("u", C.c_void_p),
         ("nslots", C.c_int32),
         ("lam", C.c_void_p),
@@ -77,6 +78,7 @@ class StAcoustic3dProblem(C.Structure):
 # every symbol include/seistorch_b200.h declares
 EXPORTS = [
     "st_version", "st_last_error",
+    "st_wave2d_taps_floats", "st_wave2d_prepare",
     "st_wave2d_forward", "st_wave2d_adjoint",
     "st_acoustic2d_forward", "st_acoustic2d_adjoint",
     "st_acoustic2d_habc_forward", "st_acoustic2d_habc_adjoint",
@@ -106,7 +108,11 @@ def lib():
     L.st_version.restype = C.c_int
     L.st_last_error.restype = C.c_char_p
     step_args = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
-    for name in EXPORTS[2:16]:
+    L.st_wave2d_taps_floats.restype = C.c_int64
+    L.st_wave2d_taps_floats.argtypes = [C.c_void_p]
+    L.st_wave2d_prepare.restype = C.c_int
+    L.st_wave2d_prepare.argtypes = [C.c_void_p, C.c_void_p]
+    for name in EXPORTS[4:18]:
         fn = getattr(L, name)
         fn.restype = C.c_int
         fn.argtypes = step_args

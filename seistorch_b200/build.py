@@ -33,7 +33,7 @@ def _nvcc():
 def _units():
     units = [("st_api", "st_api.cu", []), ("st_elastic2d", "st_elastic2d.cu", []),
              ("st_acoustic3d", "st_acoustic3d.cu", []), ("st_misfit", "st_misfit.cu", []),
-             ("st_wave2d_tb", "st_wave2d_tb.cu", []),
+             ("st_wave2d_band", "st_wave2d_band.cu", []),
              ("st_wave2d_dispatch", "st_wave2d.cu", ["-DST_W2_DISPATCH_ONLY"])]
     for fl in W2_FLAG_SETS:
         units.append((f"st_wave2d_{fl}", "st_wave2d.cu", [f"-DST_W2_INSTANCE={fl}"]))
@@ -49,6 +49,8 @@ def _digest():
                 h.update(name.encode())
                 h.update(f.read())
     with open(os.path.join(os.path.dirname(HERE), "include", "seistorch_b200.h"), "rb") as f:
+        h.update(f.read())
+    with open(os.path.abspath(__file__), "rb") as f:
         h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -76,6 +78,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    import ctypes
+    ctypes.CDLL(LIB)        # fails here (not on the GPU box) if a symbol is unresolved
     with open(stamp, "w") as f:
         f.write(dig)
     if verbose:

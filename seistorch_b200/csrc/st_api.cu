@@ -6,6 +6,7 @@
 #include "../../include/seistorch_b200.h"
 #include "st_common.cuh"
 #include "st_wave2d.cuh"
+#include "st_wave2d_band.cuh"
 #include "st_elastic2d.cuh"
 #include "st_acoustic3d.cuh"
 
@@ -63,6 +64,13 @@ static int w2_check(const st_wave2d_problem* p) {
     return check_acq(p->acq, (p->flags & ST_EQ_BORN) ? 2 : 1);
 }
 
+// precomputed frame taps: acoustic_habc only, and only when the band rectangles do not overlap
+static bool w2_uses_taps(const st_wave2d_problem* p) {
+    if (p->flags != (ST_EQ_ISO | ST_EQ_HABC)) return false;
+    W2Geom g{p->nz, p->nx, p->ld, p->bw, p->multiple};
+    return st_band_ok(g, p->bw + 1);
+}
+
 static void w2_fill(const st_wave2d_problem* p, W2Args& a) {
     memset(&a, 0, sizeof(a));
     a.g.nz = p->nz; a.g.nx = p->nx; a.g.ld = p->ld; a.g.bw = p->bw; a.g.multiple = p->multiple;
@@ -70,12 +78,29 @@ static void w2_fill(const st_wave2d_problem* p, W2Args& a) {
     a.fs = (long long)p->nz * p->ld;
     a.cs = a.fs * p->B;
     for (int k = 0; k < 8; ++k) a.coef[k] = p->coef[k];
+    a.taps = w2_uses_taps(p) ? p->taps : nullptr;
     a.ns = p->acq.ns; a.src_b = p->acq.src_b; a.src_z = p->acq.src_i1; a.src_x = p->acq.src_i2;
     a.src_fmask = p->acq.src_fmask;
     a.row_start = p->acq.row_start; a.rec_x = p->acq.rec_col; a.rec_orig = p->acq.rec_orig;
     a.R = p->acq.R; a.nchan = p->acq.nchan;
     for (int c = 0; c < 4; ++c) a.chan_f[c] = p->acq.chan_f[c];
     a.bchunk = p->bchunk > 0 ? p->bchunk : 1;
+}
+
+extern "C" int64_t st_wave2d_taps_floats(const st_wave2d_problem* p) {
+    if (!p || !w2_uses_taps(p)) return 0;
+    return (int64_t)ST_TAP_PLANES * p->nz * p->ld;
+}
+
+extern "C" int st_wave2d_prepare(const st_wave2d_problem* p, void* stream) {
+    int rc = w2_check(p);
+    if (rc) return rc;
+    if (!w2_uses_taps(p) || p->taps == nullptr) return ST_OK;
+    W2Args a;
+    w2_fill(p, a);
+    rc = st_wave2d_launch_prepare(a, (cudaStream_t)stream);
+    if (rc) st_set_error("wave2d_prepare: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
 }
 
 extern "C" int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream) {

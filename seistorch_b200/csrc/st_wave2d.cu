@@ -19,6 +19,7 @@
 // every row starts 16-byte aligned and columns [nx, ld) stay zero; coefficient planes
 // [nz][ld] shared by all shots (L2-resident: <= 8 MB each at the BASELINE sizes).
 #include "st_wave2d.cuh"
+#include "st_wave2d_band.cuh"
 
 namespace {
 
@@ -159,6 +160,227 @@ __device__ __forceinline__ void forward_tail(const W2Args& a, int b, int z0, int
                 for (int ch = 0; ch < a.nchan; ++ch)
                     a.rec_out[o + ch] = a.next[a.chan_f[ch] * a.cs + boff + (long long)z * g.ld + rx];
             }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------ band (tap gather)
+// rows touched by the 256 consecutive band cells of a block -> shared list (<= 16 rows)
+__device__ __forceinline__ int band_block_rows(const BandCells& bc, int i, int tid, int* s_rows, int* s_cnt) {
+    if (tid == 0) *s_cnt = 0;
+    __syncthreads();
+    if (i < bc.total) {
+        int z, x, zp = -1, xp;
+        st_band_decode(bc, i, z, x);
+        if (tid > 0) st_band_decode(bc, i - 1, zp, xp);
+        if (z != zp) {
+            const int k = atomicAdd(s_cnt, 1);
+            if (k < 16) s_rows[k] = z;
+        }
+    }
+    __syncthreads();
+    return min(*s_cnt, 16);
+}
+
+// Every thread owns ONE band cell and walks all shots with its taps held in registers, so the
+// tap planes are read once per step, not once per shot.
+__device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int tid) {
+    const W2Geom g = a.g;
+    const BandCells bc = st_band_cells(g, g.bw);
+    const int i0 = blk * NT, i = i0 + tid;
+    const long long plane = (long long)g.nz * g.ld;
+    auto mine = [&](int z, int x) {
+        if (z < 0 || z >= g.nz || x < 0 || x >= g.nx || !w2_in_frame(z, x, g)) return false;
+        const int e = st_band_encode(bc, z, x);
+        return e >= i0 && e < i0 + NT;
+    };
+    if (i < bc.total) {
+        int z, x;
+        st_band_decode(bc, i, z, x);
+        const int idx = z * g.ld + x;
+        // increment form: Y = h1 + (h1 - h2) + sum_{o != 0} F1[o] (h1(p+o) - h1(p)) + F2[o] (h2(p+o) - h2(p))
+        // (the taps of h1 sum to 2 and those of h2 to -1 exactly, DESIGN.md "numerics")
+        float t1[ST_NTAP1 - 1], t2[ST_NTAP2 - 1];
+        int q1[ST_NTAP1 - 1];
+#pragma unroll
+        for (int o = 1; o < ST_NTAP1; ++o) {
+            const int zz = z + st_tap_dz(o), xx = x + st_tap_dx(o);
+            const bool in = zz >= 0 && zz < g.nz && xx >= 0 && xx < g.nx;
+            q1[o - 1] = in ? zz * g.ld + xx : -1;
+            t1[o - 1] = __ldg(a.taps + o * plane + idx);
+            if (o < ST_NTAP2) t2[o - 1] = __ldg(a.taps + (ST_NTAP1 + o) * plane + idx);
+        }
+        for (int b = 0; b < a.B; ++b) {
+            const long long boff = (long long)b * a.fs;
+            const float* cur = a.cur + boff;
+            const float* prv = a.prev + boff;
+            const float c = __ldg(cur + idx), p = __ldg(prv + idx);
+            float acc = 0.f;
+#pragma unroll
+            for (int o = 1; o < ST_NTAP1; ++o) {
+                const float v = q1[o - 1] >= 0 ? __ldg(cur + q1[o - 1]) : 0.f;
+                acc += t1[o - 1] * (v - c);
+                if (o < ST_NTAP2) {
+                    const float v2 = q1[o - 1] >= 0 ? __ldg(prv + q1[o - 1]) : 0.f;
+                    acc += t2[o - 1] * (v2 - p);
+                }
+            }
+            a.next[boff + idx] = c + ((c - p) + acc);
+        }
+    }
+    __syncthreads();
+    // wrap-around neighbour of the strip (at most 4 cells of the whole grid)
+    if (tid < 4) {
+        int z, x, s, zw, xw;
+        st_wrap_candidate(g, tid, z, x, s, zw, xw);
+        if (mine(z, x)) {
+            float f[4];
+            w2_side_weights(z, x, g, f);
+            const int idx = z * g.ld + x;
+            const float r = __ldg(a.coef[0] + idx), w = __ldg(a.coef[1] + idx) * f[s];
+            // true operator: -mu*w*h1(wrap); the increment form above assumed taps summing to 2, i.e. it
+            // implicitly carries -mu*w*h1(q) for the missing tap: replace it
+            if (w != 0.f)
+                for (int b = 0; b < a.B; ++b) {
+                    const long long boff = (long long)b * a.fs;
+                    a.next[boff + idx] += w * (-r * r) * (__ldg(a.cur + boff + (zw * g.ld + xw)) - __ldg(a.cur + boff + idx));
+                }
+        }
+    }
+    __syncthreads();
+    for (int s = tid; s < a.ns; s += NT) {
+        const int sz = a.src_z[s], sx = a.src_x[s];
+        if (mine(sz, sx) && (a.src_fmask & 1)) atomicAdd(a.next + (long long)a.src_b[s] * a.fs + (sz * g.ld + sx), a.amp[s]);
+    }
+    if (!a.rec_out) return;
+    __shared__ int s_cnt, s_rows[16];
+    const int cnt = band_block_rows(bc, i, tid, s_rows, &s_cnt);
+    for (int k = 0; k < cnt; ++k) {
+        const int z = s_rows[k];
+        for (int b = 0; b < a.B; ++b) {
+            const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
+            for (int r = lo + tid; r < hi; r += NT) {
+                const int rx = a.rec_x[r];
+                if (mine(z, rx)) {
+                    const long long o = (long long)a.rec_orig[r] * a.nchan;
+                    for (int ch = 0; ch < a.nchan; ++ch) a.rec_out[o + ch] = a.next[(long long)b * a.fs + (z * g.ld + rx)];
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int tid) {
+    const W2Geom g = a.g;
+    const int bd = g.bw + 1;
+    const BandCells bc = st_band_cells(g, bd);
+    const int i0 = blk * NT, i = i0 + tid;
+    const long long plane = (long long)g.nz * g.ld;
+    const bool want_grad = a.gacc != nullptr;
+    auto inb = [&](int z, int x) { return z >= 0 && z < g.nz && x >= 0 && x < g.nx; };
+    auto mine = [&](int z, int x) {
+        if (!inb(z, x)) return false;
+        const int e = st_band_encode(bc, z, x);
+        return e >= i0 && e < i0 + NT;
+    };
+    if (i < bc.total) {
+        int z, x;
+        st_band_decode(bc, i, z, x);
+        const int idx = z * g.ld + x;
+        // transposed taps: coefficient of L(p+o) is the tap -o of cell p+o
+        float g1[ST_NTAP1], g2[ST_NTAP2], h1[ST_NTAP1], h2[ST_NTAP2];
+        int q[ST_NTAP1];
+        const bool frame = w2_in_frame(z, x, g);
+        const float pre = frame ? 1.f - __ldg(a.coef[1] + idx) : 1.f;
+#pragma unroll
+        for (int o = 0; o < ST_NTAP1; ++o) {
+            const int zz = z + st_tap_dz(o), xx = x + st_tap_dx(o);
+            const bool in = inb(zz, xx);
+            q[o] = in ? zz * g.ld + xx : -1;
+            g1[o] = in ? __ldg(a.taps + st_tap_neg(o) * plane + q[o]) : 0.f;
+            if (o < ST_NTAP2) g2[o] = in ? __ldg(a.taps + (ST_NTAP1 + st_tap_neg(o)) * plane + q[o]) : 0.f;
+            h1[o] = (want_grad && frame) ? __ldg(a.taps + (ST_NTAP1 + ST_NTAP2 + o) * plane + idx) : 0.f;
+            if (o < ST_NTAP2) h2[o] = (want_grad && frame) ? __ldg(a.taps + (2 * ST_NTAP1 + ST_NTAP2 + o) * plane + idx) : 0.f;
+        }
+        float gr = 0.f, gc = 0.f;
+        for (int b = 0; b < a.B; ++b) {
+            const long long boff = (long long)b * a.fs;
+            const float* l1 = a.lam1 + boff;
+            const float* l2 = a.lam2 + boff;
+            float acc = 0.f, v1[ST_NTAP1];
+#pragma unroll
+            for (int o = 0; o < ST_NTAP1; ++o) {
+                v1[o] = q[o] >= 0 ? __ldg(l1 + q[o]) : 0.f;
+                acc += g1[o] * v1[o];
+                if (o < ST_NTAP2) acc += g2[o] * (q[o] >= 0 ? __ldg(l2 + q[o]) : 0.f);
+            }
+            a.lam0[boff + idx] = acc;
+            if (want_grad) {
+                const float* S1 = a.s1 + boff;
+                const float* S2 = a.s2 + boff;
+                float s[ST_NTAP1];
+#pragma unroll
+                for (int o = 0; o < ST_NTAP1; ++o) s[o] = (q[o] >= 0 && (o < ST_NTAP2 || frame)) ? __ldg(S1 + q[o]) : 0.f;
+                const float lc = v1[0];
+                gc += pre * lc * (((s[1] - s[0]) + (s[2] - s[0])) + ((s[3] - s[0]) + (s[4] - s[0])));
+                if (frame) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int o = 0; o < ST_NTAP1; ++o) {
+                        t += h1[o] * s[o];
+                        if (o < ST_NTAP2) t += h2[o] * (q[o] >= 0 ? __ldg(S2 + q[o]) : 0.f);
+                    }
+                    gr += lc * t;
+                }
+            }
+        }
+        if (want_grad) {
+            a.gacc[plane + idx] += gc;          // plane 0, slot 1: d/d ciso
+            if (frame) a.gacc[idx] += gr;       // plane 0, slot 0: d/d r
+        }
+    }
+    __syncthreads();
+    if (tid < 4) {
+        int z, x, s, zw, xw;
+        st_wrap_candidate(g, tid, z, x, s, zw, xw);
+        float f[4];
+        w2_side_weights(z, x, g, f);
+        const int qq = z * g.ld + x, qw = zw * g.ld + xw;
+        const float r = __ldg(a.coef[0] + qq), w = __ldg(a.coef[1] + qq) * f[s];
+        if (w != 0.f) {
+            for (int b = 0; b < a.B; ++b) {
+                const long long boff = (long long)b * a.fs;
+                const float lq = __ldg(a.lam1 + boff + qq);
+                if (mine(zw, xw)) atomicAdd(a.lam0 + boff + qw, w * (-r * r) * lq);
+                if (want_grad && mine(z, x)) atomicAdd(a.gacc + qq, lq * w * (-2.f * r) * __ldg(a.s1 + boff + qw));
+            }
+        }
+    }
+    __syncthreads();
+    if (a.rec_adj) {
+        __shared__ int s_cnt, s_rows[16];
+        const int cnt = band_block_rows(bc, i, tid, s_rows, &s_cnt);
+        for (int k = 0; k < cnt; ++k) {
+            const int z = s_rows[k];
+            for (int b = 0; b < a.B; ++b) {
+                const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
+                for (int r = lo + tid; r < hi; r += NT) {
+                    const int rx = a.rec_x[r];
+                    if (mine(z, rx)) {
+                        const long long o = (long long)a.rec_orig[r] * a.nchan;
+                        for (int ch = 0; ch < a.nchan; ++ch)
+                            atomicAdd(a.lam0 + (long long)b * a.fs + (z * g.ld + rx), a.rec_adj[o + ch]);
+                    }
+                }
+            }
+        }
+    }
+    if (a.gamp) {
+        __syncthreads();
+        for (int s = tid; s < a.ns; s += NT) {
+            const int sz = a.src_z[s], sx = a.src_x[s];
+            if (mine(sz, sx) && (a.src_fmask & 1)) a.gamp[s] = a.lam0[(long long)a.src_b[s] * a.fs + (sz * g.ld + sx)];
         }
     }
 }
@@ -370,6 +592,8 @@ __global__ void __launch_bounds__(NT, 4) wave2d_forward_kernel(const W2Args a, i
     const int nframe = HABC ? bt.count : 0;
     if (bid >= nframe) {
         forward_fast_block<FL>(a, bid - nframe, nfx, b, tid);
+    } else if (FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr) {
+        if (b == 0) forward_band_block(a, bid, tid);          // walks all shots itself
     } else {
         if constexpr (HABC) {
             int tz, tx;
@@ -663,10 +887,13 @@ __global__ void __launch_bounds__(NT, 3) wave2d_adjoint_kernel(const W2Args a, i
     // grid.x = [band blocks: one per (tile, shot)] ++ [fast blocks: one per (fast tile, shot chunk)]
     // for the fast-path equations, else one general block per (tile, shot chunk).
     if constexpr (adj_fast<FL>()) {
-        const int nband = (FL & ST_F_HABC) ? bt.count * a.B : 0;
+        const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
+        const int nband = (FL & ST_F_HABC) ? bt.count * (tapped ? 1 : a.B) : 0;
         if (bid >= nband) {
             const int q = bid - nband;
             adjoint_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid, reinterpret_cast<float (*)[FRZ][FW]>(smem));
+        } else if (tapped) {
+            adjoint_band_block(a, bid, tid);                  // walks all shots itself
         } else {
             if constexpr (NEED_GEN) {
                 int tz, tx;
@@ -701,6 +928,7 @@ int st_w2_launch_fwd(const W2Args& a, cudaStream_t st) {
     const int nfast = nfx * nfz;
     BandTiles bt = band_tiles(a.g, a.g.bw);
     if (!(FL & ST_F_HABC)) bt.count = 0;
+    if (FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
     dim3 grid(nfast + bt.count, a.B);
     wave2d_forward_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
@@ -711,8 +939,10 @@ int st_w2_launch_adj(const W2Args& a, cudaStream_t st) {
     const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
     const int nfast = nfx * nfz;
     BandTiles bt = band_tiles(a.g, a.g.bw + 1);
+    const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
+    if (tapped) bt.count = (st_band_cells(a.g, a.g.bw + 1).total + NT - 1) / NT;
     long long nblocks;
-    if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)bt.count * a.B : 0);
+    if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)bt.count * (tapped ? 1 : a.B) : 0);
     else nblocks = (long long)bt.nxt * bt.nzt * nchunk;
     dim3 grid((unsigned)nblocks);
     wave2d_adjoint_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);

@@ -9,6 +9,7 @@ struct W2Args {
     long long fs;           // floats per (shot, field) plane  = nz*ld
     long long cs;           // floats per field channel        = B*fs
     const float* coef[8];   // r,b,cxx,czz,cxz,ax,az,m  each [nz][ld]; nullptr if unused
+    float* taps;            // ISO|HABC: ST_TAP_PLANES precomputed frame-tap planes (st_wave2d_band.cuh) or nullptr
     // ---- forward: field states  [NF][B][nz][ld]
     const float* prev;      // S_{i-2}
     const float* cur;       // S_{i-1}

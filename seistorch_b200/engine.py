@@ -214,6 +214,8 @@ class _Problem:
         self.rec_out = None
         self.rec_adj = None
         self.gamp = None
+        self.taps = None
+        self._prepared = False
         L = _lib.lib()
         fam = spec.family
         if fam == "wave2d":
@@ -248,6 +250,19 @@ class _Problem:
             p.dt = float(s.dt)
             p.coef[0] = self.coefp[0].data_ptr()
             p.coef[1] = self.coefp[1].data_ptr()
+        if s.family == "wave2d":
+            if not self._prepared:
+                p.taps = None
+                n = int(_lib.lib().st_wave2d_taps_floats(C.byref(p)))
+                if n > 0:
+                    self.taps = torch.empty(n, dtype=torch.float32, device=self.coefp.device)
+                    p.taps = self.taps.data_ptr()
+                    p.u = self.u.data_ptr()
+                    p.nslots = self.nslots
+                    self.acq.fill(p.acq, self.amp, None, s.src_fmask, s.chan_f, None, None)
+                    _lib.check(_lib.lib().st_wave2d_prepare(C.byref(p), _stream_ptr()), "wave2d_prepare")
+                self._prepared = True
+            p.taps = _lib.ptr(self.taps)
         p.u = self.u.data_ptr()
         p.nslots = self.nslots
         p.lam = _lib.ptr(self.lam)
