@@ -21,7 +21,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libseistorch_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
+              "-Xcompiler", "-fPIC", "-diag-suppress", "177"] + os.environ.get("SEISTORCH_B200_NVCC_EXTRA", "").split()
 
 W2_FLAG_SETS = [3, 5, 4, 12, 21, 36, 44]
 

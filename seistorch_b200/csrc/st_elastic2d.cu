@@ -87,10 +87,18 @@ __global__ void __launch_bounds__(NT) elastic2d_forward_kernel(const E2Args a) {
                 if (a.src_fmask >> f & 1) atomicAdd(nxt + f * a.cs + (long long)sz * ld + sx, v);
         }
     }
-    __syncthreads();
     if (a.rec_out) {
-        const int zend = min(z0 + TZ, nz);
-        for (int z = z0; z < zend; ++z) {
+        __shared__ int s_cnt, s_rows[TZ];
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        if (tid < TZ && z0 + tid < nz) {
+            const int row = b * nz + z0 + tid;
+            if (a.row_start[row + 1] > a.row_start[row]) s_rows[atomicAdd(&s_cnt, 1)] = z0 + tid;
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        for (int i = 0; i < cnt; ++i) {
+            const int z = s_rows[i];
             const int lo = a.row_start[b * nz + z], hi = a.row_start[b * nz + z + 1];
             for (int r = lo + tid; r < hi; r += NT) {
                 const int rx = a.rec_x[r];
@@ -247,8 +255,17 @@ __global__ void __launch_bounds__(NT) elastic2d_adjoint_kernel(const E2Args a) {
         }
         __syncthreads();
         if (a.rec_adj) {
-            const int zend = min(z0 + TZ, nz);
-            for (int z = z0; z < zend; ++z) {
+            __shared__ int s_cnt, s_rows[TZ];
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            if (tid < TZ && z0 + tid < nz) {
+                const int row = b * nz + z0 + tid;
+                if (a.row_start[row + 1] > a.row_start[row]) s_rows[atomicAdd(&s_cnt, 1)] = z0 + tid;
+            }
+            __syncthreads();
+            const int cnt = s_cnt;
+            for (int i = 0; i < cnt; ++i) {
+                const int z = s_rows[i];
                 const int lo = a.row_start[b * nz + z], hi = a.row_start[b * nz + z + 1];
                 for (int r = lo + tid; r < hi; r += NT) {
                     const int rx = a.rec_x[r];

@@ -30,7 +30,13 @@ constexpr int SW = TX + 2 * HALO, SH = TZ + 2 * HALO;
 constexpr int NTX = 64, NTY = 4, RPT = TZ / NTY;
 // ---- fast tiles
 constexpr int FW = 128;                     // columns per warp (32 lanes x float4)
-constexpr int FRZ = 8;                      // rows per warp
+#ifndef ST_FRZ
+#define ST_FRZ 4
+#endif
+#ifndef ST_ADJ_MINB
+#define ST_ADJ_MINB 4
+#endif
+constexpr int FRZ = ST_FRZ;                 // rows per warp
 constexpr int NWARP = NT / 32;
 constexpr int FH = FRZ * NWARP;             // rows per fast block (64)
 
@@ -877,7 +883,7 @@ __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, i
 }
 
 template <int FL>
-__global__ void __launch_bounds__(NT, 3) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
+__global__ void __launch_bounds__(NT, ST_ADJ_MINB) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     constexpr bool NEED_GEN = !adj_fast<FL>() || (FL & ST_F_HABC);
     constexpr int GEN_FLOATS = NEED_GEN ? 2 * NF * SH * SW : 1;
