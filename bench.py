@@ -209,6 +209,7 @@ def main():
 
     # micro-batch: largest divisor of nshots whose full wavefield history fits (no recompute)
     free, total = torch.cuda.mem_get_info(dev)
+    free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
     state_bytes = 851 * 2404 * 4
     if args.microbatch:
         mb = args.microbatch

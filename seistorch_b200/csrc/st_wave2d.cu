@@ -512,8 +512,13 @@ __device__ __forceinline__ void forward_fast_rows(const W2Args& a, const W2Geom&
                     *reinterpret_cast<float4*>(o) = Y[f];
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (x + e < g.nx && (!HABC || !w2_in_frame(z, x + e, g))) o[e] = f4get(Y[f], e);
+                    for (int e = 0; e < 4; ++e) {
+                        if (x + e < g.nx) {
+                            if (!HABC || !w2_in_frame(z, x + e, g)) o[e] = f4get(Y[f], e);
+                        } else if (x + e < ld) {
+                            o[e] = 0.f;          // keep the pitch padding zero (history slots are not pre-cleared)
+                        }
+                    }
                 }
                 U[f] = Cc[f];
                 Cc[f] = D[f];
@@ -744,8 +749,13 @@ __device__ __forceinline__ void adjoint_fast_rows(const W2Args& a, const W2Geom&
                 *reinterpret_cast<float4*>(o) = out;
             } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (x + e < g.nx && owns(z, x + e)) o[e] = f4get(out, e);
+                for (int e = 0; e < 4; ++e) {
+                    if (x + e < g.nx) {
+                        if (owns(z, x + e)) o[e] = f4get(out, e);
+                    } else if (x + e < ld) {
+                        o[e] = 0.f;
+                    }
+                }
             }
             if (want_grad) {
                 float4 acc = gsl[k * (FW / 4)];

@@ -207,7 +207,12 @@ class _Problem:
         self.amp = amp                # [nt, ns] fp32 contiguous
         dev = coefp.device
         self.nslots = nslots
-        self.u = u if u is not None else torch.zeros(nslots * spec.slot_elems, dtype=torch.float32, device=dev)
+        if u is None:
+            # history slots are written in full by the kernels (incl. zero pitch padding), so only the
+            # initial state needs clearing -- a 100+ GB memset per forward call would cost ~40 ms
+            u = torch.empty(nslots * spec.slot_elems, dtype=torch.float32, device=dev)
+            u[:min(nslots, spec.order + 1) * spec.slot_elems].zero_()
+        self.u = u
         self.lam = None
         self.gacc = None
         self.bchunk = 1
@@ -318,6 +323,8 @@ def _history_plan(spec: Spec, dev) -> tuple:
             budget = int(float(env) * 2 ** 30)
         else:
             free, _total = torch.cuda.mem_get_info(dev)
+            # blocks cached by torch's allocator (e.g. the previous call's history) are reusable
+            free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
             reserve = (spec.nlam + 2) * slot_bytes + spec.ngrad * spec.plane * 4 * spec.B + (1 << 30)
             budget = int(0.85 * free) - reserve
     nslots_max = max(budget // slot_bytes, p + 2)
