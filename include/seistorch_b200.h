@@ -161,7 +161,9 @@ int st_elastic2d_adjoint(const st_elastic2d_problem* p, int32_t i_hi, int32_t ns
  * probe.py:46-48 inside the time loop; adjoint replaces checkpoint_new.py + the
  * host-staged face copies of equations3d/utils.py:57-121.  Tensor layout (B, n0, n1, n2)
  * = the reference's (B, x, z, y), n2 fastest with pitch ld.
- * coef[0] = r = vp*dt/h, coef[1] = b (PML damping), each [n0][n1][ld].
+ * coef[0] = ciso = (vp*dt/h)^2/(1+b*dt), coef[1] = alpha = (1-b*dt)/(1+b*dt), each [n0][n1][ld].
+ * The adjoint state `lam` holds the SCALED cotangent w = ciso * dL/dS (the damped acoustic
+ * operator is self-adjoint up to that diagonal scaling); gacc receives dL/d ciso.
  * ---------------------------------------------------------------------------------- */
 typedef struct st_acoustic3d_problem {
     int32_t B, n0, n1, n2, ld, nt;
@@ -170,7 +172,7 @@ typedef struct st_acoustic3d_problem {
     float* u;                   /* [nslots][B][n0][n1][ld] */
     int32_t nslots;
     float* lam;                 /* [3][B][n0][n1][ld] */
-    float* gacc;                /* [nchunk][n0][n1][ld] += d loss / d r, or NULL */
+    float* gacc;                /* [nchunk][n0][n1][ld] += d loss / d ciso, or NULL */
     int32_t bchunk;
     st_acquisition acq;
 } st_acoustic3d_problem;

@@ -125,5 +125,10 @@ def elastic_coefficients(params, dt, h, d):
 
 
 def acoustic3d_coefficients(params, dt, h, d):
+    """(ciso, alpha) of the 3D damped acoustic update  y = h1 + alpha (h1-h2) + ciso lap7(h1)
+    (equations3d/acoustic.py:72-85 in increment form)."""
+    dt, h = float(dt), float(h)
     vp = _f64(params[0])
-    return [(vp * (float(dt) / float(h))).to(torch.float32), _f64(d).to(torch.float32)]
+    bd = _f64(d) * dt
+    r = vp * (dt / h)
+    return [(r * r / (1 + bd)).to(torch.float32), ((1 - bd) / (1 + bd)).to(torch.float32)]

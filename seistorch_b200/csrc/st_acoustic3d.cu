@@ -2,169 +2,194 @@
 // Reference: equations3d/acoustic.py:65-85 (conv3d 7-point Laplacian + ~12 elementwise
 // passes per step, each over a 300 MB field at the BASELINE size).
 //
-// 2.5-D marching: a block owns an (n1,n2) tile and walks CH planes along n0; the
-// in-plane neighbours come from a shared-memory plane tile, the out-of-plane ones from a
-// three-register pipeline, so every field value is read from HBM/L2 once per brick.
+//   forward:  y = h1 + alpha (h1 - h2) + ciso * lap7(h1)            ciso = (vp dt/h)^2/(1+b dt)
+//   adjoint:  the damped acoustic operator is self-adjoint up to the diagonal scaling ciso:
+//             with the scaled cotangent  w = ciso * Lam  the exact discrete adjoint
+//                 Lam_i = (1+alpha) Lam_{i+1} + lap7(ciso Lam_{i+1}) - alpha Lam_{i+2}
+//             becomes  w_i = w1 + alpha (w1 - w2) + ciso * lap7(w1)  -- the forward kernel --
+//             plus the imaging condition  g_ciso += (w1/ciso) * lap7(S_i)  and receiver terms
+//             scaled by ciso.  One template serves both.
+//
+// Same streaming structure as the 2D fast path: a warp owns 128 columns (n2, fastest) x RZ
+// rows (n1) of one n0-plane; rows are 128-bit vector loads marched through a 3-row register
+// pipeline, n2 neighbours by warp shuffle, the n0 neighbours are two more vector loads that
+// hit L2 (planes are visited in order, a plane is 0.6 MB at the BASELINE size).
 #include "st_acoustic3d.cuh"
 
 namespace {
 
-constexpr int TX = 64, TY = 8, NT = TX * TY;
-constexpr int CH = 16;      // planes per brick
+constexpr int NT = 256, NWARP = NT / 32;
+constexpr int FW = 128;         // columns per warp
+constexpr int RZ = 4;           // rows per warp
+constexpr int FH = RZ * NWARP;  // rows per block
 
-__device__ __forceinline__ float ld0(const float* p, long long plane_off, int i1, int i2, int n1, int n2, int ld) {
-    if (i1 < 0 || i1 >= n1 || i2 < 0 || i2 >= n2) return 0.f;
-    return __ldg(p + plane_off + (long long)i1 * ld + i2);
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float f4get(const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void f4set(float4& v, int e, float s) { if (e == 0) v.x = s; else if (e == 1) v.y = s; else if (e == 2) v.z = s; else v.w = s; }
+
+struct G3 { int n0, n1, n2, ld; long long ps; };
+
+// row (i0, i1) of a field as one float4 per lane, zero outside the domain / pitch
+__device__ __forceinline__ float4 ldrow3(const float* __restrict__ base, int i0, int i1, int x, const G3& g) {
+    if (i0 < 0 || i0 >= g.n0 || i1 < 0 || i1 >= g.n1 || x >= g.ld) return f4zero();
+    return __ldg(reinterpret_cast<const float4*>(base + (i0 * g.ps + (long long)i1 * g.ld + x)));
 }
-
-__global__ void __launch_bounds__(NT) acoustic3d_forward_kernel(const A3Args a) {
-    __shared__ float sp[TY + 2][TX + 2];
-    const int n0 = a.n0, n1 = a.n1, n2 = a.n2, ld = a.ld;
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
-    const int nch = (n0 + CH - 1) / CH;
-    const int b = blockIdx.z / nch, c0 = (blockIdx.z % nch) * CH, c1 = min(c0 + CH, n0);
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int i2 = x0 + tx, i1 = y0 + ty;
-    const bool active = i2 < n2 && i1 < n1;
-    const long long col = (long long)i1 * ld + i2;
-    const float* cur = a.cur + (long long)b * a.fs;
-    const float* prv = a.prev + (long long)b * a.fs;
-    float* nxt = a.next + (long long)b * a.fs;
-
-    float behind = (active && c0 > 0) ? __ldg(cur + (long long)(c0 - 1) * a.ps + col) : 0.f;
-    float center = active ? __ldg(cur + (long long)c0 * a.ps + col) : 0.f;
-    for (int i0 = c0; i0 < c1; ++i0) {
-        const long long po = (long long)i0 * a.ps;
-        const float ahead = (active && i0 + 1 < n0) ? __ldg(cur + po + a.ps + col) : 0.f;
-        __syncthreads();
-        sp[ty + 1][tx + 1] = center;
-        if (ty == 0) sp[0][tx + 1] = ld0(cur, po, i1 - 1, i2, n1, n2, ld);
-        if (ty == TY - 1) sp[TY + 1][tx + 1] = ld0(cur, po, i1 + 1, i2, n1, n2, ld);
-        if (tx == 0) sp[ty + 1][0] = ld0(cur, po, i1, i2 - 1, n1, n2, ld);
-        if (tx == TX - 1) sp[ty + 1][TX + 1] = ld0(cur, po, i1, i2 + 1, n1, n2, ld);
-        __syncthreads();
-        if (active) {
-            const float lap = ((sp[ty][tx + 1] - center) + (sp[ty + 2][tx + 1] - center))
-                            + ((sp[ty + 1][tx] - center) + (sp[ty + 1][tx + 2] - center))
-                            + ((behind - center) + (ahead - center));
-            const float r = __ldg(a.r + po + col), bd = __ldg(a.b + po + col) * a.dt;
-            const float inv = 1.f / (1.f + bd);
-            const float h2 = __ldg(prv + po + col);
-            nxt[po + col] = center + ((1.f - bd) * inv) * (center - h2) + (r * r * inv) * lap;
-        }
-        behind = center;
-        center = ahead;
-    }
-    __syncthreads();
-    // ---- fused source add (source.py:59-70)
-    for (int s = tid; s < a.ns; s += NT) {
-        if (a.src_b[s] != b) continue;
-        const int s0 = a.src_i0[s], s1 = a.src_i1[s], s2 = a.src_i2[s];
-        if (s0 >= c0 && s0 < c1 && s1 >= y0 && s1 < y0 + TY && s2 >= x0 && s2 < x0 + TX)
-            atomicAdd(nxt + (long long)s0 * a.ps + (long long)s1 * ld + s2, a.amp[s]);
-    }
-    __syncthreads();
-    // ---- fused receiver gather (probe.py:46-48)
-    if (a.rec_out) {
-        const int nrow = (c1 - c0) * TY;
-        for (int q = tid; q < nrow; q += NT) {
-            const int i0 = c0 + q / TY, r1 = y0 + q % TY;
-            if (r1 >= n1) continue;
-            const long long row = ((long long)b * n0 + i0) * n1 + r1;
-            const int lo = a.row_start[row], hi = a.row_start[row + 1];
-            for (int r = lo; r < hi; ++r) {
-                const int rc = a.rec_col[r];
-                if (rc >= x0 && rc < x0 + TX)
-                    a.rec_out[a.rec_orig[r]] = nxt[(long long)i0 * a.ps + (long long)r1 * ld + rc];
-            }
-        }
+__device__ __forceinline__ void halo3(const float4& c, const float* __restrict__ base, int i0, int i1, int x0, int lane,
+                                      const G3& g, float& left, float& right) {
+    left = __shfl_up_sync(0xffffffffu, c.w, 1);
+    right = __shfl_down_sync(0xffffffffu, c.x, 1);
+    if (lane == 0 || lane == 31) {
+        const int xx = lane == 0 ? x0 - 1 : x0 + FW;
+        float v = 0.f;
+        if (i1 >= 0 && i1 < g.n1 && xx >= 0 && xx < g.n2) v = __ldg(base + (i0 * g.ps + (long long)i1 * g.ld + xx));
+        if (lane == 0) left = v; else right = v;
     }
 }
+__device__ __forceinline__ float lap7(const float4& C, const float4& U, const float4& D, const float4& F, const float4& Bk,
+                                      float l, float r, int e) {
+    const float c = f4get(C, e);
+    const float w = e == 0 ? l : f4get(C, e - 1), ea = e == 3 ? r : f4get(C, e + 1);
+    return (((f4get(U, e) - c) + (f4get(D, e) - c)) + ((ea - c) + (w - c))) + ((f4get(F, e) - c) + (f4get(Bk, e) - c));
+}
 
-__global__ void __launch_bounds__(NT) acoustic3d_adjoint_kernel(const A3Args a) {
-    __shared__ float sw[TY + 2][TX + 2];     // a3 * Lam_{i+1}
-    __shared__ float ss[TY + 2][TX + 2];     // S_i
-    const int n0 = a.n0, n1 = a.n1, n2 = a.n2, ld = a.ld;
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
-    const int nch = (n0 + CH - 1) / CH;
-    const int chunk = blockIdx.z / nch, c0 = (blockIdx.z % nch) * CH, c1 = min(c0 + CH, n0);
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int i2 = x0 + tx, i1 = y0 + ty;
-    const bool active = i2 < n2 && i1 < n1;
-    const long long col = (long long)i1 * ld + i2;
-    const bool want_grad = a.gacc != nullptr;
-    const float dt = a.dt;
-
-    auto wval = [&](const float* l1, long long po, int j1, int j2) -> float {
-        if (j1 < 0 || j1 >= n1 || j2 < 0 || j2 >= n2) return 0.f;
-        const long long o = po + (long long)j1 * ld + j2;
-        const float r = __ldg(a.r + o), bd = __ldg(a.b + o) * dt;
-        return r * r / (1.f + bd) * __ldg(l1 + o);
-    };
-
-    const int b_lo = chunk * a.bchunk, b_hi = min(b_lo + a.bchunk, a.B);
+template <bool ADJ>
+__global__ void __launch_bounds__(NT, ADJ ? 3 : 4) acoustic3d_kernel(const A3Args a, int nfx, int nfz) {
+    __shared__ __align__(16) float gsm[ADJ ? NWARP * RZ * FW : 4];
+    __shared__ int s_cnt, s_rows[FH];
+    const G3 g{a.n0, a.n1, a.n2, a.ld, a.ps};
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // blockIdx.x enumerates (i0, tile) with i0 slowest so neighbouring planes are processed close in time
+    const int tiles = nfx * nfz;
+    const int i0 = blockIdx.x / tiles, t = blockIdx.x - i0 * tiles;
+    const int fz = t / nfx, fx = t - fz * nfx;
+    const int x0 = fx * FW, zb0 = fz * FH, z0 = zb0 + warp * RZ;
+    const int x = x0 + 4 * lane;
+    const bool rows = z0 < g.n1;
+    const int zn = min(z0 + RZ, g.n1);
+    const bool full = x0 + FW <= g.n2;                       // all four cells of every lane are inside the domain
+    const bool want_grad = ADJ && a.gacc != nullptr;
+    float4* gsl = reinterpret_cast<float4*>(gsm + (warp * RZ) * FW + 4 * lane);
+    if (want_grad) {
+#pragma unroll
+        for (int k = 0; k < RZ; ++k) gsl[k * (FW / 4)] = f4zero();
+    }
+    const int b_lo = ADJ ? blockIdx.y * a.bchunk : blockIdx.y;
+    const int b_hi = ADJ ? min(b_lo + a.bchunk, a.B) : b_lo + 1;
     for (int b = b_lo; b < b_hi; ++b) {
-        const float* l1 = a.lam1 + (long long)b * a.fs;
-        const float* l2 = a.lam2 + (long long)b * a.fs;
-        const float* S = a.s1 + (long long)b * a.fs;
-        float* l0 = a.lam0 + (long long)b * a.fs;
-        float* gb = want_grad ? a.gacc + (long long)chunk * a.fs : nullptr;
-
-        float wb = 0.f, sb = 0.f, wc = 0.f, sc = 0.f;
-        if (active) {
-            if (c0 > 0) { wb = wval(l1, (long long)(c0 - 1) * a.ps, i1, i2); sb = __ldg(S + (long long)(c0 - 1) * a.ps + col); }
-            wc = wval(l1, (long long)c0 * a.ps, i1, i2);
-            sc = __ldg(S + (long long)c0 * a.ps + col);
-        }
-        for (int i0 = c0; i0 < c1; ++i0) {
-            const long long po = (long long)i0 * a.ps;
-            float wa = 0.f, sa = 0.f;
-            if (active && i0 + 1 < n0) { wa = wval(l1, po + a.ps, i1, i2); sa = __ldg(S + po + a.ps + col); }
-            __syncthreads();
-            sw[ty + 1][tx + 1] = wc;
-            ss[ty + 1][tx + 1] = sc;
-            if (ty == 0) { sw[0][tx + 1] = wval(l1, po, i1 - 1, i2); ss[0][tx + 1] = ld0(S, po, i1 - 1, i2, n1, n2, ld); }
-            if (ty == TY - 1) { sw[TY + 1][tx + 1] = wval(l1, po, i1 + 1, i2); ss[TY + 1][tx + 1] = ld0(S, po, i1 + 1, i2, n1, n2, ld); }
-            if (tx == 0) { sw[ty + 1][0] = wval(l1, po, i1, i2 - 1); ss[ty + 1][0] = ld0(S, po, i1, i2 - 1, n1, n2, ld); }
-            if (tx == TX - 1) { sw[ty + 1][TX + 1] = wval(l1, po, i1, i2 + 1); ss[ty + 1][TX + 1] = ld0(S, po, i1, i2 + 1, n1, n2, ld); }
-            __syncthreads();
-            if (active) {
-                const float lapw = ((sw[ty][tx + 1] - wc) + (sw[ty + 2][tx + 1] - wc))
-                                 + ((sw[ty + 1][tx] - wc) + (sw[ty + 1][tx + 2] - wc)) + ((wb - wc) + (wa - wc));
-                const float r = __ldg(a.r + po + col), bd = __ldg(a.b + po + col) * dt;
-                const float inv = 1.f / (1.f + bd), a2 = (1.f - bd) * inv;
-                const float l1c = __ldg(l1 + po + col), l2c = __ldg(l2 + po + col);
-                l0[po + col] = (1.f + a2) * l1c + lapw - a2 * l2c;
-                if (want_grad) {
-                    const float laps = ((ss[ty][tx + 1] - sc) + (ss[ty + 2][tx + 1] - sc))
-                                     + ((ss[ty + 1][tx] - sc) + (ss[ty + 1][tx + 2] - sc)) + ((sb - sc) + (sa - sc));
-                    gb[po + col] += l1c * (2.f * r * inv) * laps;
+        const long long boff = (long long)b * a.fs;
+        const float* cur = (ADJ ? a.lam1 : a.cur) + boff;
+        const float* prv = (ADJ ? a.lam2 : a.prev) + boff;
+        float* out = (ADJ ? a.lam0 : a.next) + boff;
+        const float* S = ADJ ? a.s1 + boff : nullptr;
+        if (rows) {
+            float4 U = ldrow3(cur, i0, z0 - 1, x, g), C = ldrow3(cur, i0, z0, x, g), D;
+            float4 sU = f4zero(), sC = f4zero(), sD = f4zero();
+            if (want_grad) { sU = ldrow3(S, i0, z0 - 1, x, g); sC = ldrow3(S, i0, z0, x, g); }
+#pragma unroll
+            for (int k = 0; k < RZ; ++k) {
+                const int z = z0 + k;
+                if (z < zn) {
+                    D = ldrow3(cur, i0, z + 1, x, g);
+                    const float4 F = ldrow3(cur, i0 + 1, z, x, g), Bk = ldrow3(cur, i0 - 1, z, x, g);
+                    const float4 P = ldrow3(prv, i0, z, x, g);
+                    const float4 CI = ldrow3(a.r, i0, z, x, g), AL = ldrow3(a.b, i0, z, x, g);
+                    float l, r;
+                    halo3(C, cur, i0, z, x0, lane, g, l, r);
+                    float4 Y;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float c = f4get(C, e);
+                        f4set(Y, e, c + f4get(AL, e) * (c - f4get(P, e)) + f4get(CI, e) * lap7(C, U, D, F, Bk, l, r, e));
+                    }
+                    float* o = out + (i0 * g.ps + (long long)z * g.ld + x);
+                    if (full) {
+                        *reinterpret_cast<float4*>(o) = Y;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (x + e < g.n2) o[e] = f4get(Y, e);
+                            else if (x + e < g.ld) o[e] = 0.f;
+                        }
+                    }
+                    if (want_grad) {
+                        sD = ldrow3(S, i0, z + 1, x, g);
+                        const float4 sF = ldrow3(S, i0 + 1, z, x, g), sB = ldrow3(S, i0 - 1, z, x, g);
+                        float sl, sr;
+                        halo3(sC, S, i0, z, x0, lane, g, sl, sr);
+                        float4 acc = gsl[k * (FW / 4)];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float ci = f4get(CI, e);
+                            const float lam = ci != 0.f ? f4get(C, e) / ci : 0.f;          // Lam_{i+1} = w1 / ciso
+                            f4set(acc, e, f4get(acc, e) + lam * lap7(sC, sU, sD, sF, sB, sl, sr, e));
+                        }
+                        gsl[k * (FW / 4)] = acc;
+                        sU = sC; sC = sD;
+                    }
+                    U = C; C = D;
                 }
             }
-            wb = wc; wc = wa; sb = sc; sc = sa;
         }
         __syncthreads();
-        if (a.rec_adj) {
-            const int nrow = (c1 - c0) * TY;
-            for (int q = tid; q < nrow; q += NT) {
-                const int i0 = c0 + q / TY, r1 = y0 + q % TY;
-                if (r1 >= n1) continue;
-                const long long row = ((long long)b * n0 + i0) * n1 + r1;
+        // ---- source term: forward adds the wavelet sample; adjoint reads d loss / d amplitude = Lam_i(src)
+        for (int s = tid; s < a.ns; s += NT) {
+            if (a.src_b[s] != b) continue;
+            const int s0 = a.src_i0[s], s1 = a.src_i1[s], s2 = a.src_i2[s];
+            if (s0 == i0 && s1 >= zb0 && s1 < zb0 + FH && s2 >= x0 && s2 < x0 + FW) {
+                const long long q = s0 * g.ps + (long long)s1 * g.ld + s2;
+                if (!ADJ) atomicAdd(out + q, a.amp[s]);
+            }
+        }
+        // ---- receivers of this tile: rows found by one thread each, then served by the block
+        const float* rsrc = ADJ ? a.rec_adj : a.rec_out;
+        if (rsrc) {
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            if (tid < FH && zb0 + tid < g.n1) {
+                const long long row = ((long long)b * g.n0 + i0) * g.n1 + zb0 + tid;
+                if (a.row_start[row + 1] > a.row_start[row]) s_rows[atomicAdd(&s_cnt, 1)] = zb0 + tid;
+            }
+            __syncthreads();
+            const int cnt = s_cnt;
+            for (int k = 0; k < cnt; ++k) {
+                const int z = s_rows[k];
+                const long long row = ((long long)b * g.n0 + i0) * g.n1 + z;
                 const int lo = a.row_start[row], hi = a.row_start[row + 1];
-                for (int r = lo; r < hi; ++r) {
+                for (int r = lo + tid; r < hi; r += NT) {
                     const int rc = a.rec_col[r];
-                    if (rc >= x0 && rc < x0 + TX)
-                        atomicAdd(l0 + (long long)i0 * a.ps + (long long)r1 * ld + rc, a.rec_adj[a.rec_orig[r]]);
+                    if (rc >= x0 && rc < x0 + FW) {
+                        const long long q = i0 * g.ps + (long long)z * g.ld + rc;
+                        if (ADJ) atomicAdd(out + q, __ldg(a.r + q) * a.rec_adj[a.rec_orig[r]]);     // w += ciso * dL/drec
+                        else a.rec_out[a.rec_orig[r]] = out[q];
+                    }
                 }
             }
         }
-        if (a.gamp) {
+        if (ADJ && a.gamp) {
             __syncthreads();
             for (int s = tid; s < a.ns; s += NT) {
                 if (a.src_b[s] != b) continue;
                 const int s0 = a.src_i0[s], s1 = a.src_i1[s], s2 = a.src_i2[s];
-                if (s0 >= c0 && s0 < c1 && s1 >= y0 && s1 < y0 + TY && s2 >= x0 && s2 < x0 + TX)
-                    a.gamp[s] = l0[(long long)s0 * a.ps + (long long)s1 * ld + s2];
+                if (s0 == i0 && s1 >= zb0 && s1 < zb0 + FH && s2 >= x0 && s2 < x0 + FW) {
+                    const long long q = s0 * g.ps + (long long)s1 * g.ld + s2;
+                    const float ci = __ldg(a.r + q);
+                    a.gamp[s] = ci != 0.f ? out[q] / ci : 0.f;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (want_grad && rows && x < g.ld) {
+        float* gb = a.gacc + (long long)blockIdx.y * a.fs;
+#pragma unroll
+        for (int k = 0; k < RZ; ++k) {
+            const int z = z0 + k;
+            if (z < zn) {
+                float* o = gb + (i0 * g.ps + (long long)z * g.ld + x);
+                const float4 acc = gsl[k * (FW / 4)];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (x + e < g.n2) o[e] += f4get(acc, e);
             }
         }
     }
@@ -173,16 +198,16 @@ __global__ void __launch_bounds__(NT) acoustic3d_adjoint_kernel(const A3Args a) 
 }  // namespace
 
 int st_acoustic3d_launch_forward(const A3Args& a, cudaStream_t st) {
-    const int nch = (a.n0 + CH - 1) / CH;
-    dim3 grid((a.n2 + TX - 1) / TX, (a.n1 + TY - 1) / TY, a.B * nch), block(TX, TY);
-    acoustic3d_forward_kernel<<<grid, block, 0, st>>>(a);
+    const int nfx = (a.n2 + FW - 1) / FW, nfz = (a.n1 + FH - 1) / FH;
+    dim3 grid(a.n0 * nfx * nfz, a.B);
+    acoustic3d_kernel<false><<<grid, NT, 0, st>>>(a, nfx, nfz);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
 
 int st_acoustic3d_launch_adjoint(const A3Args& a, cudaStream_t st) {
-    const int nch = (a.n0 + CH - 1) / CH;
+    const int nfx = (a.n2 + FW - 1) / FW, nfz = (a.n1 + FH - 1) / FH;
     const int nchunk = (a.B + a.bchunk - 1) / a.bchunk;
-    dim3 grid((a.n2 + TX - 1) / TX, (a.n1 + TY - 1) / TY, nchunk * nch), block(TX, TY);
-    acoustic3d_adjoint_kernel<<<grid, block, 0, st>>>(a);
+    dim3 grid(a.n0 * nfx * nfz, nchunk);
+    acoustic3d_kernel<true><<<grid, NT, 0, st>>>(a, nfx, nfz);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }

@@ -75,7 +75,13 @@ class _Step(torch.autograd.Function):
         prob.gacc = torch.zeros(nplanes * spec.ngrad * spec.plane, dtype=torch.float32, device=dev)
         unpad = lambda buf: buf.view(spec.nf, spec.B, *spec.shape[:-1], spec.ld)[..., :nx]
         if spec.order == 2:
-            gy = _to_slots(gouts[0::2], spec).reshape(-1)
+            gy = _to_slots(gouts[0::2], spec)
+            scale = None
+            if spec.family == "acoustic3d":
+                # the 3D adjoint kernel works on the scaled cotangent w = ciso * Lam (include/seistorch_b200.h)
+                scale = prob.coefp[0].view(*spec.shape[:-1], spec.ld)
+                gy = gy * scale
+            gy = gy.reshape(-1)
             zero = torch.zeros_like(gy)
             # call A: Lam_{i+1} = g_y, Lam_{i+2} = 0  ->  d/d cur (minus the pass-through) + coefficient grads
             prob.lam = torch.cat([zero, gy, zero])          # slots: 0 out, 1 lam1, 2 lam2
@@ -88,6 +94,9 @@ class _Step(torch.autograd.Function):
             prob.adjoint(0, 1, 1)
             g_prev = unpad(prob.lam[:e]).clone()
             prob.gacc = gacc
+            if scale is not None:
+                inv = torch.where(scale != 0, 1.0 / scale, torch.zeros_like(scale))[..., :nx]
+                g_cur, g_prev = g_cur * inv, g_prev * inv
             gfields = []
             for k in range(spec.nf):
                 gfields += [g_cur[k] + gouts[2 * k + 1], g_prev[k]]
