@@ -70,6 +70,9 @@ typedef struct st_acquisition {
     int32_t chan_f[4];          /* field channel sampled by each receiver channel      */
     float* rec_out;             /* [nt][R][nchan] seismograms (forward), or NULL       */
     const float* rec_adj;       /* [nt][R][nchan] d loss / d seismogram (adjoint)      */
+    int32_t row_lo, row_hi;     /* hint: every source and receiver has row index (2D: z, 3D: first dim) in
+                                   [row_lo, row_hi]; blocks outside skip the source/receiver epilogue.
+                                   row_lo > row_hi means "no hint" (all blocks run it)                   */
 } st_acquisition;
 
 /* ------------------------------------------------------------------------------------

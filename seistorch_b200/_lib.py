@@ -26,6 +26,7 @@ class StAcquisition(C.Structure):
         ("nchan", C.c_int32),
         ("chan_f", C.c_int32 * 4),
         ("rec_out", C.c_void_p), ("rec_adj", C.c_void_p),
+        ("row_lo", C.c_int32), ("row_hi", C.c_int32),
     ]
 
 

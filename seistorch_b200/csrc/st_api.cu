@@ -79,6 +79,8 @@ static void w2_fill(const st_wave2d_problem* p, W2Args& a) {
     a.cs = a.fs * p->B;
     for (int k = 0; k < 8; ++k) a.coef[k] = p->coef[k];
     a.taps = w2_uses_taps(p) ? p->taps : nullptr;
+    a.row_lo = p->acq.row_lo; a.row_hi = p->acq.row_hi;
+    if (a.row_lo > a.row_hi) { a.row_lo = 0; a.row_hi = p->nz - 1; }
     a.ns = p->acq.ns; a.src_b = p->acq.src_b; a.src_z = p->acq.src_i1; a.src_x = p->acq.src_i2;
     a.src_fmask = p->acq.src_fmask;
     a.row_start = p->acq.row_start; a.rec_x = p->acq.rec_col; a.rec_orig = p->acq.rec_orig;

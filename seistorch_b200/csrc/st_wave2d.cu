@@ -130,6 +130,7 @@ __device__ __forceinline__ void row_halo(const float4& c, const float* __restric
 // source add + receiver gather for the cells this block stored
 template <int NF, class Own>
 __device__ __forceinline__ void forward_tail(const W2Args& a, int b, int z0, int zn, int x0, int xn, int tid, Own owns) {
+    if (zn <= a.row_lo || z0 > a.row_hi) return;          // no source / receiver in these rows (block-uniform)
     const W2Geom& g = a.g;
     const long long boff = (long long)b * a.fs;
     __syncthreads();
@@ -207,30 +208,34 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
         const int idx = z * g.ld + x;
         // increment form: Y = h1 + (h1 - h2) + sum_{o != 0} F1[o] (h1(p+o) - h1(p)) + F2[o] (h2(p+o) - h2(p))
         // (the taps of h1 sum to 2 and those of h2 to -1 exactly, DESIGN.md "numerics")
-        float t1[ST_NTAP1 - 1], t2[ST_NTAP2 - 1];
+        // taps that fall outside the domain read zero: t (0 - c) is folded into a self coefficient so
+        // every load below is unconditional (index clamped to the cell itself)
+        float t1[ST_NTAP1 - 1], t2[ST_NTAP2 - 1], t1self = 0.f, t2self = 0.f;
         int q1[ST_NTAP1 - 1];
 #pragma unroll
         for (int o = 1; o < ST_NTAP1; ++o) {
             const int zz = z + st_tap_dz(o), xx = x + st_tap_dx(o);
             const bool in = zz >= 0 && zz < g.nz && xx >= 0 && xx < g.nx;
-            q1[o - 1] = in ? zz * g.ld + xx : -1;
-            t1[o - 1] = __ldg(a.taps + o * plane + idx);
-            if (o < ST_NTAP2) t2[o - 1] = __ldg(a.taps + (ST_NTAP1 + o) * plane + idx);
+            q1[o - 1] = in ? zz * g.ld + xx : idx;
+            const float t = __ldg(a.taps + o * plane + idx);
+            t1[o - 1] = in ? t : 0.f;
+            t1self -= in ? 0.f : t;
+            if (o < ST_NTAP2) {
+                const float u = __ldg(a.taps + (ST_NTAP1 + o) * plane + idx);
+                t2[o - 1] = in ? u : 0.f;
+                t2self -= in ? 0.f : u;
+            }
         }
         for (int b = 0; b < a.B; ++b) {
             const long long boff = (long long)b * a.fs;
             const float* cur = a.cur + boff;
             const float* prv = a.prev + boff;
             const float c = __ldg(cur + idx), p = __ldg(prv + idx);
-            float acc = 0.f;
+            float acc = t1self * c + t2self * p;
 #pragma unroll
             for (int o = 1; o < ST_NTAP1; ++o) {
-                const float v = q1[o - 1] >= 0 ? __ldg(cur + q1[o - 1]) : 0.f;
-                acc += t1[o - 1] * (v - c);
-                if (o < ST_NTAP2) {
-                    const float v2 = q1[o - 1] >= 0 ? __ldg(prv + q1[o - 1]) : 0.f;
-                    acc += t2[o - 1] * (v2 - p);
-                }
+                acc += t1[o - 1] * (__ldg(cur + q1[o - 1]) - c);
+                if (o < ST_NTAP2) acc += t2[o - 1] * (__ldg(prv + q1[o - 1]) - p);
             }
             a.next[boff + idx] = c + ((c - p) + acc);
         }
@@ -295,7 +300,7 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
         st_band_decode(bc, i, z, x);
         const int idx = z * g.ld + x;
         // transposed taps: coefficient of L(p+o) is the tap -o of cell p+o
-        float g1[ST_NTAP1], g2[ST_NTAP2], h1[ST_NTAP1], h2[ST_NTAP2];
+        float g1[ST_NTAP1], g2[ST_NTAP2], h1[ST_NTAP1], h2[ST_NTAP2], m[ST_NTAP2];
         int q[ST_NTAP1];
         const bool frame = w2_in_frame(z, x, g);
         const float pre = frame ? 1.f - __ldg(a.coef[1] + idx) : 1.f;
@@ -303,42 +308,45 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
         for (int o = 0; o < ST_NTAP1; ++o) {
             const int zz = z + st_tap_dz(o), xx = x + st_tap_dx(o);
             const bool in = inb(zz, xx);
-            q[o] = in ? zz * g.ld + xx : -1;
+            q[o] = in ? zz * g.ld + xx : idx;                 // clamped: every load below is unconditional
             g1[o] = in ? __ldg(a.taps + st_tap_neg(o) * plane + q[o]) : 0.f;
-            if (o < ST_NTAP2) g2[o] = in ? __ldg(a.taps + (ST_NTAP1 + st_tap_neg(o)) * plane + q[o]) : 0.f;
-            h1[o] = (want_grad && frame) ? __ldg(a.taps + (ST_NTAP1 + ST_NTAP2 + o) * plane + idx) : 0.f;
-            if (o < ST_NTAP2) h2[o] = (want_grad && frame) ? __ldg(a.taps + (2 * ST_NTAP1 + ST_NTAP2 + o) * plane + idx) : 0.f;
+            h1[o] = (want_grad && frame && in) ? __ldg(a.taps + (ST_NTAP1 + ST_NTAP2 + o) * plane + idx) : 0.f;
+            if (o < ST_NTAP2) {
+                g2[o] = in ? __ldg(a.taps + (ST_NTAP1 + st_tap_neg(o)) * plane + q[o]) : 0.f;
+                h2[o] = (want_grad && frame && in) ? __ldg(a.taps + (2 * ST_NTAP1 + ST_NTAP2 + o) * plane + idx) : 0.f;
+                m[o] = in ? 1.f : 0.f;
+            }
         }
         float gr = 0.f, gc = 0.f;
         for (int b = 0; b < a.B; ++b) {
             const long long boff = (long long)b * a.fs;
             const float* l1 = a.lam1 + boff;
             const float* l2 = a.lam2 + boff;
-            float acc = 0.f, v1[ST_NTAP1];
+            float acc = 0.f, lc = 0.f;
 #pragma unroll
             for (int o = 0; o < ST_NTAP1; ++o) {
-                v1[o] = q[o] >= 0 ? __ldg(l1 + q[o]) : 0.f;
-                acc += g1[o] * v1[o];
-                if (o < ST_NTAP2) acc += g2[o] * (q[o] >= 0 ? __ldg(l2 + q[o]) : 0.f);
+                const float v = __ldg(l1 + q[o]);
+                if (o == 0) lc = v;
+                acc += g1[o] * v;
+                if (o < ST_NTAP2) acc += g2[o] * __ldg(l2 + q[o]);
             }
             a.lam0[boff + idx] = acc;
             if (want_grad) {
                 const float* S1 = a.s1 + boff;
                 const float* S2 = a.s2 + boff;
-                float s[ST_NTAP1];
+                float s[ST_NTAP2], t = 0.f;
 #pragma unroll
-                for (int o = 0; o < ST_NTAP1; ++o) s[o] = (q[o] >= 0 && (o < ST_NTAP2 || frame)) ? __ldg(S1 + q[o]) : 0.f;
-                const float lc = v1[0];
-                gc += pre * lc * (((s[1] - s[0]) + (s[2] - s[0])) + ((s[3] - s[0]) + (s[4] - s[0])));
-                if (frame) {
-                    float t = 0.f;
-#pragma unroll
-                    for (int o = 0; o < ST_NTAP1; ++o) {
+                for (int o = 0; o < ST_NTAP1; ++o) {
+                    if (o < ST_NTAP2) {
+                        s[o] = m[o] * __ldg(S1 + q[o]);
                         t += h1[o] * s[o];
-                        if (o < ST_NTAP2) t += h2[o] * (q[o] >= 0 ? __ldg(S2 + q[o]) : 0.f);
+                        if (frame) t += h2[o] * __ldg(S2 + q[o]);
+                    } else if (frame) {
+                        t += h1[o] * __ldg(S1 + q[o]);
                     }
-                    gr += lc * t;
                 }
+                gc += pre * lc * (((s[1] - s[0]) + (s[2] - s[0])) + ((s[3] - s[0]) + (s[4] - s[0])));
+                gr += lc * t;
             }
         }
         if (want_grad) {
@@ -598,17 +606,21 @@ __global__ void __launch_bounds__(NT, 4) wave2d_forward_kernel(const W2Args a, i
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     constexpr bool HABC = (FL & ST_F_HABC) != 0;
     __shared__ float s1[HABC ? NF : 1][HABC ? SH : 1][SW];
-    const int bid = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    // the (slower) frame blocks get the low block ids so they are scheduled first
-    const int nframe = HABC ? bt.count : 0;
+    const int bid = blockIdx.x, tid = threadIdx.x;
+    // grid.x = [frame blocks] ++ [fast blocks x shots]; the (slower) frame blocks get the low ids so
+    // they are scheduled first.  Tapped frame blocks walk all shots themselves.
+    const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
+    const int nframe = HABC ? bt.count * (tapped ? 1 : a.B) : 0;
     if (bid >= nframe) {
-        forward_fast_block<FL>(a, bid - nframe, nfx, b, tid);
-    } else if (FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr) {
-        if (b == 0) forward_band_block(a, bid, tid);          // walks all shots itself
+        const int q = bid - nframe;
+        forward_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid);
+    } else if (tapped) {
+        forward_band_block(a, bid, tid);
     } else {
         if constexpr (HABC) {
             int tz, tx;
-            band_tile_decode(bt, bid, tz, tx);
+            const int b = bid / bt.count;
+            band_tile_decode(bt, bid - b * bt.count, tz, tx);
             forward_frame_block<FL>(a, tz, tx, b, tid, reinterpret_cast<float (*)[SH][SW]>(s1));
         }
     }
@@ -632,6 +644,7 @@ __host__ __device__ constexpr bool adj_fast() { return FL == (ST_F_ISO | ST_F_PM
 // receiver-adjoint scatter + source-amplitude gradient for the cells this block stored
 template <int NF, class Own>
 __device__ __forceinline__ void adjoint_tail(const W2Args& a, int b, int z0, int zn, int x0, int xn, int tid, Own owns) {
+    if (zn <= a.row_lo || z0 > a.row_hi) return;          // no source / receiver in these rows (block-uniform)
     const W2Geom& g = a.g;
     const long long boff = (long long)b * a.fs;
     __shared__ int s_cnt, s_rows[FH];
@@ -944,8 +957,9 @@ int st_w2_launch_fwd(const W2Args& a, cudaStream_t st) {
     const int nfast = nfx * nfz;
     BandTiles bt = band_tiles(a.g, a.g.bw);
     if (!(FL & ST_F_HABC)) bt.count = 0;
-    if (FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
-    dim3 grid(nfast + bt.count, a.B);
+    const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
+    if (tapped) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
+    dim3 grid((unsigned)((long long)nfast * a.B + (long long)bt.count * (tapped ? 1 : a.B)));
     wave2d_forward_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }

@@ -30,6 +30,7 @@ struct W2Args {
     int src_fmask;          // bit f set: inject into field channel f
     // ---- receivers, sorted by (shot, z, x); CSR over rows (shot*nz + z)
     const int* row_start; const int* rec_x; const int* rec_orig;
+    int row_lo, row_hi;     // rows that hold sources/receivers (epilogue skipped elsewhere)
     int R;                  // total receivers (all shots)
     int nchan; int chan_f[4];
     float* rec_out;         // forward:  [R][nchan] sample of this step

@@ -78,6 +78,13 @@ class Acquisition:
             bad |= bool(((rec_idx < 0) | (rec_idx >= lim)).any() or (rec_b < 0).any() or (rec_b >= B).any())
         if bad:
             raise IndexError("seistorch_b200: source/receiver index outside the padded domain")
+        # row range of all sources and receivers (kernels skip the source/receiver epilogue elsewhere)
+        rows = [t[:, 0] for t in (src_idx, rec_idx) if t.numel()]
+        if rows:
+            allrows = torch.cat(rows)
+            self.row_lo, self.row_hi = int(allrows.min()), int(allrows.max())
+        else:
+            self.row_lo, self.row_hi = 1, 0
         self.src_b = src_b.to(torch.int32).contiguous()
         self.src_i = [src_idx[:, k].to(torch.int32).contiguous() for k in range(self.ndim)]
         # receivers: sort by row key, CSR over rows
@@ -123,6 +130,7 @@ class Acquisition:
             q.chan_f[k] = int(chan_f[k]) if k < len(chan_f) else 0
         q.rec_out = _lib.ptr(rec_out)
         q.rec_adj = _lib.ptr(rec_adj)
+        q.row_lo, q.row_hi = self.row_lo, self.row_hi
 
 
 # ======================================================================== plan
