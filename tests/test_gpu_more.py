@@ -1,0 +1,140 @@
+"""GPU (-m gpu): edge cases and size-independent properties of the product path."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import cat_records, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(case, mode="inversion", **kw):
+    import seistorch_b200 as sb
+    cfg, model = sb.model_from_case(case, device="cuda", mode=mode, **kw)
+    x = torch.as_tensor(np.asarray(case["wavelet"]), dtype=torch.float32, device="cuda").unsqueeze(0)
+    return cfg, model, x
+
+
+def test_3d_single_step_value_and_vjp():
+    from oracle import cases, equations, loop
+    import seistorch_b200.equations3d.acoustic as mod
+    case = cases.make_case("acoustic", nz=6, nx=7, ny=5, nshots=2, nt=2)
+    names, params, d, *_ = loop.build_geometry(case, torch.float64)
+    shape = tuple(params[0].shape)
+    g = torch.Generator().manual_seed(5)
+    F = [torch.randn((2,) + shape, generator=g, dtype=torch.float64).requires_grad_(True) for _ in range(2)]
+    G = [torch.randn((2,) + shape, generator=g, dtype=torch.float64) for _ in range(2)]
+    P = [params[0].clone().requires_grad_(True)]
+    dt, h = torch.tensor(1e-3, dtype=torch.float64), torch.tensor(10.0, dtype=torch.float64)
+    outs = equations.get_step("acoustic3d")(P, F, dt, h, d)
+    torch.autograd.backward(list(outs), G)
+    Pc = [params[0].float().cuda().requires_grad_(True)]
+    Fc = [f.detach().float().cuda().requires_grad_(True) for f in F]
+    outs_c = mod._time_step(*Pc, *Fc, torch.tensor(1e-3).cuda(), torch.tensor(10.0).cuda(), d.float().cuda())
+    for a, b in zip(outs_c, outs):
+        assert rel(a.detach().cpu().numpy(), b.detach().numpy()) < 2e-6
+    torch.autograd.backward(list(outs_c), [g_.float().cuda() for g_ in G])
+    for a, b in zip(Fc, F):
+        assert rel(a.grad.cpu().numpy(), b.grad.numpy()) < 1e-5
+    assert rel(Pc[0].grad.cpu().numpy(), P[0].grad.numpy()) < 1e-4
+
+
+def test_source_encoding_and_per_source_wavelets():
+    """codingfwi.py mode: all sources fire into ONE wavefield, each with its own
+    wavelet (source.py:54-55, rnn.py:113,162) == sum of the single-shot wavefields (linearity)."""
+    from oracle import cases
+    case = cases.make_case("acoustic_habc", nz=30, nx=50, nshots=3, nt=90)
+    case["receivers"] = [case["receivers"][0]]          # one common receiver spread
+    # encoded run: batch 1, 3 sources, per-source wavelets
+    import seistorch_b200 as sb
+    enc = dict(case)
+    cfg, model = sb.model_from_case(dict(case, receivers=case["receivers"] * 3), device="cuda", mode="forward",
+                                    source_encoding=True)
+    model.reset_probes(model.probes[0])
+    w = np.stack([np.asarray(case["wavelet"]) * s for s in (1.0, -0.5, 2.0)]).astype(np.float32)
+    with torch.no_grad():
+        rec_enc = model(torch.as_tensor(w, device="cuda"))[0].cpu().numpy()
+    # reference by superposition of three ordinary single-shot runs
+    tot = 0.0
+    for k, s in enumerate((1.0, -0.5, 2.0)):
+        one = dict(case, sources=[case["sources"][k]], wavelet=np.asarray(case["wavelet"]) * s)
+        cfg1, m1, x1 = _model(one, mode="forward")
+        with torch.no_grad():
+            tot = tot + m1(x1)[0].cpu().numpy().astype(np.float64)
+    assert rel(rec_enc, tot) < 2e-6
+
+
+def test_empty_receivers_and_zero_wavelet():
+    from oracle import cases
+    case = cases.make_case("acoustic", nz=20, nx=30, nshots=2, nt=20)
+    case["wavelet"] = np.zeros(20, np.float32)
+    cfg, model, x = _model(case, mode="forward")
+    with torch.no_grad():
+        out = model(x)
+    assert all(float(o.abs().max()) == 0.0 for o in out)
+
+
+def test_out_of_domain_receiver_raises():
+    from oracle import cases
+    case = cases.make_case("acoustic", nz=20, nx=30, nshots=1, nt=5)
+    case["receivers"] = [[[500], [2]]]
+    cfg, model, x = _model(case, mode="forward")
+    with pytest.raises(IndexError):
+        model(x)
+
+
+def test_nan_in_model_raises_value_error():
+    """type.py:41-46: NaN in the records raises ValueError."""
+    from oracle import cases
+    case = cases.make_case("acoustic", nz=20, nx=30, nshots=1, nt=30)
+    case["models"]["vp"] = case["models"]["vp"].copy()
+    case["models"]["vp"][2, 10] = np.nan
+    cfg, model, x = _model(case, mode="forward")
+    with pytest.raises(ValueError):
+        model(x)
+
+
+def test_baseline_size_properties():
+    """BASELINE configs[1] grid (2301x751, padded 2401x851), short horizon: (i) checkpoint-recompute
+    equals stored history bit for bit, (ii) linearity in the wavelet, (iii) shot independence:
+    a 2-shot batch equals the two single-shot runs."""
+    import bench
+    true, init = bench.make_models()
+    case = bench.make_case(2, vp=init, nt=150)
+    def grad_of(c, segment=None):
+        cfg, model, x = _model(c)
+        model.segment = segment
+        syn = model(x)
+        loss = sum((s ** 2).sum() for s in syn)
+        loss.backward()
+        return [s.detach().cpu().numpy() for s in syn], model.cell.geom.vp.grad.cpu().numpy()
+    r0, g0 = grad_of(case)
+    r1, g1 = grad_of(case, segment=37)
+    assert all(np.array_equal(a, b) for a, b in zip(r0, r1)) and np.array_equal(g0, g1)
+    ra, ga = grad_of(dict(case, sources=case["sources"][:1], receivers=case["receivers"][:1]))
+    rb, gb = grad_of(dict(case, sources=case["sources"][1:], receivers=case["receivers"][1:]))
+    assert np.array_equal(r0[0], ra[0]) and np.array_equal(r0[1], rb[0])
+    assert rel(g0, ga + gb) < 1e-5
+    r4, _ = grad_of(dict(case, wavelet=np.asarray(case["wavelet"]) * 4.0))
+    assert rel(cat_records(r4), 4.0 * cat_records(r0)) < 1e-6
+
+
+def test_l2_and_envelope_misfit_kernels_against_oracle():
+    from oracle import misfit
+    import seistorch_b200 as sb
+    g = torch.Generator().manual_seed(1)
+    syn = torch.randn(2, 64, 5, 2, generator=g)
+    obs = torch.randn(2, 64, 5, 2, generator=g)
+    for name, fn in (("l2", misfit.l2), ("envelope", misfit.envelope_loss)):
+        s64 = syn.double().requires_grad_(True)
+        lo = fn(list(s64), list(obs.double()))
+        lo.backward()
+        sc = syn.cuda().requires_grad_(True)
+        lc = sb.Loss(name).loss(None)(sc, obs.cuda())
+        lc.backward()
+        assert abs(float(lc) - float(lo)) <= 2e-5 * abs(float(lo)), name
+        assert rel(sc.grad.cpu().numpy(), s64.grad.numpy()) < 2e-5, name
+        # list-of-shots form (ragged-capable)
+        sc2 = [syn[k].cuda().requires_grad_(True) for k in range(2)]
+        l2_ = sb.Loss(name).loss(None)(sc2, [obs[k].cuda() for k in range(2)])
+        assert abs(float(l2_) - float(lo)) <= 2e-5 * abs(float(lo)), name

@@ -38,3 +38,25 @@ def test_side_weights_tile_the_frame():
         assert np.array_equal(f, habc_side_weights(nz, nx, 50, mult).astype(np.float32))
         assert np.array_equal(f.sum(0) == 1.0, fr.astype(bool))
         assert np.all(f.sum(0)[fr == 0] == 0)
+
+
+def test_wrap_cells_are_the_four_closed_form_candidates():
+    """The one-way blend reads a wrapped neighbour only at depth bw-1; with the reference's HABC
+    weights that carries a non-zero weight for at most the four cells st_wrap_candidate()
+    enumerates (csrc/st_wave2d_band.cuh) -- checked here against the oracle's masks/weights."""
+    import torch
+    from oracle import boundary
+    from oracle.equations import habc_side_weights
+    for nz, nx, mult in [(130, 144, False), (851, 2401, False), (101, 103, False), (80, 144, True)]:
+        f = habc_side_weights(nz, nx, 50, mult)
+        b = boundary.habc_coefficients_2d((nz, nx), 50, mult, torch.float64).numpy()
+        zz, xx = np.meshgrid(np.arange(nz), np.arange(nx), indexing="ij")
+        depth = [zz, nz - 1 - zz, xx, nx - 1 - xx]
+        found = set()
+        for s in range(4):
+            sel = (depth[s] == 49) & (f[s] != 0) & (b != 0)
+            found |= {(int(z), int(x), s) for z, x in zip(zz[sel], xx[sel])}
+        cand = {(49, nx - 1, 0), (0, nx - 50, 3), (nz - 50, 0, 1), (nz - 1, 49, 2)}
+        assert found <= cand, (nz, nx, mult, found - cand)
+        if not mult:
+            assert found == cand
