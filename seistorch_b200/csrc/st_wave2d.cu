@@ -38,7 +38,11 @@ constexpr int FW = 128;                     // columns per warp (32 lanes x floa
 #endif
 constexpr int FRZ = ST_FRZ;                 // rows per warp
 constexpr int NWARP = NT / 32;
-constexpr int FH = FRZ * NWARP;             // rows per fast block (64)
+constexpr int FH = FRZ * NWARP;             // rows per fast block
+#ifndef ST_BAND_SHOTS
+#define ST_BAND_SHOTS 8
+#endif
+constexpr int BSH = ST_BAND_SHOTS;          // shots a band thread walks with its taps in registers
 
 template <int FL>
 __device__ __forceinline__ W2Coef load_coef_fl(const W2Args& a, long long idx) {
@@ -192,7 +196,18 @@ __device__ __forceinline__ int band_block_rows(const BandCells& bc, int i, int t
 
 // Every thread owns ONE band cell and walks all shots with its taps held in registers, so the
 // tap planes are read once per step, not once per shot.
-__device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int tid) {
+// true when none of the block's band cells lies in the acquisition row range (block-uniform)
+__device__ __forceinline__ bool band_block_outside_rows(const W2Args& a, const BandCells& bc, int i0) {
+    int zf, xf, zl, xl;
+    st_band_decode(bc, i0, zf, xf);
+    st_band_decode(bc, min(i0 + NT, bc.total) - 1, zl, xl);
+    const int lo = min(zf, zl), hi = max(zf, zl);
+    // rows of a block are contiguous inside one rectangle; straddling blocks are never skipped
+    const bool same = (i0 + NT <= bc.n_top) || (i0 >= bc.n_top && i0 + NT <= bc.n_top + bc.n_bot) || (i0 >= bc.n_top + bc.n_bot);
+    return same && (hi < a.row_lo || lo > a.row_hi);
+}
+
+__device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int b_lo, int b_hi, int tid) {
     const W2Geom g = a.g;
     const BandCells bc = st_band_cells(g, g.bw);
     const int i0 = blk * NT, i = i0 + tid;
@@ -226,18 +241,28 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
                 t2self -= in ? 0.f : u;
             }
         }
-        for (int b = 0; b < a.B; ++b) {
-            const long long boff = (long long)b * a.fs;
-            const float* cur = a.cur + boff;
-            const float* prv = a.prev + boff;
-            const float c = __ldg(cur + idx), p = __ldg(prv + idx);
-            float acc = t1self * c + t2self * p;
+        for (int b = b_lo; b < b_hi; b += 2) {
+            // two shots per iteration: two independent load chains in flight
+            const bool two = b + 1 < b_hi;
+            const long long boff0 = (long long)b * a.fs, boff1 = two ? boff0 + a.fs : boff0;
+            const float* cur0 = a.cur + boff0;
+            const float* prv0 = a.prev + boff0;
+            const float* cur1 = a.cur + boff1;
+            const float* prv1 = a.prev + boff1;
+            const float c0 = __ldg(cur0 + idx), p0 = __ldg(prv0 + idx);
+            const float c1 = __ldg(cur1 + idx), p1 = __ldg(prv1 + idx);
+            float acc0 = t1self * c0 + t2self * p0, acc1 = t1self * c1 + t2self * p1;
 #pragma unroll
             for (int o = 1; o < ST_NTAP1; ++o) {
-                acc += t1[o - 1] * (__ldg(cur + q1[o - 1]) - c);
-                if (o < ST_NTAP2) acc += t2[o - 1] * (__ldg(prv + q1[o - 1]) - p);
+                acc0 += t1[o - 1] * (__ldg(cur0 + q1[o - 1]) - c0);
+                acc1 += t1[o - 1] * (__ldg(cur1 + q1[o - 1]) - c1);
+                if (o < ST_NTAP2) {
+                    acc0 += t2[o - 1] * (__ldg(prv0 + q1[o - 1]) - p0);
+                    acc1 += t2[o - 1] * (__ldg(prv1 + q1[o - 1]) - p1);
+                }
             }
-            a.next[boff + idx] = c + ((c - p) + acc);
+            a.next[boff0 + idx] = c0 + ((c0 - p0) + acc0);
+            if (two) a.next[boff1 + idx] = c1 + ((c1 - p1) + acc1);
         }
     }
     __syncthreads();
@@ -253,23 +278,24 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
             // true operator: -mu*w*h1(wrap); the increment form above assumed taps summing to 2, i.e. it
             // implicitly carries -mu*w*h1(q) for the missing tap: replace it
             if (w != 0.f)
-                for (int b = 0; b < a.B; ++b) {
+                for (int b = b_lo; b < b_hi; ++b) {
                     const long long boff = (long long)b * a.fs;
                     a.next[boff + idx] += w * (-r * r) * (__ldg(a.cur + boff + (zw * g.ld + xw)) - __ldg(a.cur + boff + idx));
                 }
         }
     }
+    if (band_block_outside_rows(a, bc, i0)) return;
     __syncthreads();
     for (int s = tid; s < a.ns; s += NT) {
-        const int sz = a.src_z[s], sx = a.src_x[s];
-        if (mine(sz, sx) && (a.src_fmask & 1)) atomicAdd(a.next + (long long)a.src_b[s] * a.fs + (sz * g.ld + sx), a.amp[s]);
+        const int sz = a.src_z[s], sx = a.src_x[s], sb = a.src_b[s];
+        if (sb >= b_lo && sb < b_hi && mine(sz, sx) && (a.src_fmask & 1)) atomicAdd(a.next + (long long)sb * a.fs + (sz * g.ld + sx), a.amp[s]);
     }
     if (!a.rec_out) return;
     __shared__ int s_cnt, s_rows[16];
     const int cnt = band_block_rows(bc, i, tid, s_rows, &s_cnt);
     for (int k = 0; k < cnt; ++k) {
         const int z = s_rows[k];
-        for (int b = 0; b < a.B; ++b) {
+        for (int b = b_lo; b < b_hi; ++b) {
             const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
             for (int r = lo + tid; r < hi; r += NT) {
                 const int rx = a.rec_x[r];
@@ -282,7 +308,7 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
     }
 }
 
-__device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int tid) {
+__device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int b_lo, int b_hi, int gplane, int tid) {
     const W2Geom g = a.g;
     const int bd = g.bw + 1;
     const BandCells bc = st_band_cells(g, bd);
@@ -318,7 +344,9 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
             }
         }
         float gr = 0.f, gc = 0.f;
-        for (int b = 0; b < a.B; ++b) {
+        // one shot: Lam_i(p) and the gradient contributions; written as a lambda so two shots can be
+        // issued back to back (two independent load chains in flight)
+        auto one_shot = [&](int b, float& accOut, float& gcOut, float& grOut) {
             const long long boff = (long long)b * a.fs;
             const float* l1 = a.lam1 + boff;
             const float* l2 = a.lam2 + boff;
@@ -330,7 +358,7 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
                 acc += g1[o] * v;
                 if (o < ST_NTAP2) acc += g2[o] * __ldg(l2 + q[o]);
             }
-            a.lam0[boff + idx] = acc;
+            accOut = acc;
             if (want_grad) {
                 const float* S1 = a.s1 + boff;
                 const float* S2 = a.s2 + boff;
@@ -345,13 +373,24 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
                         t += h1[o] * __ldg(S1 + q[o]);
                     }
                 }
-                gc += pre * lc * (((s[1] - s[0]) + (s[2] - s[0])) + ((s[3] - s[0]) + (s[4] - s[0])));
-                gr += lc * t;
+                gcOut += pre * lc * (((s[1] - s[0]) + (s[2] - s[0])) + ((s[3] - s[0]) + (s[4] - s[0])));
+                grOut += lc * t;
             }
+        };
+        for (int b = b_lo; b < b_hi; b += 2) {
+            float acc0, acc1 = 0.f, gc1 = 0.f, gr1 = 0.f;
+            one_shot(b, acc0, gc, gr);
+            const bool two = b + 1 < b_hi;
+            if (two) one_shot(b + 1, acc1, gc1, gr1);
+            a.lam0[(long long)b * a.fs + idx] = acc0;
+            if (two) a.lam0[(long long)(b + 1) * a.fs + idx] = acc1;
+            gc += gc1;
+            gr += gr1;
         }
         if (want_grad) {
-            a.gacc[plane + idx] += gc;          // plane 0, slot 1: d/d ciso
-            if (frame) a.gacc[idx] += gr;       // plane 0, slot 0: d/d r
+            float* gb = a.gacc + (long long)gplane * 7 * plane;
+            gb[plane + idx] += gc;              // slot 1: d/d ciso
+            if (frame) gb[idx] += gr;           // slot 0: d/d r
         }
     }
     __syncthreads();
@@ -363,21 +402,22 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
         const int qq = z * g.ld + x, qw = zw * g.ld + xw;
         const float r = __ldg(a.coef[0] + qq), w = __ldg(a.coef[1] + qq) * f[s];
         if (w != 0.f) {
-            for (int b = 0; b < a.B; ++b) {
+            for (int b = b_lo; b < b_hi; ++b) {
                 const long long boff = (long long)b * a.fs;
                 const float lq = __ldg(a.lam1 + boff + qq);
                 if (mine(zw, xw)) atomicAdd(a.lam0 + boff + qw, w * (-r * r) * lq);
-                if (want_grad && mine(z, x)) atomicAdd(a.gacc + qq, lq * w * (-2.f * r) * __ldg(a.s1 + boff + qw));
+                if (want_grad && mine(z, x)) atomicAdd(a.gacc + (long long)gplane * 7 * plane + qq, lq * w * (-2.f * r) * __ldg(a.s1 + boff + qw));
             }
         }
     }
+    if (band_block_outside_rows(a, bc, i0)) return;
     __syncthreads();
     if (a.rec_adj) {
         __shared__ int s_cnt, s_rows[16];
         const int cnt = band_block_rows(bc, i, tid, s_rows, &s_cnt);
         for (int k = 0; k < cnt; ++k) {
             const int z = s_rows[k];
-            for (int b = 0; b < a.B; ++b) {
+            for (int b = b_lo; b < b_hi; ++b) {
                 const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
                 for (int r = lo + tid; r < hi; r += NT) {
                     const int rx = a.rec_x[r];
@@ -393,8 +433,8 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
     if (a.gamp) {
         __syncthreads();
         for (int s = tid; s < a.ns; s += NT) {
-            const int sz = a.src_z[s], sx = a.src_x[s];
-            if (mine(sz, sx) && (a.src_fmask & 1)) a.gamp[s] = a.lam0[(long long)a.src_b[s] * a.fs + (sz * g.ld + sx)];
+            const int sz = a.src_z[s], sx = a.src_x[s], sb = a.src_b[s];
+            if (sb >= b_lo && sb < b_hi && mine(sz, sx) && (a.src_fmask & 1)) a.gamp[s] = a.lam0[(long long)sb * a.fs + (sz * g.ld + sx)];
         }
     }
 }
@@ -601,8 +641,11 @@ __device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int
     forward_tail<NF>(a, b, z0, z0 + TZ, x0, x0 + TX, tid, [&](int z, int xx) { return w2_in_frame(z, xx, g); });
 }
 
+#ifndef ST_FWD_MINB
+#define ST_FWD_MINB 4
+#endif
 template <int FL>
-__global__ void __launch_bounds__(NT, 4) wave2d_forward_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
+__global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     constexpr bool HABC = (FL & ST_F_HABC) != 0;
     __shared__ float s1[HABC ? NF : 1][HABC ? SH : 1][SW];
@@ -610,12 +653,14 @@ __global__ void __launch_bounds__(NT, 4) wave2d_forward_kernel(const W2Args a, i
     // grid.x = [frame blocks] ++ [fast blocks x shots]; the (slower) frame blocks get the low ids so
     // they are scheduled first.  Tapped frame blocks walk all shots themselves.
     const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
-    const int nframe = HABC ? bt.count * (tapped ? 1 : a.B) : 0;
+    const int ngrp = (a.B + BSH - 1) / BSH;
+    const int nframe = HABC ? bt.count * (tapped ? ngrp : a.B) : 0;
     if (bid >= nframe) {
         const int q = bid - nframe;
         forward_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid);
     } else if (tapped) {
-        forward_band_block(a, bid, tid);
+        const int grp = bid / bt.count;
+        forward_band_block(a, bid - grp * bt.count, grp * BSH, min(grp * BSH + BSH, a.B), tid);
     } else {
         if constexpr (HABC) {
             int tz, tx;
@@ -917,12 +962,14 @@ __global__ void __launch_bounds__(NT, ST_ADJ_MINB) wave2d_adjoint_kernel(const W
     // for the fast-path equations, else one general block per (tile, shot chunk).
     if constexpr (adj_fast<FL>()) {
         const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
-        const int nband = (FL & ST_F_HABC) ? bt.count * (tapped ? 1 : a.B) : 0;
+        const int ngrp = (a.B + BSH - 1) / BSH;
+        const int nband = (FL & ST_F_HABC) ? bt.count * (tapped ? ngrp : a.B) : 0;
         if (bid >= nband) {
             const int q = bid - nband;
             adjoint_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid, reinterpret_cast<float (*)[FRZ][FW]>(smem));
         } else if (tapped) {
-            adjoint_band_block(a, bid, tid);                  // walks all shots itself
+            const int grp = bid / bt.count;                   // gradient plane = group id (< B planes exist)
+            adjoint_band_block(a, bid - grp * bt.count, grp * BSH, min(grp * BSH + BSH, a.B), grp, tid);
         } else {
             if constexpr (NEED_GEN) {
                 int tz, tx;
@@ -959,7 +1006,7 @@ int st_w2_launch_fwd(const W2Args& a, cudaStream_t st) {
     if (!(FL & ST_F_HABC)) bt.count = 0;
     const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
-    dim3 grid((unsigned)((long long)nfast * a.B + (long long)bt.count * (tapped ? 1 : a.B)));
+    dim3 grid((unsigned)((long long)nfast * a.B + (long long)bt.count * (tapped ? (a.B + BSH - 1) / BSH : a.B)));
     wave2d_forward_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
@@ -972,7 +1019,7 @@ int st_w2_launch_adj(const W2Args& a, cudaStream_t st) {
     const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw + 1).total + NT - 1) / NT;
     long long nblocks;
-    if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)bt.count * (tapped ? 1 : a.B) : 0);
+    if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)bt.count * (tapped ? (a.B + BSH - 1) / BSH : a.B) : 0);
     else nblocks = (long long)bt.nxt * bt.nzt * nchunk;
     dim3 grid((unsigned)nblocks);
     wave2d_adjoint_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);

@@ -1,43 +1,30 @@
-"""WaveProbe -- same constructor, buffers and attributes as seistorch/probe.py.
+"""WaveProbe -- constructor, buffers and attributes of seistorch/probe.py.
 
-On the whole-loop path the receiver gather is fused into the step kernel; the methods
-below back the per-step compatibility surface (probe.py:42-48)."""
+On the whole-loop path the receiver gather is fused into the step kernels; ``forward2d`` /
+``forward3d`` serve step-by-step callers with the reference's indexing (probe.py:42-48):
+``field[bidx, y, x]`` in 2D and ``field[bidx, x, z, y]`` in 3D, receivers of all shots
+concatenated, ``bidx`` = shot of every receiver.
+"""
 from __future__ import annotations
 
-import torch
-
-from .utils import to_tensor
+from .points import GridPoints
 
 
-class WaveProbe(torch.nn.Module):
+class WaveProbe(GridPoints):
     def __init__(self, batchidx=None, reccounts=None, **kwargs):
-        super().__init__()
-        self._ndim = len(kwargs)
-        self.coord_labels = list(kwargs.keys())
-        for key, value in kwargs.items():
-            self.register_buffer(key, to_tensor(value, dtype=torch.int64))
-        self.forward = self.get_forward_func()
-        self.batchsize = self.x.size(0) if self.x.ndim > 1 else 1
+        super().__init__(False, **kwargs)
         self.bidx = batchidx
-        self.reccounts = [] if reccounts is None else reccounts   # used by WaveRNN to split records
-
-    @property
-    def ndim(self):
-        return self._ndim
-
-    def coords(self):
-        return dict(zip(self.coord_labels, [getattr(self, key) for key in self.coord_labels]))
-
-    def get_forward_func(self):
-        return getattr(self, f"forward{self.ndim}d")
+        self.batchsize = self.x.size(0) if self.x.ndim > 1 else 1
+        # receivers per shot: WaveRNN splits the stacked records with it (rnn.py:211)
+        self.reccounts = list(reccounts) if reccounts is not None else []
 
     def forward2d(self, x):
-        return x[self.bidx, self.y, self.x]
+        return x[self._field_index(self.bidx)]
 
     def forward3d(self, x):
-        return x[self.bidx, self.x, self.z, self.y]
+        return x[self._field_index(self.bidx)]
 
 
 class WaveIntensityProbe(WaveProbe):
-    def __init__(self, **kwargs):
-        super().__init__(**kwargs)
+    """Same sampling as WaveProbe (the reference's squared-intensity variant is commented out,
+    probe.py:50-56)."""
