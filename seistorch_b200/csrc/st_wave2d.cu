@@ -254,9 +254,12 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
             float acc0 = t1self * c0 + t2self * p0, acc1 = t1self * c1 + t2self * p1;
 #pragma unroll
             for (int o = 1; o < ST_NTAP1; ++o) {
-                acc0 += t1[o - 1] * (__ldg(cur0 + q1[o - 1]) - c0);
-                acc1 += t1[o - 1] * (__ldg(cur1 + q1[o - 1]) - c1);
-                if (o < ST_NTAP2) {
+                // most cells use one side only: 3 of the 4 far taps and 3 of the 4 h2 taps are zero
+                if (t1[o - 1] != 0.f) {
+                    acc0 += t1[o - 1] * (__ldg(cur0 + q1[o - 1]) - c0);
+                    acc1 += t1[o - 1] * (__ldg(cur1 + q1[o - 1]) - c1);
+                }
+                if (o < ST_NTAP2 && t2[o - 1] != 0.f) {
                     acc0 += t2[o - 1] * (__ldg(prv0 + q1[o - 1]) - p0);
                     acc1 += t2[o - 1] * (__ldg(prv1 + q1[o - 1]) - p1);
                 }
@@ -353,10 +356,14 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
             float acc = 0.f, lc = 0.f;
 #pragma unroll
             for (int o = 0; o < ST_NTAP1; ++o) {
-                const float v = __ldg(l1 + q[o]);
-                if (o == 0) lc = v;
-                acc += g1[o] * v;
-                if (o < ST_NTAP2) acc += g2[o] * __ldg(l2 + q[o]);
+                // zero taps (most far taps of single-side cells) are skipped; the centre value is
+                // always needed for the imaging condition
+                if (o == 0 || g1[o] != 0.f) {
+                    const float v = __ldg(l1 + q[o]);
+                    if (o == 0) lc = v;
+                    acc += g1[o] * v;
+                }
+                if (o < ST_NTAP2 && g2[o] != 0.f) acc += g2[o] * __ldg(l2 + q[o]);
             }
             accOut = acc;
             if (want_grad) {
@@ -368,8 +375,8 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
                     if (o < ST_NTAP2) {
                         s[o] = m[o] * __ldg(S1 + q[o]);
                         t += h1[o] * s[o];
-                        if (frame) t += h2[o] * __ldg(S2 + q[o]);
-                    } else if (frame) {
+                        if (h2[o] != 0.f) t += h2[o] * __ldg(S2 + q[o]);
+                    } else if (h1[o] != 0.f) {
                         t += h1[o] * __ldg(S1 + q[o]);
                     }
                 }
