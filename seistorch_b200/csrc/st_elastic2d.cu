@@ -29,36 +29,42 @@ __global__ void __launch_bounds__(NT) elastic2d_forward_kernel(const E2Args a) {
     const float* cur = a.cur + boff;
     float* nxt = a.next + boff;
 
-    for (int i = tid; i < VH * VW; i += NT) {
-        const int lz = i / VW, lx = i - lz * VW;
-        const int z = z0 - 2 + lz, x = x0 - 2 + lx;
-        float v0 = 0.f, v1 = 0.f;
-        if (z >= 0 && z < nz && x >= 0 && x < nx) {
-            const long long idx = (long long)z * ld + x;
-            v0 = __ldg(cur + idx);
-            v1 = __ldg(cur + a.cs + idx);
+    // tile completely inside the domain (incl. its 2-cell halo): no bounds predicates needed
+    const bool inner = z0 >= 2 && z0 + TZ + 2 <= nz && x0 >= 2 && x0 + TX + 2 <= nx;
+    for (int lz = threadIdx.y; lz < VH; lz += NTY) {
+        const int z = z0 - 2 + lz;
+        for (int lx = threadIdx.x; lx < VW; lx += NTX) {
+            const int x = x0 - 2 + lx;
+            float v0 = 0.f, v1 = 0.f;
+            if (inner || (z >= 0 && z < nz && x >= 0 && x < nx)) {
+                const int idx = z * ld + x;
+                v0 = __ldg(cur + idx);
+                v1 = __ldg(cur + a.cs + idx);
+            }
+            sv[0][lz][lx] = v0;
+            sv[1][lz][lx] = v1;
         }
-        sv[0][lz][lx] = v0;
-        sv[1][lz][lx] = v1;
     }
     __syncthreads();
     auto V = [&](int f, int zz, int xx) -> float { return sv[f][zz - z0 + 2][xx - x0 + 2]; };
-    for (int i = tid; i < SH * SW; i += NT) {
-        const int lz = i / SW, lx = i - lz * SW;
-        const int z = z0 - 1 + lz, x = x0 - 1 + lx;
-        float t[3] = {0.f, 0.f, 0.f};
-        if (z >= 0 && z < nz && x >= 0 && x < nx) {
-            const long long idx = (long long)z * ld + x;
-            const E2Coef c = load_ecoef(a, idx);
-            e2_stress_cell(z, x, nz, nx, c, V, __ldg(cur + 2 * a.cs + idx), __ldg(cur + 3 * a.cs + idx),
-                           __ldg(cur + 4 * a.cs + idx), t);
-            if (lz >= 1 && lz <= TZ && lx >= 1 && lx <= TX) {
-                nxt[2 * a.cs + idx] = t[0];
-                nxt[3 * a.cs + idx] = t[1];
-                nxt[4 * a.cs + idx] = t[2];
+    for (int lz = threadIdx.y; lz < SH; lz += NTY) {
+        const int z = z0 - 1 + lz;
+        for (int lx = threadIdx.x; lx < SW; lx += NTX) {
+            const int x = x0 - 1 + lx;
+            float t[3] = {0.f, 0.f, 0.f};
+            if (inner || (z >= 0 && z < nz && x >= 0 && x < nx)) {
+                const int idx = z * ld + x;
+                const E2Coef c = load_ecoef(a, idx);
+                e2_stress_cell(z, x, nz, nx, c, V, __ldg(cur + 2 * a.cs + idx), __ldg(cur + 3 * a.cs + idx),
+                               __ldg(cur + 4 * a.cs + idx), t);
+                if (lz >= 1 && lz <= TZ && lx >= 1 && lx <= TX) {
+                    nxt[2 * a.cs + idx] = t[0];
+                    nxt[3 * a.cs + idx] = t[1];
+                    nxt[4 * a.cs + idx] = t[2];
+                }
             }
+            st[0][lz][lx] = t[0]; st[1][lz][lx] = t[1]; st[2][lz][lx] = t[2];
         }
-        st[0][lz][lx] = t[0]; st[1][lz][lx] = t[1]; st[2][lz][lx] = t[2];
     }
     __syncthreads();
     auto T = [&](int f, int zz, int xx) -> float { return st[f][zz - z0 + 1][xx - x0 + 1]; };
