@@ -941,8 +941,9 @@ __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, i
                     return __ldg(a.s2 + f * a.cs + boff + (long long)zz * g.ld + xx);
                 };
                 auto CF = [&](int zz, int xx) -> W2Coef { return load_coef_fl<FL>(a, (long long)zz * g.ld + xx); };
+                auto CK = [&](int k, int zz, int xx) -> float { return __ldg(a.coef[k] + (zz * g.ld + xx)); };
                 float out[2], gr[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                w2_adjoint_cell<FL>(z, x, g, a.dt, L1, L2, S1, S2, CF, out, gr, want_grad);
+                w2_adjoint_cell<FL>(z, x, g, a.dt, L1, L2, S1, S2, CF, CK, out, gr, want_grad);
 #pragma unroll
                 for (int f = 0; f < NF; ++f) a.lam0[f * a.cs + boff + idx] = out[f];
                 if (want_grad) {

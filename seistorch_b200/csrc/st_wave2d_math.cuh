@@ -157,36 +157,38 @@ ST_HD void w2_forward_cell(int z, int x, const W2Geom& g, const W2Coef& c, float
 //   L1 = Lam_{i+1}, L2 = Lam_{i+2}   (zero outside the domain)
 // and the contribution of forward step i+1 (which maps S_i, S_{i-1} -> S_{i+1}) to the
 // coefficient gradients at p:   S1 = S_i, S2 = S_{i-1}.
-//   CF(z,x) returns the W2Coef of an arbitrary in-domain cell.
+//   CF(z,x) returns the W2Coef of an in-domain cell (used for the centre cell only);
+//   CK(k,z,x) returns ONE coefficient plane value (k: 0 r, 1 b, 2 cxx, 3 czz, 4 cxz, 5 ax, 6 az, 7 m)
+//   so neighbour cells load just what the transposed stencil needs.
 // grad[] layout: 0:r (one-way blend only) 1:cxx (= ciso for ISO) 2:czz 3:cxz 4:ax 5:az 6:m   (accumulated, +=)
 //
 // Transpose algebra (DESIGN.md "adjoint"):  forward  Y = (1-b*M) y + b*sum_s f_s one_s,
 //   y = h1 + alpha (h1-h2) + A[h1]  =>
 //   Lam_i = (1+alpha) l1' + A^T[l1'] + Ha^T[L1] - alpha l2' + Hb^T[L2],   l' = (1-b*M) L.
-template <int FL, class FL1, class FL2, class FS1, class FS2, class FC>
+template <int FL, class FL1, class FL2, class FS1, class FS2, class FC, class FK>
 ST_HD void w2_adjoint_cell(int z, int x, const W2Geom& g, float dt,
-                           FL1 L1, FL2 L2, FS1 S1, FS2 S2, FC CF,
+                           FL1 L1, FL2 L2, FS1 S1, FS2 S2, FC CF, FK CK,
                            float out[2], float grad[7], bool want_grad) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     const bool habc = (FL & ST_F_HABC) != 0;
     auto inside = [&](int zz, int xx) { return zz >= 0 && zz < g.nz && xx >= 0 && xx < g.nx; };
     // pre-blend cotangent factor (1 - b*M) at q
-    auto pre = [&](int zz, int xx, const W2Coef& c) {
-        if (!habc) return 1.f;
-        return w2_in_frame(zz, xx, g) ? (1.f - c.b) : 1.f;
+    // Note: inside the frame sum_s f_s == 1 (habc.py masks tile the frame; checked by
+    // tests/test_hostcheck.py), so M == in_frame.
+    auto preq = [&](int zz, int xx) {
+        if (!habc || !w2_in_frame(zz, xx, g)) return 1.f;
+        return 1.f - CK(1, zz, xx);
     };
-    // Note: inside the frame sum_s f_s == 1 except where no side owns the cell, which
-    // cannot happen for frame cells (habc.py masks tile the frame), so M == in_frame.
-    auto iso_coef = [&](const W2Coef& c) { return c.cxx; };
     // effective cotangent that multiplies the spatial operator of field f at q
-    auto leff = [&](int f, int zz, int xx, const W2Coef& c) {
-        float v = pre(zz, xx, c) * L1(f, zz, xx);
-        if ((FL & ST_F_BORN) && f == 0) v += c.m * (pre(zz, xx, c) * L1(1, zz, xx));
+    auto leffq = [&](int f, int zz, int xx) {
+        const float pq = preq(zz, xx);
+        float v = pq * L1(f, zz, xx);
+        if ((FL & ST_F_BORN) && f == 0) v += CK(7, zz, xx) * (pq * L1(1, zz, xx));
         return v;
     };
     const W2Coef cp = CF(z, x);
     const float alpha = (FL & ST_F_PML) ? cp.czz : 1.f;
-    const float prep = pre(z, x, cp);
+    const float prep = (habc && w2_in_frame(z, x, g)) ? 1.f - cp.b : 1.f;
 
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
@@ -195,15 +197,8 @@ ST_HD void w2_adjoint_cell(int z, int x, const W2Geom& g, float dt,
         // ---- transposed spatial operator: stencil applied to the products C(q)*leff(q)
         auto wk = [&](int kind, int zz, int xx) -> float {
             if (!inside(zz, xx)) return 0.f;
-            const W2Coef c = CF(zz, xx);
-            const float l = leff(f, zz, xx, c);
-            float cf;
-            if (kind == 0) cf = c.cxx;
-            else if (kind == 1) cf = c.czz;
-            else if (kind == 2) cf = c.cxz;
-            else if (kind == 3) cf = c.ax;
-            else cf = c.az;
-            return cf * l;
+            // kind 0: cxx (= ciso for ISO), 1: czz, 2: cxz, 3: ax, 4: az  -> coefficient planes 2..6
+            return CK(2 + kind, zz, xx) * leffq(f, zz, xx);
         };
         if (FL & ST_F_ISO) {
             const float wc = wk(0, z, x);
@@ -233,9 +228,9 @@ ST_HD void w2_adjoint_cell(int z, int x, const W2Geom& g, float dt,
                     float fq[4];
                     w2_side_weights(zq, xq, g, fq);
                     if (fq[s] == 0.f) continue;
-                    const W2Coef cq = CF(zq, xq);
-                    const float lam = 2.f * cq.r, mu = cq.r * cq.r;
-                    const float wgt = cq.b * fq[s];
+                    const float rq = CK(0, zq, xq);
+                    const float lam = 2.f * rq, mu = rq * rq;
+                    const float wgt = CK(1, zq, xq) * fq[s];
                     const float a = kk == 0 ? (2.f - lam - mu) : (kk == 1 ? (lam + 2.f * mu) : -mu);
                     acc += wgt * a * L1(f, zq, xq);
                     if (kk <= 1) {
@@ -251,7 +246,7 @@ ST_HD void w2_adjoint_cell(int z, int x, const W2Geom& g, float dt,
     if (!want_grad) return;
     // ---- coefficient gradients of forward step i+1 at p
     {
-        const float ci = iso_coef(cp);
+        const float ci = cp.cxx;
         float A0 = 0.f;
 #pragma unroll
         for (int f = 0; f < NF; ++f) {

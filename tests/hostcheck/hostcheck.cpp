@@ -55,8 +55,9 @@ static void w2_adj(const HcW2& p, const float* l1, const float* l2, const float*
                     return [=](int f, int zz, int xx) -> float { return inb(zz, xx) ? a[f * cs + b * fs + (long long)zz * p.ld + xx] : 0.f; };
                 };
                 auto CF = [&](int zz, int xx) { return hc_coef(p, (long long)zz * p.ld + xx); };
+                auto CK = [&](int k, int zz, int xx) -> float { return p.coef[k] ? p.coef[k][(long long)zz * p.ld + xx] : 0.f; };
                 float out[2], gr[7] = {0, 0, 0, 0, 0, 0, 0};
-                w2_adjoint_cell<FL>(z, x, g, p.dt, mk(l1), mk(l2), mk(s1), mk(s2), CF, out, gr, gacc != nullptr);
+                w2_adjoint_cell<FL>(z, x, g, p.dt, mk(l1), mk(l2), mk(s1), mk(s2), CF, CK, out, gr, gacc != nullptr);
                 for (int f = 0; f < NF; ++f) l0[f * cs + b * fs + (long long)z * p.ld + x] = out[f];
                 if (gacc)
                     for (int q = 0; q < 7; ++q) gacc[q * fs + (long long)z * p.ld + x] += gr[q];
