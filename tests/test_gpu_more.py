@@ -138,3 +138,21 @@ def test_l2_and_envelope_misfit_kernels_against_oracle():
         sc2 = [syn[k].cuda().requires_grad_(True) for k in range(2)]
         l2_ = sb.Loss(name).loss(None)(sc2, [obs[k].cuda() for k in range(2)])
         assert abs(float(l2_) - float(lo)) <= 2e-5 * abs(float(lo)), name
+
+
+@pytest.mark.parametrize("eq", ["elastic", "acoustic", "tti_habc"])
+def test_mid_size_grid_against_oracle(eq):
+    """250x400 padded grid: large enough that every kernel variant (vectorised interior tiles,
+    border / frame tiles, tap-gather band) is exercised; compared with the oracle in float64."""
+    from oracle import cases, loop, misfit
+    case = cases.make_case(eq, nz=150, nx=300, nshots=2, nt=70, rec_step=9)
+    cfg, model, x = _model(case)
+    syn = model(x)
+    loss = sum((s ** 2).sum() for s in syn)
+    loss.backward()
+    inv = [k for k, v in case["invlist"].items() if v]
+    orecs, params = loop.simulate(case, dtype=torch.float64, requires_grad=inv)
+    misfit.l2(orecs, [torch.zeros_like(r) for r in orecs]).backward()
+    assert rel(cat_records([s.detach().cpu().numpy() for s in syn]), cat_records([r.detach().numpy() for r in orecs])) < 1e-5
+    for k in inv:
+        assert rel(getattr(model.cell.geom, k).grad.cpu().numpy(), params[k].grad.numpy()) < 1e-4, k
