@@ -176,6 +176,215 @@ __device__ __forceinline__ void forward_tail(const W2Args& a, int b, int z0, int
 }
 
 
+// ------------------------------------------------------------------------------ band: straight strips
+// The straight part of the top / bottom band (columns [52, nx-52), 70 % of the band cells at the
+// BASELINE size) has only z-direction far taps, so it vectorises like the interior: a warp owns one
+// band row x 128 columns, each lane 4 cells (128-bit loads of fields AND tap planes), x-neighbours
+// by shuffle; every lane walks all shots of its group with the transposed taps in registers.
+struct StripGeom { int xs, xe, ncol, toprows, nrows, bd; };
+__host__ __device__ inline StripGeom strip_geom(const W2Geom& g, int bd) {
+    StripGeom t;
+    t.bd = bd;
+    t.xs = (g.bw + 2 + 3) / 4 * 4;
+    t.xe = (g.nx - g.bw - 2) / 4 * 4;
+    if (t.xe < t.xs) t.xe = t.xs;
+    t.ncol = (t.xe - t.xs + FW - 1) / FW;
+    t.toprows = g.multiple ? 0 : bd;
+    t.nrows = t.toprows + bd;
+    return t;
+}
+__host__ __device__ inline int strip_blocks(const StripGeom& t) { return (t.nrows * t.ncol + NWARP - 1) / NWARP; }
+__device__ __forceinline__ bool in_strip(const StripGeom& t, const W2Geom& g, int z, int x) {
+    return x >= t.xs && x < t.xe && ((!g.multiple && z < t.bd) || z >= g.nz - t.bd);
+}
+// aligned float4 of plane/field row z at column x (zero outside the domain rows / past the grid)
+__device__ __forceinline__ float4 strip_row(const float* __restrict__ p, int z, int x, const W2Geom& g) {
+    if (z < 0 || z >= g.nz || x + 3 >= g.nx) return f4zero();
+    return __ldg(reinterpret_cast<const float4*>(p + (z * g.ld + x)));
+}
+// values at x-1 / x+4 of the lane's float4 (shuffle + scalar loads at the warp edges)
+__device__ __forceinline__ void strip_lr(const float4& c, const float* __restrict__ p, int z, int x0c, int lane,
+                                         const W2Geom& g, float& left, float& right) {
+    left = __shfl_up_sync(0xffffffffu, c.w, 1);
+    right = __shfl_down_sync(0xffffffffu, c.x, 1);
+    if (lane == 0) left = __ldg(p + (z * g.ld + x0c - 1));
+    if (lane == 31) right = (x0c + FW < g.nx) ? __ldg(p + (z * g.ld + x0c + FW)) : 0.f;
+}
+__device__ __forceinline__ float4 f4fma(const float4& a, const float4& b, const float4& c) {
+    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float4 f4sub(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 f4add(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4mul(const float4& a, const float4& b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+// shifted views of a row: cells x-1..x+2 and x+1..x+4
+__device__ __forceinline__ float4 f4shl(const float4& c, float left) { return make_float4(left, c.x, c.y, c.z); }
+__device__ __forceinline__ float4 f4shr(const float4& c, float right) { return make_float4(c.y, c.z, c.w, right); }
+
+__device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, int b_lo, int b_hi, int tid) {
+    const W2Geom g = a.g;
+    const StripGeom t = strip_geom(g, g.bw);
+    const int warp = tid >> 5, lane = tid & 31;
+    const int item = blk * NWARP + warp;
+    if (item >= t.nrows * t.ncol) return;                       // whole warp
+    const int row = item / t.ncol, chunk = item - row * t.ncol;
+    const bool top = row < t.toprows;
+    const int z = top ? row : g.nz - t.bd + (row - t.toprows);
+    const int n = top ? 1 : -1;
+    const int x0c = t.xs + chunk * FW, x = x0c + 4 * lane;
+    const bool active = x < t.xe;
+    const long long plane = (long long)g.nz * g.ld;
+    const int on1 = top ? 2 : 1, on2 = top ? 6 : 5;
+    // forward taps of this cell (increment form, st_wave2d_band.cuh)
+    const float4 Tm = strip_row(a.taps + 1 * plane, z, x, g), Tp = strip_row(a.taps + 2 * plane, z, x, g);
+    const float4 Tl = strip_row(a.taps + 3 * plane, z, x, g), Tr = strip_row(a.taps + 4 * plane, z, x, g);
+    const float4 Tf = strip_row(a.taps + on2 * plane, z, x, g);
+    const float4 T2 = strip_row(a.taps + (ST_NTAP1 + on1) * plane, z, x, g);
+    for (int b = b_lo; b < b_hi; ++b) {
+        const long long boff = (long long)b * a.fs;
+        const float* cur = a.cur + boff;
+        const float* prv = a.prev + boff;
+        const float4 C = strip_row(cur, z, x, g), Um = strip_row(cur, z - 1, x, g), Up = strip_row(cur, z + 1, x, g);
+        const float4 Uf = strip_row(cur, z + 2 * n, x, g);
+        const float4 P = strip_row(prv, z, x, g), Pn = strip_row(prv, z + n, x, g);
+        float l, r;
+        strip_lr(C, cur, z, x0c, lane, g, l, r);
+        float4 acc = f4mul(Tm, f4sub(Um, C));
+        acc = f4fma(Tp, f4sub(Up, C), acc);
+        acc = f4fma(Tl, f4sub(f4shl(C, l), C), acc);
+        acc = f4fma(Tr, f4sub(f4shr(C, r), C), acc);
+        acc = f4fma(Tf, f4sub(Uf, C), acc);
+        acc = f4fma(T2, f4sub(Pn, P), acc);
+        if (active) *reinterpret_cast<float4*>(a.next + boff + (z * g.ld + x)) = f4add(C, f4add(f4sub(C, P), acc));
+    }
+    // sources / receivers inside this warp's cells (ordering only needs the warp's own stores)
+    if (z < a.row_lo || z > a.row_hi) return;
+    __syncwarp();
+    const int xhi = min(x0c + FW, t.xe);
+    for (int s = lane; s < a.ns; s += 32) {
+        const int sb = a.src_b[s], sx = a.src_x[s];
+        if (a.src_z[s] == z && sx >= x0c && sx < xhi && sb >= b_lo && sb < b_hi && (a.src_fmask & 1))
+            atomicAdd(a.next + (long long)sb * a.fs + (z * g.ld + sx), a.amp[s]);
+    }
+    if (!a.rec_out) return;
+    __syncwarp();
+    for (int b = b_lo; b < b_hi; ++b) {
+        const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
+        for (int r = lo + lane; r < hi; r += 32) {
+            const int rx = a.rec_x[r];
+            if (rx >= x0c && rx < xhi) {
+                const long long o = (long long)a.rec_orig[r] * a.nchan;
+                for (int ch = 0; ch < a.nchan; ++ch) a.rec_out[o + ch] = a.next[(long long)b * a.fs + (z * g.ld + rx)];
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, int b_lo, int b_hi, int gplane, int tid) {
+    const W2Geom g = a.g;
+    const StripGeom t = strip_geom(g, g.bw + 1);
+    const int warp = tid >> 5, lane = tid & 31;
+    const int item = blk * NWARP + warp;
+    if (item >= t.nrows * t.ncol) return;
+    const int row = item / t.ncol, chunk = item - row * t.ncol;
+    const bool top = row < t.toprows;
+    const int z = top ? row : g.nz - t.bd + (row - t.toprows);
+    const int n = top ? 1 : -1;
+    const int x0c = t.xs + chunk * FW, x = x0c + 4 * lane;
+    const bool active = x < t.xe;
+    const long long plane = (long long)g.nz * g.ld;
+    const bool want_grad = a.gacc != nullptr;
+    const bool frame = top ? z < g.bw : z >= g.nz - g.bw;       // the deepest band row is not a frame row
+    const float* F1 = a.taps;
+    const float* F2 = a.taps + ST_NTAP1 * plane;
+    // transposed taps: coefficient of L(p+o) is tap -o of cell p+o
+    const float4 G0 = strip_row(F1, z, x, g);
+    const float4 Gm = strip_row(F1 + 2 * plane, z - 1, x, g), Gp = strip_row(F1 + 1 * plane, z + 1, x, g);
+    const float4 Gmm = strip_row(F1 + 6 * plane, z - 2, x, g), Gpp = strip_row(F1 + 5 * plane, z + 2, x, g);
+    const float4 A4 = strip_row(F1 + 4 * plane, z, x, g), B4 = strip_row(F1 + 3 * plane, z, x, g);
+    float al, ar, bl, br;
+    strip_lr(A4, F1 + 4 * plane, z, x0c, lane, g, al, ar);
+    strip_lr(B4, F1 + 3 * plane, z, x0c, lane, g, bl, br);
+    const float4 Gl = f4shl(A4, al);                  // F1[+x](z, x-1): the left neighbour reads us through its +x tap
+    const float4 Gr = f4shr(B4, br);                  // F1[-x](z, x+1)
+    const float4 K0 = strip_row(F2, z, x, g), Km = strip_row(F2 + 2 * plane, z - 1, x, g), Kp = strip_row(F2 + 1 * plane, z + 1, x, g);
+    float4 pre = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (frame) { const float4 bb = strip_row(a.coef[1], z, x, g); pre = make_float4(1.f - bb.x, 1.f - bb.y, 1.f - bb.z, 1.f - bb.w); }
+    const int on1 = top ? 2 : 1, on2 = top ? 6 : 5;
+    const float* H1 = a.taps + (ST_NTAP1 + ST_NTAP2) * plane;
+    const float* H2 = a.taps + (2 * ST_NTAP1 + ST_NTAP2) * plane;
+    float4 gc = f4zero(), gr = f4zero();
+    for (int b = b_lo; b < b_hi; ++b) {
+        const long long boff = (long long)b * a.fs;
+        const float* l1 = a.lam1 + boff;
+        const float* l2 = a.lam2 + boff;
+        const float4 L0 = strip_row(l1, z, x, g);
+        float ll, lr;
+        strip_lr(L0, l1, z, x0c, lane, g, ll, lr);
+        float4 acc = f4mul(G0, L0);
+        acc = f4fma(Gm, strip_row(l1, z - 1, x, g), acc);
+        acc = f4fma(Gp, strip_row(l1, z + 1, x, g), acc);
+        acc = f4fma(Gmm, strip_row(l1, z - 2, x, g), acc);
+        acc = f4fma(Gpp, strip_row(l1, z + 2, x, g), acc);
+        acc = f4fma(Gl, f4shl(L0, ll), acc);
+        acc = f4fma(Gr, f4shr(L0, lr), acc);
+        acc = f4fma(K0, strip_row(l2, z, x, g), acc);
+        acc = f4fma(Km, strip_row(l2, z - 1, x, g), acc);
+        acc = f4fma(Kp, strip_row(l2, z + 1, x, g), acc);
+        if (active) *reinterpret_cast<float4*>(a.lam0 + boff + (z * g.ld + x)) = acc;
+        if (want_grad) {
+            const float* S1 = a.s1 + boff;
+            const float4 s0 = strip_row(S1, z, x, g), sm = strip_row(S1, z - 1, x, g), sp = strip_row(S1, z + 1, x, g);
+            float sl, sr;
+            strip_lr(s0, S1, z, x0c, lane, g, sl, sr);
+            const float4 lap = f4add(f4add(f4sub(sm, s0), f4sub(sp, s0)), f4add(f4sub(f4shl(s0, sl), s0), f4sub(f4shr(s0, sr), s0)));
+            gc = f4fma(f4mul(pre, L0), lap, gc);
+            if (frame) {
+                const float* S2 = a.s2 + boff;
+                const float4 sn = top ? sp : sm;
+                float4 tt = f4mul(strip_row(H1, z, x, g), s0);
+                tt = f4fma(strip_row(H1 + on1 * plane, z, x, g), sn, tt);
+                tt = f4fma(strip_row(H1 + on2 * plane, z, x, g), strip_row(S1, z + 2 * n, x, g), tt);
+                tt = f4fma(strip_row(H2, z, x, g), strip_row(S2, z, x, g), tt);
+                tt = f4fma(strip_row(H2 + on1 * plane, z, x, g), strip_row(S2, z + n, x, g), tt);
+                gr = f4fma(L0, tt, gr);
+            }
+        }
+    }
+    if (want_grad && active) {
+        float* gb = a.gacc + (long long)gplane * 7 * plane + (z * g.ld + x);
+        float4 v = *reinterpret_cast<float4*>(gb + plane);
+        *reinterpret_cast<float4*>(gb + plane) = f4add(v, gc);                  // slot 1: d/d ciso
+        if (frame) {
+            float4 w = *reinterpret_cast<float4*>(gb);
+            *reinterpret_cast<float4*>(gb) = f4add(w, gr);                      // slot 0: d/d r
+        }
+    }
+    if (z < a.row_lo || z > a.row_hi) return;
+    __syncwarp();
+    const int xhi = min(x0c + FW, t.xe);
+    if (a.rec_adj) {
+        for (int b = b_lo; b < b_hi; ++b) {
+            const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
+            for (int r = lo + lane; r < hi; r += 32) {
+                const int rx = a.rec_x[r];
+                if (rx >= x0c && rx < xhi) {
+                    const long long o = (long long)a.rec_orig[r] * a.nchan;
+                    for (int ch = 0; ch < a.nchan; ++ch)
+                        atomicAdd(a.lam0 + (long long)b * a.fs + (z * g.ld + rx), a.rec_adj[o + ch]);
+                }
+            }
+        }
+    }
+    if (a.gamp) {
+        __syncwarp();
+        for (int s = lane; s < a.ns; s += 32) {
+            const int sb = a.src_b[s], sx = a.src_x[s];
+            if (a.src_z[s] == z && sx >= x0c && sx < xhi && sb >= b_lo && sb < b_hi && (a.src_fmask & 1))
+                a.gamp[s] = a.lam0[(long long)sb * a.fs + (z * g.ld + sx)];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ band (tap gather)
 // rows touched by the 256 consecutive band cells of a block -> shared list (<= 16 rows)
 __device__ __forceinline__ int band_block_rows(const BandCells& bc, int i, int tid, int* s_rows, int* s_cnt) {
@@ -212,14 +421,16 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
     const BandCells bc = st_band_cells(g, g.bw);
     const int i0 = blk * NT, i = i0 + tid;
     const long long plane = (long long)g.nz * g.ld;
+    const StripGeom sg = strip_geom(g, g.bw);
     auto mine = [&](int z, int x) {
-        if (z < 0 || z >= g.nz || x < 0 || x >= g.nx || !w2_in_frame(z, x, g)) return false;
+        if (z < 0 || z >= g.nz || x < 0 || x >= g.nx || !w2_in_frame(z, x, g) || in_strip(sg, g, z, x)) return false;
         const int e = st_band_encode(bc, z, x);
         return e >= i0 && e < i0 + NT;
     };
-    if (i < bc.total) {
-        int z, x;
-        st_band_decode(bc, i, z, x);
+    int zc = -1, xc = -1;
+    if (i < bc.total) st_band_decode(bc, i, zc, xc);
+    if (i < bc.total && !in_strip(sg, g, zc, xc)) {          // strip cells belong to the vectorised strip blocks
+        const int z = zc, x = xc;
         const int idx = z * g.ld + x;
         // increment form: Y = h1 + (h1 - h2) + sum_{o != 0} F1[o] (h1(p+o) - h1(p)) + F2[o] (h2(p+o) - h2(p))
         // (the taps of h1 sum to 2 and those of h2 to -1 exactly, DESIGN.md "numerics")
@@ -319,14 +530,16 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
     const long long plane = (long long)g.nz * g.ld;
     const bool want_grad = a.gacc != nullptr;
     auto inb = [&](int z, int x) { return z >= 0 && z < g.nz && x >= 0 && x < g.nx; };
+    const StripGeom sg = strip_geom(g, bd);
     auto mine = [&](int z, int x) {
-        if (!inb(z, x)) return false;
+        if (!inb(z, x) || in_strip(sg, g, z, x)) return false;
         const int e = st_band_encode(bc, z, x);
         return e >= i0 && e < i0 + NT;
     };
-    if (i < bc.total) {
-        int z, x;
-        st_band_decode(bc, i, z, x);
+    int zc = -1, xc = -1;
+    if (i < bc.total) st_band_decode(bc, i, zc, xc);
+    if (i < bc.total && !in_strip(sg, g, zc, xc)) {          // strip cells belong to the vectorised strip blocks
+        const int z = zc, x = xc;
         const int idx = z * g.ld + x;
         // transposed taps: coefficient of L(p+o) is the tap -o of cell p+o
         float g1[ST_NTAP1], g2[ST_NTAP2], h1[ST_NTAP1], h2[ST_NTAP2], m[ST_NTAP2];
@@ -445,6 +658,7 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
         }
     }
 }
+
 
 // ------------------------------------------------------------------------------ forward
 // rows of one warp tile.  SAFE: every load of the tile (rows z0-1..z0+FRZ, columns x0-1..x0+FW)
@@ -661,13 +875,16 @@ __global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W
     // they are scheduled first.  Tapped frame blocks walk all shots themselves.
     const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
     const int ngrp = (a.B + BSH - 1) / BSH;
-    const int nframe = HABC ? bt.count * (tapped ? ngrp : a.B) : 0;
+    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
+    const int nframe = HABC ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
     if (bid >= nframe) {
         const int q = bid - nframe;
         forward_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid);
     } else if (tapped) {
-        const int grp = bid / bt.count;
-        forward_band_block(a, bid - grp * bt.count, grp * BSH, min(grp * BSH + BSH, a.B), tid);
+        const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;
+        const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
+        if (k < nstrip) forward_strip_block(a, k, b_lo, b_hi, tid);
+        else forward_band_block(a, k - nstrip, b_lo, b_hi, tid);
     } else {
         if constexpr (HABC) {
             int tz, tx;
@@ -971,13 +1188,16 @@ __global__ void __launch_bounds__(NT, ST_ADJ_MINB) wave2d_adjoint_kernel(const W
     if constexpr (adj_fast<FL>()) {
         const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
         const int ngrp = (a.B + BSH - 1) / BSH;
-        const int nband = (FL & ST_F_HABC) ? bt.count * (tapped ? ngrp : a.B) : 0;
+        const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
+        const int nband = (FL & ST_F_HABC) ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
         if (bid >= nband) {
             const int q = bid - nband;
             adjoint_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid, reinterpret_cast<float (*)[FRZ][FW]>(smem));
         } else if (tapped) {
-            const int grp = bid / bt.count;                   // gradient plane = group id (< B planes exist)
-            adjoint_band_block(a, bid - grp * bt.count, grp * BSH, min(grp * BSH + BSH, a.B), grp, tid);
+            const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;     // gradient plane = group id (< B planes exist)
+            const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
+            if (k < nstrip) adjoint_strip_block(a, k, b_lo, b_hi, grp, tid);
+            else adjoint_band_block(a, k - nstrip, b_lo, b_hi, grp, tid);
         } else {
             if constexpr (NEED_GEN) {
                 int tz, tx;
@@ -1014,7 +1234,8 @@ int st_w2_launch_fwd(const W2Args& a, cudaStream_t st) {
     if (!(FL & ST_F_HABC)) bt.count = 0;
     const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
-    dim3 grid((unsigned)((long long)nfast * a.B + (long long)bt.count * (tapped ? (a.B + BSH - 1) / BSH : a.B)));
+    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
+    dim3 grid((unsigned)((long long)nfast * a.B + (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B)));
     wave2d_forward_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
@@ -1027,7 +1248,8 @@ int st_w2_launch_adj(const W2Args& a, cudaStream_t st) {
     const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw + 1).total + NT - 1) / NT;
     long long nblocks;
-    if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)bt.count * (tapped ? (a.B + BSH - 1) / BSH : a.B) : 0);
+    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
+    if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B) : 0);
     else nblocks = (long long)bt.nxt * bt.nzt * nchunk;
     dim3 grid((unsigned)nblocks);
     wave2d_adjoint_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
