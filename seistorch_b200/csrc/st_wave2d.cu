@@ -34,7 +34,7 @@ constexpr int FW = 128;                     // columns per warp (32 lanes x floa
 #define ST_FRZ 4
 #endif
 #ifndef ST_ADJ_MINB
-#define ST_ADJ_MINB 4
+#define ST_ADJ_MINB 3
 #endif
 constexpr int FRZ = ST_FRZ;                 // rows per warp
 constexpr int NWARP = NT / 32;
