@@ -908,7 +908,10 @@ __host__ __device__ constexpr bool grad_used(int q) {
 }
 // flag sets with a vectorised adjoint fast path (the acoustic flagship equations)
 template <int FL>
-__host__ __device__ constexpr bool adj_fast() { return FL == (ST_F_ISO | ST_F_PML) || FL == (ST_F_ISO | ST_F_HABC); }
+__host__ __device__ constexpr bool adj_fast() { return !(FL & ST_F_BORN); }
+// ... of which the two acoustic ones keep their gradient partial sums in shared memory
+template <int FL>
+__host__ __device__ constexpr bool adj_iso_only() { return FL == (ST_F_ISO | ST_F_PML) || FL == (ST_F_ISO | ST_F_HABC); }
 
 // receiver-adjoint scatter + source-amplitude gradient for the cells this block stored
 template <int NF, class Own>
@@ -1049,6 +1052,127 @@ __device__ __forceinline__ void adjoint_fast_rows(const W2Args& a, const W2Geom&
     }
 }
 
+
+// Single-field, non-Born flag sets (vti_habc2, tti_habc, acoustic_fwim_habc): interior cells
+//   Lam_i = 2 L1 - L2 + dxx(cxx L1) + dzz(czz L1) + dxz^T(cxz L1) - dx(ax L1) - dz(az L1)
+// evaluated on rows of the coefficient-times-cotangent products, which are formed once per row
+// when it is loaded and marched through 3-row register pipelines; coefficient gradients
+// (imaging condition) are added straight to the block's gradient plane.
+template <int FL, class Own>
+__device__ __forceinline__ void adjoint_fast_rows_gen(const W2Args& a, const W2Geom& g, int b, int chunk, int x0, int z0,
+                                                      int zn, int lane, bool clean, bool want_grad, Own owns) {
+    constexpr bool ISO = (FL & ST_F_ISO) != 0, XZ = (FL & ST_F_XZ) != 0, G1 = (FL & ST_F_G1) != 0;
+    const int x = x0 + 4 * lane;
+    const int ld = g.ld;
+    const long long boff = (long long)b * a.fs, plane = (long long)g.nz * ld;
+    const float* l1 = a.lam1 + boff;
+    const float* l2 = a.lam2 + boff;
+    const float* S = a.s1 + boff;
+    float* l0 = a.lam0 + boff;
+    float* gb = want_grad ? a.gacc + (long long)chunk * 7 * plane : nullptr;
+    const bool edge = lane == 0 || lane == 31;
+    const int xh = lane == 0 ? x0 - 1 : x0 + FW;
+    // product rows of row z:  PA = cxx*L (ciso*L for ISO), PB = czz*L, PC = cxz*L / az*L, PD = ax*L
+    struct Prod { float4 l, a, b, c, d; float al, ar, cl, cr, dl, dr; };
+    auto load_prod = [&](int z) {
+        Prod p;
+        p.l = ldrow(l1, z, x, g);
+        const float4 ca = ldrow(a.coef[2], z, x, g);
+        p.a = f4mul(ca, p.l);
+        p.b = ISO ? p.a : f4mul(ldrow(a.coef[3], z, x, g), p.l);
+        p.c = XZ ? f4mul(ldrow(a.coef[4], z, x, g), p.l) : (G1 ? f4mul(ldrow(a.coef[6], z, x, g), p.l) : f4zero());
+        p.d = G1 ? f4mul(ldrow(a.coef[5], z, x, g), p.l) : f4zero();
+        // x-neighbours of the products (shuffles; the warp's edge lanes read coefficient and cotangent)
+        p.al = __shfl_up_sync(0xffffffffu, p.a.w, 1); p.ar = __shfl_down_sync(0xffffffffu, p.a.x, 1);
+        p.cl = p.cr = p.dl = p.dr = 0.f;
+        if (XZ) { p.cl = __shfl_up_sync(0xffffffffu, p.c.w, 1); p.cr = __shfl_down_sync(0xffffffffu, p.c.x, 1); }
+        if (G1) { p.dl = __shfl_up_sync(0xffffffffu, p.d.w, 1); p.dr = __shfl_down_sync(0xffffffffu, p.d.x, 1); }
+        if (edge) {
+            float va = 0.f, vc = 0.f, vd = 0.f;
+            if (z >= 0 && z < g.nz && xh >= 0 && xh < g.nx) {
+                const int o = z * ld + xh;
+                const float lv = __ldg(l1 + o);
+                va = __ldg(a.coef[2] + o) * lv;
+                if (XZ) vc = __ldg(a.coef[4] + o) * lv;
+                if (G1) vd = __ldg(a.coef[5] + o) * lv;
+            }
+            if (lane == 0) { p.al = va; p.cl = vc; p.dl = vd; } else { p.ar = va; p.cr = vc; p.dr = vd; }
+        }
+        return p;
+    };
+    struct SRow { float4 s; float l, r; };
+    auto load_s = [&](int z) {
+        SRow q;
+        q.s = ldrow(S, z, x, g);
+        row_halo(q.s, S, z, x0, lane, g, q.l, q.r);
+        return q;
+    };
+    Prod U = load_prod(z0 - 1), C = load_prod(z0), D;
+    SRow sU, sC, sD;
+    if (want_grad) { sU = load_s(z0 - 1); sC = load_s(z0); }
+#pragma unroll
+    for (int k = 0; k < FRZ; ++k) {
+        const int z = z0 + k;
+        if (z < zn) {
+            D = load_prod(z + 1);
+            const float4 p2 = ldrow(l2, z, x, g);
+            if (want_grad) sD = load_s(z + 1);
+            float4 out, g1v = f4zero(), g2v = f4zero(), g3v = f4zero(), g4v = f4zero(), g5v = f4zero();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float lc = f4get(C.l, e);
+                const float ac = f4get(C.a, e);
+                const float aw = e == 0 ? C.al : f4get(C.a, e - 1), ae = e == 3 ? C.ar : f4get(C.a, e + 1);
+                float acc = 2.f * lc - f4get(p2, e);
+                acc += ((ae - ac) + (aw - ac));                                              // dxx of cxx*L (or ciso*L)
+                acc += ((f4get(U.b, e) - f4get(C.b, e)) + (f4get(D.b, e) - f4get(C.b, e)));  // dzz of czz*L (or ciso*L)
+                if (XZ) {
+                    const float uw = e == 0 ? U.cl : f4get(U.c, e - 1), ue = e == 3 ? U.cr : f4get(U.c, e + 1);
+                    const float dw = e == 0 ? D.cl : f4get(D.c, e - 1), de = e == 3 ? D.cr : f4get(D.c, e + 1);
+                    acc += (uw - ue) - (dw - de);
+                }
+                if (G1) {
+                    const float dwv = e == 0 ? C.dl : f4get(C.d, e - 1), dev = e == 3 ? C.dr : f4get(C.d, e + 1);
+                    acc += (dwv - dev) + (f4get(U.c, e) - f4get(D.c, e));                    // -dx(ax L) - dz(az L)
+                }
+                f4set(out, e, acc);
+                if (want_grad) {
+                    const float sc = f4get(sC.s, e);
+                    const float sw_ = e == 0 ? sC.l : f4get(sC.s, e - 1), se_ = e == 3 ? sC.r : f4get(sC.s, e + 1);
+                    const float sn = f4get(sU.s, e), ss = f4get(sD.s, e);
+                    const float sxx = (se_ - sc) + (sw_ - sc), szz = (sn - sc) + (ss - sc);
+                    if (ISO) f4set(g1v, e, lc * (szz + sxx));
+                    else { f4set(g1v, e, lc * sxx); f4set(g2v, e, lc * szz); }
+                    if (XZ) {
+                        const float nw = e == 0 ? sU.l : f4get(sU.s, e - 1), ne = e == 3 ? sU.r : f4get(sU.s, e + 1);
+                        const float sw2 = e == 0 ? sD.l : f4get(sD.s, e - 1), se2 = e == 3 ? sD.r : f4get(sD.s, e + 1);
+                        f4set(g3v, e, lc * ((se2 - sw2) - (ne - nw)));
+                    }
+                    if (G1) { f4set(g4v, e, lc * (se_ - sw_)); f4set(g5v, e, lc * (ss - sn)); }
+                }
+            }
+            const int ro = z * ld + x;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool mine = x + e < g.nx && (clean || owns(z, x + e));
+                if (mine) {
+                    l0[ro + e] = f4get(out, e);
+                    if (want_grad) {
+                        gb[plane + ro + e] += f4get(g1v, e);
+                        if (!ISO) gb[2 * plane + ro + e] += f4get(g2v, e);
+                        if (XZ) gb[3 * plane + ro + e] += f4get(g3v, e);
+                        if (G1) { gb[4 * plane + ro + e] += f4get(g4v, e); gb[5 * plane + ro + e] += f4get(g5v, e); }
+                    }
+                } else if (x + e >= g.nx && x + e < ld) {
+                    l0[ro + e] = 0.f;
+                }
+            }
+            U = C; C = D;
+            if (want_grad) { sU = sC; sC = sD; }
+        }
+    }
+}
+
 template <int FL>
 __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int nfx, int chunk, int tid,
                                                    float (*gsm)[FRZ][FW]) {
@@ -1073,19 +1197,23 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
     const bool safe = z0 >= 1 && z0 + FRZ + 1 <= g.nz && x0 >= 1 && x0 + FW + 1 <= g.nx;
     auto owns = [&](int z, int xx) { return !HABC || edge_depth(z, xx, g) >= band; };
     float4* gsl = reinterpret_cast<float4*>(&gsm[warp][0][4 * lane]);      // stride FW/4 float4 per row
-    if (want_grad) {
+    if (want_grad && adj_iso_only<FL>()) {
 #pragma unroll
         for (int k = 0; k < FRZ; ++k) gsl[k * (FW / 4)] = f4zero();
     }
     const int b_lo = chunk * a.bchunk, b_hi = min(b_lo + a.bchunk, a.B);
     for (int b = b_lo; b < b_hi; ++b) {
         if (rows) {
-            if (safe) adjoint_fast_rows<FL, true>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
-            else adjoint_fast_rows<FL, false>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
+            if constexpr (adj_iso_only<FL>()) {
+                if (safe) adjoint_fast_rows<FL, true>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
+                else adjoint_fast_rows<FL, false>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
+            } else {
+                adjoint_fast_rows_gen<FL>(a, g, b, chunk, x0, z0, zn, lane, clean, want_grad, owns);
+            }
         }
         adjoint_tail<1>(a, b, zb0, zb0 + FH, x0, x0 + FW, tid, owns);
     }
-    if (want_grad && rows && x < g.ld) {
+    if (want_grad && adj_iso_only<FL>() && rows && x < g.ld) {
         float* gb = a.gacc + ((long long)chunk * 7 + 1) * ((long long)g.nz * g.ld);       // slot 1: d/d ciso
 #pragma unroll
         for (int k = 0; k < FRZ; ++k) {
@@ -1180,7 +1308,7 @@ __global__ void __launch_bounds__(NT, ST_ADJ_MINB) wave2d_adjoint_kernel(const W
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     constexpr bool NEED_GEN = !adj_fast<FL>() || (FL & ST_F_HABC);
     constexpr int GEN_FLOATS = NEED_GEN ? 2 * NF * SH * SW : 1;
-    constexpr int FAST_FLOATS = adj_fast<FL>() ? NWARP * FRZ * FW : 1;
+    constexpr int FAST_FLOATS = adj_iso_only<FL>() ? NWARP * FRZ * FW : 1;
     __shared__ __align__(16) float smem[GEN_FLOATS > FAST_FLOATS ? GEN_FLOATS : FAST_FLOATS];
     const int bid = blockIdx.x, tid = threadIdx.x;
     // grid.x = [band blocks: one per (tile, shot)] ++ [fast blocks: one per (fast tile, shot chunk)]

@@ -140,7 +140,7 @@ def test_l2_and_envelope_misfit_kernels_against_oracle():
         assert abs(float(l2_) - float(lo)) <= 2e-5 * abs(float(lo)), name
 
 
-@pytest.mark.parametrize("eq", ["elastic", "acoustic", "tti_habc"])
+@pytest.mark.parametrize("eq", ["elastic", "acoustic", "vti_habc2", "tti_habc", "acoustic_fwim_habc", "acoustic_tti_lsrtm_habc"])
 def test_mid_size_grid_against_oracle(eq):
     """250x400 padded grid: large enough that every kernel variant (vectorised interior tiles,
     border / frame tiles, tap-gather band) is exercised; compared with the oracle in float64."""
