@@ -64,9 +64,9 @@ static int w2_check(const st_wave2d_problem* p) {
     return check_acq(p->acq, (p->flags & ST_EQ_BORN) ? 2 : 1);
 }
 
-// precomputed frame taps: acoustic_habc only, and only when the band rectangles do not overlap
+// precomputed frame taps: 9-tap HABC equations, and only when the band rectangles do not overlap
 static bool w2_uses_taps(const st_wave2d_problem* p) {
-    if (p->flags != (ST_EQ_ISO | ST_EQ_HABC)) return false;
+    if (!st_flags_tapped(p->flags)) return false;
     W2Geom g{p->nz, p->nx, p->ld, p->bw, p->multiple};
     return st_band_ok(g, p->bw + 1);
 }
@@ -100,7 +100,7 @@ extern "C" int st_wave2d_prepare(const st_wave2d_problem* p, void* stream) {
     if (!w2_uses_taps(p) || p->taps == nullptr) return ST_OK;
     W2Args a;
     w2_fill(p, a);
-    rc = st_wave2d_launch_prepare(a, (cudaStream_t)stream);
+    rc = st_wave2d_launch_prepare(p->flags, a, (cudaStream_t)stream);
     if (rc) st_set_error("wave2d_prepare: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return rc;
 }

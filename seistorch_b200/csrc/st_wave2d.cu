@@ -279,6 +279,7 @@ __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, in
     }
 }
 
+template <int FL>
 __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, int b_lo, int b_hi, int gplane, int tid) {
     const W2Geom g = a.g;
     const StripGeom t = strip_geom(g, g.bw + 1);
@@ -312,7 +313,7 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
     const int on1 = top ? 2 : 1, on2 = top ? 6 : 5;
     const float* H1 = a.taps + (ST_NTAP1 + ST_NTAP2) * plane;
     const float* H2 = a.taps + (2 * ST_NTAP1 + ST_NTAP2) * plane;
-    float4 gc = f4zero(), gr = f4zero();
+    float4 gc = f4zero(), gr = f4zero(), gz = f4zero(), gax = f4zero(), gaz = f4zero();
     for (int b = b_lo; b < b_hi; ++b) {
         const long long boff = (long long)b * a.fs;
         const float* l1 = a.lam1 + boff;
@@ -336,8 +337,12 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
             const float4 s0 = strip_row(S1, z, x, g), sm = strip_row(S1, z - 1, x, g), sp = strip_row(S1, z + 1, x, g);
             float sl, sr;
             strip_lr(s0, S1, z, x0c, lane, g, sl, sr);
-            const float4 lap = f4add(f4add(f4sub(sm, s0), f4sub(sp, s0)), f4add(f4sub(f4shl(s0, sl), s0), f4sub(f4shr(s0, sr), s0)));
-            gc = f4fma(f4mul(pre, L0), lap, gc);
+            const float4 sw4 = f4shl(s0, sl), se4 = f4shr(s0, sr);
+            const float4 szz = f4add(f4sub(sm, s0), f4sub(sp, s0)), sxx = f4add(f4sub(sw4, s0), f4sub(se4, s0));
+            const float4 pl = f4mul(pre, L0);
+            if (FL & ST_F_ISO) gc = f4fma(pl, f4add(szz, sxx), gc);
+            else { gc = f4fma(pl, sxx, gc); gz = f4fma(pl, szz, gz); }
+            if (FL & ST_F_G1) { gax = f4fma(pl, f4sub(se4, sw4), gax); gaz = f4fma(pl, f4sub(sp, sm), gaz); }
             if (frame) {
                 const float* S2 = a.s2 + boff;
                 const float4 sn = top ? sp : sm;
@@ -353,7 +358,16 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
     if (want_grad && active) {
         float* gb = a.gacc + (long long)gplane * 7 * plane + (z * g.ld + x);
         float4 v = *reinterpret_cast<float4*>(gb + plane);
-        *reinterpret_cast<float4*>(gb + plane) = f4add(v, gc);                  // slot 1: d/d ciso
+        *reinterpret_cast<float4*>(gb + plane) = f4add(v, gc);                  // slot 1: d/d ciso (ISO) or d/d cxx
+        if (!(FL & ST_F_ISO)) {
+            float4 u = *reinterpret_cast<float4*>(gb + 2 * plane);
+            *reinterpret_cast<float4*>(gb + 2 * plane) = f4add(u, gz);          // slot 2: d/d czz
+        }
+        if (FL & ST_F_G1) {
+            float4 u4 = *reinterpret_cast<float4*>(gb + 4 * plane), u5 = *reinterpret_cast<float4*>(gb + 5 * plane);
+            *reinterpret_cast<float4*>(gb + 4 * plane) = f4add(u4, gax);
+            *reinterpret_cast<float4*>(gb + 5 * plane) = f4add(u5, gaz);
+        }
         if (frame) {
             float4 w = *reinterpret_cast<float4*>(gb);
             *reinterpret_cast<float4*>(gb) = f4add(w, gr);                      // slot 0: d/d r
@@ -522,6 +536,7 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
     }
 }
 
+template <int FL>
 __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int b_lo, int b_hi, int gplane, int tid) {
     const W2Geom g = a.g;
     const int bd = g.bw + 1;
@@ -559,10 +574,10 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
                 m[o] = in ? 1.f : 0.f;
             }
         }
-        float gr = 0.f, gc = 0.f;
+        float gr = 0.f, gc = 0.f, gz = 0.f, gax = 0.f, gaz = 0.f;
         // one shot: Lam_i(p) and the gradient contributions; written as a lambda so two shots can be
         // issued back to back (two independent load chains in flight)
-        auto one_shot = [&](int b, float& accOut, float& gcOut, float& grOut) {
+        auto one_shot = [&](int b, float& accOut, float& gcOut, float& grOut, float& gzOut, float& gaxOut, float& gazOut) {
             const long long boff = (long long)b * a.fs;
             const float* l1 = a.lam1 + boff;
             const float* l2 = a.lam2 + boff;
@@ -593,23 +608,27 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
                         t += h1[o] * __ldg(S1 + q[o]);
                     }
                 }
-                gcOut += pre * lc * (((s[1] - s[0]) + (s[2] - s[0])) + ((s[3] - s[0]) + (s[4] - s[0])));
+                const float szz = (s[1] - s[0]) + (s[2] - s[0]), sxx = (s[3] - s[0]) + (s[4] - s[0]);
+                if (FL & ST_F_ISO) gcOut += pre * lc * (szz + sxx);
+                else { gcOut += pre * lc * sxx; gzOut += pre * lc * szz; }
+                if (FL & ST_F_G1) { gaxOut += pre * lc * (s[4] - s[3]); gazOut += pre * lc * (s[2] - s[1]); }
                 grOut += lc * t;
             }
         };
         for (int b = b_lo; b < b_hi; b += 2) {
-            float acc0, acc1 = 0.f, gc1 = 0.f, gr1 = 0.f;
-            one_shot(b, acc0, gc, gr);
+            float acc0, acc1 = 0.f, gc1 = 0.f, gr1 = 0.f, gz1 = 0.f, gax1 = 0.f, gaz1 = 0.f;
+            one_shot(b, acc0, gc, gr, gz, gax, gaz);
             const bool two = b + 1 < b_hi;
-            if (two) one_shot(b + 1, acc1, gc1, gr1);
+            if (two) one_shot(b + 1, acc1, gc1, gr1, gz1, gax1, gaz1);
             a.lam0[(long long)b * a.fs + idx] = acc0;
             if (two) a.lam0[(long long)(b + 1) * a.fs + idx] = acc1;
-            gc += gc1;
-            gr += gr1;
+            gc += gc1; gr += gr1; gz += gz1; gax += gax1; gaz += gaz1;
         }
         if (want_grad) {
             float* gb = a.gacc + (long long)gplane * 7 * plane;
-            gb[plane + idx] += gc;              // slot 1: d/d ciso
+            gb[plane + idx] += gc;              // slot 1: d/d ciso (ISO) or d/d cxx
+            if (!(FL & ST_F_ISO)) gb[2 * plane + idx] += gz;                   // slot 2: d/d czz
+            if (FL & ST_F_G1) { gb[4 * plane + idx] += gax; gb[5 * plane + idx] += gaz; }
             if (frame) gb[idx] += gr;           // slot 0: d/d r
         }
     }
@@ -873,7 +892,7 @@ __global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W
     const int bid = blockIdx.x, tid = threadIdx.x;
     // grid.x = [frame blocks] ++ [fast blocks x shots]; the (slower) frame blocks get the low ids so
     // they are scheduled first.  Tapped frame blocks walk all shots themselves.
-    const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
+    const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     const int ngrp = (a.B + BSH - 1) / BSH;
     const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
     const int nframe = HABC ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
@@ -1314,7 +1333,7 @@ __global__ void __launch_bounds__(NT, ST_ADJ_MINB) wave2d_adjoint_kernel(const W
     // grid.x = [band blocks: one per (tile, shot)] ++ [fast blocks: one per (fast tile, shot chunk)]
     // for the fast-path equations, else one general block per (tile, shot chunk).
     if constexpr (adj_fast<FL>()) {
-        const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
+        const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
         const int ngrp = (a.B + BSH - 1) / BSH;
         const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
         const int nband = (FL & ST_F_HABC) ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
@@ -1324,8 +1343,8 @@ __global__ void __launch_bounds__(NT, ST_ADJ_MINB) wave2d_adjoint_kernel(const W
         } else if (tapped) {
             const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;     // gradient plane = group id (< B planes exist)
             const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
-            if (k < nstrip) adjoint_strip_block(a, k, b_lo, b_hi, grp, tid);
-            else adjoint_band_block(a, k - nstrip, b_lo, b_hi, grp, tid);
+            if (k < nstrip) adjoint_strip_block<FL>(a, k, b_lo, b_hi, grp, tid);
+            else adjoint_band_block<FL>(a, k - nstrip, b_lo, b_hi, grp, tid);
         } else {
             if constexpr (NEED_GEN) {
                 int tz, tx;
@@ -1360,7 +1379,7 @@ int st_w2_launch_fwd(const W2Args& a, cudaStream_t st) {
     const int nfast = nfx * nfz;
     BandTiles bt = band_tiles(a.g, a.g.bw);
     if (!(FL & ST_F_HABC)) bt.count = 0;
-    const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
+    const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
     const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
     dim3 grid((unsigned)((long long)nfast * a.B + (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B)));
@@ -1373,7 +1392,7 @@ int st_w2_launch_adj(const W2Args& a, cudaStream_t st) {
     const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
     const int nfast = nfx * nfz;
     BandTiles bt = band_tiles(a.g, a.g.bw + 1);
-    const bool tapped = FL == (ST_F_ISO | ST_F_HABC) && a.taps != nullptr;
+    const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw + 1).total + NT - 1) / NT;
     long long nblocks;
     const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;

@@ -1,17 +1,21 @@
-// One-off (per call) evaluation of the frame taps of the ISO|HABC equation; see
-// st_wave2d_band.cuh.  Reads r, b, ciso planes, writes ST_TAP_PLANES planes [nz][ld]:
+// One-off (per call) evaluation of the frame taps of the 9-tap HABC equations (acoustic_habc,
+// vti_habc2, acoustic_fwim_habc); see
+// st_wave2d_band.cuh.  Reads the coefficient planes, writes ST_TAP_PLANES planes [nz][ld]:
 //   F1[0..8], F2[0..4], H1[0..8] = dF1/dr, H2[0..4] = dF2/dr   (ciso held fixed).
 #include "st_wave2d_band.cuh"
 
 namespace {
 
-__global__ void __launch_bounds__(256) wave2d_prepare_kernel(const W2Args a) {
+__global__ void __launch_bounds__(256) wave2d_prepare_kernel(const W2Args a, int flags) {
     const W2Geom g = a.g;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
     if (x >= g.nx || z >= g.nz) return;
     const long long plane = (long long)g.nz * g.ld;
     const long long idx = (long long)z * g.ld + x;
-    const float r = a.coef[0][idx], b = a.coef[1][idx], ciso = a.coef[2][idx];
+    const float r = a.coef[0][idx], b = a.coef[1][idx];
+    const float cx = a.coef[2][idx];
+    const float cz = (flags & ST_F_ISO) ? cx : a.coef[3][idx];
+    const float ax = (flags & ST_F_G1) ? a.coef[5][idx] : 0.f, az = (flags & ST_F_G1) ? a.coef[6][idx] : 0.f;
     float F1[ST_NTAP1], F2[ST_NTAP2], H1[ST_NTAP1], H2[ST_NTAP2];
 #pragma unroll
     for (int o = 0; o < ST_NTAP1; ++o) F1[o] = H1[o] = 0.f;
@@ -19,9 +23,12 @@ __global__ void __launch_bounds__(256) wave2d_prepare_kernel(const W2Args a) {
     for (int o = 0; o < ST_NTAP2; ++o) F2[o] = H2[o] = 0.f;
     const bool frame = w2_in_frame(z, x, g);
     const float pre = frame ? 1.f - b : 1.f;
-    // y = 2 h1 - h2 + ciso (N + S + E + W - 4 C)
-    F1[0] = pre * (2.f - 4.f * ciso);
-    F1[1] = F1[2] = F1[3] = F1[4] = pre * ciso;
+    // y = 2 h1 - h2 + cx (E + W - 2C) + cz (N + S - 2C) + ax (E - W) + az (S - N)
+    F1[0] = pre * (2.f - 2.f * cx - 2.f * cz);
+    F1[1] = pre * (cz - az);      // N = (z-1, x)
+    F1[2] = pre * (cz + az);      // S
+    F1[3] = pre * (cx - ax);      // W = (z, x-1)
+    F1[4] = pre * (cx + ax);      // E
     F2[0] = -pre;
     if (frame) {
         float f[4];
@@ -54,8 +61,8 @@ __global__ void __launch_bounds__(256) wave2d_prepare_kernel(const W2Args a) {
 
 }  // namespace
 
-int st_wave2d_launch_prepare(const W2Args& a, cudaStream_t st) {
+int st_wave2d_launch_prepare(int flags, const W2Args& a, cudaStream_t st) {
     dim3 grid((a.g.nx + 255) / 256, a.g.nz);
-    wave2d_prepare_kernel<<<grid, 256, 0, st>>>(a);
+    wave2d_prepare_kernel<<<grid, 256, 0, st>>>(a, flags);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }

@@ -68,6 +68,11 @@ ST_HD void st_wrap_candidate(const W2Geom& g, int k, int& z, int& x, int& s, int
     else { z = g.nz - 1; x = w - 1; s = 2; zw = z; xw = 0; }                        // BL diagonal end, left side
 }
 
+// flag sets whose spatial operator fits the 9 taps (no mixed derivative, single field)
+ST_HD bool st_flags_tapped(int fl) {
+    return fl == (ST_F_ISO | ST_F_HABC) || fl == ST_F_HABC || fl == (ST_F_ISO | ST_F_HABC | ST_F_G1);
+}
+
 #ifdef __CUDACC__
-int st_wave2d_launch_prepare(const W2Args& a, cudaStream_t st);
+int st_wave2d_launch_prepare(int flags, const W2Args& a, cudaStream_t st);
 #endif
