@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libseistorch_b200.so")
+LIB_PATH = os.environ.get("SEISTORCH_B200_LIB") or os.path.join(_HERE, "libseistorch_b200.so")
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int32)

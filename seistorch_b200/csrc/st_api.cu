@@ -1,5 +1,6 @@
 // C-ABI entry points (include/seistorch_b200.h): argument checks + host time loops.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
 
@@ -89,6 +90,13 @@ static void w2_fill(const st_wave2d_problem* p, W2Args& a) {
     a.bchunk = p->bchunk > 0 ? p->bchunk : 1;
 }
 
+// SEISTORCH_B200_TMA: "0" = never use the TMA interior path, "1" = whenever a rectangle exists, unset = auto
+static int w2_tma_mode() {
+    const char* e = getenv("SEISTORCH_B200_TMA");
+    if (!e || !*e) return -1;
+    return atoi(e) != 0 ? 1 : 0;
+}
+
 extern "C" int64_t st_wave2d_taps_floats(const st_wave2d_problem* p) {
     if (!p || !w2_uses_taps(p)) return 0;
     return (int64_t)ST_TAP_PLANES * p->nz * p->ld;
@@ -115,14 +123,20 @@ extern "C" int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t
     const int nf = (p->flags & ST_EQ_BORN) ? 2 : 1;
     const long long slot = a.cs * nf;
     cudaStream_t st = (cudaStream_t)stream;
+    W2Tma tm;
+    const int planes = nf * p->B;                // field planes per slot
+    rc = st_wave2d_tma_setup(p->flags, a, p->u, (long long)planes * p->nslots, nullptr, 0, false, nsteps > 0 ? w2_tma_mode() : 0, tm);
+    if (rc) return rc;
     for (int k = 0; k < nsteps; ++k) {
         const int i = i0 + k;
+        tm.pl_prev = planes * pmod(slot0 + k, p->nslots);
+        tm.pl_cur = planes * pmod(slot0 + k + 1, p->nslots);
         a.prev = p->u + slot * pmod(slot0 + k, p->nslots);
         a.cur = p->u + slot * pmod(slot0 + k + 1, p->nslots);
         a.next = p->u + slot * pmod(slot0 + k + 2, p->nslots);
         a.amp = p->acq.amp ? p->acq.amp + (long long)i * p->acq.ns : nullptr;
         a.rec_out = (p->acq.rec_out && p->acq.R > 0) ? p->acq.rec_out + (long long)i * p->acq.R * p->acq.nchan : nullptr;
-        rc = st_wave2d_launch_forward(p->flags, a, st);
+        rc = st_wave2d_launch_forward(p->flags, a, tm, st);
         if (rc) { if (rc == ST_ERR_CUDA) st_set_error("wave2d_forward: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
     }
     return ST_OK;
@@ -139,8 +153,16 @@ extern "C" int st_wave2d_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32
     const long long slot = a.cs * nf;
     cudaStream_t st = (cudaStream_t)stream;
     a.gacc = p->gacc;
+    W2Tma tm;
+    const int planes = nf * p->B;
+    rc = st_wave2d_tma_setup(p->flags, a, p->u, (long long)planes * p->nslots, p->lam, 3LL * planes, true, nsteps > 0 ? w2_tma_mode() : 0, tm);
+    if (rc) return rc;
     for (int k = 0; k < nsteps; ++k) {
         const int i = i_hi - k;
+        tm.pl_l1 = planes * pmod(i + 1, 3);
+        tm.pl_l2 = planes * pmod(i + 2, 3);
+        tm.pl_s1 = planes * pmod(slot_hi - k, p->nslots);
+        tm.pl_s2 = planes * pmod(slot_hi - k - 1, p->nslots);
         a.lam0 = p->lam + slot * pmod(i, 3);
         a.lam1 = p->lam + slot * pmod(i + 1, 3);
         a.lam2 = p->lam + slot * pmod(i + 2, 3);
@@ -148,7 +170,7 @@ extern "C" int st_wave2d_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32
         a.s2 = p->u + slot * pmod(slot_hi - k - 1, p->nslots);
         a.rec_adj = (p->acq.rec_adj && p->acq.R > 0) ? p->acq.rec_adj + (long long)i * p->acq.R * p->acq.nchan : nullptr;
         a.gamp = p->acq.gamp ? p->acq.gamp + (long long)i * p->acq.ns : nullptr;
-        rc = st_wave2d_launch_adjoint(p->flags, a, st);
+        rc = st_wave2d_launch_adjoint(p->flags, a, tm, st);
         if (rc) { if (rc == ST_ERR_CUDA) st_set_error("wave2d_adjoint: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
     }
     return ST_OK;

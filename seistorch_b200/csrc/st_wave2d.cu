@@ -18,6 +18,9 @@
 // Data layout in HBM: fields [NF][B][nz][ld] fp32, row pitch ld a multiple of 4 so that
 // every row starts 16-byte aligned and columns [nx, ld) stay zero; coefficient planes
 // [nz][ld] shared by all shots (L2-resident: <= 8 MB each at the BASELINE sizes).
+#include <cstdlib>
+#include <cstring>
+
 #include "st_wave2d.cuh"
 #include "st_wave2d_band.cuh"
 
@@ -42,8 +45,76 @@ constexpr int FH = FRZ * NWARP;             // rows per fast block
 #ifndef ST_BAND_SHOTS
 #define ST_BAND_SHOTS 8
 #endif
+#ifndef ST_DBG_SKIP
+#define ST_DBG_SKIP 0                       // tuning only: bit 0/1/2 = fast/strip/band blocks return at once (wrong results)
+#endif
 constexpr int BSH = ST_BAND_SHOTS;          // shots a band thread walks with its taps in registers
+// ---- TMA-staged tiles (st_wave2d.cuh: W2Tma)
+constexpr int TC = ST_TMA_TC, TR = ST_TMA_TR, HC = ST_TMA_HC, H1R = ST_TMA_H1, H2R = ST_TMA_H2;
+static_assert(TC == FW && TR == 2 * NWARP && FH % TR == 0, "TMA tile = one float4 per lane, two rows per warp");
+constexpr int TMA_H1_BYTES = (H1R * HC * 4 + 127) / 128 * 128;       // 9856  (box: 9792)
+constexpr int TMA_H2_BYTES = (H2R * HC * 4 + 127) / 128 * 128;       // 10880
+constexpr int TMA_CORE_BYTES = TR * TC * 4;                          // 8192
+#ifndef ST_TMA_FWD_STAGES
+#define ST_TMA_FWD_STAGES 3
+#endif
+#ifndef ST_TMA_ADJ_STAGES
+#define ST_TMA_ADJ_STAGES 2
+#endif
+// stage layouts (sized for the frame tiles; interior tiles use smaller boxes at the same offsets)
+//   forward: [cur: 2-deep halo][prev: 1-deep halo]          interior: [cur: 1-deep halo][prev: core]
+//   adjoint: [Lam1: 2-deep][S_i: 2-deep][Lam2: 1-deep][S_{i-1}: 1-deep]   interior: [Lam1: 1-deep][S_i: 1-deep][Lam2: core]
+constexpr int TMA_FWD_STAGE = TMA_H2_BYTES + TMA_H1_BYTES;
+constexpr int TMA_ADJ_STAGE = 2 * TMA_H2_BYTES + 2 * TMA_H1_BYTES;
+constexpr int TMA_FWD_SMEM = ST_TMA_FWD_STAGES * TMA_FWD_STAGE;
+constexpr int TMA_ADJ_SMEM = ST_TMA_ADJ_STAGES * TMA_ADJ_STAGE;
+// flag sets with a TMA path
+template <int FL>
+__host__ __device__ constexpr bool tma_ok() { return FL == (ST_F_ISO | ST_F_PML) || FL == (ST_F_ISO | ST_F_HABC); }
 
+__host__ __device__ inline int tma_side_tiles(const W2Tma& tm) { return tm.sr1 > tm.sr0 ? 2 * (tm.sr1 - tm.sr0) : 0; }
+__host__ __device__ inline int tma_tiles(const W2Tma& tm) { return tma_side_tiles(tm) + tm.ntr * (tm.tx1 - tm.tx0); }
+__host__ __device__ inline int tma_blocks(const W2Tma& tm, int B) { return tm.enabled ? tma_tiles(tm) * ((B + tm.tsh - 1) / tm.tsh) : 0; }
+// t-th TMA tile -> origin and kind (0 frame-free, +1/-1 top/bottom frame, +2/-2 left/right frame).  Heaviest first:
+// side tiles, bottom-frame rows, top-frame rows, then the frame-free rows.
+__device__ __forceinline__ void tma_tile_decode(const W2Tma& tm, const W2Geom& g, bool habc, int nfx, int t, int& z0, int& x0, int& kind) {
+    const int ns = tma_side_tiles(tm);
+    if (t < ns) {
+        const int per = tm.sr1 - tm.sr0, side = t / per;
+        z0 = (tm.sr0 + t - side * per) * TR;
+        x0 = side ? (nfx - 1) * FW : 0;
+        kind = side ? -2 : 2;
+        return;
+    }
+    t -= ns;
+    const int ntx = tm.tx1 - tm.tx0;
+    int tr = t / ntx;
+    const int tc = t - tr * ntx;
+    tr = tr < tm.nbot ? tm.ntr - tm.nbot + tr : tr - tm.nbot;
+    z0 = tr * TR;
+    x0 = (tm.tx0 + tc) * FW;
+    kind = 0;
+    if (habc) {
+        if (!g.multiple && z0 < tm.band) kind = 1;
+        else if (z0 + TR > g.nz - tm.band) kind = -1;
+    }
+    if (ST_DBG_SKIP & 16) kind = 0;
+}
+// fast tiles (FH x FW) that stay with the register path: everything outside the column band, minus the side tiles
+__host__ __device__ inline int fast_tiles_outside(int nfx, int nfz, const W2Tma& tm) {
+    if (!tm.enabled) return nfx * nfz;
+    const int rows = nfz - (tm.sr1 > tm.sr0 ? (tm.sr1 - tm.sr0) * TR / FH : 0);
+    return rows * (tm.tx0 + (nfx - tm.tx1));
+}
+// j-th of them -> linear fast-tile id (identity when there is no TMA region)
+__device__ __forceinline__ int fast_tile_outside(int j, int nfx, const W2Tma& tm) {
+    if (!tm.enabled) return j;
+    const int w = tm.tx0 + (nfx - tm.tx1);
+    int r = j / w;
+    const int c = j - r * w;
+    if (tm.sr1 > tm.sr0 && r >= tm.sr0 * TR / FH) r += (tm.sr1 - tm.sr0) * TR / FH;
+    return r * nfx + (c < tm.tx0 ? c : tm.tx1 + (c - tm.tx0));
+}
 template <int FL>
 __device__ __forceinline__ W2Coef load_coef_fl(const W2Args& a, long long idx) {
     W2Coef c;
@@ -181,20 +252,35 @@ __device__ __forceinline__ void forward_tail(const W2Args& a, int b, int z0, int
 // BASELINE size) has only z-direction far taps, so it vectorises like the interior: a warp owns one
 // band row x 128 columns, each lane 4 cells (128-bit loads of fields AND tap planes), x-neighbours
 // by shuffle; every lane walks all shots of its group with the transposed taps in registers.
-struct StripGeom { int xs, xe, ncol, toprows, nrows, bd; };
-__host__ __device__ inline StripGeom strip_geom(const W2Geom& g, int bd) {
+struct StripGeom { int xs, xe, ncol, toprows, nrows, bd, x0e, x1s, sz0, sz1; };
+// With a TMA column band [tma_x0, tma_x1) the strips shrink to the two pieces [xs, tma_x0) and [tma_x1, xe)
+// (each narrower than FW: one chunk per piece).
+__host__ __device__ inline StripGeom strip_geom(const W2Args& a, int bd) {
+    const W2Geom& g = a.g;
     StripGeom t;
     t.bd = bd;
     t.xs = (g.bw + 2 + 3) / 4 * 4;
     t.xe = (g.nx - g.bw - 2) / 4 * 4;
     if (t.xe < t.xs) t.xe = t.xs;
     t.ncol = (t.xe - t.xs + FW - 1) / FW;
+    t.x0e = t.x1s = 0;
+    if (a.tma_x1 > a.tma_x0) { t.ncol = 2; t.x0e = a.tma_x0; t.x1s = a.tma_x1; }
+    t.sz0 = a.tma_z0; t.sz1 = a.tma_z1;
     t.toprows = g.multiple ? 0 : bd;
     t.nrows = t.toprows + bd;
     return t;
 }
+// first column / end column of chunk `c` of a strip row
+__host__ __device__ inline int strip_chunk_x0(const StripGeom& t, int c) { return t.x1s > t.x0e ? (c == 0 ? t.xs : t.x1s) : t.xs + c * FW; }
+__host__ __device__ inline int strip_chunk_xe(const StripGeom& t, int c) {
+    if (t.x1s > t.x0e) return c == 0 ? (t.x0e < t.xe ? t.x0e : t.xe) : t.xe;
+    return t.xs + (c + 1) * FW < t.xe ? t.xs + (c + 1) * FW : t.xe;
+}
 __host__ __device__ inline int strip_blocks(const StripGeom& t) { return (t.nrows * t.ncol + NWARP - 1) / NWARP; }
+// band cells that do NOT belong to the per-cell band blocks: the straight top / bottom strips (strip blocks or
+// TMA frame tiles) and, with TMA side tiles, every band cell of rows [sz0, sz1)
 __device__ __forceinline__ bool in_strip(const StripGeom& t, const W2Geom& g, int z, int x) {
+    if (z >= t.sz0 && z < t.sz1) return true;
     return x >= t.xs && x < t.xe && ((!g.multiple && z < t.bd) || z >= g.nz - t.bd);
 }
 // aligned float4 of plane/field row z at column x (zero outside the domain rows / past the grid)
@@ -222,7 +308,7 @@ __device__ __forceinline__ float4 f4shr(const float4& c, float right) { return m
 
 __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, int b_lo, int b_hi, int tid) {
     const W2Geom g = a.g;
-    const StripGeom t = strip_geom(g, g.bw);
+    const StripGeom t = strip_geom(a, g.bw);
     const int warp = tid >> 5, lane = tid & 31;
     const int item = blk * NWARP + warp;
     if (item >= t.nrows * t.ncol) return;                       // whole warp
@@ -230,8 +316,9 @@ __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, in
     const bool top = row < t.toprows;
     const int z = top ? row : g.nz - t.bd + (row - t.toprows);
     const int n = top ? 1 : -1;
-    const int x0c = t.xs + chunk * FW, x = x0c + 4 * lane;
-    const bool active = x < t.xe;
+    const int x0c = strip_chunk_x0(t, chunk), x = x0c + 4 * lane;
+    const int xend = strip_chunk_xe(t, chunk);
+    const bool active = x < xend;
     const long long plane = (long long)g.nz * g.ld;
     const int on1 = top ? 2 : 1, on2 = top ? 6 : 5;
     // forward taps of this cell (increment form, st_wave2d_band.cuh)
@@ -259,7 +346,7 @@ __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, in
     // sources / receivers inside this warp's cells (ordering only needs the warp's own stores)
     if (z < a.row_lo || z > a.row_hi) return;
     __syncwarp();
-    const int xhi = min(x0c + FW, t.xe);
+    const int xhi = xend;
     for (int s = lane; s < a.ns; s += 32) {
         const int sb = a.src_b[s], sx = a.src_x[s];
         if (a.src_z[s] == z && sx >= x0c && sx < xhi && sb >= b_lo && sb < b_hi && (a.src_fmask & 1))
@@ -282,7 +369,7 @@ __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, in
 template <int FL>
 __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, int b_lo, int b_hi, int gplane, int tid) {
     const W2Geom g = a.g;
-    const StripGeom t = strip_geom(g, g.bw + 1);
+    const StripGeom t = strip_geom(a, g.bw + 1);
     const int warp = tid >> 5, lane = tid & 31;
     const int item = blk * NWARP + warp;
     if (item >= t.nrows * t.ncol) return;
@@ -290,8 +377,9 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
     const bool top = row < t.toprows;
     const int z = top ? row : g.nz - t.bd + (row - t.toprows);
     const int n = top ? 1 : -1;
-    const int x0c = t.xs + chunk * FW, x = x0c + 4 * lane;
-    const bool active = x < t.xe;
+    const int x0c = strip_chunk_x0(t, chunk), x = x0c + 4 * lane;
+    const int xend = strip_chunk_xe(t, chunk);
+    const bool active = x < xend;
     const long long plane = (long long)g.nz * g.ld;
     const bool want_grad = a.gacc != nullptr;
     const bool frame = top ? z < g.bw : z >= g.nz - g.bw;       // the deepest band row is not a frame row
@@ -375,7 +463,7 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
     }
     if (z < a.row_lo || z > a.row_hi) return;
     __syncwarp();
-    const int xhi = min(x0c + FW, t.xe);
+    const int xhi = xend;
     if (a.rec_adj) {
         for (int b = b_lo; b < b_hi; ++b) {
             const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
@@ -435,7 +523,7 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
     const BandCells bc = st_band_cells(g, g.bw);
     const int i0 = blk * NT, i = i0 + tid;
     const long long plane = (long long)g.nz * g.ld;
-    const StripGeom sg = strip_geom(g, g.bw);
+    const StripGeom sg = strip_geom(a, g.bw);
     auto mine = [&](int z, int x) {
         if (z < 0 || z >= g.nz || x < 0 || x >= g.nx || !w2_in_frame(z, x, g) || in_strip(sg, g, z, x)) return false;
         const int e = st_band_encode(bc, z, x);
@@ -545,7 +633,7 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
     const long long plane = (long long)g.nz * g.ld;
     const bool want_grad = a.gacc != nullptr;
     auto inb = [&](int z, int x) { return z >= 0 && z < g.nz && x >= 0 && x < g.nx; };
-    const StripGeom sg = strip_geom(g, bd);
+    const StripGeom sg = strip_geom(a, bd);
     auto mine = [&](int z, int x) {
         if (!inb(z, x) || in_strip(sg, g, z, x)) return false;
         const int e = st_band_encode(bc, z, x);
@@ -881,38 +969,177 @@ __device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int
     forward_tail<NF>(a, b, z0, z0 + TZ, x0, x0 + TX, tid, [&](int z, int xx) { return w2_in_frame(z, xx, g); });
 }
 
+// TMA block: one TR x TC tile, `tsh` shots pulled through a ring of bulk tensor loads.
+// Tile kinds (block-uniform): 0 = frame-free rows (same arithmetic as forward_fast_rows<ISO>); +1 / -1 / +2 / -2 =
+// the tile touches the straight top / bottom / left / right absorbing frame: every cell gets y + b (one - y)
+// with the one-way extrapolation along the inward normal +z / -z / +x / -x (w2_habc_blend on a straight
+// side; b == 0 on the frame-free cells of the tile).  The coefficient rows stay in registers across the shots.
+template <int FL>
+__device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& tm, int nfx, int bid, int tid, unsigned char* dsm) {
+    constexpr bool PML = (FL & ST_F_PML) != 0, HABC = (FL & ST_F_HABC) != 0;
+    constexpr int NS = ST_TMA_FWD_STAGES;
+    __shared__ __align__(8) uint64_t bars[NS];
+    const W2Geom& g = a.g;
+    const int ld = g.ld;
+    const int ntile = tma_tiles(tm);
+    const int grp = bid / ntile;
+    int z0, x0, kind;
+    tma_tile_decode(tm, g, HABC, nfx, bid - grp * ntile, z0, x0, kind);
+    const int b_lo = grp * tm.tsh, nsh = min(tm.tsh, a.B - b_lo);
+    const int warp = tid >> 5, lane = tid & 31;
+    const int zr = z0 + 2 * warp, x = x0 + 4 * lane;
+    const bool zdir = kind == 1 || kind == -1;
+    const int hoff = zdir ? 2 : 1;                          // rows above z0 in the `cur` box
+    const CUtensorMap* mcur = zdir ? &tm.u_h2 : &tm.u_h1;
+    const CUtensorMap* mprev = kind ? &tm.u_h1 : &tm.u_core;
+    if (tid == 0) {
+        st_tma_prefetch_desc(mcur);
+        st_tma_prefetch_desc(mprev);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) st_mbar_init(&bars[s], 1);
+        st_mbar_init_fence();
+    }
+    __syncthreads();
+    auto issue = [&](int s) {
+        const int stg = s % NS;
+        unsigned char* dst = dsm + stg * TMA_FWD_STAGE;
+        st_mbar_expect_tx(&bars[stg], (zdir ? H2R : H1R) * HC * 4 + (kind ? H1R * HC * 4 : TMA_CORE_BYTES));
+        st_tma_load_3d(dst, mcur, &bars[stg], x0 - 4, z0 - hoff, tm.pl_cur + b_lo + s);
+        if (kind) st_tma_load_3d(dst + TMA_H2_BYTES, mprev, &bars[stg], x0 - 4, z0 - 1, tm.pl_prev + b_lo + s);
+        else st_tma_load_3d(dst + TMA_H2_BYTES, mprev, &bars[stg], x0, z0, tm.pl_prev + b_lo + s);
+    };
+    if (tid == 0)
+        for (int s = 0; s < NS && s < nsh; ++s) issue(s);
+    float4 ci[2], al[2], bb[2], rr[2];
+    bool zok[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        zok[k] = zr + k < g.nz && x < ld;
+        const int o = (zr + k) * ld + x;
+        ci[k] = zok[k] ? __ldg(reinterpret_cast<const float4*>(a.coef[2] + o)) : f4zero();
+        al[k] = (PML && zok[k]) ? __ldg(reinterpret_cast<const float4*>(a.coef[3] + o)) : f4zero();
+        bb[k] = (HABC && kind && zok[k]) ? __ldg(reinterpret_cast<const float4*>(a.coef[1] + o)) : f4zero();
+        rr[k] = (HABC && kind && zok[k]) ? __ldg(reinterpret_cast<const float4*>(a.coef[0] + o)) : f4zero();
+    }
+    // `prev` box geometry: core box (frame-free tiles) or 1-deep halo box (frame tiles)
+    const int ppitch = kind ? HC : TC, poff = kind ? HC + 4 : 0;       // offset of (z0, x0)
+    for (int s = 0; s < nsh; ++s) {
+        const int stg = s % NS, b = b_lo + s;
+        st_mbar_wait(&bars[stg], (s / NS) & 1);
+        const float* h1 = reinterpret_cast<const float*>(dsm + stg * TMA_FWD_STAGE);
+        const float* h2 = reinterpret_cast<const float*>(dsm + stg * TMA_FWD_STAGE + TMA_H2_BYTES) + poff;
+        float* out = a.next + (long long)b * a.fs + (zr * ld + x);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float* rowc = h1 + (2 * warp + k + hoff) * HC;                                    // box row of z = zr + k
+            const float* rowp = h2 + (2 * warp + k) * ppitch;
+            const float4 C = *reinterpret_cast<const float4*>(rowc + 4 + 4 * lane);
+            const float4 U = *reinterpret_cast<const float4*>(rowc - HC + 4 + 4 * lane);
+            const float4 D = *reinterpret_cast<const float4*>(rowc + HC + 4 + 4 * lane);
+            const float4 P = *reinterpret_cast<const float4*>(rowp + 4 * lane);
+            float lc = __shfl_up_sync(0xffffffffu, C.w, 1), rc = __shfl_down_sync(0xffffffffu, C.x, 1);
+            if (lane == 0) lc = rowc[3];
+            if (lane == 31) rc = rowc[4 + TC];
+            float4 Y;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float c = f4get(C, e), n = f4get(U, e), s_ = f4get(D, e);
+                const float w = e == 0 ? lc : f4get(C, e - 1);
+                const float ea = e == 3 ? rc : f4get(C, e + 1);
+                const float A = f4get(ci[k], e) * (((n - c) + (s_ - c)) + ((ea - c) + (w - c)));
+                const float alpha = PML ? f4get(al[k], e) : 1.f;
+                f4set(Y, e, c + alpha * (c - f4get(P, e)) + A);
+            }
+            if (HABC && kind) {
+                float4 A1, A2, P1;                          // h1 one / two cells inward, h2 one cell inward
+                if (zdir) {
+                    A1 = kind > 0 ? D : U;
+                    A2 = *reinterpret_cast<const float4*>(rowc + 2 * kind * HC + 4 + 4 * lane);
+                    P1 = *reinterpret_cast<const float4*>(rowp + kind * ppitch + 4 * lane);
+                } else if (kind > 0) {
+                    float rc2 = __shfl_down_sync(0xffffffffu, C.y, 1), prc = __shfl_down_sync(0xffffffffu, P.x, 1);
+                    if (lane == 31) { rc2 = rowc[5 + TC]; prc = rowp[TC]; }
+                    A1 = f4shr(C, rc);
+                    A2 = make_float4(C.z, C.w, rc, rc2);
+                    P1 = f4shr(P, prc);
+                } else {
+                    float lc2 = __shfl_up_sync(0xffffffffu, C.z, 1), plc = __shfl_up_sync(0xffffffffu, P.w, 1);
+                    if (lane == 0) { lc2 = rowc[2]; plc = rowp[-1]; }
+                    A1 = f4shl(C, lc);
+                    A2 = make_float4(lc2, lc, C.x, C.y);
+                    P1 = f4shl(P, plc);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float a0 = f4get(C, e), a1 = f4get(A1, e), a2 = f4get(A2, e);
+                    const float p0 = f4get(P, e), p1 = f4get(P1, e);
+                    const float r = f4get(rr[k], e), lam = 2.f * r, mu = r * r;
+                    const float base = a0 + (a0 - p0);
+                    const float dlam = (a1 - a0) - (p1 - p0);
+                    const float dmu = (a1 - a0) - (a2 - a1);
+                    const float one = base + lam * dlam + mu * dmu;
+                    const float y = f4get(Y, e);
+                    f4set(Y, e, x + e < g.nx ? y + f4get(bb[k], e) * (one - y) : 0.f);      // pitch padding stays zero
+                }
+            }
+            if (zok[k]) *reinterpret_cast<float4*>(out + k * ld) = Y;
+        }
+        forward_tail<1>(a, b, z0, z0 + TR, x0, x0 + FW, tid, [](int, int) { return true; });
+        __syncthreads();                                   // every warp is done with this stage
+        if (tid == 0 && s + NS < nsh) issue(s + NS);
+    }
+}
+
 #ifndef ST_FWD_MINB
 #define ST_FWD_MINB 4
 #endif
+// resident blocks per SM the forward is compiled for (HABC: the 3 x 20 KB TMA ring allows 3)
 template <int FL>
-__global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
+__host__ __device__ constexpr int fwd_minb() { return FL == (ST_F_ISO | ST_F_HABC) ? 3 : ST_FWD_MINB; }
+
+template <int FL>
+__global__ void __launch_bounds__(NT, fwd_minb<FL>()) wave2d_forward_kernel(const W2Args a, int nfx, int nfast, BandTiles bt,
+                                                                         const __grid_constant__ W2Tma tm) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     constexpr bool HABC = (FL & ST_F_HABC) != 0;
-    __shared__ float s1[HABC ? NF : 1][HABC ? SH : 1][SW];
-    const int bid = blockIdx.x, tid = threadIdx.x;
-    // grid.x = [frame blocks] ++ [fast blocks x shots]; the (slower) frame blocks get the low ids so
-    // they are scheduled first.  Tapped frame blocks walk all shots themselves.
+    extern __shared__ __align__(128) unsigned char dsm[];     // frame tile [NF][SH][SW]  or  the TMA ring
+    int bid = blockIdx.x;
+    const int tid = threadIdx.x;
+    // grid.x = [frame blocks] ++ [fast blocks x shots] ++ [TMA blocks]: the register-path blocks are long
+    // dependent-load chains, so they start first and the TMA blocks fill the machine around them.  Tapped frame blocks walk all shots themselves; `nfast` counts
+    // the fast tiles outside the TMA rectangle.
+    if constexpr (tma_ok<FL>()) {
+        const int nold = gridDim.x - tma_blocks(tm, a.B);
+        if (bid >= nold) {
+            if (ST_DBG_SKIP & 8) return;
+            forward_tma_block<FL>(a, tm, nfx, bid - nold, tid, dsm);
+            return;
+        }
+    }
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     const int ngrp = (a.B + BSH - 1) / BSH;
-    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
+    const int nstrip = tapped ? strip_blocks(strip_geom(a, a.g.bw)) : 0;
     const int nframe = HABC ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
     if (bid >= nframe) {
+        if (ST_DBG_SKIP & 1) return;
         const int q = bid - nframe;
-        forward_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid);
+        forward_fast_block<FL>(a, fast_tile_outside(q % nfast, nfx, tm), nfx, q / nfast, tid);
     } else if (tapped) {
         const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;
         const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
-        if (k < nstrip) forward_strip_block(a, k, b_lo, b_hi, tid);
-        else forward_band_block(a, k - nstrip, b_lo, b_hi, tid);
+        if (k < nstrip) { if (ST_DBG_SKIP & 2) return; forward_strip_block(a, k, b_lo, b_hi, tid); }
+        else { if (ST_DBG_SKIP & 4) return; forward_band_block(a, k - nstrip, b_lo, b_hi, tid); }
     } else {
         if constexpr (HABC) {
             int tz, tx;
             const int b = bid / bt.count;
             band_tile_decode(bt, bid - b * bt.count, tz, tx);
-            forward_frame_block<FL>(a, tz, tx, b, tid, reinterpret_cast<float (*)[SH][SW]>(s1));
+            forward_frame_block<FL>(a, tz, tx, b, tid, reinterpret_cast<float (*)[SH][SW]>(dsm));
         }
     }
 }
+template <int FL>
+constexpr int fwd_static_smem() { return (FL & ST_F_HABC) ? ((FL & ST_F_BORN) ? 2 : 1) * SH * SW * 4 : 0; }
 
 // ------------------------------------------------------------------------------ adjoint
 // which of the 7 gradient accumulators (r,cxx,czz,cxz,ax,az,m) a flag set touches
@@ -1254,6 +1481,289 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
     }
 }
 
+// TMA block of the adjoint (tile kinds as in forward_tma_block).  Interior tiles: the arithmetic of
+// adjoint_fast_rows.  Frame tiles (straight top / bottom side, inward normal n = +z / -z), per cell p:
+//   Lam_i(p) = lap(c pre L1)(p) + [2 pre + b (2 - lam - mu)](p) L1(p) + [b (lam + 2 mu)](p-n) L1(p-n) - [b mu](p-2n) L1(p-2n)
+//              + [-pre + b (lam - 1)](p) L2(p) - [b lam](p-n) L2(p-n),      pre = 1 - b, lam = 2 r, mu = r^2
+//   g_ciso(p) += pre L1 lap(S_i)(p)
+//   g_r(p)    += b L1(p) [(-2 - 2r) S_i(p) + (2 + 4r) S_i(p+n) - 2r S_i(p+2n) + 2 S_{i-1}(p) - 2 S_{i-1}(p+n)]
+// (the transposed st_wave2d_band.cu taps of a straight side; b == 0 beyond the frame makes the rows at
+// depth bw, bw+1 and the frame-free rows of the tile come out right with the same expression).
+// Coefficient rows and gradient partial sums stay in registers across the block's shots.
+template <int FL, int KIND>
+__device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& tm, int z0, int x0, int grp, int tid,
+                                                 unsigned char* dsm, uint64_t* bars) {
+    constexpr bool PML = (FL & ST_F_PML) != 0;
+    constexpr bool ZDIR = KIND == 1 || KIND == -1, XDIR = KIND == 2 || KIND == -2;
+    constexpr int N = KIND > 0 ? 1 : -1;                    // inward normal along z (ZDIR) or x (XDIR)
+    constexpr int NS = ST_TMA_ADJ_STAGES;
+    constexpr int HOFF = ZDIR ? 2 : 1;                      // rows above z0 in the Lam1 / S_i boxes
+    const W2Geom& g = a.g;
+    const int ld = g.ld;
+    const int b_lo = grp * tm.tsh, nsh = min(tm.tsh, a.B - b_lo);
+    const int warp = tid >> 5, lane = tid & 31;
+    const int zr = z0 + 2 * warp, x = x0 + 4 * lane;
+    const bool want_grad = a.gacc != nullptr;
+    auto issue = [&](int s) {
+        const int stg = s % NS;
+        unsigned char* dst = dsm + stg * TMA_ADJ_STAGE;
+        if (KIND == 0) {
+            st_mbar_expect_tx(&bars[stg], 2 * H1R * HC * 4 + TMA_CORE_BYTES);
+            st_tma_load_3d(dst, &tm.l_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_l1 + b_lo + s);
+            st_tma_load_3d(dst + TMA_H2_BYTES, &tm.u_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_s1 + b_lo + s);
+            st_tma_load_3d(dst + 2 * TMA_H2_BYTES, &tm.l_core, &bars[stg], x0, z0, tm.pl_l2 + b_lo + s);
+        } else {
+            st_mbar_expect_tx(&bars[stg], 2 * (ZDIR ? H2R : H1R) * HC * 4 + 2 * H1R * HC * 4);
+            st_tma_load_3d(dst, ZDIR ? &tm.l_h2 : &tm.l_h1, &bars[stg], x0 - 4, z0 - HOFF, tm.pl_l1 + b_lo + s);
+            st_tma_load_3d(dst + TMA_H2_BYTES, ZDIR ? &tm.u_h2 : &tm.u_h1, &bars[stg], x0 - 4, z0 - HOFF, tm.pl_s1 + b_lo + s);
+            st_tma_load_3d(dst + 2 * TMA_H2_BYTES, &tm.l_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_l2 + b_lo + s);
+            st_tma_load_3d(dst + 2 * TMA_H2_BYTES + TMA_H1_BYTES, &tm.u_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_s2 + b_lo + s);
+        }
+    };
+    if (tid == 0)
+        for (int s = 0; s < NS && s < nsh; ++s) issue(s);
+    auto inz = [&](int z) { return z >= 0 && z < g.nz; };
+    auto ldc4 = [&](int q, int z) { return (inz(z) && x < ld) ? __ldg(reinterpret_cast<const float4*>(a.coef[q] + (z * ld + x))) : f4zero(); };
+    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    // cp = ciso (1 - b) on rows zr-1 .. zr+2 and on the halo column of the edge lanes (rows zr, zr+1)
+    float4 cp[4], al[2], gc[2], gr[2];
+    float ch[2] = {0.f, 0.f};
+    const int xh = lane == 0 ? x0 - 1 : x0 + FW;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        cp[k] = ldc4(2, zr - 1 + k);
+        if (KIND) cp[k] = f4mul(cp[k], f4sub(one4, ldc4(1, zr - 1 + k)));
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        al[k] = PML ? ldc4(3, zr + k) : f4zero();
+        gc[k] = gr[k] = f4zero();
+        if ((lane == 0 || lane == 31) && xh >= 0 && xh < g.nx && inz(zr + k)) {
+            ch[k] = __ldg(a.coef[2] + ((zr + k) * ld + xh));
+            if (KIND) ch[k] *= 1.f - __ldg(a.coef[1] + ((zr + k) * ld + xh));
+        }
+    }
+    // frame tiles: b and r.  ZDIR: the four rows {own rows, the two rows outward of them}
+    //   (N = +1: rows zr-2 .. zr+1, own rows at index 2, 3;  N = -1: rows zr .. zr+3, own rows at index 0, 1);
+    //   XDIR: the two own rows (index 0, 1).
+    float4 bb[4], rr[4];
+    constexpr int OWN0 = (ZDIR && N > 0) ? 2 : 0;
+    if (KIND) {
+#pragma unroll
+        for (int j = 0; j < (ZDIR ? 4 : 2); ++j) {
+            const int z = zr - OWN0 + j;
+            bb[j] = ldc4(1, z);
+            rr[j] = ldc4(0, z);
+        }
+    }
+    for (int s = 0; s < nsh; ++s) {
+        const int stg = s % NS, b = b_lo + s;
+        st_mbar_wait(&bars[stg], (s / NS) & 1);
+        const float* l1 = reinterpret_cast<const float*>(dsm + stg * TMA_ADJ_STAGE);
+        const float* S = reinterpret_cast<const float*>(dsm + stg * TMA_ADJ_STAGE + TMA_H2_BYTES);
+        // Lam2 / S_{i-1}: pointer to (z0, x0), row pitch
+        const float* l2 = reinterpret_cast<const float*>(dsm + stg * TMA_ADJ_STAGE + 2 * TMA_H2_BYTES) + (KIND ? HC + 4 : 0);
+        const float* S2 = reinterpret_cast<const float*>(dsm + stg * TMA_ADJ_STAGE + 2 * TMA_H2_BYTES + TMA_H1_BYTES) + HC + 4;
+        constexpr int P2 = KIND ? HC : TC;
+        float* out = a.lam0 + (long long)b * a.fs + (zr * ld + x);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int ro = (2 * warp + k + HOFF) * HC + 4 + 4 * lane;                  // box offset of row z = zr + k, this lane
+            const int hrow = (2 * warp + k + HOFF) * HC;
+            const float* l2r = l2 + (2 * warp + k) * P2;
+            const int z = zr + k;
+            constexpr int IO = OWN0;                                                   // index of own row k is IO + k
+            // ---- phase A: the cotangent
+            {
+                const float4 lC = *reinterpret_cast<const float4*>(l1 + ro);
+                const float4 lU = *reinterpret_cast<const float4*>(l1 + ro - HC), lD = *reinterpret_cast<const float4*>(l1 + ro + HC);
+                const float4 p2 = *reinterpret_cast<const float4*>(l2r + 4 * lane);
+                const float4 wU = f4mul(cp[k], lU), wC = f4mul(cp[k + 1], lC), wD = f4mul(cp[k + 2], lD);
+                float wl = __shfl_up_sync(0xffffffffu, wC.w, 1), wr = __shfl_down_sync(0xffffffffu, wC.x, 1);
+                if (lane == 0) wl = ch[k] * l1[hrow + 3];
+                if (lane == 31) wr = ch[k] * l1[hrow + 4 + TC];
+                float4 o4;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float c = f4get(wC, e);
+                    const float w = e == 0 ? wl : f4get(wC, e - 1), ea = e == 3 ? wr : f4get(wC, e + 1);
+                    const float lapw = ((f4get(wU, e) - c) + (f4get(wD, e) - c)) + ((ea - c) + (w - c));
+                    if (KIND == 0) {
+                        const float alpha = PML ? f4get(al[k], e) : 1.f;
+                        f4set(o4, e, (1.f + alpha) * f4get(lC, e) + lapw - alpha * f4get(p2, e));
+                    } else {
+                        f4set(o4, e, lapw);
+                    }
+                }
+                if (KIND) {
+                    const float4 bz = bb[IO + k], rz = rr[IO + k];
+                    // one-way terms of the cells outward of p:  X1 = [b (lam + 2 mu) L1](p-n),  X2 = [b mu L1](p-2n),
+                    // X3 = [b lam L2](p-n); X2 only where the j+2 tap stays inside the strip (depth(p) <= bw)
+                    float4 X1, X2, X3;
+                    if (ZDIR) {
+                        const float4 b1 = bb[IO + k - N], r1 = rr[IO + k - N];
+                        const float4 b2 = bb[(IO + k - 2 * N) & 3], r2 = rr[(IO + k - 2 * N) & 3];
+                        const int depth = N > 0 ? z : g.nz - 1 - z;
+                        const float4 lO1 = N > 0 ? lU : lD;
+                        const float4 lO2 = *reinterpret_cast<const float4*>(l1 + ro - 2 * N * HC);
+                        const float4 p2O = *reinterpret_cast<const float4*>(l2r - N * P2 + 4 * lane);
+                        const float far = depth <= g.bw ? 1.f : 0.f;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float b1e = f4get(b1, e), r1e = f4get(r1, e), r2e = f4get(r2, e);
+                            f4set(X1, e, b1e * (2.f * r1e + 2.f * r1e * r1e) * f4get(lO1, e));
+                            f4set(X2, e, far * f4get(b2, e) * (r2e * r2e) * f4get(lO2, e));
+                            f4set(X3, e, b1e * (2.f * r1e) * f4get(p2O, e));
+                        }
+                    } else {
+                        float4 T1, T2, T3;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float be = f4get(bz, e), re = f4get(rz, e);
+                            f4set(T1, e, be * (2.f * re + 2.f * re * re) * f4get(lC, e));
+                            f4set(T2, e, be * (re * re) * f4get(lC, e));
+                            f4set(T3, e, be * (2.f * re) * f4get(p2, e));
+                        }
+                        // the products of the cells beyond the tile's outward edge are zero (outside the grid)
+                        if (N > 0) {
+                            float t1 = __shfl_up_sync(0xffffffffu, T1.w, 1), t3 = __shfl_up_sync(0xffffffffu, T3.w, 1);
+                            float t2a = __shfl_up_sync(0xffffffffu, T2.z, 1), t2b = __shfl_up_sync(0xffffffffu, T2.w, 1);
+                            if (lane == 0) t1 = t3 = t2a = t2b = 0.f;
+                            X1 = f4shl(T1, t1);
+                            X3 = f4shl(T3, t3);
+                            X2 = make_float4(t2a, t2b, T2.x, T2.y);
+                        } else {
+                            float t1 = __shfl_down_sync(0xffffffffu, T1.x, 1), t3 = __shfl_down_sync(0xffffffffu, T3.x, 1);
+                            float t2a = __shfl_down_sync(0xffffffffu, T2.x, 1), t2b = __shfl_down_sync(0xffffffffu, T2.y, 1);
+                            if (lane == 31) t1 = t3 = t2a = t2b = 0.f;
+                            X1 = f4shr(T1, t1);
+                            X3 = f4shr(T3, t3);
+                            X2 = make_float4(T2.z, T2.w, t2a, t2b);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int depth = N > 0 ? x + e : g.nx - 1 - (x + e);
+                            if (depth > g.bw) f4set(X2, e, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float bze = f4get(bz, e), rze = f4get(rz, e), pre = 1.f - bze;
+                        float v = f4get(o4, e);
+                        v += (2.f * pre + bze * (2.f - 2.f * rze - rze * rze)) * f4get(lC, e);
+                        v += f4get(X1, e);
+                        v -= f4get(X2, e);
+                        v += (bze * (2.f * rze - 1.f) - pre) * f4get(p2, e);
+                        v -= f4get(X3, e);
+                        f4set(o4, e, x + e < g.nx ? v : 0.f);                            // pitch padding stays zero
+                    }
+                }
+                if (z < g.nz && x < ld) *reinterpret_cast<float4*>(out + k * ld) = o4;
+            }
+            // ---- phase B: imaging condition
+            if (want_grad) {
+                const float4 lC = *reinterpret_cast<const float4*>(l1 + ro);
+                const float4 sC = *reinterpret_cast<const float4*>(S + ro);
+                const float4 sU = *reinterpret_cast<const float4*>(S + ro - HC), sD = *reinterpret_cast<const float4*>(S + ro + HC);
+                float sl = __shfl_up_sync(0xffffffffu, sC.w, 1), sr = __shfl_down_sync(0xffffffffu, sC.x, 1);
+                if (lane == 0) sl = S[hrow + 3];
+                if (lane == 31) sr = S[hrow + 4 + TC];
+                float4 gq;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float sc = f4get(sC, e);
+                    const float sw_ = e == 0 ? sl : f4get(sC, e - 1), se_ = e == 3 ? sr : f4get(sC, e + 1);
+                    const float laps = ((f4get(sU, e) - sc) + (f4get(sD, e) - sc)) + ((se_ - sc) + (sw_ - sc));
+                    float pl = f4get(lC, e);
+                    if (KIND) pl *= 1.f - f4get(bb[IO + k], e);
+                    f4set(gq, e, pl * laps);
+                }
+                gc[k] = f4add(gc[k], gq);
+                if (KIND) {
+                    const float4 bz = bb[IO + k], rz = rr[IO + k];
+                    const float* s2r = S2 + (2 * warp + k) * HC;
+                    const float4 q0 = *reinterpret_cast<const float4*>(s2r + 4 * lane);
+                    float4 sI1, sI2, q1, far;                 // S_i one / two cells inward, S_{i-1} one cell inward, j+2 <= bw
+                    if (ZDIR) {
+                        const int depth = N > 0 ? z : g.nz - 1 - z;
+                        const float f = depth + 2 <= g.bw ? 1.f : 0.f;
+                        far = make_float4(f, f, f, f);
+                        sI1 = N > 0 ? sD : sU;
+                        sI2 = *reinterpret_cast<const float4*>(S + ro + 2 * N * HC);
+                        q1 = *reinterpret_cast<const float4*>(s2r + N * HC + 4 * lane);
+                    } else if (N > 0) {
+                        float sr2 = __shfl_down_sync(0xffffffffu, sC.y, 1), qr = __shfl_down_sync(0xffffffffu, q0.x, 1);
+                        if (lane == 31) { sr2 = S[hrow + 5 + TC]; qr = s2r[TC]; }
+                        sI1 = f4shr(sC, sr);
+                        sI2 = make_float4(sC.z, sC.w, sr, sr2);
+                        q1 = f4shr(q0, qr);
+                    } else {
+                        float sl2 = __shfl_up_sync(0xffffffffu, sC.z, 1), ql = __shfl_up_sync(0xffffffffu, q0.w, 1);
+                        if (lane == 0) { sl2 = S[hrow + 2]; ql = s2r[-1]; }
+                        sI1 = f4shl(sC, sl);
+                        sI2 = make_float4(sl2, sl, sC.x, sC.y);
+                        q1 = f4shl(q0, ql);
+                    }
+                    if (XDIR) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int depth = N > 0 ? x + e : g.nx - 1 - (x + e);
+                            f4set(far, e, depth + 2 <= g.bw ? 1.f : 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float rze = f4get(rz, e);
+                        const float tt = (-2.f - 2.f * rze) * f4get(sC, e) + (2.f + 4.f * rze) * f4get(sI1, e)
+                                       - f4get(far, e) * 2.f * rze * f4get(sI2, e) + 2.f * f4get(q0, e) - 2.f * f4get(q1, e);
+                        f4set(gr[k], e, f4get(gr[k], e) + f4get(bz, e) * f4get(lC, e) * tt);
+                    }
+                }
+            }
+        }
+        adjoint_tail<1>(a, b, z0, z0 + TR, x0, x0 + FW, tid, [](int, int) { return true; });
+        __syncthreads();                                   // every warp is done with this stage
+        if (tid == 0 && s + NS < nsh) issue(s + NS);
+    }
+    if (want_grad && x < ld) {
+        float* gb = a.gacc + (long long)grp * 7 * ((long long)g.nz * ld) + (zr * ld + x);
+        const long long plane = (long long)g.nz * ld;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (zr + k >= g.nz) continue;
+            float4 v = *reinterpret_cast<float4*>(gb + plane + k * ld);
+            *reinterpret_cast<float4*>(gb + plane + k * ld) = f4add(v, gc[k]);            // slot 1: d/d ciso
+            if (KIND) {
+                float4 u = *reinterpret_cast<float4*>(gb + k * ld);
+                *reinterpret_cast<float4*>(gb + k * ld) = f4add(u, gr[k]);                // slot 0: d/d r
+            }
+        }
+    }
+}
+
+template <int FL>
+__device__ __forceinline__ void adjoint_tma_block(const W2Args& a, const W2Tma& tm, int nfx, int bid, int tid, unsigned char* dsm) {
+    constexpr int NS = ST_TMA_ADJ_STAGES;
+    __shared__ __align__(8) uint64_t bars[NS];
+    const int ntile = tma_tiles(tm);
+    const int grp = bid / ntile;
+    int z0, x0, kind;
+    tma_tile_decode(tm, a.g, (FL & ST_F_HABC) != 0, nfx, bid - grp * ntile, z0, x0, kind);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) st_mbar_init(&bars[s], 1);
+        st_mbar_init_fence();
+    }
+    __syncthreads();
+    if constexpr ((FL & ST_F_HABC) != 0) {
+        if (kind == 1) { adjoint_tma_tile<FL, 1>(a, tm, z0, x0, grp, tid, dsm, bars); return; }
+        if (kind == -1) { adjoint_tma_tile<FL, -1>(a, tm, z0, x0, grp, tid, dsm, bars); return; }
+        if (kind == 2) { adjoint_tma_tile<FL, 2>(a, tm, z0, x0, grp, tid, dsm, bars); return; }
+        if (kind == -2) { adjoint_tma_tile<FL, -2>(a, tm, z0, x0, grp, tid, dsm, bars); return; }
+    }
+    adjoint_tma_tile<FL, 0>(a, tm, z0, x0, grp, tid, dsm, bars);
+}
+
 // general cell-by-cell adjoint of one TX x TZ tile; `band` < 0: every cell, else only the
 // cells closer than `band` to an absorbing edge
 // Shots b_lo..b_hi-1 are processed in turn; gradient contributions go to plane `gplane`.
@@ -1323,28 +1833,53 @@ __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, i
 }
 
 template <int FL>
-__global__ void __launch_bounds__(NT, ST_ADJ_MINB) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
+constexpr int adj_static_smem() {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     constexpr bool NEED_GEN = !adj_fast<FL>() || (FL & ST_F_HABC);
     constexpr int GEN_FLOATS = NEED_GEN ? 2 * NF * SH * SW : 1;
     constexpr int FAST_FLOATS = adj_iso_only<FL>() ? NWARP * FRZ * FW : 1;
-    __shared__ __align__(16) float smem[GEN_FLOATS > FAST_FLOATS ? GEN_FLOATS : FAST_FLOATS];
-    const int bid = blockIdx.x, tid = threadIdx.x;
-    // grid.x = [band blocks: one per (tile, shot)] ++ [fast blocks: one per (fast tile, shot chunk)]
-    // for the fast-path equations, else one general block per (tile, shot chunk).
+    return 4 * (GEN_FLOATS > FAST_FLOATS ? GEN_FLOATS : FAST_FLOATS);
+}
+
+// resident blocks per SM the adjoint is compiled for: the TMA ring of the HABC frame tiles takes 2 x 41.5 KB
+template <int FL>
+__host__ __device__ constexpr int adj_minb() { return FL == (ST_F_ISO | ST_F_HABC) ? 2 : ST_ADJ_MINB; }
+
+template <int FL>
+__global__ void __launch_bounds__(NT, adj_minb<FL>()) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt,
+                                                                         const __grid_constant__ W2Tma tm) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    constexpr bool NEED_GEN = !adj_fast<FL>() || (FL & ST_F_HABC);
+    extern __shared__ __align__(128) unsigned char dsm[];     // general tiles / fast-path gradient sums / the TMA ring
+    float* smem = reinterpret_cast<float*>(dsm);
+    int bid = blockIdx.x;
+    const int tid = threadIdx.x;
+    // grid.x = [band blocks: one per (tile, shot)] ++ [fast blocks: one per
+    // (fast tile outside the TMA band, shot chunk)] ++ [TMA blocks] for the fast-path equations, else one
+    // general block per (tile, shot chunk).
+    if constexpr (tma_ok<FL>()) {
+        const int nold = gridDim.x - tma_blocks(tm, a.B);
+        if (bid >= nold) {
+            if (ST_DBG_SKIP & 8) return;
+            adjoint_tma_block<FL>(a, tm, nfx, bid - nold, tid, dsm);
+            return;
+        }
+    }
     if constexpr (adj_fast<FL>()) {
         const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
         const int ngrp = (a.B + BSH - 1) / BSH;
-        const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
+        const int nstrip = tapped ? strip_blocks(strip_geom(a, a.g.bw + 1)) : 0;
         const int nband = (FL & ST_F_HABC) ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
         if (bid >= nband) {
+            if (ST_DBG_SKIP & 1) return;
             const int q = bid - nband;
-            adjoint_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid, reinterpret_cast<float (*)[FRZ][FW]>(smem));
+            adjoint_fast_block<FL>(a, fast_tile_outside(q % nfast, nfx, tm), nfx, q / nfast, tid,
+                                   reinterpret_cast<float (*)[FRZ][FW]>(smem));
         } else if (tapped) {
             const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;     // gradient plane = group id (< B planes exist)
             const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
-            if (k < nstrip) adjoint_strip_block<FL>(a, k, b_lo, b_hi, grp, tid);
-            else adjoint_band_block<FL>(a, k - nstrip, b_lo, b_hi, grp, tid);
+            if (k < nstrip) { if (ST_DBG_SKIP & 2) return; adjoint_strip_block<FL>(a, k, b_lo, b_hi, grp, tid); }
+            else { if (ST_DBG_SKIP & 4) return; adjoint_band_block<FL>(a, k - nstrip, b_lo, b_hi, grp, tid); }
         } else {
             if constexpr (NEED_GEN) {
                 int tz, tx;
@@ -1368,59 +1903,140 @@ __global__ void __launch_bounds__(NT, ST_ADJ_MINB) wave2d_adjoint_kernel(const W
 }  // namespace
 
 template <int FL>
-int st_w2_launch_fwd(const W2Args& a, cudaStream_t st);
+int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st);
 template <int FL>
-int st_w2_launch_adj(const W2Args& a, cudaStream_t st);
+int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st);
 
 #ifndef ST_W2_DISPATCH_ONLY
 template <int FL>
-int st_w2_launch_fwd(const W2Args& a, cudaStream_t st) {
+int st_w2_launch_fwd(const W2Args& a_in, const W2Tma& tm, cudaStream_t st) {
+    W2Args a = a_in;
+    a.tma_x0 = a.tma_x1 = 0;
+    a.tma_z0 = a.tma_z1 = 0;
+    if (tma_ok<FL>() && tm.enabled) {
+        a.tma_x0 = tm.tx0 * FW; a.tma_x1 = tm.tx1 * FW;
+        if (tm.sr1 > tm.sr0) { a.tma_z0 = tm.sr0 * TR; a.tma_z1 = tm.sr1 * TR; }
+    }
     const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
-    const int nfast = nfx * nfz;
+    const bool use_tma = tma_ok<FL>() && tm.enabled;
+    W2Tma off;
+    memset(&off, 0, sizeof(off));
+    const int nfast = fast_tiles_outside(nfx, nfz, use_tma ? tm : off);
     BandTiles bt = band_tiles(a.g, a.g.bw);
     if (!(FL & ST_F_HABC)) bt.count = 0;
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
-    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
-    dim3 grid((unsigned)((long long)nfast * a.B + (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B)));
-    wave2d_forward_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
+    const int nstrip = tapped ? strip_blocks(strip_geom(a, a.g.bw)) : 0;
+    const long long ntma = use_tma ? tma_blocks(tm, a.B) : 0;
+    dim3 grid((unsigned)(ntma + (long long)nfast * a.B + (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B)));
+    int smem = fwd_static_smem<FL>();
+    if (tma_ok<FL>()) {
+        static const cudaError_t attr = cudaFuncSetAttribute(wave2d_forward_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_FWD_SMEM);
+        if (attr != cudaSuccess) return ST_ERR_CUDA;
+        if (use_tma && smem < TMA_FWD_SMEM) smem = TMA_FWD_SMEM;
+    }
+    wave2d_forward_kernel<FL><<<grid, NT, smem, st>>>(a, nfx, nfast, bt, use_tma ? tm : off);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
 template <int FL>
-int st_w2_launch_adj(const W2Args& a, cudaStream_t st) {
+int st_w2_launch_adj(const W2Args& a_in, const W2Tma& tm, cudaStream_t st) {
+    W2Args a = a_in;
+    a.tma_x0 = a.tma_x1 = 0;
+    a.tma_z0 = a.tma_z1 = 0;
+    if (tma_ok<FL>() && tm.enabled) {
+        a.tma_x0 = tm.tx0 * FW; a.tma_x1 = tm.tx1 * FW;
+        if (tm.sr1 > tm.sr0) { a.tma_z0 = tm.sr0 * TR; a.tma_z1 = tm.sr1 * TR; }
+    }
     const int nchunk = (a.B + a.bchunk - 1) / a.bchunk;
     const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
-    const int nfast = nfx * nfz;
+    const bool use_tma = tma_ok<FL>() && tm.enabled;
+    W2Tma off;
+    memset(&off, 0, sizeof(off));
+    const int nfast = fast_tiles_outside(nfx, nfz, use_tma ? tm : off);
     BandTiles bt = band_tiles(a.g, a.g.bw + 1);
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw + 1).total + NT - 1) / NT;
     long long nblocks;
-    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
+    const int nstrip = tapped ? strip_blocks(strip_geom(a, a.g.bw + 1)) : 0;
     if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B) : 0);
     else nblocks = (long long)bt.nxt * bt.nzt * nchunk;
+    if (use_tma) nblocks += tma_blocks(tm, a.B);
     dim3 grid((unsigned)nblocks);
-    wave2d_adjoint_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
+    int smem = adj_static_smem<FL>();
+    if (tma_ok<FL>()) {
+        static const cudaError_t attr = cudaFuncSetAttribute(wave2d_adjoint_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_ADJ_SMEM);
+        if (attr != cudaSuccess) return ST_ERR_CUDA;
+        if (use_tma && smem < TMA_ADJ_SMEM) smem = TMA_ADJ_SMEM;
+    }
+    wave2d_adjoint_kernel<FL><<<grid, NT, smem, st>>>(a, nfx, nfast, bt, use_tma ? tm : off);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
 #ifdef ST_W2_INSTANCE
-template int st_w2_launch_fwd<ST_W2_INSTANCE>(const W2Args&, cudaStream_t);
-template int st_w2_launch_adj<ST_W2_INSTANCE>(const W2Args&, cudaStream_t);
+template int st_w2_launch_fwd<ST_W2_INSTANCE>(const W2Args&, const W2Tma&, cudaStream_t);
+template int st_w2_launch_adj<ST_W2_INSTANCE>(const W2Args&, const W2Tma&, cudaStream_t);
 #endif
 #endif  // !ST_W2_DISPATCH_ONLY
 
 #if defined(ST_W2_DISPATCH_ONLY) || !defined(ST_W2_INSTANCE)
-#define ST_W2_DISPATCH(FN)                                                                      \
-    switch (flags) {                                                                            \
-        case ST_F_ISO | ST_F_PML: return FN<ST_F_ISO | ST_F_PML>(a, st);                        \
-        case ST_F_ISO | ST_F_HABC: return FN<ST_F_ISO | ST_F_HABC>(a, st);                      \
-        case ST_F_HABC: return FN<ST_F_HABC>(a, st);                                            \
-        case ST_F_HABC | ST_F_XZ: return FN<ST_F_HABC | ST_F_XZ>(a, st);                        \
-        case ST_F_ISO | ST_F_HABC | ST_F_G1: return FN<ST_F_ISO | ST_F_HABC | ST_F_G1>(a, st);  \
-        case ST_F_HABC | ST_F_BORN: return FN<ST_F_HABC | ST_F_BORN>(a, st);                    \
-        case ST_F_HABC | ST_F_XZ | ST_F_BORN: return FN<ST_F_HABC | ST_F_XZ | ST_F_BORN>(a, st);\
+#define ST_W2_DISPATCH(FN)                                                                          \
+    switch (flags) {                                                                                \
+        case ST_F_ISO | ST_F_PML: return FN<ST_F_ISO | ST_F_PML>(a, tm, st);                        \
+        case ST_F_ISO | ST_F_HABC: return FN<ST_F_ISO | ST_F_HABC>(a, tm, st);                      \
+        case ST_F_HABC: return FN<ST_F_HABC>(a, tm, st);                                            \
+        case ST_F_HABC | ST_F_XZ: return FN<ST_F_HABC | ST_F_XZ>(a, tm, st);                        \
+        case ST_F_ISO | ST_F_HABC | ST_F_G1: return FN<ST_F_ISO | ST_F_HABC | ST_F_G1>(a, tm, st);  \
+        case ST_F_HABC | ST_F_BORN: return FN<ST_F_HABC | ST_F_BORN>(a, tm, st);                    \
+        case ST_F_HABC | ST_F_XZ | ST_F_BORN: return FN<ST_F_HABC | ST_F_XZ | ST_F_BORN>(a, tm, st);\
         default: st_set_error("wave2d: unsupported flag set %d", flags); return ST_ERR_UNSUPPORTED; \
     }
 
-int st_wave2d_launch_forward(int flags, const W2Args& a, cudaStream_t st) { ST_W2_DISPATCH(st_w2_launch_fwd) }
-int st_wave2d_launch_adjoint(int flags, const W2Args& a, cudaStream_t st) { ST_W2_DISPATCH(st_w2_launch_adj) }
+int st_wave2d_launch_forward(int flags, const W2Args& a, const W2Tma& tm, cudaStream_t st) { ST_W2_DISPATCH(st_w2_launch_fwd) }
+int st_wave2d_launch_adjoint(int flags, const W2Args& a, const W2Tma& tm, cudaStream_t st) { ST_W2_DISPATCH(st_w2_launch_adj) }
+
+// Where the TMA path applies: a band of whole fast-tile columns [tx0, tx1) x all rows whose cells are either
+// frame-free or belong to the STRAIGHT part of the top / bottom frame (every cell of the band and its
+// x-neighbours deeper than bw+1 from the left / right edge), so that the only frame formula needed is the
+// one-way blend along z.  The side columns and corners stay with the register / tap-gather blocks.
+int st_wave2d_tma_setup(int flags, const W2Args& a, const float* u, long long u_planes, const float* lam, long long lam_planes,
+                        bool adjoint, int mode, W2Tma& tm) {
+    memset(&tm, 0, sizeof(tm));
+    if (mode == 0) return ST_OK;
+    if (flags != (ST_F_ISO | ST_F_PML) && flags != (ST_F_ISO | ST_F_HABC)) return ST_OK;
+    const W2Geom& g = a.g;
+    int tx0 = 0, tx1 = g.nx / FW;
+    if (flags & ST_F_HABC) {
+        tx0 = (g.bw + 2 + FW - 1) / FW;
+        tx1 = (g.nx - g.bw - 2) / FW;
+        // frame tiles use the precomputed-tap blocks' conventions: needs their workspace decision (taps) to agree,
+        // and top / bottom frame rows must not share a tile
+        if (a.taps == nullptr || g.nz < 2 * (g.bw + 2) + 2 * TR) return ST_OK;
+    }
+    if (tx1 <= tx0) return ST_OK;
+    const long long work = (long long)g.nz * (tx1 - tx0) * FW * a.B;
+    if (mode < 0 && (a.B < 2 || work < (1LL << 21))) return ST_OK;       // too little work to fill a ring
+    tm.tx0 = tx0; tm.tx1 = tx1;
+    tm.ntr = (g.nz + TR - 1) / TR;
+    tm.band = adjoint ? g.bw + 2 : g.bw;
+    if (flags & ST_F_HABC) {
+        tm.nbot = tm.ntr - (g.nz - tm.band) / TR;            // tile rows with z0 + TR > nz - band
+        // side columns: exactly one tile column per side, rows a whole number of fast tiles clear of the corners
+        const int nfx = (g.nx + FW - 1) / FW;
+        if (tx0 == 1 && tx1 == nfx - 1 && getenv("SEISTORCH_B200_TMA_SIDES") == nullptr) {
+            const int fz0 = (g.bw + 2 + FH - 1) / FH, fz1 = (g.nz - g.bw - 2) / FH;
+            if (fz1 > fz0) { tm.sr0 = fz0 * (FH / TR); tm.sr1 = fz1 * (FH / TR); }
+        }
+    }
+    tm.tsh = adjoint ? a.bchunk : (a.B < 4 ? a.B : 4);
+    if (const char* e = getenv("SEISTORCH_B200_TSH")) { if (!adjoint && atoi(e) > 0) tm.tsh = atoi(e) < a.B ? atoi(e) : a.B; }
+    const long long fs = a.fs;
+    int rc = st_tma_encode_planes(&tm.u_h1, u, g.nx, g.nz, u_planes, g.ld, fs, HC, H1R);
+    if (!rc) rc = st_tma_encode_planes(&tm.u_h2, u, g.nx, g.nz, u_planes, g.ld, fs, HC, H2R);
+    if (!rc && !adjoint) rc = st_tma_encode_planes(&tm.u_core, u, g.nx, g.nz, u_planes, g.ld, fs, TC, TR);
+    if (!rc && adjoint) rc = st_tma_encode_planes(&tm.l_h1, lam, g.nx, g.nz, lam_planes, g.ld, fs, HC, H1R);
+    if (!rc && adjoint) rc = st_tma_encode_planes(&tm.l_h2, lam, g.nx, g.nz, lam_planes, g.ld, fs, HC, H2R);
+    if (!rc && adjoint) rc = st_tma_encode_planes(&tm.l_core, lam, g.nx, g.nz, lam_planes, g.ld, fs, TC, TR);
+    if (rc) { st_set_error("wave2d: cuTensorMapEncodeTiled failed (%d)", rc); return ST_ERR_CUDA; }
+    tm.enabled = 1;
+    return ST_OK;
+}
 #endif

@@ -156,3 +156,33 @@ def test_mid_size_grid_against_oracle(eq):
     assert rel(cat_records([s.detach().cpu().numpy() for s in syn]), cat_records([r.detach().numpy() for r in orecs])) < 1e-5
     for k in inv:
         assert rel(getattr(model.cell.geom, k).grad.cpu().numpy(), params[k].grad.numpy()) < 1e-4, k
+
+
+@pytest.mark.parametrize("eq,multiple,nx", [("acoustic", False, 300), ("acoustic_habc", False, 300), ("acoustic_habc", True, 300),
+                                            ("acoustic_habc", False, 216), ("acoustic_habc", True, 216)])
+def test_tma_path_against_oracle_and_register_path(eq, multiple, nx, monkeypatch):
+    """The TMA-staged blocks (forced on: SEISTORCH_B200_TMA=1) against the float64 oracle and against the
+    register/shuffle + tap-gather path (SEISTORCH_B200_TMA=0), 3 shots (ragged last shot group), sources
+    and receivers inside TMA tiles.  Padded 250x400: frame-free + top/bottom frame tiles; padded 250x316:
+    also the left/right frame tiles (one tile column per side)."""
+    from oracle import cases, loop, misfit
+    case = cases.make_case(eq, nz=150, nx=nx, nshots=3, nt=70, rec_step=9, multiple=multiple)
+    # put the acquisition deep enough to fall into the TMA rectangle as well as the frame rows
+    case["sources"] = [[s[0], 40.2] for s in case["sources"]]
+    case["receivers"] = [[r[0], [30] * len(r[0])] for r in case["receivers"]]
+
+    def run(mode):
+        monkeypatch.setenv("SEISTORCH_B200_TMA", mode)
+        cfg, model, x = _model(case)
+        syn = model(x)
+        loss = sum((s ** 2).sum() for s in syn)
+        loss.backward()
+        return cat_records([s.detach().cpu().numpy() for s in syn]), model.cell.geom.vp.grad.cpu().numpy()
+
+    r_tma, g_tma = run("1")
+    r_reg, g_reg = run("0")
+    assert rel(r_tma, r_reg) < 1e-6 and rel(g_tma, g_reg) < 1e-6
+    orecs, params = loop.simulate(case, dtype=torch.float64, requires_grad=["vp"])
+    misfit.l2(orecs, [torch.zeros_like(r) for r in orecs]).backward()
+    assert rel(r_tma, cat_records([r.detach().numpy() for r in orecs])) < 1e-5
+    assert rel(g_tma, params["vp"].grad.numpy()) < 1e-4
