@@ -45,10 +45,10 @@ constexpr int FH = FRZ * NWARP;             // rows per fast block
 #ifndef ST_BAND_SHOTS
 #define ST_BAND_SHOTS 8
 #endif
-#ifndef ST_DBG_SKIP
-#define ST_DBG_SKIP 0                       // tuning only: bit 0/1/2 = fast/strip/band blocks return at once (wrong results)
-#endif
 constexpr int BSH = ST_BAND_SHOTS;          // shots a band thread walks with its taps in registers
+#ifndef ST_DBG_SKIP
+#define ST_DBG_SKIP 0                       // tuning only: bit 3 = TMA blocks return at once, bit 4 = all tiles as kind 0, bit 5 = corner blocks return
+#endif
 // ---- TMA-staged tiles (st_wave2d.cuh: W2Tma)
 constexpr int TC = ST_TMA_TC, TR = ST_TMA_TR, HC = ST_TMA_HC, H1R = ST_TMA_H1, H2R = ST_TMA_H2;
 static_assert(TC == FW && TR == 2 * NWARP && FH % TR == 0, "TMA tile = one float4 per lane, two rows per warp");
@@ -64,57 +64,62 @@ constexpr int TMA_CORE_BYTES = TR * TC * 4;                          // 8192
 // stage layouts (sized for the frame tiles; interior tiles use smaller boxes at the same offsets)
 //   forward: [cur: 2-deep halo][prev: 1-deep halo]          interior: [cur: 1-deep halo][prev: core]
 //   adjoint: [Lam1: 2-deep][S_i: 2-deep][Lam2: 1-deep][S_{i-1}: 1-deep]   interior: [Lam1: 1-deep][S_i: 1-deep][Lam2: core]
-constexpr int TMA_FWD_STAGE = TMA_H2_BYTES + TMA_H1_BYTES;
-constexpr int TMA_ADJ_STAGE = 2 * TMA_H2_BYTES + 2 * TMA_H1_BYTES;
-constexpr int TMA_FWD_SMEM = ST_TMA_FWD_STAGES * TMA_FWD_STAGE;
-constexpr int TMA_ADJ_SMEM = ST_TMA_ADJ_STAGES * TMA_ADJ_STAGE;
+// (PML has frame-free tiles only: the regions shrink to the interior boxes and more blocks fit an SM)
+template <int FL> __host__ __device__ constexpr int tma_r0() { return (FL & ST_F_HABC) ? TMA_H2_BYTES : TMA_H1_BYTES; }   // first region
+template <int FL> __host__ __device__ constexpr int tma_fwd_stage() { return (FL & ST_F_HABC) ? TMA_H2_BYTES + TMA_H1_BYTES : TMA_H1_BYTES + TMA_CORE_BYTES; }
+template <int FL> __host__ __device__ constexpr int tma_adj_stage() { return (FL & ST_F_HABC) ? 2 * TMA_H2_BYTES + 2 * TMA_H1_BYTES : 2 * TMA_H1_BYTES + TMA_CORE_BYTES; }
+template <int FL> __host__ __device__ constexpr int tma_fwd_smem() { return ST_TMA_FWD_STAGES * tma_fwd_stage<FL>(); }
+template <int FL> __host__ __device__ constexpr int tma_adj_smem() { return ST_TMA_ADJ_STAGES * tma_adj_stage<FL>(); }
+// resident blocks per SM the TMA kernels are compiled for
+template <int FL> __host__ __device__ constexpr int tma_fwd_minb() { return (FL & ST_F_HABC) ? 3 : 4; }
+template <int FL> __host__ __device__ constexpr int tma_adj_minb() { return (FL & ST_F_HABC) ? 2 : 3; }
 // flag sets with a TMA path
 template <int FL>
 __host__ __device__ constexpr bool tma_ok() { return FL == (ST_F_ISO | ST_F_PML) || FL == (ST_F_ISO | ST_F_HABC); }
 
-__host__ __device__ inline int tma_side_tiles(const W2Tma& tm) { return tm.sr1 > tm.sr0 ? 2 * (tm.sr1 - tm.sr0) : 0; }
-__host__ __device__ inline int tma_tiles(const W2Tma& tm) { return tma_side_tiles(tm) + tm.ntr * (tm.tx1 - tm.tx0); }
-__host__ __device__ inline int tma_blocks(const W2Tma& tm, int B) { return tm.enabled ? tma_tiles(tm) * ((B + tm.tsh - 1) / tm.tsh) : 0; }
-// t-th TMA tile -> origin and kind (0 frame-free, +1/-1 top/bottom frame, +2/-2 left/right frame).  Heaviest first:
-// side tiles, bottom-frame rows, top-frame rows, then the frame-free rows.
-__device__ __forceinline__ void tma_tile_decode(const W2Tma& tm, const W2Geom& g, bool habc, int nfx, int t, int& z0, int& x0, int& kind) {
-    const int ns = tma_side_tiles(tm);
-    if (t < ns) {
-        const int per = tm.sr1 - tm.sr0, side = t / per;
-        z0 = (tm.sr0 + t - side * per) * TR;
-        x0 = side ? (nfx - 1) * FW : 0;
-        kind = side ? -2 : 2;
-        return;
+// A TMA block streams a CHUNK of up to `tpb` consecutive tiles of one kind (along x inside a tile row of the
+// column band, along z inside a side column) x `tsh` shots through its ring.
+__host__ __device__ inline int tma_side_chunks(const W2Tma& tm) { return tm.sr1 > tm.sr0 ? (tm.sr1 - tm.sr0 + tm.tpb - 1) / tm.tpb : 0; }
+__host__ __device__ inline int tma_row_chunks(const W2Tma& tm) { return (tm.tx1 - tm.tx0 + tm.tpb - 1) / tm.tpb; }
+__host__ __device__ inline int tma_chunks(const W2Tma& tm) { return 2 * tma_side_chunks(tm) + tm.ntr * tma_row_chunks(tm); }
+__host__ __device__ inline int tma_blocks(const W2Tma& tm, int B) { return tm.enabled ? tma_chunks(tm) * ((B + tm.tsh - 1) / tm.tsh) : 0; }
+struct TmaChunk { int z0, x0, kind, ntile, dz, dx; };
+// c-th chunk -> first tile origin, kind (0 frame-free, +1/-1 top/bottom frame, +2/-2 left/right frame), tile
+// count and step.  Heaviest first: side chunks, bottom-frame rows, top-frame rows, then the frame-free rows.
+__device__ __forceinline__ TmaChunk tma_chunk_decode(const W2Tma& tm, const W2Geom& g, bool habc, int nfx, int c) {
+    TmaChunk q;
+    const int nsc = tma_side_chunks(tm);
+    if (c < 2 * nsc) {
+        const int side = c / nsc, i = c - side * nsc;
+        const int nr = tm.sr1 - tm.sr0;
+        const int r0 = tm.sr0 + i * nr / nsc;               // balanced split of the column into nsc chunks
+        q.z0 = r0 * TR;
+        q.x0 = side ? (nfx - 1) * FW : 0;
+        q.kind = side ? -2 : 2;
+        q.ntile = tm.sr0 + (i + 1) * nr / nsc - r0;
+        q.dz = TR; q.dx = 0;
+    } else {
+        c -= 2 * nsc;
+        const int nrc = tma_row_chunks(tm);
+        int tr = c / nrc;
+        const int i = c - tr * nrc;
+        tr = tr < tm.nbot ? tm.ntr - tm.nbot + tr : tr - tm.nbot;
+        const int ntx = tm.tx1 - tm.tx0;
+        const int c0 = tm.tx0 + i * ntx / nrc;              // balanced split of the tile row into nrc chunks
+        q.z0 = tr * TR;
+        q.x0 = c0 * FW;
+        q.ntile = tm.tx0 + (i + 1) * ntx / nrc - c0;
+        q.dz = 0; q.dx = FW;
+        q.kind = 0;
+        if (habc) {
+            if (!g.multiple && q.z0 < tm.band) q.kind = 1;
+            else if (q.z0 + TR > g.nz - tm.band) q.kind = -1;
+        }
     }
-    t -= ns;
-    const int ntx = tm.tx1 - tm.tx0;
-    int tr = t / ntx;
-    const int tc = t - tr * ntx;
-    tr = tr < tm.nbot ? tm.ntr - tm.nbot + tr : tr - tm.nbot;
-    z0 = tr * TR;
-    x0 = (tm.tx0 + tc) * FW;
-    kind = 0;
-    if (habc) {
-        if (!g.multiple && z0 < tm.band) kind = 1;
-        else if (z0 + TR > g.nz - tm.band) kind = -1;
-    }
-    if (ST_DBG_SKIP & 16) kind = 0;
+    if (ST_DBG_SKIP & 16) q.kind = 0;
+    return q;
 }
-// fast tiles (FH x FW) that stay with the register path: everything outside the column band, minus the side tiles
-__host__ __device__ inline int fast_tiles_outside(int nfx, int nfz, const W2Tma& tm) {
-    if (!tm.enabled) return nfx * nfz;
-    const int rows = nfz - (tm.sr1 > tm.sr0 ? (tm.sr1 - tm.sr0) * TR / FH : 0);
-    return rows * (tm.tx0 + (nfx - tm.tx1));
-}
-// j-th of them -> linear fast-tile id (identity when there is no TMA region)
-__device__ __forceinline__ int fast_tile_outside(int j, int nfx, const W2Tma& tm) {
-    if (!tm.enabled) return j;
-    const int w = tm.tx0 + (nfx - tm.tx1);
-    int r = j / w;
-    const int c = j - r * w;
-    if (tm.sr1 > tm.sr0 && r >= tm.sr0 * TR / FH) r += (tm.sr1 - tm.sr0) * TR / FH;
-    return r * nfx + (c < tm.tx0 ? c : tm.tx1 + (c - tm.tx0));
-}
+
 template <int FL>
 __device__ __forceinline__ W2Coef load_coef_fl(const W2Args& a, long long idx) {
     W2Coef c;
@@ -252,35 +257,20 @@ __device__ __forceinline__ void forward_tail(const W2Args& a, int b, int z0, int
 // BASELINE size) has only z-direction far taps, so it vectorises like the interior: a warp owns one
 // band row x 128 columns, each lane 4 cells (128-bit loads of fields AND tap planes), x-neighbours
 // by shuffle; every lane walks all shots of its group with the transposed taps in registers.
-struct StripGeom { int xs, xe, ncol, toprows, nrows, bd, x0e, x1s, sz0, sz1; };
-// With a TMA column band [tma_x0, tma_x1) the strips shrink to the two pieces [xs, tma_x0) and [tma_x1, xe)
-// (each narrower than FW: one chunk per piece).
-__host__ __device__ inline StripGeom strip_geom(const W2Args& a, int bd) {
-    const W2Geom& g = a.g;
+struct StripGeom { int xs, xe, ncol, toprows, nrows, bd; };
+__host__ __device__ inline StripGeom strip_geom(const W2Geom& g, int bd) {
     StripGeom t;
     t.bd = bd;
     t.xs = (g.bw + 2 + 3) / 4 * 4;
     t.xe = (g.nx - g.bw - 2) / 4 * 4;
     if (t.xe < t.xs) t.xe = t.xs;
     t.ncol = (t.xe - t.xs + FW - 1) / FW;
-    t.x0e = t.x1s = 0;
-    if (a.tma_x1 > a.tma_x0) { t.ncol = 2; t.x0e = a.tma_x0; t.x1s = a.tma_x1; }
-    t.sz0 = a.tma_z0; t.sz1 = a.tma_z1;
     t.toprows = g.multiple ? 0 : bd;
     t.nrows = t.toprows + bd;
     return t;
 }
-// first column / end column of chunk `c` of a strip row
-__host__ __device__ inline int strip_chunk_x0(const StripGeom& t, int c) { return t.x1s > t.x0e ? (c == 0 ? t.xs : t.x1s) : t.xs + c * FW; }
-__host__ __device__ inline int strip_chunk_xe(const StripGeom& t, int c) {
-    if (t.x1s > t.x0e) return c == 0 ? (t.x0e < t.xe ? t.x0e : t.xe) : t.xe;
-    return t.xs + (c + 1) * FW < t.xe ? t.xs + (c + 1) * FW : t.xe;
-}
 __host__ __device__ inline int strip_blocks(const StripGeom& t) { return (t.nrows * t.ncol + NWARP - 1) / NWARP; }
-// band cells that do NOT belong to the per-cell band blocks: the straight top / bottom strips (strip blocks or
-// TMA frame tiles) and, with TMA side tiles, every band cell of rows [sz0, sz1)
 __device__ __forceinline__ bool in_strip(const StripGeom& t, const W2Geom& g, int z, int x) {
-    if (z >= t.sz0 && z < t.sz1) return true;
     return x >= t.xs && x < t.xe && ((!g.multiple && z < t.bd) || z >= g.nz - t.bd);
 }
 // aligned float4 of plane/field row z at column x (zero outside the domain rows / past the grid)
@@ -308,7 +298,7 @@ __device__ __forceinline__ float4 f4shr(const float4& c, float right) { return m
 
 __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, int b_lo, int b_hi, int tid) {
     const W2Geom g = a.g;
-    const StripGeom t = strip_geom(a, g.bw);
+    const StripGeom t = strip_geom(g, g.bw);
     const int warp = tid >> 5, lane = tid & 31;
     const int item = blk * NWARP + warp;
     if (item >= t.nrows * t.ncol) return;                       // whole warp
@@ -316,9 +306,8 @@ __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, in
     const bool top = row < t.toprows;
     const int z = top ? row : g.nz - t.bd + (row - t.toprows);
     const int n = top ? 1 : -1;
-    const int x0c = strip_chunk_x0(t, chunk), x = x0c + 4 * lane;
-    const int xend = strip_chunk_xe(t, chunk);
-    const bool active = x < xend;
+    const int x0c = t.xs + chunk * FW, x = x0c + 4 * lane;
+    const bool active = x < t.xe;
     const long long plane = (long long)g.nz * g.ld;
     const int on1 = top ? 2 : 1, on2 = top ? 6 : 5;
     // forward taps of this cell (increment form, st_wave2d_band.cuh)
@@ -346,7 +335,7 @@ __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, in
     // sources / receivers inside this warp's cells (ordering only needs the warp's own stores)
     if (z < a.row_lo || z > a.row_hi) return;
     __syncwarp();
-    const int xhi = xend;
+    const int xhi = min(x0c + FW, t.xe);
     for (int s = lane; s < a.ns; s += 32) {
         const int sb = a.src_b[s], sx = a.src_x[s];
         if (a.src_z[s] == z && sx >= x0c && sx < xhi && sb >= b_lo && sb < b_hi && (a.src_fmask & 1))
@@ -369,7 +358,7 @@ __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, in
 template <int FL>
 __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, int b_lo, int b_hi, int gplane, int tid) {
     const W2Geom g = a.g;
-    const StripGeom t = strip_geom(a, g.bw + 1);
+    const StripGeom t = strip_geom(g, g.bw + 1);
     const int warp = tid >> 5, lane = tid & 31;
     const int item = blk * NWARP + warp;
     if (item >= t.nrows * t.ncol) return;
@@ -377,9 +366,8 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
     const bool top = row < t.toprows;
     const int z = top ? row : g.nz - t.bd + (row - t.toprows);
     const int n = top ? 1 : -1;
-    const int x0c = strip_chunk_x0(t, chunk), x = x0c + 4 * lane;
-    const int xend = strip_chunk_xe(t, chunk);
-    const bool active = x < xend;
+    const int x0c = t.xs + chunk * FW, x = x0c + 4 * lane;
+    const bool active = x < t.xe;
     const long long plane = (long long)g.nz * g.ld;
     const bool want_grad = a.gacc != nullptr;
     const bool frame = top ? z < g.bw : z >= g.nz - g.bw;       // the deepest band row is not a frame row
@@ -463,7 +451,7 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
     }
     if (z < a.row_lo || z > a.row_hi) return;
     __syncwarp();
-    const int xhi = xend;
+    const int xhi = min(x0c + FW, t.xe);
     if (a.rec_adj) {
         for (int b = b_lo; b < b_hi; ++b) {
             const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
@@ -523,7 +511,7 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
     const BandCells bc = st_band_cells(g, g.bw);
     const int i0 = blk * NT, i = i0 + tid;
     const long long plane = (long long)g.nz * g.ld;
-    const StripGeom sg = strip_geom(a, g.bw);
+    const StripGeom sg = strip_geom(g, g.bw);
     auto mine = [&](int z, int x) {
         if (z < 0 || z >= g.nz || x < 0 || x >= g.nx || !w2_in_frame(z, x, g) || in_strip(sg, g, z, x)) return false;
         const int e = st_band_encode(bc, z, x);
@@ -633,7 +621,7 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
     const long long plane = (long long)g.nz * g.ld;
     const bool want_grad = a.gacc != nullptr;
     auto inb = [&](int z, int x) { return z >= 0 && z < g.nz && x >= 0 && x < g.nx; };
-    const StripGeom sg = strip_geom(a, bd);
+    const StripGeom sg = strip_geom(g, bd);
     auto mine = [&](int z, int x) {
         if (!inb(z, x) || in_strip(sg, g, z, x)) return false;
         const int e = st_band_encode(bc, z, x);
@@ -930,7 +918,8 @@ __device__ __forceinline__ void forward_fast_block(const W2Args& a, int bid, int
                      [&](int z, int xx) { return !HABC || !w2_in_frame(z, xx, g); });
 }
 
-template <int FL>
+// ALL: every cell of the tile (the corner tiles of the TMA kernels), else only the frame cells
+template <int FL, bool ALL = false>
 __device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int tx, int b, int tid, float (*s1)[SH][SW]) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     const W2Geom g = a.g;
@@ -945,7 +934,7 @@ __device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int
         for (int k = 0; k < RPT; ++k) {
             const int z = z0 + ty + k * NTY;
             if (z >= g.nz) break;
-            if (!w2_in_frame(z, x, g)) continue;
+            if (!ALL && !w2_in_frame(z, x, g)) continue;
             const long long idx = (long long)z * g.ld + x;
             const W2Coef c = load_coef_fl<FL>(a, idx);
             // current field: smem tile with global fallback (only the wrapped one-way
@@ -966,7 +955,36 @@ __device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int
             for (int f = 0; f < NF; ++f) a.next[f * a.cs + boff + idx] = out[f];
         }
     }
-    forward_tail<NF>(a, b, z0, z0 + TZ, x0, x0 + TX, tid, [&](int z, int xx) { return w2_in_frame(z, xx, g); });
+    if (ALL && x >= g.nx && x < g.ld) {                    // keep the pitch padding zero (history slots are not pre-cleared)
+        for (int k = 0; k < RPT; ++k) {
+            const int z = z0 + ty + k * NTY;
+            if (z >= g.nz) break;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) a.next[f * a.cs + boff + (long long)z * g.ld + x] = 0.f;
+        }
+    }
+    forward_tail<NF>(a, b, z0, z0 + TZ, x0, x0 + TX, tid, [&](int z, int xx) { return ALL || w2_in_frame(z, xx, g); });
+}
+
+
+// The cells the TMA tiles do not cover (HABC: the four corners, where side ownership, corner diagonals and the
+// wrap-around neighbour live) as generic TX x TZ tiles: rows [0, sr0 TR) and [sr1 TR, nz) of the columns
+// [0, tx0 FW) and [tx1 FW, nx).
+struct CornerTiles { int rt, rb, cl, cr, count; };
+__host__ __device__ inline CornerTiles corner_tiles(const W2Tma& tm, const W2Geom& g) {
+    CornerTiles c{0, 0, 0, 0, 0};
+    if (tm.sr1 <= tm.sr0) return c;
+    c.rt = tm.sr0 * TR / TZ;
+    c.rb = (g.nz - tm.sr1 * TR + TZ - 1) / TZ;
+    c.cl = tm.tx0 * FW / TX;
+    c.cr = (g.nx - tm.tx1 * FW + TX - 1) / TX;
+    c.count = (c.rt + c.rb) * (c.cl + c.cr);
+    return c;
+}
+__device__ __forceinline__ void corner_tile_decode(const CornerTiles& c, const W2Tma& tm, int i, int& tz, int& tx) {
+    const int w = c.cl + c.cr, ri = i / w, ci = i - ri * w;
+    tz = ri < c.rt ? ri : tm.sr1 * TR / TZ + (ri - c.rt);
+    tx = ci < c.cl ? ci : tm.tx1 * FW / TX + (ci - c.cl);
 }
 
 // TMA block: one TR x TC tile, `tsh` shots pulled through a ring of bulk tensor loads.
@@ -977,17 +995,17 @@ __device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int
 template <int FL>
 __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& tm, int nfx, int bid, int tid, unsigned char* dsm) {
     constexpr bool PML = (FL & ST_F_PML) != 0, HABC = (FL & ST_F_HABC) != 0;
-    constexpr int NS = ST_TMA_FWD_STAGES;
+    constexpr int NS = ST_TMA_FWD_STAGES, STAGE = tma_fwd_stage<FL>(), R0 = tma_r0<FL>();
     __shared__ __align__(8) uint64_t bars[NS];
     const W2Geom& g = a.g;
     const int ld = g.ld;
-    const int ntile = tma_tiles(tm);
-    const int grp = bid / ntile;
-    int z0, x0, kind;
-    tma_tile_decode(tm, g, HABC, nfx, bid - grp * ntile, z0, x0, kind);
+    const int nchunk = tma_chunks(tm);
+    const int grp = bid / nchunk;
+    const TmaChunk q = tma_chunk_decode(tm, g, HABC, nfx, bid - grp * nchunk);
+    const int kind = q.kind;
     const int b_lo = grp * tm.tsh, nsh = min(tm.tsh, a.B - b_lo);
+    const int nitem = q.ntile * nsh;                        // item j = (tile j / nsh, shot j % nsh)
     const int warp = tid >> 5, lane = tid & 31;
-    const int zr = z0 + 2 * warp, x = x0 + 4 * lane;
     const bool zdir = kind == 1 || kind == -1;
     const int hoff = zdir ? 2 : 1;                          // rows above z0 in the `cur` box
     const CUtensorMap* mcur = zdir ? &tm.u_h2 : &tm.u_h1;
@@ -1000,34 +1018,40 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
         st_mbar_init_fence();
     }
     __syncthreads();
-    auto issue = [&](int s) {
-        const int stg = s % NS;
-        unsigned char* dst = dsm + stg * TMA_FWD_STAGE;
+    auto issue = [&](int j) {
+        const int stg = j % NS, ti = j / nsh, sh = j - ti * nsh;
+        const int z0 = q.z0 + ti * q.dz, x0 = q.x0 + ti * q.dx;
+        unsigned char* dst = dsm + stg * STAGE;
         st_mbar_expect_tx(&bars[stg], (zdir ? H2R : H1R) * HC * 4 + (kind ? H1R * HC * 4 : TMA_CORE_BYTES));
-        st_tma_load_3d(dst, mcur, &bars[stg], x0 - 4, z0 - hoff, tm.pl_cur + b_lo + s);
-        if (kind) st_tma_load_3d(dst + TMA_H2_BYTES, mprev, &bars[stg], x0 - 4, z0 - 1, tm.pl_prev + b_lo + s);
-        else st_tma_load_3d(dst + TMA_H2_BYTES, mprev, &bars[stg], x0, z0, tm.pl_prev + b_lo + s);
+        st_tma_load_3d(dst, mcur, &bars[stg], x0 - 4, z0 - hoff, tm.pl_cur + b_lo + sh);
+        if (kind) st_tma_load_3d(dst + R0, mprev, &bars[stg], x0 - 4, z0 - 1, tm.pl_prev + b_lo + sh);
+        else st_tma_load_3d(dst + R0, mprev, &bars[stg], x0, z0, tm.pl_prev + b_lo + sh);
     };
     if (tid == 0)
-        for (int s = 0; s < NS && s < nsh; ++s) issue(s);
-    float4 ci[2], al[2], bb[2], rr[2];
-    bool zok[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        zok[k] = zr + k < g.nz && x < ld;
-        const int o = (zr + k) * ld + x;
-        ci[k] = zok[k] ? __ldg(reinterpret_cast<const float4*>(a.coef[2] + o)) : f4zero();
-        al[k] = (PML && zok[k]) ? __ldg(reinterpret_cast<const float4*>(a.coef[3] + o)) : f4zero();
-        bb[k] = (HABC && kind && zok[k]) ? __ldg(reinterpret_cast<const float4*>(a.coef[1] + o)) : f4zero();
-        rr[k] = (HABC && kind && zok[k]) ? __ldg(reinterpret_cast<const float4*>(a.coef[0] + o)) : f4zero();
-    }
+        for (int j = 0; j < NS && j < nitem; ++j) issue(j);
     // `prev` box geometry: core box (frame-free tiles) or 1-deep halo box (frame tiles)
     const int ppitch = kind ? HC : TC, poff = kind ? HC + 4 : 0;       // offset of (z0, x0)
-    for (int s = 0; s < nsh; ++s) {
-        const int stg = s % NS, b = b_lo + s;
-        st_mbar_wait(&bars[stg], (s / NS) & 1);
-        const float* h1 = reinterpret_cast<const float*>(dsm + stg * TMA_FWD_STAGE);
-        const float* h2 = reinterpret_cast<const float*>(dsm + stg * TMA_FWD_STAGE + TMA_H2_BYTES) + poff;
+    float4 ci[2], al[2], bb[2], rr[2];
+    bool zok[2];
+    int z0 = q.z0, x0 = q.x0, zr = 0, x = 0;
+    for (int j = 0, sh = 0; j < nitem; ++j) {
+        if (sh == 0) {                                      // new tile: its coefficient rows
+            zr = z0 + 2 * warp;
+            x = x0 + 4 * lane;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                zok[k] = zr + k < g.nz && x < ld;
+                const int o = (zr + k) * ld + x;
+                ci[k] = zok[k] ? __ldg(reinterpret_cast<const float4*>(a.coef[2] + o)) : f4zero();
+                al[k] = (PML && zok[k]) ? __ldg(reinterpret_cast<const float4*>(a.coef[3] + o)) : f4zero();
+                bb[k] = (HABC && kind && zok[k]) ? __ldg(reinterpret_cast<const float4*>(a.coef[1] + o)) : f4zero();
+                rr[k] = (HABC && kind && zok[k]) ? __ldg(reinterpret_cast<const float4*>(a.coef[0] + o)) : f4zero();
+            }
+        }
+        const int stg = j % NS, b = b_lo + sh;
+        st_mbar_wait(&bars[stg], (j / NS) & 1);
+        const float* h1 = reinterpret_cast<const float*>(dsm + stg * STAGE);
+        const float* h2 = reinterpret_cast<const float*>(dsm + stg * STAGE + R0) + poff;
         float* out = a.next + (long long)b * a.fs + (zr * ld + x);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -1048,7 +1072,7 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
                 const float ea = e == 3 ? rc : f4get(C, e + 1);
                 const float A = f4get(ci[k], e) * (((n - c) + (s_ - c)) + ((ea - c) + (w - c)));
                 const float alpha = PML ? f4get(al[k], e) : 1.f;
-                f4set(Y, e, c + alpha * (c - f4get(P, e)) + A);
+                f4set(Y, e, (!PML || x + e < g.nx) ? c + alpha * (c - f4get(P, e)) + A : 0.f);   // PML: the tile column past nx
             }
             if (HABC && kind) {
                 float4 A1, A2, P1;                          // h1 one / two cells inward, h2 one cell inward
@@ -1086,60 +1110,65 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
         }
         forward_tail<1>(a, b, z0, z0 + TR, x0, x0 + FW, tid, [](int, int) { return true; });
         __syncthreads();                                   // every warp is done with this stage
-        if (tid == 0 && s + NS < nsh) issue(s + NS);
+        if (tid == 0 && j + NS < nitem) issue(j + NS);
+        if (++sh == nsh) { sh = 0; z0 += q.dz; x0 += q.dx; }
     }
 }
 
 #ifndef ST_FWD_MINB
 #define ST_FWD_MINB 4
 #endif
-// resident blocks per SM the forward is compiled for (HABC: the 3 x 20 KB TMA ring allows 3)
 template <int FL>
-__host__ __device__ constexpr int fwd_minb() { return FL == (ST_F_ISO | ST_F_HABC) ? 3 : ST_FWD_MINB; }
-
-template <int FL>
-__global__ void __launch_bounds__(NT, fwd_minb<FL>()) wave2d_forward_kernel(const W2Args a, int nfx, int nfast, BandTiles bt,
-                                                                         const __grid_constant__ W2Tma tm) {
+__global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     constexpr bool HABC = (FL & ST_F_HABC) != 0;
-    extern __shared__ __align__(128) unsigned char dsm[];     // frame tile [NF][SH][SW]  or  the TMA ring
-    int bid = blockIdx.x;
-    const int tid = threadIdx.x;
-    // grid.x = [frame blocks] ++ [fast blocks x shots] ++ [TMA blocks]: the register-path blocks are long
-    // dependent-load chains, so they start first and the TMA blocks fill the machine around them.  Tapped frame blocks walk all shots themselves; `nfast` counts
-    // the fast tiles outside the TMA rectangle.
-    if constexpr (tma_ok<FL>()) {
-        const int nold = gridDim.x - tma_blocks(tm, a.B);
-        if (bid >= nold) {
-            if (ST_DBG_SKIP & 8) return;
-            forward_tma_block<FL>(a, tm, nfx, bid - nold, tid, dsm);
-            return;
-        }
-    }
+    __shared__ float s1[HABC ? NF : 1][HABC ? SH : 1][SW];
+    const int bid = blockIdx.x, tid = threadIdx.x;
+    // grid.x = [frame blocks] ++ [fast blocks x shots]; the (slower) frame blocks get the low ids so
+    // they are scheduled first.  Tapped frame blocks walk all shots themselves.
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     const int ngrp = (a.B + BSH - 1) / BSH;
-    const int nstrip = tapped ? strip_blocks(strip_geom(a, a.g.bw)) : 0;
+    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
     const int nframe = HABC ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
     if (bid >= nframe) {
-        if (ST_DBG_SKIP & 1) return;
         const int q = bid - nframe;
-        forward_fast_block<FL>(a, fast_tile_outside(q % nfast, nfx, tm), nfx, q / nfast, tid);
+        forward_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid);
     } else if (tapped) {
         const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;
         const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
-        if (k < nstrip) { if (ST_DBG_SKIP & 2) return; forward_strip_block(a, k, b_lo, b_hi, tid); }
-        else { if (ST_DBG_SKIP & 4) return; forward_band_block(a, k - nstrip, b_lo, b_hi, tid); }
+        if (k < nstrip) forward_strip_block(a, k, b_lo, b_hi, tid);
+        else forward_band_block(a, k - nstrip, b_lo, b_hi, tid);
     } else {
         if constexpr (HABC) {
             int tz, tx;
             const int b = bid / bt.count;
             band_tile_decode(bt, bid - b * bt.count, tz, tx);
-            forward_frame_block<FL>(a, tz, tx, b, tid, reinterpret_cast<float (*)[SH][SW]>(dsm));
+            forward_frame_block<FL>(a, tz, tx, b, tid, reinterpret_cast<float (*)[SH][SW]>(s1));
         }
     }
 }
+
+// TMA forward kernel: grid.x = [corner tiles x shots (generic per-cell code, one shot each: short blocks that
+// start first)] ++ [TMA chunk blocks].
 template <int FL>
-constexpr int fwd_static_smem() { return (FL & ST_F_HABC) ? ((FL & ST_F_BORN) ? 2 : 1) * SH * SW * 4 : 0; }
+__global__ void __launch_bounds__(NT, tma_fwd_minb<FL>()) wave2d_forward_tma_kernel(const W2Args a, int nfx, const __grid_constant__ W2Tma tm) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    const int bid = blockIdx.x, tid = threadIdx.x;
+    const CornerTiles ct = corner_tiles(tm, a.g);
+    const int ncorner = ct.count * a.B;
+    if (bid < ncorner) {
+        if (ST_DBG_SKIP & 32) return;
+        if constexpr ((FL & ST_F_HABC) != 0) {
+            int tz, tx;
+            const int b = bid / ct.count;
+            corner_tile_decode(ct, tm, bid - b * ct.count, tz, tx);
+            forward_frame_block<FL, true>(a, tz, tx, b, tid, reinterpret_cast<float (*)[SH][SW]>(dsm));
+        }
+        return;
+    }
+    if (ST_DBG_SKIP & 8) return;
+    forward_tma_block<FL>(a, tm, nfx, bid - ncorner, tid, dsm);
+}
 
 // ------------------------------------------------------------------------------ adjoint
 // which of the 7 gradient accumulators (r,cxx,czz,cxz,ax,az,m) a flag set touches
@@ -1481,6 +1510,117 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
     }
 }
 
+// general cell-by-cell adjoint of one TX x TZ tile; `band` < 0: every cell, else only the
+// cells closer than `band` to an absorbing edge
+// Shots b_lo..b_hi-1 are processed in turn; gradient contributions go to plane `gplane`.
+template <int FL>
+__device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, int tx, int b_lo, int b_hi, int gplane,
+                                                      int tid, int band, float (*sl)[SH][SW], float (*ss)[SH][SW]) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    const W2Geom g = a.g;
+    const int x0 = tx * TX, z0 = tz * TZ;
+    const int x = x0 + (tid & (NTX - 1)), ty = tid / NTX;
+    const bool want_grad = a.gacc != nullptr;
+    const long long plane = (long long)g.nz * g.ld;
+    auto owns = [&](int z, int xx) { return band < 0 || edge_depth(z, xx, g) < band; };
+    for (int b = b_lo; b < b_hi; ++b) {
+        const long long boff = (long long)b * a.fs;
+        __syncthreads();
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            load_tile(sl[f], a.lam1 + f * a.cs + boff, z0, x0, g, tid);
+            load_tile(ss[f], a.s1 + f * a.cs + boff, z0, x0, g, tid);
+        }
+        __syncthreads();
+        if (x < g.nx) {
+#pragma unroll 1
+            for (int k = 0; k < RPT; ++k) {
+                const int z = z0 + ty + k * NTY;
+                if (z >= g.nz) break;
+                if (!owns(z, x)) continue;
+                const long long idx = (long long)z * g.ld + x;
+                auto inb = [&](int zz, int xx) { return zz >= 0 && zz < g.nz && xx >= 0 && xx < g.nx; };
+                auto L1 = [&](int f, int zz, int xx) -> float {
+                    const int lz = zz - z0 + HALO, lx = xx - x0 + HALO;
+                    if (lz >= 0 && lz < SH && lx >= 0 && lx < SW) return sl[f][lz][lx];
+                    if (!inb(zz, xx)) return 0.f;
+                    return __ldg(a.lam1 + f * a.cs + boff + (long long)zz * g.ld + xx);
+                };
+                auto S1 = [&](int f, int zz, int xx) -> float {
+                    const int lz = zz - z0 + HALO, lx = xx - x0 + HALO;
+                    if (lz >= 0 && lz < SH && lx >= 0 && lx < SW) return ss[f][lz][lx];
+                    if (!inb(zz, xx)) return 0.f;
+                    return __ldg(a.s1 + f * a.cs + boff + (long long)zz * g.ld + xx);
+                };
+                auto L2 = [&](int f, int zz, int xx) -> float {
+                    if (!inb(zz, xx)) return 0.f;
+                    return __ldg(a.lam2 + f * a.cs + boff + (long long)zz * g.ld + xx);
+                };
+                auto S2 = [&](int f, int zz, int xx) -> float {
+                    if (!inb(zz, xx)) return 0.f;
+                    return __ldg(a.s2 + f * a.cs + boff + (long long)zz * g.ld + xx);
+                };
+                auto CF = [&](int zz, int xx) -> W2Coef { return load_coef_fl<FL>(a, (long long)zz * g.ld + xx); };
+                auto CK = [&](int k, int zz, int xx) -> float { return __ldg(a.coef[k] + (zz * g.ld + xx)); };
+                float out[2], gr[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                w2_adjoint_cell<FL>(z, x, g, a.dt, L1, L2, S1, S2, CF, CK, out, gr, want_grad);
+#pragma unroll
+                for (int f = 0; f < NF; ++f) a.lam0[f * a.cs + boff + idx] = out[f];
+                if (want_grad) {
+                    float* gb = a.gacc + (long long)gplane * 7 * plane + idx;
+#pragma unroll
+                    for (int q = 0; q < 7; ++q)
+                        if (grad_used<FL>(q)) gb[q * plane] += gr[q];
+                }
+            }
+        }
+        adjoint_tail<NF>(a, b, z0, z0 + TZ, x0, x0 + TX, tid, owns);
+    }
+}
+
+template <int FL>
+__global__ void __launch_bounds__(NT, ST_ADJ_MINB) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    constexpr bool NEED_GEN = !adj_fast<FL>() || (FL & ST_F_HABC);
+    constexpr int GEN_FLOATS = NEED_GEN ? 2 * NF * SH * SW : 1;
+    constexpr int FAST_FLOATS = adj_iso_only<FL>() ? NWARP * FRZ * FW : 1;
+    __shared__ __align__(16) float smem[GEN_FLOATS > FAST_FLOATS ? GEN_FLOATS : FAST_FLOATS];
+    const int bid = blockIdx.x, tid = threadIdx.x;
+    // grid.x = [band blocks: one per (tile, shot)] ++ [fast blocks: one per (fast tile, shot chunk)]
+    // for the fast-path equations, else one general block per (tile, shot chunk).
+    if constexpr (adj_fast<FL>()) {
+        const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
+        const int ngrp = (a.B + BSH - 1) / BSH;
+        const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
+        const int nband = (FL & ST_F_HABC) ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
+        if (bid >= nband) {
+            const int q = bid - nband;
+            adjoint_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid, reinterpret_cast<float (*)[FRZ][FW]>(smem));
+        } else if (tapped) {
+            const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;     // gradient plane = group id (< B planes exist)
+            const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
+            if (k < nstrip) adjoint_strip_block<FL>(a, k, b_lo, b_hi, grp, tid);
+            else adjoint_band_block<FL>(a, k - nstrip, b_lo, b_hi, grp, tid);
+        } else {
+            if constexpr (NEED_GEN) {
+                int tz, tx;
+                const int b = bid / bt.count;
+                band_tile_decode(bt, bid - b * bt.count, tz, tx);
+                // band gradients of shot b accumulate in gradient plane b (see nchunk in the launcher)
+                adjoint_general_block<FL>(a, tz, tx, b, b + 1, b, tid, a.g.bw + 1, reinterpret_cast<float (*)[SH][SW]>(smem),
+                                          reinterpret_cast<float (*)[SH][SW]>(smem + NF * SH * SW));
+            }
+        }
+    } else {
+        const int ntile = bt.nxt * bt.nzt;
+        const int chunk = bid / ntile, t = bid - chunk * ntile;
+        const int tz = t / bt.nxt, tx = t - tz * bt.nxt;
+        const int b_lo = chunk * a.bchunk, b_hi = min(b_lo + a.bchunk, a.B);
+        adjoint_general_block<FL>(a, tz, tx, b_lo, b_hi, chunk, tid, -1, reinterpret_cast<float (*)[SH][SW]>(smem),
+                                  reinterpret_cast<float (*)[SH][SW]>(smem + NF * SH * SW));
+    }
+}
+
 // TMA block of the adjoint (tile kinds as in forward_tma_block).  Interior tiles: the arithmetic of
 // adjoint_fast_rows.  Frame tiles (straight top / bottom side, inward normal n = +z / -z), per cell p:
 //   Lam_i(p) = lap(c pre L1)(p) + [2 pre + b (2 - lam - mu)](p) L1(p) + [b (lam + 2 mu)](p-n) L1(p-n) - [b mu](p-2n) L1(p-2n)
@@ -1491,79 +1631,87 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
 // depth bw, bw+1 and the frame-free rows of the tile come out right with the same expression).
 // Coefficient rows and gradient partial sums stay in registers across the block's shots.
 template <int FL, int KIND>
-__device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& tm, int z0, int x0, int grp, int tid,
+__device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& tm, const TmaChunk& q, int grp, int tid,
                                                  unsigned char* dsm, uint64_t* bars) {
     constexpr bool PML = (FL & ST_F_PML) != 0;
     constexpr bool ZDIR = KIND == 1 || KIND == -1, XDIR = KIND == 2 || KIND == -2;
     constexpr int N = KIND > 0 ? 1 : -1;                    // inward normal along z (ZDIR) or x (XDIR)
-    constexpr int NS = ST_TMA_ADJ_STAGES;
+    constexpr int NS = ST_TMA_ADJ_STAGES, STAGE = tma_adj_stage<FL>(), R0 = tma_r0<FL>();
     constexpr int HOFF = ZDIR ? 2 : 1;                      // rows above z0 in the Lam1 / S_i boxes
     const W2Geom& g = a.g;
     const int ld = g.ld;
     const int b_lo = grp * tm.tsh, nsh = min(tm.tsh, a.B - b_lo);
+    const int nitem = q.ntile * nsh;                        // item j = (tile j / nsh, shot j % nsh)
     const int warp = tid >> 5, lane = tid & 31;
-    const int zr = z0 + 2 * warp, x = x0 + 4 * lane;
     const bool want_grad = a.gacc != nullptr;
-    auto issue = [&](int s) {
-        const int stg = s % NS;
-        unsigned char* dst = dsm + stg * TMA_ADJ_STAGE;
+    auto issue = [&](int j) {
+        const int stg = j % NS, ti = j / nsh, s = j - ti * nsh;
+        const int z0 = q.z0 + ti * q.dz, x0 = q.x0 + ti * q.dx;
+        unsigned char* dst = dsm + stg * STAGE;
         if (KIND == 0) {
             st_mbar_expect_tx(&bars[stg], 2 * H1R * HC * 4 + TMA_CORE_BYTES);
             st_tma_load_3d(dst, &tm.l_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_l1 + b_lo + s);
-            st_tma_load_3d(dst + TMA_H2_BYTES, &tm.u_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_s1 + b_lo + s);
-            st_tma_load_3d(dst + 2 * TMA_H2_BYTES, &tm.l_core, &bars[stg], x0, z0, tm.pl_l2 + b_lo + s);
+            st_tma_load_3d(dst + R0, &tm.u_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_s1 + b_lo + s);
+            st_tma_load_3d(dst + 2 * R0, &tm.l_core, &bars[stg], x0, z0, tm.pl_l2 + b_lo + s);
         } else {
             st_mbar_expect_tx(&bars[stg], 2 * (ZDIR ? H2R : H1R) * HC * 4 + 2 * H1R * HC * 4);
             st_tma_load_3d(dst, ZDIR ? &tm.l_h2 : &tm.l_h1, &bars[stg], x0 - 4, z0 - HOFF, tm.pl_l1 + b_lo + s);
-            st_tma_load_3d(dst + TMA_H2_BYTES, ZDIR ? &tm.u_h2 : &tm.u_h1, &bars[stg], x0 - 4, z0 - HOFF, tm.pl_s1 + b_lo + s);
-            st_tma_load_3d(dst + 2 * TMA_H2_BYTES, &tm.l_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_l2 + b_lo + s);
-            st_tma_load_3d(dst + 2 * TMA_H2_BYTES + TMA_H1_BYTES, &tm.u_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_s2 + b_lo + s);
+            st_tma_load_3d(dst + R0, ZDIR ? &tm.u_h2 : &tm.u_h1, &bars[stg], x0 - 4, z0 - HOFF, tm.pl_s1 + b_lo + s);
+            st_tma_load_3d(dst + 2 * R0, &tm.l_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_l2 + b_lo + s);
+            st_tma_load_3d(dst + 2 * R0 + TMA_H1_BYTES, &tm.u_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_s2 + b_lo + s);
         }
     };
     if (tid == 0)
-        for (int s = 0; s < NS && s < nsh; ++s) issue(s);
+        for (int j = 0; j < NS && j < nitem; ++j) issue(j);
+    int z0 = q.z0, x0 = q.x0, zr = 0, x = 0;
     auto inz = [&](int z) { return z >= 0 && z < g.nz; };
     auto ldc4 = [&](int q, int z) { return (inz(z) && x < ld) ? __ldg(reinterpret_cast<const float4*>(a.coef[q] + (z * ld + x))) : f4zero(); };
     const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
     // cp = ciso (1 - b) on rows zr-1 .. zr+2 and on the halo column of the edge lanes (rows zr, zr+1)
     float4 cp[4], al[2], gc[2], gr[2];
     float ch[2] = {0.f, 0.f};
-    const int xh = lane == 0 ? x0 - 1 : x0 + FW;
+    float4 bb[4], rr[4];
+    constexpr int OWN0 = (ZDIR && N > 0) ? 2 : 0;
+    for (int j = 0, sh = 0; j < nitem; ++j) {
+      if (sh == 0) {                                        // new tile: its coefficient rows, cleared gradient sums
+        zr = z0 + 2 * warp;
+        x = x0 + 4 * lane;
+        const int xh = lane == 0 ? x0 - 1 : x0 + FW;
+        ch[0] = ch[1] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        cp[k] = ldc4(2, zr - 1 + k);
-        if (KIND) cp[k] = f4mul(cp[k], f4sub(one4, ldc4(1, zr - 1 + k)));
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        al[k] = PML ? ldc4(3, zr + k) : f4zero();
-        gc[k] = gr[k] = f4zero();
-        if ((lane == 0 || lane == 31) && xh >= 0 && xh < g.nx && inz(zr + k)) {
-            ch[k] = __ldg(a.coef[2] + ((zr + k) * ld + xh));
-            if (KIND) ch[k] *= 1.f - __ldg(a.coef[1] + ((zr + k) * ld + xh));
+        for (int k = 0; k < 4; ++k) {
+            cp[k] = ldc4(2, zr - 1 + k);
+            if (KIND) cp[k] = f4mul(cp[k], f4sub(one4, ldc4(1, zr - 1 + k)));
         }
-    }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            al[k] = PML ? ldc4(3, zr + k) : f4zero();
+            gc[k] = gr[k] = f4zero();
+            if ((lane == 0 || lane == 31) && xh >= 0 && xh < g.nx && inz(zr + k)) {
+                ch[k] = __ldg(a.coef[2] + ((zr + k) * ld + xh));
+                if (KIND) ch[k] *= 1.f - __ldg(a.coef[1] + ((zr + k) * ld + xh));
+            }
+        }
     // frame tiles: b and r.  ZDIR: the four rows {own rows, the two rows outward of them}
     //   (N = +1: rows zr-2 .. zr+1, own rows at index 2, 3;  N = -1: rows zr .. zr+3, own rows at index 0, 1);
     //   XDIR: the two own rows (index 0, 1).
-    float4 bb[4], rr[4];
-    constexpr int OWN0 = (ZDIR && N > 0) ? 2 : 0;
-    if (KIND) {
+        if (KIND) {
 #pragma unroll
-        for (int j = 0; j < (ZDIR ? 4 : 2); ++j) {
-            const int z = zr - OWN0 + j;
-            bb[j] = ldc4(1, z);
-            rr[j] = ldc4(0, z);
+            for (int i = 0; i < (ZDIR ? 4 : 2); ++i) {
+                const int z = zr - OWN0 + i;
+                bb[i] = ldc4(1, z);
+                rr[i] = ldc4(0, z);
+            }
         }
-    }
-    for (int s = 0; s < nsh; ++s) {
-        const int stg = s % NS, b = b_lo + s;
-        st_mbar_wait(&bars[stg], (s / NS) & 1);
-        const float* l1 = reinterpret_cast<const float*>(dsm + stg * TMA_ADJ_STAGE);
-        const float* S = reinterpret_cast<const float*>(dsm + stg * TMA_ADJ_STAGE + TMA_H2_BYTES);
+      }
+      {
+        const int stg = j % NS, b = b_lo + sh;
+        st_mbar_wait(&bars[stg], (j / NS) & 1);
+        const float* l1 = reinterpret_cast<const float*>(dsm + stg * STAGE);
+        const float* S = reinterpret_cast<const float*>(dsm + stg * STAGE + R0);
         // Lam2 / S_{i-1}: pointer to (z0, x0), row pitch
-        const float* l2 = reinterpret_cast<const float*>(dsm + stg * TMA_ADJ_STAGE + 2 * TMA_H2_BYTES) + (KIND ? HC + 4 : 0);
-        const float* S2 = reinterpret_cast<const float*>(dsm + stg * TMA_ADJ_STAGE + 2 * TMA_H2_BYTES + TMA_H1_BYTES) + HC + 4;
+        const float* l2 = reinterpret_cast<const float*>(dsm + stg * STAGE + 2 * R0) + (KIND ? HC + 4 : 0);
+        const float* S2 = reinterpret_cast<const float*>(dsm + stg * STAGE + 2 * R0 + TMA_H1_BYTES) + HC + 4;
         constexpr int P2 = KIND ? HC : TC;
         float* out = a.lam0 + (long long)b * a.fs + (zr * ld + x);
 #pragma unroll
@@ -1590,7 +1738,7 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
                     const float lapw = ((f4get(wU, e) - c) + (f4get(wD, e) - c)) + ((ea - c) + (w - c));
                     if (KIND == 0) {
                         const float alpha = PML ? f4get(al[k], e) : 1.f;
-                        f4set(o4, e, (1.f + alpha) * f4get(lC, e) + lapw - alpha * f4get(p2, e));
+                        f4set(o4, e, (!PML || x + e < g.nx) ? (1.f + alpha) * f4get(lC, e) + lapw - alpha * f4get(p2, e) : 0.f);
                     } else {
                         f4set(o4, e, lapw);
                     }
@@ -1723,9 +1871,12 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
         }
         adjoint_tail<1>(a, b, z0, z0 + TR, x0, x0 + FW, tid, [](int, int) { return true; });
         __syncthreads();                                   // every warp is done with this stage
-        if (tid == 0 && s + NS < nsh) issue(s + NS);
-    }
-    if (want_grad && x < ld) {
+        if (tid == 0 && j + NS < nitem) issue(j + NS);
+      }
+      if (++sh < nsh) continue;
+      // tile done: flush its gradient sums, move on
+      sh = 0;
+      if (want_grad && x < ld) {
         float* gb = a.gacc + (long long)grp * 7 * ((long long)g.nz * ld) + (zr * ld + x);
         const long long plane = (long long)g.nz * ld;
 #pragma unroll
@@ -1738,6 +1889,9 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
                 *reinterpret_cast<float4*>(gb + k * ld) = f4add(u, gr[k]);                // slot 0: d/d r
             }
         }
+      }
+      z0 += q.dz;
+      x0 += q.dx;
     }
 }
 
@@ -1745,10 +1899,10 @@ template <int FL>
 __device__ __forceinline__ void adjoint_tma_block(const W2Args& a, const W2Tma& tm, int nfx, int bid, int tid, unsigned char* dsm) {
     constexpr int NS = ST_TMA_ADJ_STAGES;
     __shared__ __align__(8) uint64_t bars[NS];
-    const int ntile = tma_tiles(tm);
-    const int grp = bid / ntile;
-    int z0, x0, kind;
-    tma_tile_decode(tm, a.g, (FL & ST_F_HABC) != 0, nfx, bid - grp * ntile, z0, x0, kind);
+    const int nchunk = tma_chunks(tm);
+    const int grp = bid / nchunk;
+    const TmaChunk q = tma_chunk_decode(tm, a.g, (FL & ST_F_HABC) != 0, nfx, bid - grp * nchunk);
+    const int kind = q.kind;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NS; ++s) st_mbar_init(&bars[s], 1);
@@ -1756,148 +1910,35 @@ __device__ __forceinline__ void adjoint_tma_block(const W2Args& a, const W2Tma& 
     }
     __syncthreads();
     if constexpr ((FL & ST_F_HABC) != 0) {
-        if (kind == 1) { adjoint_tma_tile<FL, 1>(a, tm, z0, x0, grp, tid, dsm, bars); return; }
-        if (kind == -1) { adjoint_tma_tile<FL, -1>(a, tm, z0, x0, grp, tid, dsm, bars); return; }
-        if (kind == 2) { adjoint_tma_tile<FL, 2>(a, tm, z0, x0, grp, tid, dsm, bars); return; }
-        if (kind == -2) { adjoint_tma_tile<FL, -2>(a, tm, z0, x0, grp, tid, dsm, bars); return; }
+        if (kind == 1) { adjoint_tma_tile<FL, 1>(a, tm, q, grp, tid, dsm, bars); return; }
+        if (kind == -1) { adjoint_tma_tile<FL, -1>(a, tm, q, grp, tid, dsm, bars); return; }
+        if (kind == 2) { adjoint_tma_tile<FL, 2>(a, tm, q, grp, tid, dsm, bars); return; }
+        if (kind == -2) { adjoint_tma_tile<FL, -2>(a, tm, q, grp, tid, dsm, bars); return; }
     }
-    adjoint_tma_tile<FL, 0>(a, tm, z0, x0, grp, tid, dsm, bars);
+    adjoint_tma_tile<FL, 0>(a, tm, q, grp, tid, dsm, bars);
 }
 
-// general cell-by-cell adjoint of one TX x TZ tile; `band` < 0: every cell, else only the
-// cells closer than `band` to an absorbing edge
-// Shots b_lo..b_hi-1 are processed in turn; gradient contributions go to plane `gplane`.
+// TMA adjoint kernel: grid.x = [corner tiles x shots (generic per-cell code; gradient plane = shot)] ++ [TMA chunk blocks]
 template <int FL>
-__device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, int tx, int b_lo, int b_hi, int gplane,
-                                                      int tid, int band, float (*sl)[SH][SW], float (*ss)[SH][SW]) {
-    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
-    const W2Geom g = a.g;
-    const int x0 = tx * TX, z0 = tz * TZ;
-    const int x = x0 + (tid & (NTX - 1)), ty = tid / NTX;
-    const bool want_grad = a.gacc != nullptr;
-    const long long plane = (long long)g.nz * g.ld;
-    auto owns = [&](int z, int xx) { return band < 0 || edge_depth(z, xx, g) < band; };
-    for (int b = b_lo; b < b_hi; ++b) {
-        const long long boff = (long long)b * a.fs;
-        __syncthreads();
-#pragma unroll
-        for (int f = 0; f < NF; ++f) {
-            load_tile(sl[f], a.lam1 + f * a.cs + boff, z0, x0, g, tid);
-            load_tile(ss[f], a.s1 + f * a.cs + boff, z0, x0, g, tid);
+__global__ void __launch_bounds__(NT, tma_adj_minb<FL>()) wave2d_adjoint_tma_kernel(const W2Args a, int nfx, const __grid_constant__ W2Tma tm) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    const int bid = blockIdx.x, tid = threadIdx.x;
+    const CornerTiles ct = corner_tiles(tm, a.g);
+    const int ncorner = ct.count * a.B;
+    if (bid < ncorner) {
+        if (ST_DBG_SKIP & 32) return;
+        if constexpr ((FL & ST_F_HABC) != 0) {
+            int tz, tx;
+            const int b = bid / ct.count;
+            corner_tile_decode(ct, tm, bid - b * ct.count, tz, tx);
+            float* smem = reinterpret_cast<float*>(dsm);
+            adjoint_general_block<FL>(a, tz, tx, b, b + 1, b, tid, -1, reinterpret_cast<float (*)[SH][SW]>(smem),
+                                      reinterpret_cast<float (*)[SH][SW]>(smem + SH * SW));
         }
-        __syncthreads();
-        if (x < g.nx) {
-#pragma unroll 1
-            for (int k = 0; k < RPT; ++k) {
-                const int z = z0 + ty + k * NTY;
-                if (z >= g.nz) break;
-                if (!owns(z, x)) continue;
-                const long long idx = (long long)z * g.ld + x;
-                auto inb = [&](int zz, int xx) { return zz >= 0 && zz < g.nz && xx >= 0 && xx < g.nx; };
-                auto L1 = [&](int f, int zz, int xx) -> float {
-                    const int lz = zz - z0 + HALO, lx = xx - x0 + HALO;
-                    if (lz >= 0 && lz < SH && lx >= 0 && lx < SW) return sl[f][lz][lx];
-                    if (!inb(zz, xx)) return 0.f;
-                    return __ldg(a.lam1 + f * a.cs + boff + (long long)zz * g.ld + xx);
-                };
-                auto S1 = [&](int f, int zz, int xx) -> float {
-                    const int lz = zz - z0 + HALO, lx = xx - x0 + HALO;
-                    if (lz >= 0 && lz < SH && lx >= 0 && lx < SW) return ss[f][lz][lx];
-                    if (!inb(zz, xx)) return 0.f;
-                    return __ldg(a.s1 + f * a.cs + boff + (long long)zz * g.ld + xx);
-                };
-                auto L2 = [&](int f, int zz, int xx) -> float {
-                    if (!inb(zz, xx)) return 0.f;
-                    return __ldg(a.lam2 + f * a.cs + boff + (long long)zz * g.ld + xx);
-                };
-                auto S2 = [&](int f, int zz, int xx) -> float {
-                    if (!inb(zz, xx)) return 0.f;
-                    return __ldg(a.s2 + f * a.cs + boff + (long long)zz * g.ld + xx);
-                };
-                auto CF = [&](int zz, int xx) -> W2Coef { return load_coef_fl<FL>(a, (long long)zz * g.ld + xx); };
-                auto CK = [&](int k, int zz, int xx) -> float { return __ldg(a.coef[k] + (zz * g.ld + xx)); };
-                float out[2], gr[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                w2_adjoint_cell<FL>(z, x, g, a.dt, L1, L2, S1, S2, CF, CK, out, gr, want_grad);
-#pragma unroll
-                for (int f = 0; f < NF; ++f) a.lam0[f * a.cs + boff + idx] = out[f];
-                if (want_grad) {
-                    float* gb = a.gacc + (long long)gplane * 7 * plane + idx;
-#pragma unroll
-                    for (int q = 0; q < 7; ++q)
-                        if (grad_used<FL>(q)) gb[q * plane] += gr[q];
-                }
-            }
-        }
-        adjoint_tail<NF>(a, b, z0, z0 + TZ, x0, x0 + TX, tid, owns);
+        return;
     }
-}
-
-template <int FL>
-constexpr int adj_static_smem() {
-    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
-    constexpr bool NEED_GEN = !adj_fast<FL>() || (FL & ST_F_HABC);
-    constexpr int GEN_FLOATS = NEED_GEN ? 2 * NF * SH * SW : 1;
-    constexpr int FAST_FLOATS = adj_iso_only<FL>() ? NWARP * FRZ * FW : 1;
-    return 4 * (GEN_FLOATS > FAST_FLOATS ? GEN_FLOATS : FAST_FLOATS);
-}
-
-// resident blocks per SM the adjoint is compiled for: the TMA ring of the HABC frame tiles takes 2 x 41.5 KB
-template <int FL>
-__host__ __device__ constexpr int adj_minb() { return FL == (ST_F_ISO | ST_F_HABC) ? 2 : ST_ADJ_MINB; }
-
-template <int FL>
-__global__ void __launch_bounds__(NT, adj_minb<FL>()) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt,
-                                                                         const __grid_constant__ W2Tma tm) {
-    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
-    constexpr bool NEED_GEN = !adj_fast<FL>() || (FL & ST_F_HABC);
-    extern __shared__ __align__(128) unsigned char dsm[];     // general tiles / fast-path gradient sums / the TMA ring
-    float* smem = reinterpret_cast<float*>(dsm);
-    int bid = blockIdx.x;
-    const int tid = threadIdx.x;
-    // grid.x = [band blocks: one per (tile, shot)] ++ [fast blocks: one per
-    // (fast tile outside the TMA band, shot chunk)] ++ [TMA blocks] for the fast-path equations, else one
-    // general block per (tile, shot chunk).
-    if constexpr (tma_ok<FL>()) {
-        const int nold = gridDim.x - tma_blocks(tm, a.B);
-        if (bid >= nold) {
-            if (ST_DBG_SKIP & 8) return;
-            adjoint_tma_block<FL>(a, tm, nfx, bid - nold, tid, dsm);
-            return;
-        }
-    }
-    if constexpr (adj_fast<FL>()) {
-        const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
-        const int ngrp = (a.B + BSH - 1) / BSH;
-        const int nstrip = tapped ? strip_blocks(strip_geom(a, a.g.bw + 1)) : 0;
-        const int nband = (FL & ST_F_HABC) ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
-        if (bid >= nband) {
-            if (ST_DBG_SKIP & 1) return;
-            const int q = bid - nband;
-            adjoint_fast_block<FL>(a, fast_tile_outside(q % nfast, nfx, tm), nfx, q / nfast, tid,
-                                   reinterpret_cast<float (*)[FRZ][FW]>(smem));
-        } else if (tapped) {
-            const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;     // gradient plane = group id (< B planes exist)
-            const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
-            if (k < nstrip) { if (ST_DBG_SKIP & 2) return; adjoint_strip_block<FL>(a, k, b_lo, b_hi, grp, tid); }
-            else { if (ST_DBG_SKIP & 4) return; adjoint_band_block<FL>(a, k - nstrip, b_lo, b_hi, grp, tid); }
-        } else {
-            if constexpr (NEED_GEN) {
-                int tz, tx;
-                const int b = bid / bt.count;
-                band_tile_decode(bt, bid - b * bt.count, tz, tx);
-                // band gradients of shot b accumulate in gradient plane b (see nchunk in the launcher)
-                adjoint_general_block<FL>(a, tz, tx, b, b + 1, b, tid, a.g.bw + 1, reinterpret_cast<float (*)[SH][SW]>(smem),
-                                          reinterpret_cast<float (*)[SH][SW]>(smem + NF * SH * SW));
-            }
-        }
-    } else {
-        const int ntile = bt.nxt * bt.nzt;
-        const int chunk = bid / ntile, t = bid - chunk * ntile;
-        const int tz = t / bt.nxt, tx = t - tz * bt.nxt;
-        const int b_lo = chunk * a.bchunk, b_hi = min(b_lo + a.bchunk, a.B);
-        adjoint_general_block<FL>(a, tz, tx, b_lo, b_hi, chunk, tid, -1, reinterpret_cast<float (*)[SH][SW]>(smem),
-                                  reinterpret_cast<float (*)[SH][SW]>(smem + NF * SH * SW));
-    }
+    if (ST_DBG_SKIP & 8) return;
+    adjoint_tma_block<FL>(a, tm, nfx, bid - ncorner, tid, dsm);
 }
 
 }  // namespace
@@ -1909,66 +1950,50 @@ int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st);
 
 #ifndef ST_W2_DISPATCH_ONLY
 template <int FL>
-int st_w2_launch_fwd(const W2Args& a_in, const W2Tma& tm, cudaStream_t st) {
-    W2Args a = a_in;
-    a.tma_x0 = a.tma_x1 = 0;
-    a.tma_z0 = a.tma_z1 = 0;
-    if (tma_ok<FL>() && tm.enabled) {
-        a.tma_x0 = tm.tx0 * FW; a.tma_x1 = tm.tx1 * FW;
-        if (tm.sr1 > tm.sr0) { a.tma_z0 = tm.sr0 * TR; a.tma_z1 = tm.sr1 * TR; }
-    }
+int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
-    const bool use_tma = tma_ok<FL>() && tm.enabled;
-    W2Tma off;
-    memset(&off, 0, sizeof(off));
-    const int nfast = fast_tiles_outside(nfx, nfz, use_tma ? tm : off);
+    if constexpr (tma_ok<FL>()) {
+        if (tm.enabled) {
+            static const cudaError_t attr = cudaFuncSetAttribute(wave2d_forward_tma_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_fwd_smem<FL>());
+            if (attr != cudaSuccess) return ST_ERR_CUDA;
+            dim3 grid((unsigned)((long long)corner_tiles(tm, a.g).count * a.B + tma_blocks(tm, a.B)));
+            wave2d_forward_tma_kernel<FL><<<grid, NT, tma_fwd_smem<FL>(), st>>>(a, nfx, tm);
+            return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+        }
+    }
+    const int nfast = nfx * nfz;
     BandTiles bt = band_tiles(a.g, a.g.bw);
     if (!(FL & ST_F_HABC)) bt.count = 0;
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
-    const int nstrip = tapped ? strip_blocks(strip_geom(a, a.g.bw)) : 0;
-    const long long ntma = use_tma ? tma_blocks(tm, a.B) : 0;
-    dim3 grid((unsigned)(ntma + (long long)nfast * a.B + (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B)));
-    int smem = fwd_static_smem<FL>();
-    if (tma_ok<FL>()) {
-        static const cudaError_t attr = cudaFuncSetAttribute(wave2d_forward_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_FWD_SMEM);
-        if (attr != cudaSuccess) return ST_ERR_CUDA;
-        if (use_tma && smem < TMA_FWD_SMEM) smem = TMA_FWD_SMEM;
-    }
-    wave2d_forward_kernel<FL><<<grid, NT, smem, st>>>(a, nfx, nfast, bt, use_tma ? tm : off);
+    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
+    dim3 grid((unsigned)((long long)nfast * a.B + (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B)));
+    wave2d_forward_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
 template <int FL>
-int st_w2_launch_adj(const W2Args& a_in, const W2Tma& tm, cudaStream_t st) {
-    W2Args a = a_in;
-    a.tma_x0 = a.tma_x1 = 0;
-    a.tma_z0 = a.tma_z1 = 0;
-    if (tma_ok<FL>() && tm.enabled) {
-        a.tma_x0 = tm.tx0 * FW; a.tma_x1 = tm.tx1 * FW;
-        if (tm.sr1 > tm.sr0) { a.tma_z0 = tm.sr0 * TR; a.tma_z1 = tm.sr1 * TR; }
-    }
+int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     const int nchunk = (a.B + a.bchunk - 1) / a.bchunk;
     const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
-    const bool use_tma = tma_ok<FL>() && tm.enabled;
-    W2Tma off;
-    memset(&off, 0, sizeof(off));
-    const int nfast = fast_tiles_outside(nfx, nfz, use_tma ? tm : off);
+    if constexpr (tma_ok<FL>()) {
+        if (tm.enabled) {
+            static const cudaError_t attr = cudaFuncSetAttribute(wave2d_adjoint_tma_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_adj_smem<FL>());
+            if (attr != cudaSuccess) return ST_ERR_CUDA;
+            dim3 grid((unsigned)((long long)corner_tiles(tm, a.g).count * a.B + tma_blocks(tm, a.B)));
+            wave2d_adjoint_tma_kernel<FL><<<grid, NT, tma_adj_smem<FL>(), st>>>(a, nfx, tm);
+            return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+        }
+    }
+    const int nfast = nfx * nfz;
     BandTiles bt = band_tiles(a.g, a.g.bw + 1);
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw + 1).total + NT - 1) / NT;
     long long nblocks;
-    const int nstrip = tapped ? strip_blocks(strip_geom(a, a.g.bw + 1)) : 0;
+    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
     if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B) : 0);
     else nblocks = (long long)bt.nxt * bt.nzt * nchunk;
-    if (use_tma) nblocks += tma_blocks(tm, a.B);
     dim3 grid((unsigned)nblocks);
-    int smem = adj_static_smem<FL>();
-    if (tma_ok<FL>()) {
-        static const cudaError_t attr = cudaFuncSetAttribute(wave2d_adjoint_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_ADJ_SMEM);
-        if (attr != cudaSuccess) return ST_ERR_CUDA;
-        if (use_tma && smem < TMA_ADJ_SMEM) smem = TMA_ADJ_SMEM;
-    }
-    wave2d_adjoint_kernel<FL><<<grid, NT, smem, st>>>(a, nfx, nfast, bt, use_tma ? tm : off);
+    wave2d_adjoint_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
 #ifdef ST_W2_INSTANCE
@@ -1993,41 +2018,45 @@ template int st_w2_launch_adj<ST_W2_INSTANCE>(const W2Args&, const W2Tma&, cudaS
 int st_wave2d_launch_forward(int flags, const W2Args& a, const W2Tma& tm, cudaStream_t st) { ST_W2_DISPATCH(st_w2_launch_fwd) }
 int st_wave2d_launch_adjoint(int flags, const W2Args& a, const W2Tma& tm, cudaStream_t st) { ST_W2_DISPATCH(st_w2_launch_adj) }
 
-// Where the TMA path applies: a band of whole fast-tile columns [tx0, tx1) x all rows whose cells are either
-// frame-free or belong to the STRAIGHT part of the top / bottom frame (every cell of the band and its
-// x-neighbours deeper than bw+1 from the left / right edge), so that the only frame formula needed is the
-// one-way blend along z.  The side columns and corners stay with the register / tap-gather blocks.
+// Whether the TMA kernels apply, and their tiling.  They take over the WHOLE launch or nothing:
+//   acoustic (PML): every tile is a frame-free tile (the tile column past nx is masked);
+//   acoustic_habc : a band of whole tile columns [tx0, tx1) whose cells and x-neighbours are deeper than bw+1 from
+//                   the left / right edge (straight top / bottom frame only), plus rows [sr0, sr1) of the one tile
+//                   column on either side (straight left / right frame only); the four corners run the generic
+//                   per-cell code.  Needs exactly one tile column per side and room between the corners.
 int st_wave2d_tma_setup(int flags, const W2Args& a, const float* u, long long u_planes, const float* lam, long long lam_planes,
                         bool adjoint, int mode, W2Tma& tm) {
     memset(&tm, 0, sizeof(tm));
     if (mode == 0) return ST_OK;
     if (flags != (ST_F_ISO | ST_F_PML) && flags != (ST_F_ISO | ST_F_HABC)) return ST_OK;
     const W2Geom& g = a.g;
-    int tx0 = 0, tx1 = g.nx / FW;
+    const int nfx = (g.nx + FW - 1) / FW;
+    int tx0 = 0, tx1 = nfx;
+    tm.ntr = (g.nz + TR - 1) / TR;
     if (flags & ST_F_HABC) {
         tx0 = (g.bw + 2 + FW - 1) / FW;
         tx1 = (g.nx - g.bw - 2) / FW;
-        // frame tiles use the precomputed-tap blocks' conventions: needs their workspace decision (taps) to agree,
-        // and top / bottom frame rows must not share a tile
-        if (a.taps == nullptr || g.nz < 2 * (g.bw + 2) + 2 * TR) return ST_OK;
-    }
-    if (tx1 <= tx0) return ST_OK;
-    const long long work = (long long)g.nz * (tx1 - tx0) * FW * a.B;
-    if (mode < 0 && (a.B < 2 || work < (1LL << 21))) return ST_OK;       // too little work to fill a ring
-    tm.tx0 = tx0; tm.tx1 = tx1;
-    tm.ntr = (g.nz + TR - 1) / TR;
-    tm.band = adjoint ? g.bw + 2 : g.bw;
-    if (flags & ST_F_HABC) {
+        const int fz0 = (g.bw + 2 + FH - 1) / FH, fz1 = (g.nz - g.bw - 2) / FH;
+        if (tx0 != 1 || tx1 != nfx - 1 || tx1 <= tx0 || fz1 <= fz0 || !st_band_ok(g, g.bw + 1) ||
+            g.nz < 2 * (g.bw + 2) + 2 * TR) return ST_OK;
+        tm.sr0 = fz0 * (FH / TR);
+        tm.sr1 = fz1 * (FH / TR);
+        tm.band = adjoint ? g.bw + 2 : g.bw;
         tm.nbot = tm.ntr - (g.nz - tm.band) / TR;            // tile rows with z0 + TR > nz - band
-        // side columns: exactly one tile column per side, rows a whole number of fast tiles clear of the corners
-        const int nfx = (g.nx + FW - 1) / FW;
-        if (tx0 == 1 && tx1 == nfx - 1 && getenv("SEISTORCH_B200_TMA_SIDES") == nullptr) {
-            const int fz0 = (g.bw + 2 + FH - 1) / FH, fz1 = (g.nz - g.bw - 2) / FH;
-            if (fz1 > fz0) { tm.sr0 = fz0 * (FH / TR); tm.sr1 = fz1 * (FH / TR); }
-        }
     }
-    tm.tsh = adjoint ? a.bchunk : (a.B < 4 ? a.B : 4);
-    if (const char* e = getenv("SEISTORCH_B200_TSH")) { if (!adjoint && atoi(e) > 0) tm.tsh = atoi(e) < a.B ? atoi(e) : a.B; }
+    const long long work = (long long)g.nz * g.nx * a.B;
+    if (mode < 0 && (a.B < 2 || work < (1LL << 21))) return ST_OK;       // too little work to fill the rings
+    // measured (B200, 851x2401, 8 shots): the PML forward register kernel beats the TMA one (53 vs 66 us)
+    if (mode < 0 && !adjoint && !(flags & ST_F_HABC)) return ST_OK;
+    tm.tx0 = tx0; tm.tx1 = tx1;
+    // shots per block: all (up to 8) in the forward pass; in the adjoint at least bchunk (the caller sized the
+    // gradient planes for ceil(B / bchunk) groups)
+    tm.tsh = a.B < 8 ? a.B : 8;
+    if (adjoint && tm.tsh < a.bchunk) tm.tsh = a.bchunk;
+    if (const char* e = getenv("SEISTORCH_B200_TSH")) {
+        const int v = atoi(e);
+        if (v > 0 && (!adjoint || v >= a.bchunk)) tm.tsh = v < a.B ? v : a.B;
+    }
     const long long fs = a.fs;
     int rc = st_tma_encode_planes(&tm.u_h1, u, g.nx, g.nz, u_planes, g.ld, fs, HC, H1R);
     if (!rc) rc = st_tma_encode_planes(&tm.u_h2, u, g.nx, g.nz, u_planes, g.ld, fs, HC, H2R);
@@ -2036,6 +2065,8 @@ int st_wave2d_tma_setup(int flags, const W2Args& a, const float* u, long long u_
     if (!rc && adjoint) rc = st_tma_encode_planes(&tm.l_h2, lam, g.nx, g.nz, lam_planes, g.ld, fs, HC, H2R);
     if (!rc && adjoint) rc = st_tma_encode_planes(&tm.l_core, lam, g.nx, g.nz, lam_planes, g.ld, fs, TC, TR);
     if (rc) { st_set_error("wave2d: cuTensorMapEncodeTiled failed (%d)", rc); return ST_ERR_CUDA; }
+    tm.tpb = 1;
+    if (const char* e = getenv("SEISTORCH_B200_TPB")) { if (atoi(e) > 0) tm.tpb = atoi(e); }
     tm.enabled = 1;
     return ST_OK;
 }

@@ -23,8 +23,6 @@ struct W2Args {
     const float* s2;        // S_{i-1}
     float* gacc;            // [nchunk][7][nz*ld] coefficient-gradient accumulators (or nullptr)
     int bchunk;             // shots per block in the adjoint kernel
-    int tma_x0, tma_x1;     // columns [tma_x0, tma_x1) are owned by the TMA blocks of this launch (0,0: none)
-    int tma_z0, tma_z1;     // ... and so are rows [tma_z0, tma_z1) of the columns outside that band (0,0: none)
     // ---- sources (one entry per point source)
     int ns;
     const int* src_b; const int* src_z; const int* src_x;
@@ -60,6 +58,8 @@ struct alignas(64) W2Tma {
                                             // nfx-1) are TMA tiles too (straight left / right frame); sr1 <= sr0: none
     int band;                               // HABC: rows closer than this to the top / bottom edge make a frame tile
     int tsh;                                // shots per TMA block
+    int tpb;                                // consecutive tiles (same kind: along x in the band, along z in a side
+                                            // column) one TMA block streams through its ring
     // plane index (within u / lam) of shot 0 of the slots used by this step
     int pl_prev, pl_cur, pl_l1, pl_l2, pl_s1, pl_s2;
 };
