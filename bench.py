@@ -315,15 +315,16 @@ def main():
         t_adj = ev[2].elapsed_time(ev[3]) / nt                         # ms per adjoint launch (misfit + reduction amortised)
         fwd_gbs = FWD_BYTES_PER_PT * B * npts / (t_fwd * 1e-3) / 1e9
         adj_gbs = ADJ_BYTES_PER_PT * B * npts / (t_adj * 1e-3) / 1e9
-        dom = "wave2d_adjoint_kernel<ISO|HABC>" if t_adj >= t_fwd else "wave2d_forward_kernel<ISO|HABC>"
+        from seistorch_b200 import engine as _engine
+        dom = (_engine.KERNELS["adjoint"] if t_adj >= t_fwd else _engine.KERNELS["forward"]) + "<ISO|HABC>"
         ach = adj_gbs if t_adj >= t_fwd else fwd_gbs
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_source": peak_src,
-                "forward_kernel": {"ms_per_launch": t_fwd, "algorithmic_bytes_per_pt": FWD_BYTES_PER_PT, "GBps": fwd_gbs,
+                "forward_kernel": {"name": _engine.KERNELS["forward"], "ms_per_launch": t_fwd, "algorithmic_bytes_per_pt": FWD_BYTES_PER_PT, "GBps": fwd_gbs,
                                    "frac": fwd_gbs / peak, "shots_per_launch": B},
-                "adjoint_kernel": {"ms_per_launch": t_adj, "algorithmic_bytes_per_pt": ADJ_BYTES_PER_PT, "GBps": adj_gbs,
+                "adjoint_kernel": {"name": _engine.KERNELS["adjoint"], "ms_per_launch": t_adj, "algorithmic_bytes_per_pt": ADJ_BYTES_PER_PT, "GBps": adj_gbs,
                                    "frac": adj_gbs / peak, "shots_per_launch": B}}
-        prof = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        prof = os.path.join(ROOT, "profiles", "traffic_r01.json")     # per-launch dram bytes from ncu --set full
         if os.path.exists(prof):
             try:
                 roof["traffic"] = json.load(open(prof)).get(dom.split("<")[0])

@@ -113,6 +113,13 @@ int64_t st_wave2d_taps_floats(const st_wave2d_problem* p);
 /* fill p->taps from the coefficient planes (once per call, before forward/adjoint) */
 int st_wave2d_prepare(const st_wave2d_problem* p, void* stream);
 
+/* 1 if st_wave2d_forward (adjoint = 0) / st_wave2d_adjoint (adjoint = 1) will run this problem on the TMA-staged
+ * kernels (acoustic / acoustic_habc on grids with room for whole tile columns, enough work per launch; environment
+ * SEISTORCH_B200_TMA=0/1 forces the register kernels / the TMA kernels wherever they apply), else 0.  Both kernel
+ * families implement the same equations (reference: equations2d/acoustic.py:73-86, acoustic_habc.py:147-221);
+ * results agree to fp32 rounding. */
+int st_wave2d_uses_tma(const st_wave2d_problem* p, int32_t adjoint);
+
 /* advance steps i0 .. i0+nsteps-1; S_{i0-2} lives in slot `slot0`, S_{i0-1} in slot0+1,
  * step i writes slot0+2+(i-i0).                                                         */
 int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream);

@@ -113,6 +113,18 @@ extern "C" int st_wave2d_prepare(const st_wave2d_problem* p, void* stream) {
     return rc;
 }
 
+extern "C" int st_wave2d_uses_tma(const st_wave2d_problem* p, int32_t adjoint) {
+    if (w2_check(p) != ST_OK) return 0;
+    W2Args a;
+    w2_fill(p, a);
+    a.gacc = p->gacc;
+    W2Tma tm;
+    const int nf = (p->flags & ST_EQ_BORN) ? 2 : 1;
+    if (adjoint && p->lam == nullptr) return 0;
+    if (st_wave2d_tma_setup(p->flags, a, p->u, (long long)nf * p->B * p->nslots, p->lam, 3LL * nf * p->B, adjoint != 0, w2_tma_mode(), tm)) return 0;
+    return tm.enabled;
+}
+
 extern "C" int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream) {
     int rc = w2_check(p);
     if (rc) return rc;

@@ -50,7 +50,7 @@ constexpr int BSH = ST_BAND_SHOTS;          // shots a band thread walks with it
 #define ST_DBG_SKIP 0                       // tuning only: bit 3 = TMA blocks return at once, bit 4 = all tiles as kind 0, bit 5 = corner blocks return
 #endif
 // ---- TMA-staged tiles (st_wave2d.cuh: W2Tma)
-constexpr int TC = ST_TMA_TC, TR = ST_TMA_TR, HC = ST_TMA_HC, H1R = ST_TMA_H1, H2R = ST_TMA_H2;
+constexpr int TC = ST_TMA_TC, TR = ST_TMA_TR, HC = ST_TMA_HC, H1R = ST_TMA_H1, H2R = ST_TMA_H2, XO = ST_TMA_XO;
 static_assert(TC == FW && TR == 2 * NWARP && FH % TR == 0, "TMA tile = one float4 per lane, two rows per warp");
 constexpr int TMA_H1_BYTES = (H1R * HC * 4 + 127) / 128 * 128;       // 9856  (box: 9792)
 constexpr int TMA_H2_BYTES = (H2R * HC * 4 + 127) / 128 * 128;       // 10880
@@ -69,7 +69,12 @@ template <int FL> __host__ __device__ constexpr int tma_r0() { return (FL & ST_F
 template <int FL> __host__ __device__ constexpr int tma_fwd_stage() { return (FL & ST_F_HABC) ? TMA_H2_BYTES + TMA_H1_BYTES : TMA_H1_BYTES + TMA_CORE_BYTES; }
 template <int FL> __host__ __device__ constexpr int tma_adj_stage() { return (FL & ST_F_HABC) ? 2 * TMA_H2_BYTES + 2 * TMA_H1_BYTES : 2 * TMA_H1_BYTES + TMA_CORE_BYTES; }
 template <int FL> __host__ __device__ constexpr int tma_fwd_smem() { return ST_TMA_FWD_STAGES * tma_fwd_stage<FL>(); }
-template <int FL> __host__ __device__ constexpr int tma_adj_smem() { return ST_TMA_ADJ_STAGES * tma_adj_stage<FL>(); }
+// adjoint ring: ST_TMA_ADJ_STAGES frame-tile stages or one more of the (smaller) frame-free stages in the same memory
+constexpr int TMA_ADJ_STAGE0 = 2 * TMA_H1_BYTES + TMA_CORE_BYTES;   // frame-free tile: Lam1 + S_i (1-deep halo) + Lam2 (core)
+template <int FL> __host__ __device__ constexpr int tma_adj_smem() {
+    constexpr int fr = ST_TMA_ADJ_STAGES * tma_adj_stage<FL>(), in = (ST_TMA_ADJ_STAGES + 1) * TMA_ADJ_STAGE0;
+    return (FL & ST_F_HABC) ? (fr > in ? fr : in) : ST_TMA_ADJ_STAGES * tma_adj_stage<FL>();
+}
 // resident blocks per SM the TMA kernels are compiled for
 template <int FL> __host__ __device__ constexpr int tma_fwd_minb() { return (FL & ST_F_HABC) ? 3 : 4; }
 template <int FL> __host__ __device__ constexpr int tma_adj_minb() { return (FL & ST_F_HABC) ? 2 : 3; }
@@ -82,13 +87,51 @@ __host__ __device__ constexpr bool tma_ok() { return FL == (ST_F_ISO | ST_F_PML)
 __host__ __device__ inline int tma_side_chunks(const W2Tma& tm) { return tm.sr1 > tm.sr0 ? (tm.sr1 - tm.sr0 + tm.tpb - 1) / tm.tpb : 0; }
 __host__ __device__ inline int tma_row_chunks(const W2Tma& tm) { return (tm.tx1 - tm.tx0 + tm.tpb - 1) / tm.tpb; }
 __host__ __device__ inline int tma_chunks(const W2Tma& tm) { return 2 * tma_side_chunks(tm) + tm.ntr * tma_row_chunks(tm); }
-__host__ __device__ inline int tma_blocks(const W2Tma& tm, int B) { return tm.enabled ? tma_chunks(tm) * ((B + tm.tsh - 1) / tm.tsh) : 0; }
-struct TmaChunk { int z0, x0, kind, ntile, dz, dx; };
+// blocks: [acquisition-row tiles x shots (one tile, one shot each)] ++ [chunks x shot groups]
+__host__ __device__ inline int tma_acq_blocks(const W2Tma& tm, int B) { return tm.ar1 > tm.ar0 ? (tm.ar1 - tm.ar0) * (tm.tx1 - tm.tx0 + 2) * B : 0; }
+__host__ __device__ inline int tma_blocks(const W2Tma& tm, int B) {
+    return tm.enabled ? tma_acq_blocks(tm, B) + tma_chunks(tm) * ((B + tm.tsh - 1) / tm.tsh) : 0;
+}
+struct TmaChunk { int z0, x0, kind, ntile, dz, dx, b_lo, nsh, plane; };    // ntile == 0: nothing to do
 // c-th chunk -> first tile origin, kind (0 frame-free, +1/-1 top/bottom frame, +2/-2 left/right frame), tile
 // count and step.  Heaviest first: side chunks, bottom-frame rows, top-frame rows, then the frame-free rows.
-__device__ __forceinline__ TmaChunk tma_chunk_decode(const W2Tma& tm, const W2Geom& g, bool habc, int nfx, int c) {
+__device__ __forceinline__ int tma_row_kind(const W2Tma& tm, const W2Geom& g, bool habc, int z0) {
+    if (!habc || (ST_DBG_SKIP & 16)) return 0;
+    if (!g.multiple && z0 < tm.band) return 1;
+    if (z0 + TR > g.nz - tm.band) return -1;
+    return 0;
+}
+__device__ __forceinline__ TmaChunk tma_block_decode(const W2Tma& tm, const W2Geom& g, bool habc, int nfx, int B, int bid) {
     TmaChunk q;
+    const int ntx = tm.tx1 - tm.tx0;
+    const int nacq = tma_acq_blocks(tm, B);
+    if (bid < nacq) {                                       // (shot, acquisition tile row, tile): one tile, one shot
+        const int per = ntx + 2, nar = tm.ar1 - tm.ar0;
+        const int b = bid / (nar * per), rem = bid - b * nar * per;
+        const int tr = tm.ar0 + rem / per, i = rem % per;
+        q.z0 = tr * TR;
+        q.ntile = 1; q.dz = q.dx = 0;
+        q.b_lo = b; q.nsh = 1; q.plane = b;
+        if (i < ntx) {
+            q.x0 = (tm.tx0 + i) * FW;
+            q.kind = tma_row_kind(tm, g, habc, q.z0);
+        } else {
+            q.x0 = (i - ntx) ? (nfx - 1) * FW : 0;
+            q.kind = (i - ntx) ? -2 : 2;
+            if (tr < tm.sr0 || tr >= tm.sr1) q.ntile = 0;   // corner rows: the generic corner tiles own these
+            if (ST_DBG_SKIP & 16) q.kind = 0;
+        }
+        return q;
+    }
+    bid -= nacq;
+    const int nchunk = tma_chunks(tm);
+    const int grp = bid / nchunk;
+    int c = bid - grp * nchunk;
+    q.b_lo = grp * tm.tsh;
+    q.nsh = min(tm.tsh, B - q.b_lo);
+    q.plane = grp;
     const int nsc = tma_side_chunks(tm);
+    int tr0, tr1;                                           // tile rows the chunk covers
     if (c < 2 * nsc) {
         const int side = c / nsc, i = c - side * nsc;
         const int nr = tm.sr1 - tm.sr0;
@@ -98,28 +141,26 @@ __device__ __forceinline__ TmaChunk tma_chunk_decode(const W2Tma& tm, const W2Ge
         q.kind = side ? -2 : 2;
         q.ntile = tm.sr0 + (i + 1) * nr / nsc - r0;
         q.dz = TR; q.dx = 0;
+        tr0 = r0; tr1 = r0 + q.ntile;
+        if (ST_DBG_SKIP & 16) q.kind = 0;
     } else {
         c -= 2 * nsc;
         const int nrc = tma_row_chunks(tm);
         int tr = c / nrc;
         const int i = c - tr * nrc;
         tr = tr < tm.nbot ? tm.ntr - tm.nbot + tr : tr - tm.nbot;
-        const int ntx = tm.tx1 - tm.tx0;
         const int c0 = tm.tx0 + i * ntx / nrc;              // balanced split of the tile row into nrc chunks
         q.z0 = tr * TR;
         q.x0 = c0 * FW;
         q.ntile = tm.tx0 + (i + 1) * ntx / nrc - c0;
         q.dz = 0; q.dx = FW;
-        q.kind = 0;
-        if (habc) {
-            if (!g.multiple && q.z0 < tm.band) q.kind = 1;
-            else if (q.z0 + TR > g.nz - tm.band) q.kind = -1;
-        }
+        q.kind = tma_row_kind(tm, g, habc, q.z0);
+        tr0 = tr; tr1 = tr + 1;
     }
-    if (ST_DBG_SKIP & 16) q.kind = 0;
+    // tiles of the acquisition rows belong to the per-shot blocks above (side chunks: tpb == 1 whenever ar1 > ar0)
+    if (tm.ar1 > tm.ar0 && tr0 < tm.ar1 && tr1 > tm.ar0) q.ntile = 0;
     return q;
 }
-
 template <int FL>
 __device__ __forceinline__ W2Coef load_coef_fl(const W2Args& a, long long idx) {
     W2Coef c;
@@ -999,11 +1040,10 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
     __shared__ __align__(8) uint64_t bars[NS];
     const W2Geom& g = a.g;
     const int ld = g.ld;
-    const int nchunk = tma_chunks(tm);
-    const int grp = bid / nchunk;
-    const TmaChunk q = tma_chunk_decode(tm, g, HABC, nfx, bid - grp * nchunk);
+    const TmaChunk q = tma_block_decode(tm, g, HABC, nfx, a.B, bid);
+    if (q.ntile == 0) return;
     const int kind = q.kind;
-    const int b_lo = grp * tm.tsh, nsh = min(tm.tsh, a.B - b_lo);
+    const int b_lo = q.b_lo, nsh = q.nsh;
     const int nitem = q.ntile * nsh;                        // item j = (tile j / nsh, shot j % nsh)
     const int warp = tid >> 5, lane = tid & 31;
     const bool zdir = kind == 1 || kind == -1;
@@ -1018,19 +1058,21 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
         st_mbar_init_fence();
     }
     __syncthreads();
-    auto issue = [&](int j) {
+    // the two boxes of an item are issued by two different warps (which = 0: cur + expect_tx, 1: prev)
+    auto issue = [&](int j, int which) {
         const int stg = j % NS, ti = j / nsh, sh = j - ti * nsh;
         const int z0 = q.z0 + ti * q.dz, x0 = q.x0 + ti * q.dx;
         unsigned char* dst = dsm + stg * STAGE;
-        st_mbar_expect_tx(&bars[stg], (zdir ? H2R : H1R) * HC * 4 + (kind ? H1R * HC * 4 : TMA_CORE_BYTES));
-        st_tma_load_3d(dst, mcur, &bars[stg], x0 - 4, z0 - hoff, tm.pl_cur + b_lo + sh);
-        if (kind) st_tma_load_3d(dst + R0, mprev, &bars[stg], x0 - 4, z0 - 1, tm.pl_prev + b_lo + sh);
+        if (which == 0) {
+            st_mbar_expect_tx(&bars[stg], (zdir ? H2R : H1R) * HC * 4 + (kind ? H1R * HC * 4 : TMA_CORE_BYTES));
+            st_tma_load_3d(dst, mcur, &bars[stg], x0 - XO, z0 - hoff, tm.pl_cur + b_lo + sh);
+        } else if (kind) st_tma_load_3d(dst + R0, mprev, &bars[stg], x0 - XO, z0 - 1, tm.pl_prev + b_lo + sh);
         else st_tma_load_3d(dst + R0, mprev, &bars[stg], x0, z0, tm.pl_prev + b_lo + sh);
     };
-    if (tid == 0)
-        for (int j = 0; j < NS && j < nitem; ++j) issue(j);
+    if (tid == 0 || tid == 32)
+        for (int j = 0; j < NS && j < nitem; ++j) issue(j, tid >> 5);
     // `prev` box geometry: core box (frame-free tiles) or 1-deep halo box (frame tiles)
-    const int ppitch = kind ? HC : TC, poff = kind ? HC + 4 : 0;       // offset of (z0, x0)
+    const int ppitch = kind ? HC : TC, poff = kind ? HC + XO : 0;       // offset of (z0, x0)
     float4 ci[2], al[2], bb[2], rr[2];
     bool zok[2];
     int z0 = q.z0, x0 = q.x0, zr = 0, x = 0;
@@ -1057,13 +1099,13 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
         for (int k = 0; k < 2; ++k) {
             const float* rowc = h1 + (2 * warp + k + hoff) * HC;                                    // box row of z = zr + k
             const float* rowp = h2 + (2 * warp + k) * ppitch;
-            const float4 C = *reinterpret_cast<const float4*>(rowc + 4 + 4 * lane);
-            const float4 U = *reinterpret_cast<const float4*>(rowc - HC + 4 + 4 * lane);
-            const float4 D = *reinterpret_cast<const float4*>(rowc + HC + 4 + 4 * lane);
+            const float4 C = *reinterpret_cast<const float4*>(rowc + XO + 4 * lane);
+            const float4 U = *reinterpret_cast<const float4*>(rowc - HC + XO + 4 * lane);
+            const float4 D = *reinterpret_cast<const float4*>(rowc + HC + XO + 4 * lane);
             const float4 P = *reinterpret_cast<const float4*>(rowp + 4 * lane);
             float lc = __shfl_up_sync(0xffffffffu, C.w, 1), rc = __shfl_down_sync(0xffffffffu, C.x, 1);
-            if (lane == 0) lc = rowc[3];
-            if (lane == 31) rc = rowc[4 + TC];
+            if (lane == 0) lc = rowc[XO - 1];
+            if (lane == 31) rc = rowc[XO + TC];
             float4 Y;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -1078,17 +1120,17 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
                 float4 A1, A2, P1;                          // h1 one / two cells inward, h2 one cell inward
                 if (zdir) {
                     A1 = kind > 0 ? D : U;
-                    A2 = *reinterpret_cast<const float4*>(rowc + 2 * kind * HC + 4 + 4 * lane);
+                    A2 = *reinterpret_cast<const float4*>(rowc + 2 * kind * HC + XO + 4 * lane);
                     P1 = *reinterpret_cast<const float4*>(rowp + kind * ppitch + 4 * lane);
                 } else if (kind > 0) {
                     float rc2 = __shfl_down_sync(0xffffffffu, C.y, 1), prc = __shfl_down_sync(0xffffffffu, P.x, 1);
-                    if (lane == 31) { rc2 = rowc[5 + TC]; prc = rowp[TC]; }
+                    if (lane == 31) { rc2 = rowc[XO + 1 + TC]; prc = rowp[TC]; }
                     A1 = f4shr(C, rc);
                     A2 = make_float4(C.z, C.w, rc, rc2);
                     P1 = f4shr(P, prc);
                 } else {
                     float lc2 = __shfl_up_sync(0xffffffffu, C.z, 1), plc = __shfl_up_sync(0xffffffffu, P.w, 1);
-                    if (lane == 0) { lc2 = rowc[2]; plc = rowp[-1]; }
+                    if (lane == 0) { lc2 = rowc[XO - 2]; plc = rowp[-1]; }
                     A1 = f4shl(C, lc);
                     A2 = make_float4(lc2, lc, C.x, C.y);
                     P1 = f4shl(P, plc);
@@ -1110,7 +1152,7 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
         }
         forward_tail<1>(a, b, z0, z0 + TR, x0, x0 + FW, tid, [](int, int) { return true; });
         __syncthreads();                                   // every warp is done with this stage
-        if (tid == 0 && j + NS < nitem) issue(j + NS);
+        if ((tid == 0 || tid == 32) && j + NS < nitem) issue(j + NS, tid >> 5);
         if (++sh == nsh) { sh = 0; z0 += q.dz; x0 += q.dx; }
     }
 }
@@ -1148,6 +1190,11 @@ __global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W
     }
 }
 
+#ifdef ST_DBG_TIMELINE
+__device__ unsigned long long g_dbg_tl[4 * 8192];
+__device__ __forceinline__ unsigned long long dbg_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned dbg_smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+#endif
 // TMA forward kernel: grid.x = [corner tiles x shots (generic per-cell code, one shot each: short blocks that
 // start first)] ++ [TMA chunk blocks].
 template <int FL>
@@ -1167,7 +1214,13 @@ __global__ void __launch_bounds__(NT, tma_fwd_minb<FL>()) wave2d_forward_tma_ker
         return;
     }
     if (ST_DBG_SKIP & 8) return;
+#ifdef ST_DBG_TIMELINE
+    unsigned long long t0 = dbg_now();
+#endif
     forward_tma_block<FL>(a, tm, nfx, bid - ncorner, tid, dsm);
+#ifdef ST_DBG_TIMELINE
+    if (tid == 0 && bid < 8192) { g_dbg_tl[4 * bid] = t0; g_dbg_tl[4 * bid + 1] = dbg_now(); g_dbg_tl[4 * bid + 2] = dbg_smid(); g_dbg_tl[4 * bid + 3] = 1; }
+#endif
 }
 
 // ------------------------------------------------------------------------------ adjoint
@@ -1631,16 +1684,18 @@ __global__ void __launch_bounds__(NT, ST_ADJ_MINB) wave2d_adjoint_kernel(const W
 // depth bw, bw+1 and the frame-free rows of the tile come out right with the same expression).
 // Coefficient rows and gradient partial sums stay in registers across the block's shots.
 template <int FL, int KIND>
-__device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& tm, const TmaChunk& q, int grp, int tid,
+__device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& tm, const TmaChunk& q, int tid,
                                                  unsigned char* dsm, uint64_t* bars) {
     constexpr bool PML = (FL & ST_F_PML) != 0;
     constexpr bool ZDIR = KIND == 1 || KIND == -1, XDIR = KIND == 2 || KIND == -2;
     constexpr int N = KIND > 0 ? 1 : -1;                    // inward normal along z (ZDIR) or x (XDIR)
-    constexpr int NS = ST_TMA_ADJ_STAGES, STAGE = tma_adj_stage<FL>(), R0 = tma_r0<FL>();
+    constexpr bool DEEP = KIND == 0 && (FL & ST_F_HABC) != 0;          // frame-free tiles of HABC: smaller stages, one more of them
+    constexpr int NS = ST_TMA_ADJ_STAGES + (DEEP ? 1 : 0), STAGE = DEEP ? TMA_ADJ_STAGE0 : tma_adj_stage<FL>();
+    constexpr int R0 = DEEP ? TMA_H1_BYTES : tma_r0<FL>();
     constexpr int HOFF = ZDIR ? 2 : 1;                      // rows above z0 in the Lam1 / S_i boxes
     const W2Geom& g = a.g;
     const int ld = g.ld;
-    const int b_lo = grp * tm.tsh, nsh = min(tm.tsh, a.B - b_lo);
+    const int b_lo = q.b_lo, nsh = q.nsh;
     const int nitem = q.ntile * nsh;                        // item j = (tile j / nsh, shot j % nsh)
     const int warp = tid >> 5, lane = tid & 31;
     const bool want_grad = a.gacc != nullptr;
@@ -1650,15 +1705,15 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
         unsigned char* dst = dsm + stg * STAGE;
         if (KIND == 0) {
             st_mbar_expect_tx(&bars[stg], 2 * H1R * HC * 4 + TMA_CORE_BYTES);
-            st_tma_load_3d(dst, &tm.l_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_l1 + b_lo + s);
-            st_tma_load_3d(dst + R0, &tm.u_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_s1 + b_lo + s);
+            st_tma_load_3d(dst, &tm.l_h1, &bars[stg], x0 - XO, z0 - 1, tm.pl_l1 + b_lo + s);
+            st_tma_load_3d(dst + R0, &tm.u_h1, &bars[stg], x0 - XO, z0 - 1, tm.pl_s1 + b_lo + s);
             st_tma_load_3d(dst + 2 * R0, &tm.l_core, &bars[stg], x0, z0, tm.pl_l2 + b_lo + s);
         } else {
             st_mbar_expect_tx(&bars[stg], 2 * (ZDIR ? H2R : H1R) * HC * 4 + 2 * H1R * HC * 4);
-            st_tma_load_3d(dst, ZDIR ? &tm.l_h2 : &tm.l_h1, &bars[stg], x0 - 4, z0 - HOFF, tm.pl_l1 + b_lo + s);
-            st_tma_load_3d(dst + R0, ZDIR ? &tm.u_h2 : &tm.u_h1, &bars[stg], x0 - 4, z0 - HOFF, tm.pl_s1 + b_lo + s);
-            st_tma_load_3d(dst + 2 * R0, &tm.l_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_l2 + b_lo + s);
-            st_tma_load_3d(dst + 2 * R0 + TMA_H1_BYTES, &tm.u_h1, &bars[stg], x0 - 4, z0 - 1, tm.pl_s2 + b_lo + s);
+            st_tma_load_3d(dst, ZDIR ? &tm.l_h2 : &tm.l_h1, &bars[stg], x0 - XO, z0 - HOFF, tm.pl_l1 + b_lo + s);
+            st_tma_load_3d(dst + R0, ZDIR ? &tm.u_h2 : &tm.u_h1, &bars[stg], x0 - XO, z0 - HOFF, tm.pl_s1 + b_lo + s);
+            st_tma_load_3d(dst + 2 * R0, &tm.l_h1, &bars[stg], x0 - XO, z0 - 1, tm.pl_l2 + b_lo + s);
+            st_tma_load_3d(dst + 2 * R0 + TMA_H1_BYTES, &tm.u_h1, &bars[stg], x0 - XO, z0 - 1, tm.pl_s2 + b_lo + s);
         }
     };
     if (tid == 0)
@@ -1710,13 +1765,13 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
         const float* l1 = reinterpret_cast<const float*>(dsm + stg * STAGE);
         const float* S = reinterpret_cast<const float*>(dsm + stg * STAGE + R0);
         // Lam2 / S_{i-1}: pointer to (z0, x0), row pitch
-        const float* l2 = reinterpret_cast<const float*>(dsm + stg * STAGE + 2 * R0) + (KIND ? HC + 4 : 0);
-        const float* S2 = reinterpret_cast<const float*>(dsm + stg * STAGE + 2 * R0 + TMA_H1_BYTES) + HC + 4;
+        const float* l2 = reinterpret_cast<const float*>(dsm + stg * STAGE + 2 * R0) + (KIND ? HC + XO : 0);
+        const float* S2 = reinterpret_cast<const float*>(dsm + stg * STAGE + 2 * R0 + TMA_H1_BYTES) + HC + XO;
         constexpr int P2 = KIND ? HC : TC;
         float* out = a.lam0 + (long long)b * a.fs + (zr * ld + x);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const int ro = (2 * warp + k + HOFF) * HC + 4 + 4 * lane;                  // box offset of row z = zr + k, this lane
+            const int ro = (2 * warp + k + HOFF) * HC + XO + 4 * lane;                  // box offset of row z = zr + k, this lane
             const int hrow = (2 * warp + k + HOFF) * HC;
             const float* l2r = l2 + (2 * warp + k) * P2;
             const int z = zr + k;
@@ -1728,8 +1783,8 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
                 const float4 p2 = *reinterpret_cast<const float4*>(l2r + 4 * lane);
                 const float4 wU = f4mul(cp[k], lU), wC = f4mul(cp[k + 1], lC), wD = f4mul(cp[k + 2], lD);
                 float wl = __shfl_up_sync(0xffffffffu, wC.w, 1), wr = __shfl_down_sync(0xffffffffu, wC.x, 1);
-                if (lane == 0) wl = ch[k] * l1[hrow + 3];
-                if (lane == 31) wr = ch[k] * l1[hrow + 4 + TC];
+                if (lane == 0) wl = ch[k] * l1[hrow + XO - 1];
+                if (lane == 31) wr = ch[k] * l1[hrow + XO + TC];
                 float4 o4;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -1814,8 +1869,8 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
                 const float4 sC = *reinterpret_cast<const float4*>(S + ro);
                 const float4 sU = *reinterpret_cast<const float4*>(S + ro - HC), sD = *reinterpret_cast<const float4*>(S + ro + HC);
                 float sl = __shfl_up_sync(0xffffffffu, sC.w, 1), sr = __shfl_down_sync(0xffffffffu, sC.x, 1);
-                if (lane == 0) sl = S[hrow + 3];
-                if (lane == 31) sr = S[hrow + 4 + TC];
+                if (lane == 0) sl = S[hrow + XO - 1];
+                if (lane == 31) sr = S[hrow + XO + TC];
                 float4 gq;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -1838,16 +1893,16 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
                         far = make_float4(f, f, f, f);
                         sI1 = N > 0 ? sD : sU;
                         sI2 = *reinterpret_cast<const float4*>(S + ro + 2 * N * HC);
-                        q1 = *reinterpret_cast<const float4*>(s2r + N * HC + 4 * lane);
+                        q1 = *reinterpret_cast<const float4*>(s2r + N * HC + XO * lane);
                     } else if (N > 0) {
                         float sr2 = __shfl_down_sync(0xffffffffu, sC.y, 1), qr = __shfl_down_sync(0xffffffffu, q0.x, 1);
-                        if (lane == 31) { sr2 = S[hrow + 5 + TC]; qr = s2r[TC]; }
+                        if (lane == 31) { sr2 = S[hrow + XO + 1 + TC]; qr = s2r[TC]; }
                         sI1 = f4shr(sC, sr);
                         sI2 = make_float4(sC.z, sC.w, sr, sr2);
                         q1 = f4shr(q0, qr);
                     } else {
                         float sl2 = __shfl_up_sync(0xffffffffu, sC.z, 1), ql = __shfl_up_sync(0xffffffffu, q0.w, 1);
-                        if (lane == 0) { sl2 = S[hrow + 2]; ql = s2r[-1]; }
+                        if (lane == 0) { sl2 = S[hrow + XO - 2]; ql = s2r[-1]; }
                         sI1 = f4shl(sC, sl);
                         sI2 = make_float4(sl2, sl, sC.x, sC.y);
                         q1 = f4shl(q0, ql);
@@ -1877,7 +1932,7 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
       // tile done: flush its gradient sums, move on
       sh = 0;
       if (want_grad && x < ld) {
-        float* gb = a.gacc + (long long)grp * 7 * ((long long)g.nz * ld) + (zr * ld + x);
+        float* gb = a.gacc + (long long)q.plane * 7 * ((long long)g.nz * ld) + (zr * ld + x);
         const long long plane = (long long)g.nz * ld;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -1897,11 +1952,10 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
 
 template <int FL>
 __device__ __forceinline__ void adjoint_tma_block(const W2Args& a, const W2Tma& tm, int nfx, int bid, int tid, unsigned char* dsm) {
-    constexpr int NS = ST_TMA_ADJ_STAGES;
+    constexpr int NS = ST_TMA_ADJ_STAGES + 1;
     __shared__ __align__(8) uint64_t bars[NS];
-    const int nchunk = tma_chunks(tm);
-    const int grp = bid / nchunk;
-    const TmaChunk q = tma_chunk_decode(tm, a.g, (FL & ST_F_HABC) != 0, nfx, bid - grp * nchunk);
+    const TmaChunk q = tma_block_decode(tm, a.g, (FL & ST_F_HABC) != 0, nfx, a.B, bid);
+    if (q.ntile == 0) return;
     const int kind = q.kind;
     if (tid == 0) {
 #pragma unroll
@@ -1910,12 +1964,12 @@ __device__ __forceinline__ void adjoint_tma_block(const W2Args& a, const W2Tma& 
     }
     __syncthreads();
     if constexpr ((FL & ST_F_HABC) != 0) {
-        if (kind == 1) { adjoint_tma_tile<FL, 1>(a, tm, q, grp, tid, dsm, bars); return; }
-        if (kind == -1) { adjoint_tma_tile<FL, -1>(a, tm, q, grp, tid, dsm, bars); return; }
-        if (kind == 2) { adjoint_tma_tile<FL, 2>(a, tm, q, grp, tid, dsm, bars); return; }
-        if (kind == -2) { adjoint_tma_tile<FL, -2>(a, tm, q, grp, tid, dsm, bars); return; }
+        if (kind == 1) { adjoint_tma_tile<FL, 1>(a, tm, q, tid, dsm, bars); return; }
+        if (kind == -1) { adjoint_tma_tile<FL, -1>(a, tm, q, tid, dsm, bars); return; }
+        if (kind == 2) { adjoint_tma_tile<FL, 2>(a, tm, q, tid, dsm, bars); return; }
+        if (kind == -2) { adjoint_tma_tile<FL, -2>(a, tm, q, tid, dsm, bars); return; }
     }
-    adjoint_tma_tile<FL, 0>(a, tm, q, grp, tid, dsm, bars);
+    adjoint_tma_tile<FL, 0>(a, tm, q, tid, dsm, bars);
 }
 
 // TMA adjoint kernel: grid.x = [corner tiles x shots (generic per-cell code; gradient plane = shot)] ++ [TMA chunk blocks]
@@ -1925,6 +1979,9 @@ __global__ void __launch_bounds__(NT, tma_adj_minb<FL>()) wave2d_adjoint_tma_ker
     const int bid = blockIdx.x, tid = threadIdx.x;
     const CornerTiles ct = corner_tiles(tm, a.g);
     const int ncorner = ct.count * a.B;
+#ifdef ST_DBG_TIMELINE
+    const unsigned long long t0 = dbg_now();
+#endif
     if (bid < ncorner) {
         if (ST_DBG_SKIP & 32) return;
         if constexpr ((FL & ST_F_HABC) != 0) {
@@ -1935,10 +1992,13 @@ __global__ void __launch_bounds__(NT, tma_adj_minb<FL>()) wave2d_adjoint_tma_ker
             adjoint_general_block<FL>(a, tz, tx, b, b + 1, b, tid, -1, reinterpret_cast<float (*)[SH][SW]>(smem),
                                       reinterpret_cast<float (*)[SH][SW]>(smem + SH * SW));
         }
-        return;
+    } else {
+        if (ST_DBG_SKIP & 8) return;
+        adjoint_tma_block<FL>(a, tm, nfx, bid - ncorner, tid, dsm);
     }
-    if (ST_DBG_SKIP & 8) return;
-    adjoint_tma_block<FL>(a, tm, nfx, bid - ncorner, tid, dsm);
+#ifdef ST_DBG_TIMELINE
+    if (tid == 0 && bid < 8192) { g_dbg_tl[4 * bid] = t0; g_dbg_tl[4 * bid + 1] = dbg_now(); g_dbg_tl[4 * bid + 2] = dbg_smid(); g_dbg_tl[4 * bid + 3] = bid < ncorner ? 2 : 1; }
+#endif
 }
 
 }  // namespace
@@ -1996,6 +2056,13 @@ int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     wave2d_adjoint_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
+#if defined(ST_DBG_TIMELINE) && defined(ST_W2_INSTANCE)
+#if ST_W2_INSTANCE == 5
+extern "C" int st_debug_timeline(unsigned long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_dbg_tl, sizeof(unsigned long long) * n);
+}
+#endif
+#endif
 #ifdef ST_W2_INSTANCE
 template int st_w2_launch_fwd<ST_W2_INSTANCE>(const W2Args&, const W2Tma&, cudaStream_t);
 template int st_w2_launch_adj<ST_W2_INSTANCE>(const W2Args&, const W2Tma&, cudaStream_t);
@@ -2016,6 +2083,7 @@ template int st_w2_launch_adj<ST_W2_INSTANCE>(const W2Args&, const W2Tma&, cudaS
     }
 
 int st_wave2d_launch_forward(int flags, const W2Args& a, const W2Tma& tm, cudaStream_t st) { ST_W2_DISPATCH(st_w2_launch_fwd) }
+
 int st_wave2d_launch_adjoint(int flags, const W2Args& a, const W2Tma& tm, cudaStream_t st) { ST_W2_DISPATCH(st_w2_launch_adj) }
 
 // Whether the TMA kernels apply, and their tiling.  They take over the WHOLE launch or nothing:
@@ -2067,6 +2135,17 @@ int st_wave2d_tma_setup(int flags, const W2Args& a, const float* u, long long u_
     if (rc) { st_set_error("wave2d: cuTensorMapEncodeTiled failed (%d)", rc); return ST_ERR_CUDA; }
     tm.tpb = 1;
     if (const char* e = getenv("SEISTORCH_B200_TPB")) { if (atoi(e) > 0) tm.tpb = atoi(e); }
+    // acquisition rows: one shot per block (measured: the source / receiver epilogue costs 3-4 us per item, a chain of
+    // dependent loads, against 0.8 us for the item itself; eight of them in a row make those blocks finish 3x later
+    // than all the others).  The adjoint needs one gradient plane per shot for that: HABC callers provide them
+    // (include/seistorch_b200.h), PML callers only ceil(B / bchunk).
+    const bool planes_ok = !adjoint || (flags & ST_F_HABC) || a.bchunk == 1 || a.gacc == nullptr;
+    const bool any_acq = a.ns > 0 || a.R > 0;
+    if (tm.tpb == 1 && tm.tsh > 1 && planes_ok && any_acq && a.row_hi >= a.row_lo && a.row_hi - a.row_lo < 8 * TR &&
+        getenv("SEISTORCH_B200_TMA_NOACQ") == nullptr) {
+        tm.ar0 = a.row_lo / TR;
+        tm.ar1 = a.row_hi / TR + 1;
+    }
     tm.enabled = 1;
     return ST_OK;
 }

@@ -44,7 +44,11 @@ struct W2Args {
 // __grid_constant__ kernel parameter.
 constexpr int ST_TMA_TC = 128;              // tile columns  (one float4 per lane)
 constexpr int ST_TMA_TR = 16;               // tile rows     (2 per warp)
-constexpr int ST_TMA_HC = ST_TMA_TC + 8;    // halo box columns: [x0-4, x0+TC+4) keeps the core 16-byte aligned
+#ifndef ST_TMA_XHALO
+#define ST_TMA_XHALO 4
+#endif
+constexpr int ST_TMA_XO = ST_TMA_XHALO;        // halo columns fetched on either side of the core (keeps it 16-byte aligned)
+constexpr int ST_TMA_HC = ST_TMA_TC + 2 * ST_TMA_XO;   // halo box columns: [x0-XO, x0+TC+XO)
 constexpr int ST_TMA_H1 = ST_TMA_TR + 2;    // 1-deep halo box rows: [z0-1, z0+TR+1)
 constexpr int ST_TMA_H2 = ST_TMA_TR + 4;    // 2-deep halo box rows: [z0-2, z0+TR+2)  (one-way blend of the top / bottom frame)
 struct alignas(64) W2Tma {
@@ -58,6 +62,9 @@ struct alignas(64) W2Tma {
                                             // nfx-1) are TMA tiles too (straight left / right frame); sr1 <= sr0: none
     int band;                               // HABC: rows closer than this to the top / bottom edge make a frame tile
     int tsh;                                // shots per TMA block
+    int ar0, ar1;                           // tile rows [ar0, ar1) hold the sources / receivers: their tiles run one shot per
+                                            // block (the source / receiver epilogue is a dependent-load chain that must
+                                            // not be repeated tsh times inside one block); ar1 <= ar0: no such rows
     int tpb;                                // consecutive tiles (same kind: along x in the band, along z in a side
                                             // column) one TMA block streams through its ring
     // plane index (within u / lam) of shot 0 of the slots used by this step

@@ -37,6 +37,7 @@ _W2_GRAD_OF_COEF = {0: 0, 2: 1, 3: 2, 4: 3, 5: 4, 6: 5, 7: 6}
 
 # number of sm_100a kernel launches issued through the C ABI (bench.py reports it)
 LAUNCHES = {"forward": 0, "adjoint": 0, "misfit": 0}
+KERNELS = {"forward": None, "adjoint": None}      # kernel family of the most recent forward / adjoint call
 
 
 def _round_up(n, m):
@@ -283,17 +284,27 @@ class _Problem:
         p.bchunk = self.bchunk
         self.acq.fill(p.acq, self.amp, self.gamp, s.src_fmask, s.chan_f, self.rec_out, self.rec_adj)
 
+    def _note_kernel(self, which):
+        """Record which kernel family serves this call (bench.py / tests report it)."""
+        if self.spec.family == "wave2d":
+            tma = bool(_lib.lib().st_wave2d_uses_tma(C.byref(self.p), 1 if which == "adjoint" else 0))
+            KERNELS[which] = f"wave2d_{which}_{'tma_' if tma else ''}kernel"
+        else:
+            KERNELS[which] = f"{self.spec.family}_{which}_kernel"
+
     def forward(self, i0, nsteps, slot0, record=True):
         keep = self.rec_out
         if not record:
             self.rec_out = None
         self._sync_struct()
+        self._note_kernel("forward")
         self.rec_out = keep
         _lib.check(self.fwd(C.byref(self.p), i0, nsteps, slot0 % self.nslots, _stream_ptr()), f"{self.spec.family}_forward")
         LAUNCHES["forward"] += nsteps
 
     def adjoint(self, i_hi, nsteps, slot_hi):
         self._sync_struct()
+        self._note_kernel("adjoint")
         _lib.check(self.adj(C.byref(self.p), i_hi, nsteps, slot_hi % self.nslots, _stream_ptr()), f"{self.spec.family}_adjoint")
         LAUNCHES["adjoint"] += nsteps
 
