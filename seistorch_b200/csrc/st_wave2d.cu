@@ -84,7 +84,7 @@ __host__ __device__ constexpr bool tma_ok() { return FL == (ST_F_ISO | ST_F_PML)
 
 // A TMA block streams a CHUNK of up to `tpb` consecutive tiles of one kind (along x inside a tile row of the
 // column band, along z inside a side column) x `tsh` shots through its ring.
-__host__ __device__ inline int tma_side_chunks(const W2Tma& tm) { return tm.sr1 > tm.sr0 ? (tm.sr1 - tm.sr0 + tm.tpb - 1) / tm.tpb : 0; }
+__host__ __device__ inline int tma_side_chunks(const W2Tma& tm) { return tm.sr1 > tm.sr0 ? tm.ntr : 0; }     // one tile each, every tile row
 __host__ __device__ inline int tma_row_chunks(const W2Tma& tm) { return (tm.tx1 - tm.tx0 + tm.tpb - 1) / tm.tpb; }
 __host__ __device__ inline int tma_chunks(const W2Tma& tm) { return 2 * tma_side_chunks(tm) + tm.ntr * tma_row_chunks(tm); }
 // blocks: [acquisition-row tiles x shots (one tile, one shot each)] ++ [chunks x shot groups]
@@ -92,34 +92,52 @@ __host__ __device__ inline int tma_acq_blocks(const W2Tma& tm, int B) { return t
 __host__ __device__ inline int tma_blocks(const W2Tma& tm, int B) {
     return tm.enabled ? tma_acq_blocks(tm, B) + tma_chunks(tm) * ((B + tm.tsh - 1) / tm.tsh) : 0;
 }
-struct TmaChunk { int z0, x0, kind, ntile, dz, dx, b_lo, nsh, plane; };    // ntile == 0: nothing to do
+struct TmaChunk { int z0, x0, kind, ntile, dz, dx, b_lo, nsh, plane, mx0, mx1; };    // ntile == 0: nothing to do; columns [mx0, mx1) are stored
 // c-th chunk -> first tile origin, kind (0 frame-free, +1/-1 top/bottom frame, +2/-2 left/right frame), tile
 // count and step.  Heaviest first: side chunks, bottom-frame rows, top-frame rows, then the frame-free rows.
+// first column of the right-hand generic corner tiles
+__host__ __device__ inline int corner_xr(const W2Tma& tm, const W2Geom& g) { return g.nx - TX > tm.tx1 * FW ? g.nx - TX : tm.tx1 * FW; }
 __device__ __forceinline__ int tma_row_kind(const W2Tma& tm, const W2Geom& g, bool habc, int z0) {
     if (!habc || (ST_DBG_SKIP & 16)) return 0;
     if (!g.multiple && z0 < tm.band) return 1;
     if (z0 + TR > g.nz - tm.band) return -1;
     return 0;
 }
+// side tile of tile row `tr` (side 0 left, 1 right): rows [sr0, sr1) are whole tiles of the straight left / right
+// frame; the corner rows keep only the columns next to the generic corner tile (straight top / bottom frame or
+// frame-free cells), selected by a column mask
+__device__ __forceinline__ void tma_side_tile(const W2Tma& tm, const W2Geom& g, bool habc, int nfx, int tr, int side, TmaChunk& q) {
+    q.z0 = tr * TR;
+    q.x0 = side ? (nfx - 1) * FW : 0;
+    q.ntile = 1; q.dz = q.dx = 0;
+    if (tr >= tm.sr0 && tr < tm.sr1) {
+        q.kind = side ? -2 : 2;
+    } else {
+        q.kind = tma_row_kind(tm, g, habc, q.z0);
+        if (side) { q.mx0 = q.x0; q.mx1 = corner_xr(tm, g); } else { q.mx0 = TX; q.mx1 = FW; }
+        if (q.mx1 <= q.mx0) q.ntile = 0;
+    }
+    if (ST_DBG_SKIP & 16) q.kind = 0;
+}
 __device__ __forceinline__ TmaChunk tma_block_decode(const W2Tma& tm, const W2Geom& g, bool habc, int nfx, int B, int bid) {
     TmaChunk q;
+    q.mx0 = 0; q.mx1 = 1 << 30;
     const int ntx = tm.tx1 - tm.tx0;
     const int nacq = tma_acq_blocks(tm, B);
     if (bid < nacq) {                                       // (shot, acquisition tile row, tile): one tile, one shot
         const int per = ntx + 2, nar = tm.ar1 - tm.ar0;
         const int b = bid / (nar * per), rem = bid - b * nar * per;
         const int tr = tm.ar0 + rem / per, i = rem % per;
-        q.z0 = tr * TR;
-        q.ntile = 1; q.dz = q.dx = 0;
         q.b_lo = b; q.nsh = 1; q.plane = b;
         if (i < ntx) {
+            q.z0 = tr * TR;
+            q.ntile = 1; q.dz = q.dx = 0;
             q.x0 = (tm.tx0 + i) * FW;
             q.kind = tma_row_kind(tm, g, habc, q.z0);
+        } else if (tm.sr1 > tm.sr0) {
+            tma_side_tile(tm, g, habc, nfx, tr, i - ntx, q);
         } else {
-            q.x0 = (i - ntx) ? (nfx - 1) * FW : 0;
-            q.kind = (i - ntx) ? -2 : 2;
-            if (tr < tm.sr0 || tr >= tm.sr1) q.ntile = 0;   // corner rows: the generic corner tiles own these
-            if (ST_DBG_SKIP & 16) q.kind = 0;
+            q.ntile = 0;
         }
         return q;
     }
@@ -131,22 +149,15 @@ __device__ __forceinline__ TmaChunk tma_block_decode(const W2Tma& tm, const W2Ge
     q.nsh = min(tm.tsh, B - q.b_lo);
     q.plane = grp;
     const int nsc = tma_side_chunks(tm);
-    int tr0, tr1;                                           // tile rows the chunk covers
+    int tr;
     if (c < 2 * nsc) {
-        const int side = c / nsc, i = c - side * nsc;
-        const int nr = tm.sr1 - tm.sr0;
-        const int r0 = tm.sr0 + i * nr / nsc;               // balanced split of the column into nsc chunks
-        q.z0 = r0 * TR;
-        q.x0 = side ? (nfx - 1) * FW : 0;
-        q.kind = side ? -2 : 2;
-        q.ntile = tm.sr0 + (i + 1) * nr / nsc - r0;
-        q.dz = TR; q.dx = 0;
-        tr0 = r0; tr1 = r0 + q.ntile;
-        if (ST_DBG_SKIP & 16) q.kind = 0;
+        const int side = c / nsc;
+        tr = c - side * nsc;
+        tma_side_tile(tm, g, habc, nfx, tr, side, q);
     } else {
         c -= 2 * nsc;
         const int nrc = tma_row_chunks(tm);
-        int tr = c / nrc;
+        tr = c / nrc;
         const int i = c - tr * nrc;
         tr = tr < tm.nbot ? tm.ntr - tm.nbot + tr : tr - tm.nbot;
         const int c0 = tm.tx0 + i * ntx / nrc;              // balanced split of the tile row into nrc chunks
@@ -155,10 +166,9 @@ __device__ __forceinline__ TmaChunk tma_block_decode(const W2Tma& tm, const W2Ge
         q.ntile = tm.tx0 + (i + 1) * ntx / nrc - c0;
         q.dz = 0; q.dx = FW;
         q.kind = tma_row_kind(tm, g, habc, q.z0);
-        tr0 = tr; tr1 = tr + 1;
     }
-    // tiles of the acquisition rows belong to the per-shot blocks above (side chunks: tpb == 1 whenever ar1 > ar0)
-    if (tm.ar1 > tm.ar0 && tr0 < tm.ar1 && tr1 > tm.ar0) q.ntile = 0;
+    // tiles of the acquisition rows belong to the per-shot blocks above
+    if (tm.ar1 > tm.ar0 && tr >= tm.ar0 && tr < tm.ar1) q.ntile = 0;
     return q;
 }
 template <int FL>
@@ -961,10 +971,10 @@ __device__ __forceinline__ void forward_fast_block(const W2Args& a, int bid, int
 
 // ALL: every cell of the tile (the corner tiles of the TMA kernels), else only the frame cells
 template <int FL, bool ALL = false>
-__device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int tx, int b, int tid, float (*s1)[SH][SW]) {
+__device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int tx, int b, int tid, float (*s1)[SH][SW], int xoff = 0) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     const W2Geom g = a.g;
-    const int x0 = tx * TX, z0 = tz * TZ;
+    const int x0 = tx * TX + xoff, z0 = tz * TZ;
     const long long boff = (long long)b * a.fs;
 #pragma unroll
     for (int f = 0; f < NF; ++f) load_tile(s1[f], a.cur + f * a.cs + boff, z0, x0, g, tid);
@@ -1009,23 +1019,21 @@ __device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int
 
 
 // The cells the TMA tiles do not cover (HABC: the four corners, where side ownership, corner diagonals and the
-// wrap-around neighbour live) as generic TX x TZ tiles: rows [0, sr0 TR) and [sr1 TR, nz) of the columns
-// [0, tx0 FW) and [tx1 FW, nx).
-struct CornerTiles { int rt, rb, cl, cr, count; };
+// wrap-around neighbour live) as generic TX-wide tiles: rows [0, sr0 TR) and [sr1 TR, nz) of the columns [0, TX) and
+// [corner_xr, nx).  The rest of those rows inside the side tile columns belongs to masked TMA tiles.
+struct CornerTiles { int rt, rb, count; };
 __host__ __device__ inline CornerTiles corner_tiles(const W2Tma& tm, const W2Geom& g) {
-    CornerTiles c{0, 0, 0, 0, 0};
+    CornerTiles c{0, 0, 0};
     if (tm.sr1 <= tm.sr0) return c;
     c.rt = tm.sr0 * TR / TZ;
     c.rb = (g.nz - tm.sr1 * TR + TZ - 1) / TZ;
-    c.cl = tm.tx0 * FW / TX;
-    c.cr = (g.nx - tm.tx1 * FW + TX - 1) / TX;
-    c.count = (c.rt + c.rb) * (c.cl + c.cr);
+    c.count = (c.rt + c.rb) * 2;
     return c;
 }
-__device__ __forceinline__ void corner_tile_decode(const CornerTiles& c, const W2Tma& tm, int i, int& tz, int& tx) {
-    const int w = c.cl + c.cr, ri = i / w, ci = i - ri * w;
+__device__ __forceinline__ void corner_tile_decode(const CornerTiles& c, const W2Tma& tm, const W2Geom& g, int i, int& tz, int& xoff) {
+    const int ri = i >> 1;
     tz = ri < c.rt ? ri : tm.sr1 * TR / TZ + (ri - c.rt);
-    tx = ci < c.cl ? ci : tm.tx1 * FW / TX + (ci - c.cl);
+    xoff = (i & 1) ? corner_xr(tm, g) : 0;
 }
 
 // TMA block: one TR x TC tile, `tsh` shots pulled through a ring of bulk tensor loads.
@@ -1047,6 +1055,7 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
     const int nitem = q.ntile * nsh;                        // item j = (tile j / nsh, shot j % nsh)
     const int warp = tid >> 5, lane = tid & 31;
     const bool zdir = kind == 1 || kind == -1;
+    const bool masked = q.mx0 > 0 || q.mx1 < (1 << 30);
     const int hoff = zdir ? 2 : 1;                          // rows above z0 in the `cur` box
     const CUtensorMap* mcur = zdir ? &tm.u_h2 : &tm.u_h1;
     const CUtensorMap* mprev = kind ? &tm.u_h1 : &tm.u_core;
@@ -1148,9 +1157,19 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
                     f4set(Y, e, x + e < g.nx ? y + f4get(bb[k], e) * (one - y) : 0.f);      // pitch padding stays zero
                 }
             }
-            if (zok[k]) *reinterpret_cast<float4*>(out + k * ld) = Y;
+            if (zok[k]) {
+                if (!masked) {
+                    *reinterpret_cast<float4*>(out + k * ld) = Y;
+                } else {                                    // corner rows: only the columns this tile owns (+ zero padding)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (x + e >= q.mx0 && x + e < q.mx1) out[k * ld + e] = f4get(Y, e);
+                        else if (x + e >= g.nx && x + e < ld) out[k * ld + e] = 0.f;
+                    }
+                }
+            }
         }
-        forward_tail<1>(a, b, z0, z0 + TR, x0, x0 + FW, tid, [](int, int) { return true; });
+        forward_tail<1>(a, b, z0, z0 + TR, x0, x0 + FW, tid, [&](int, int xx) { return xx >= q.mx0 && xx < q.mx1; });
         __syncthreads();                                   // every warp is done with this stage
         if ((tid == 0 || tid == 32) && j + NS < nitem) issue(j + NS, tid >> 5);
         if (++sh == nsh) { sh = 0; z0 += q.dz; x0 += q.dx; }
@@ -1208,8 +1227,8 @@ __global__ void __launch_bounds__(NT, tma_fwd_minb<FL>()) wave2d_forward_tma_ker
         if constexpr ((FL & ST_F_HABC) != 0) {
             int tz, tx;
             const int b = bid / ct.count;
-            corner_tile_decode(ct, tm, bid - b * ct.count, tz, tx);
-            forward_frame_block<FL, true>(a, tz, tx, b, tid, reinterpret_cast<float (*)[SH][SW]>(dsm));
+            corner_tile_decode(ct, tm, a.g, bid - b * ct.count, tz, tx);
+            forward_frame_block<FL, true>(a, tz, 0, b, tid, reinterpret_cast<float (*)[SH][SW]>(dsm), tx);
         }
         return;
     }
@@ -1568,10 +1587,10 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
 // Shots b_lo..b_hi-1 are processed in turn; gradient contributions go to plane `gplane`.
 template <int FL>
 __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, int tx, int b_lo, int b_hi, int gplane,
-                                                      int tid, int band, float (*sl)[SH][SW], float (*ss)[SH][SW]) {
+                                                      int tid, int band, float (*sl)[SH][SW], float (*ss)[SH][SW], int xoff = 0) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     const W2Geom g = a.g;
-    const int x0 = tx * TX, z0 = tz * TZ;
+    const int x0 = tx * TX + xoff, z0 = tz * TZ;
     const int x = x0 + (tid & (NTX - 1)), ty = tid / NTX;
     const bool want_grad = a.gacc != nullptr;
     const long long plane = (long long)g.nz * g.ld;
@@ -1699,6 +1718,7 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
     const int nitem = q.ntile * nsh;                        // item j = (tile j / nsh, shot j % nsh)
     const int warp = tid >> 5, lane = tid & 31;
     const bool want_grad = a.gacc != nullptr;
+    const bool masked = q.mx0 > 0 || q.mx1 < (1 << 30);
     auto issue = [&](int j) {
         const int stg = j % NS, ti = j / nsh, s = j - ti * nsh;
         const int z0 = q.z0 + ti * q.dz, x0 = q.x0 + ti * q.dx;
@@ -1861,7 +1881,15 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
                         f4set(o4, e, x + e < g.nx ? v : 0.f);                            // pitch padding stays zero
                     }
                 }
-                if (z < g.nz && x < ld) *reinterpret_cast<float4*>(out + k * ld) = o4;
+                if (z < g.nz && x < ld) {
+                    if (!masked) {
+                        *reinterpret_cast<float4*>(out + k * ld) = o4;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (x + e >= q.mx0 && x + e < q.mx1) out[k * ld + e] = f4get(o4, e);
+                    }
+                }
             }
             // ---- phase B: imaging condition
             if (want_grad) {
@@ -1924,7 +1952,7 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
                 }
             }
         }
-        adjoint_tail<1>(a, b, z0, z0 + TR, x0, x0 + FW, tid, [](int, int) { return true; });
+        adjoint_tail<1>(a, b, z0, z0 + TR, x0, x0 + FW, tid, [&](int, int xx) { return xx >= q.mx0 && xx < q.mx1; });
         __syncthreads();                                   // every warp is done with this stage
         if (tid == 0 && j + NS < nitem) issue(j + NS);
       }
@@ -1937,6 +1965,15 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             if (zr + k >= g.nz) continue;
+            if (masked) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (x + e < q.mx0 || x + e >= q.mx1) continue;
+                    gb[plane + k * ld + e] += f4get(gc[k], e);
+                    if (KIND) gb[k * ld + e] += f4get(gr[k], e);
+                }
+                continue;
+            }
             float4 v = *reinterpret_cast<float4*>(gb + plane + k * ld);
             *reinterpret_cast<float4*>(gb + plane + k * ld) = f4add(v, gc[k]);            // slot 1: d/d ciso
             if (KIND) {
@@ -1987,10 +2024,10 @@ __global__ void __launch_bounds__(NT, tma_adj_minb<FL>()) wave2d_adjoint_tma_ker
         if constexpr ((FL & ST_F_HABC) != 0) {
             int tz, tx;
             const int b = bid / ct.count;
-            corner_tile_decode(ct, tm, bid - b * ct.count, tz, tx);
+            corner_tile_decode(ct, tm, a.g, bid - b * ct.count, tz, tx);
             float* smem = reinterpret_cast<float*>(dsm);
-            adjoint_general_block<FL>(a, tz, tx, b, b + 1, b, tid, -1, reinterpret_cast<float (*)[SH][SW]>(smem),
-                                      reinterpret_cast<float (*)[SH][SW]>(smem + SH * SW));
+            adjoint_general_block<FL>(a, tz, 0, b, b + 1, b, tid, -1, reinterpret_cast<float (*)[SH][SW]>(smem),
+                                      reinterpret_cast<float (*)[SH][SW]>(smem + SH * SW), tx);
         }
     } else {
         if (ST_DBG_SKIP & 8) return;
@@ -2114,8 +2151,6 @@ int st_wave2d_tma_setup(int flags, const W2Args& a, const float* u, long long u_
     }
     const long long work = (long long)g.nz * g.nx * a.B;
     if (mode < 0 && (a.B < 2 || work < (1LL << 21))) return ST_OK;       // too little work to fill the rings
-    // measured (B200, 851x2401, 8 shots): the PML forward register kernel beats the TMA one (53 vs 66 us)
-    if (mode < 0 && !adjoint && !(flags & ST_F_HABC)) return ST_OK;
     tm.tx0 = tx0; tm.tx1 = tx1;
     // shots per block: all (up to 8) in the forward pass; in the adjoint at least bchunk (the caller sized the
     // gradient planes for ceil(B / bchunk) groups)
