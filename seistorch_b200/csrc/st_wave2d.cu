@@ -55,6 +55,9 @@ static_assert(TC == FW && TR == 2 * NWARP && FH % TR == 0, "TMA tile = one float
 constexpr int TMA_H1_BYTES = (H1R * HC * 4 + 127) / 128 * 128;       // 9856  (box: 9792)
 constexpr int TMA_H2_BYTES = (H2R * HC * 4 + 127) / 128 * 128;       // 10880
 constexpr int TMA_CORE_BYTES = TR * TC * 4;                          // 8192
+#ifndef ST_CORNER_UNROLL
+#define ST_CORNER_UNROLL 1                   // cells in flight per thread in the generic corner tiles of the TMA kernels
+#endif
 #ifndef ST_TMA_FWD_STAGES
 #define ST_TMA_FWD_STAGES 3
 #endif
@@ -970,7 +973,7 @@ __device__ __forceinline__ void forward_fast_block(const W2Args& a, int bid, int
 }
 
 // ALL: every cell of the tile (the corner tiles of the TMA kernels), else only the frame cells
-template <int FL, bool ALL = false>
+template <int FL, bool ALL = false, int UNR = 1>
 __device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int tx, int b, int tid, float (*s1)[SH][SW], int xoff = 0) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     const W2Geom g = a.g;
@@ -981,7 +984,7 @@ __device__ __forceinline__ void forward_frame_block(const W2Args& a, int tz, int
     __syncthreads();
     const int x = x0 + (tid & (NTX - 1)), ty = tid / NTX;
     if (x < g.nx) {
-#pragma unroll 1
+#pragma unroll UNR
         for (int k = 0; k < RPT; ++k) {
             const int z = z0 + ty + k * NTY;
             if (z >= g.nz) break;
@@ -1228,7 +1231,7 @@ __global__ void __launch_bounds__(NT, tma_fwd_minb<FL>()) wave2d_forward_tma_ker
             int tz, tx;
             const int b = bid / ct.count;
             corner_tile_decode(ct, tm, a.g, bid - b * ct.count, tz, tx);
-            forward_frame_block<FL, true>(a, tz, 0, b, tid, reinterpret_cast<float (*)[SH][SW]>(dsm), tx);
+            forward_frame_block<FL, true, ST_CORNER_UNROLL>(a, tz, 0, b, tid, reinterpret_cast<float (*)[SH][SW]>(dsm), tx);
         }
         return;
     }
@@ -1585,7 +1588,7 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
 // general cell-by-cell adjoint of one TX x TZ tile; `band` < 0: every cell, else only the
 // cells closer than `band` to an absorbing edge
 // Shots b_lo..b_hi-1 are processed in turn; gradient contributions go to plane `gplane`.
-template <int FL>
+template <int FL, int UNR = 1>
 __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, int tx, int b_lo, int b_hi, int gplane,
                                                       int tid, int band, float (*sl)[SH][SW], float (*ss)[SH][SW], int xoff = 0) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
@@ -1605,7 +1608,7 @@ __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, i
         }
         __syncthreads();
         if (x < g.nx) {
-#pragma unroll 1
+#pragma unroll UNR
             for (int k = 0; k < RPT; ++k) {
                 const int z = z0 + ty + k * NTY;
                 if (z >= g.nz) break;
@@ -2026,7 +2029,7 @@ __global__ void __launch_bounds__(NT, tma_adj_minb<FL>()) wave2d_adjoint_tma_ker
             const int b = bid / ct.count;
             corner_tile_decode(ct, tm, a.g, bid - b * ct.count, tz, tx);
             float* smem = reinterpret_cast<float*>(dsm);
-            adjoint_general_block<FL>(a, tz, 0, b, b + 1, b, tid, -1, reinterpret_cast<float (*)[SH][SW]>(smem),
+            adjoint_general_block<FL, ST_CORNER_UNROLL>(a, tz, 0, b, b + 1, b, tid, -1, reinterpret_cast<float (*)[SH][SW]>(smem),
                                       reinterpret_cast<float (*)[SH][SW]>(smem + SH * SW), tx);
         }
     } else {

@@ -196,3 +196,60 @@ def test_tma_path_against_oracle_and_register_path(eq, multiple, nx, monkeypatch
     misfit.l2(orecs, [torch.zeros_like(r) for r in orecs]).backward()
     assert rel(r_tma, cat_records([r.detach().numpy() for r in orecs])) < 1e-5
     assert rel(g_tma, params["vp"].grad.numpy()) < 1e-4
+
+
+def _props(case, inv, segment, scale=3.0, shot_tol=None):
+    """Size-independent properties on one case: returns nothing, asserts
+    (i) K-step checkpoint-recompute == stored history bit for bit (records and gradients),
+    (ii) linearity of the records in the wavelet,
+    (iii) shot independence: the 2-shot batch equals the two single-shot runs (records bit for bit unless
+         shot_tol is given, gradients add up)."""
+    def grad_of(c, seg=None):
+        cfg, model, x = _model(c)
+        model.segment = seg
+        syn = model(x)
+        loss = sum((s ** 2).sum() for s in syn)
+        loss.backward()
+        return ([s.detach().cpu().numpy() for s in syn],
+                {k: getattr(model.cell.geom, k).grad.cpu().numpy().astype(np.float64) for k in inv})
+    r0, g0 = grad_of(case)
+    r1, g1 = grad_of(case, seg=segment)
+    assert all(np.array_equal(a, b) for a, b in zip(r0, r1))
+    assert all(np.array_equal(g0[k], g1[k]) for k in inv)
+    assert all(np.isfinite(g0[k]).all() and np.abs(g0[k]).max() > 0 for k in inv)
+    ra, ga = grad_of(dict(case, sources=case["sources"][:1], receivers=case["receivers"][:1]))
+    rb, gb = grad_of(dict(case, sources=case["sources"][1:], receivers=case["receivers"][1:]))
+    if shot_tol is None:
+        assert np.array_equal(r0[0], ra[0]) and np.array_equal(r0[1], rb[0])
+    else:
+        assert rel(r0[0], ra[0]) < shot_tol and rel(r0[1], rb[0]) < shot_tol
+    for k in inv:
+        assert rel(g0[k], ga[k] + gb[k]) < 2e-5, k
+    rs, _ = grad_of(dict(case, wavelet=np.asarray(case["wavelet"]) * scale))
+    assert rel(cat_records(rs), scale * cat_records(r0)) < 2e-6
+
+
+def test_baseline_size_properties_cfg3_elastic():
+    """BASELINE configs[2]: elastic velocity-stress, PML, 1000x400 model (padded 1100x500), vp/vs/rho inverted,
+    source vz, receivers vx+vz; short horizon."""
+    from oracle import cases
+    case = cases.make_case("elastic", nz=400, nx=1000, nshots=2, nt=120, rec_step=2)
+    _props(case, ["vp", "vs", "rho"], segment=29)
+
+
+@pytest.mark.parametrize("eq", ["acoustic_vti_lsrtm_habc", "acoustic_tti_lsrtm_habc", "acoustic_fwim_habc"])
+def test_baseline_size_properties_cfg4(eq):
+    """BASELINE configs[3]: VTI / TTI qP LSRTM (Born pair, receivers on the scattered field, m inverted jointly
+    with vp) and the joint FWI-LSRTM equation, 1200x500 model (padded 1300x600); short horizon."""
+    from oracle import cases
+    case = cases.make_case(eq, nz=500, nx=1200, nshots=2, nt=120, rec_step=2)
+    inv = [k for k, v in case["invlist"].items() if v]
+    _props(case, inv, segment=31)
+
+
+def test_baseline_size_properties_cfg5_3d():
+    """BASELINE configs[4]: 3D acoustic, PML, model file (400,200,400) -> padded (500,300,500) tensor layout (x,z,y),
+    K-step checkpointed wavefield reconstruction; 2 shots, short horizon (75 M cells per shot and state)."""
+    from oracle import cases
+    case = cases.make_case("acoustic", nz=200, nx=400, ny=400, nshots=2, nt=24, rec_step=8)
+    _props(case, ["vp"], segment=7)
