@@ -1256,9 +1256,9 @@ __host__ __device__ constexpr bool grad_used(int q) {
          : (q == 4 || q == 5) ? (FL & ST_F_G1) != 0
          : (FL & ST_F_BORN) != 0;
 }
-// flag sets with a vectorised adjoint fast path (the acoustic flagship equations)
+// flag sets with a vectorised adjoint fast path (all of them; the generic whole-grid path below is kept for reference)
 template <int FL>
-__host__ __device__ constexpr bool adj_fast() { return !(FL & ST_F_BORN); }
+__host__ __device__ constexpr bool adj_fast() { return true; }
 // ... of which the two acoustic ones keep their gradient partial sums in shared memory
 template <int FL>
 __host__ __device__ constexpr bool adj_iso_only() { return FL == (ST_F_ISO | ST_F_PML) || FL == (ST_F_ISO | ST_F_HABC); }
@@ -1523,6 +1523,132 @@ __device__ __forceinline__ void adjoint_fast_rows_gen(const W2Args& a, const W2G
     }
 }
 
+// Born pairs (acoustic_vti_lsrtm_habc, acoustic_tti_lsrtm_habc): interior cells of both fields
+//   Lam_i(f) = 2 L1(f) - L2(f) + dxx(cxx le_f) + dzz(czz le_f) + dxz^T(cxz le_f),   le_1 = L1(1),  le_0 = L1(0) + m L1(1)
+// (the background field also receives the scattered field's cotangent through m A[p]); gradients
+//   g_cxx += le_f dxx S_f,  g_czz += le_f dzz S_f,  g_cxz += le_f dxz S_f  (both fields),   g_m += L1(1) A[S_0].
+// Same row-marching register pipeline as adjoint_fast_rows_gen, one field after the other.
+template <int FL, class Own>
+__device__ __forceinline__ void adjoint_fast_rows_born(const W2Args& a, const W2Geom& g, int b, int chunk, int x0, int z0,
+                                                       int zn, int lane, bool clean, bool want_grad, Own owns) {
+    constexpr bool XZ = (FL & ST_F_XZ) != 0;
+    const int x = x0 + 4 * lane;
+    const int ld = g.ld;
+    const long long boff = (long long)b * a.fs, plane = (long long)g.nz * ld;
+    float* gb = want_grad ? a.gacc + (long long)chunk * 7 * plane : nullptr;
+    const bool edge = lane == 0 || lane == 31;
+    const int xh = lane == 0 ? x0 - 1 : x0 + FW;
+    const float* l1s = a.lam1 + a.cs + boff;                // cotangent of the scattered field
+#pragma unroll 1
+    for (int f = 1; f >= 0; --f) {
+        const float* l1 = a.lam1 + f * a.cs + boff;
+        const float* l2 = a.lam2 + f * a.cs + boff;
+        const float* S = a.s1 + f * a.cs + boff;
+        float* l0 = a.lam0 + f * a.cs + boff;
+        // product rows of row z:  PA = cxx*le, PB = czz*le, PC = cxz*le  (+ x-neighbours of PA, PC)
+        struct Prod { float4 l, a, b, c; float al, ar, cl, cr; };
+        auto load_prod = [&](int z) {
+            Prod p;
+            p.l = ldrow(l1, z, x, g);
+            if (f == 0) p.l = f4fma(ldrow(a.coef[7], z, x, g), ldrow(l1s, z, x, g), p.l);
+            p.a = f4mul(ldrow(a.coef[2], z, x, g), p.l);
+            p.b = f4mul(ldrow(a.coef[3], z, x, g), p.l);
+            p.c = XZ ? f4mul(ldrow(a.coef[4], z, x, g), p.l) : f4zero();
+            p.al = __shfl_up_sync(0xffffffffu, p.a.w, 1); p.ar = __shfl_down_sync(0xffffffffu, p.a.x, 1);
+            p.cl = p.cr = 0.f;
+            if (XZ) { p.cl = __shfl_up_sync(0xffffffffu, p.c.w, 1); p.cr = __shfl_down_sync(0xffffffffu, p.c.x, 1); }
+            if (edge) {
+                float va = 0.f, vc = 0.f;
+                if (z >= 0 && z < g.nz && xh >= 0 && xh < g.nx) {
+                    const int o = z * ld + xh;
+                    float lv = __ldg(l1 + o);
+                    if (f == 0) lv += __ldg(a.coef[7] + o) * __ldg(l1s + o);
+                    va = __ldg(a.coef[2] + o) * lv;
+                    if (XZ) vc = __ldg(a.coef[4] + o) * lv;
+                }
+                if (lane == 0) { p.al = va; p.cl = vc; } else { p.ar = va; p.cr = vc; }
+            }
+            return p;
+        };
+        struct SRow { float4 s; float l, r; };
+        auto load_s = [&](int z) {
+            SRow q;
+            q.s = ldrow(S, z, x, g);
+            row_halo(q.s, S, z, x0, lane, g, q.l, q.r);
+            return q;
+        };
+        Prod U = load_prod(z0 - 1), C = load_prod(z0), D;
+        SRow sU, sC, sD;
+        if (want_grad) { sU = load_s(z0 - 1); sC = load_s(z0); }
+#pragma unroll
+        for (int k = 0; k < FRZ; ++k) {
+            const int z = z0 + k;
+            if (z < zn) {
+                D = load_prod(z + 1);
+                const float4 p2 = ldrow(l2, z, x, g);
+                const float4 lraw = f == 0 ? ldrow(l1, z, x, g) : C.l;     // 2 L1(f): the field's own cotangent
+                if (want_grad) sD = load_s(z + 1);
+                float4 out, g1v = f4zero(), g2v = f4zero(), g3v = f4zero(), g6v = f4zero();
+                float4 ca = f4zero(), cb = f4zero(), cc = f4zero(), ls = f4zero();
+                if (want_grad && f == 0) {                                   // g_m needs A[S_0] and L1(1) at the cell
+                    ca = ldrow(a.coef[2], z, x, g); cb = ldrow(a.coef[3], z, x, g);
+                    if (XZ) cc = ldrow(a.coef[4], z, x, g);
+                    ls = ldrow(l1s, z, x, g);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float ac = f4get(C.a, e);
+                    const float aw = e == 0 ? C.al : f4get(C.a, e - 1), ae = e == 3 ? C.ar : f4get(C.a, e + 1);
+                    float acc = 2.f * f4get(lraw, e) - f4get(p2, e);
+                    acc += ((ae - ac) + (aw - ac));                                              // dxx of cxx*le
+                    acc += ((f4get(U.b, e) - f4get(C.b, e)) + (f4get(D.b, e) - f4get(C.b, e)));  // dzz of czz*le
+                    if (XZ) {
+                        const float uw = e == 0 ? U.cl : f4get(U.c, e - 1), ue = e == 3 ? U.cr : f4get(U.c, e + 1);
+                        const float dw = e == 0 ? D.cl : f4get(D.c, e - 1), de = e == 3 ? D.cr : f4get(D.c, e + 1);
+                        acc += (uw - ue) - (dw - de);
+                    }
+                    f4set(out, e, acc);
+                    if (want_grad) {
+                        const float le = f4get(C.l, e);
+                        const float sc = f4get(sC.s, e);
+                        const float sw_ = e == 0 ? sC.l : f4get(sC.s, e - 1), se_ = e == 3 ? sC.r : f4get(sC.s, e + 1);
+                        const float sn = f4get(sU.s, e), ss = f4get(sD.s, e);
+                        const float sxx = (se_ - sc) + (sw_ - sc), szz = (sn - sc) + (ss - sc);
+                        f4set(g1v, e, le * sxx);
+                        f4set(g2v, e, le * szz);
+                        float cross = 0.f;
+                        if (XZ) {
+                            const float nw = e == 0 ? sU.l : f4get(sU.s, e - 1), ne = e == 3 ? sU.r : f4get(sU.s, e + 1);
+                            const float sw2 = e == 0 ? sD.l : f4get(sD.s, e - 1), se2 = e == 3 ? sD.r : f4get(sD.s, e + 1);
+                            cross = (se2 - sw2) - (ne - nw);
+                            f4set(g3v, e, le * cross);
+                        }
+                        if (f == 0) f4set(g6v, e, f4get(ls, e) * (f4get(ca, e) * sxx + f4get(cb, e) * szz + f4get(cc, e) * cross));
+                    }
+                }
+                const int ro = z * ld + x;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool mine = x + e < g.nx && (clean || owns(z, x + e));
+                    if (mine) {
+                        l0[ro + e] = f4get(out, e);
+                        if (want_grad) {
+                            gb[plane + ro + e] += f4get(g1v, e);
+                            gb[2 * plane + ro + e] += f4get(g2v, e);
+                            if (XZ) gb[3 * plane + ro + e] += f4get(g3v, e);
+                            if (f == 0) gb[6 * plane + ro + e] += f4get(g6v, e);
+                        }
+                    } else if (x + e >= g.nx && x + e < ld) {
+                        l0[ro + e] = 0.f;
+                    }
+                }
+                U = C; C = D;
+                if (want_grad) { sU = sC; sC = sD; }
+            }
+        }
+    }
+}
+
 template <int FL>
 __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int nfx, int chunk, int tid,
                                                    float (*gsm)[FRZ][FW]) {
@@ -1558,10 +1684,11 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
                 if (safe) adjoint_fast_rows<FL, true>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
                 else adjoint_fast_rows<FL, false>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
             } else {
-                adjoint_fast_rows_gen<FL>(a, g, b, chunk, x0, z0, zn, lane, clean, want_grad, owns);
+                if constexpr ((FL & ST_F_BORN) != 0) adjoint_fast_rows_born<FL>(a, g, b, chunk, x0, z0, zn, lane, clean, want_grad, owns);
+                else adjoint_fast_rows_gen<FL>(a, g, b, chunk, x0, z0, zn, lane, clean, want_grad, owns);
             }
         }
-        adjoint_tail<1>(a, b, zb0, zb0 + FH, x0, x0 + FW, tid, owns);
+        adjoint_tail<(FL & ST_F_BORN) ? 2 : 1>(a, b, zb0, zb0 + FH, x0, x0 + FW, tid, owns);
     }
     if (want_grad && adj_iso_only<FL>() && rows && x < g.ld) {
         float* gb = a.gacc + ((long long)chunk * 7 + 1) * ((long long)g.nz * g.ld);       // slot 1: d/d ciso
@@ -1653,8 +1780,12 @@ __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, i
     }
 }
 
+// resident blocks per SM the register adjoint is compiled for (the Born pairs carry two fields: 128 registers)
 template <int FL>
-__global__ void __launch_bounds__(NT, ST_ADJ_MINB) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
+__host__ __device__ constexpr int adj_minb() { return (FL & ST_F_BORN) ? 2 : ST_ADJ_MINB; }
+
+template <int FL>
+__global__ void __launch_bounds__(NT, adj_minb<FL>()) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     constexpr bool NEED_GEN = !adj_fast<FL>() || (FL & ST_F_HABC);
     constexpr int GEN_FLOATS = NEED_GEN ? 2 * NF * SH * SW : 1;
@@ -2175,9 +2306,8 @@ int st_wave2d_tma_setup(int flags, const W2Args& a, const float* u, long long u_
     if (const char* e = getenv("SEISTORCH_B200_TPB")) { if (atoi(e) > 0) tm.tpb = atoi(e); }
     // acquisition rows: one shot per block (measured: the source / receiver epilogue costs 3-4 us per item, a chain of
     // dependent loads, against 0.8 us for the item itself; eight of them in a row make those blocks finish 3x later
-    // than all the others).  The adjoint needs one gradient plane per shot for that: HABC callers provide them
-    // (include/seistorch_b200.h), PML callers only ceil(B / bchunk).
-    const bool planes_ok = !adjoint || (flags & ST_F_HABC) || a.bchunk == 1 || a.gacc == nullptr;
+    // than all the others).  The adjoint needs one gradient plane per shot for that.
+    const bool planes_ok = true;                            // gacc has max(nchunk, B) planes (include/seistorch_b200.h)
     const bool any_acq = a.ns > 0 || a.R > 0;
     if (tm.tpb == 1 && tm.tsh > 1 && planes_ok && any_acq && a.row_hi >= a.row_lo && a.row_hi - a.row_lo < 8 * TR &&
         getenv("SEISTORCH_B200_TMA_NOACQ") == nullptr) {
