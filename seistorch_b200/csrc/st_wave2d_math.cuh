@@ -64,6 +64,24 @@ ST_HD void w2_side_weights(int z, int x, const W2Geom& g, float f[4]) {
     }
 }
 
+// Side (0 top, 1 bottom, 2 left, 3 right) whose STRAIGHT part holds every frame cell that can interact with
+// (z,x) through a one-way blend, or -1: (z,x) is at most bw deep on that side and at least bw+2 away from the
+// two adjacent sides, so the cells q = p - k n (k = 0..2 along the inward normal n) that read it are owned by
+// that side alone with weight 1 (no corner ownership, no corner diagonal), and no other side reaches it.
+ST_HD int w2_straight_side(int z, int x, const W2Geom& g) {
+    const int w = g.bw, m = g.bw + 2;
+    const bool xmid = x >= m && x < g.nx - m, zmid = z >= m && z < g.nz - m;
+    if (xmid) {
+        if (!g.multiple && z <= w) return (g.nz - 1 - z > w) ? 0 : -1;
+        if (g.nz - 1 - z <= w) return (g.multiple || z > w) ? 1 : -1;
+    }
+    if (zmid) {
+        if (x <= w) return (g.nx - 1 - x > w) ? 2 : -1;
+        if (g.nx - 1 - x <= w) return (x > w) ? 3 : -1;
+    }
+    return -1;
+}
+
 ST_HD int w2_depth(int s, int z, int x, const W2Geom& g) {
     return s == 0 ? z : (s == 1 ? g.nz - 1 - z : (s == 2 ? x : g.nx - 1 - x));
 }
@@ -212,7 +230,29 @@ ST_HD void w2_adjoint_cell(int z, int x, const W2Geom& g, float dt,
         if (FL & ST_F_G1)
             acc += (wk(3, z, x - 1) - wk(3, z, x + 1)) + (wk(4, z - 1, x) - wk(4, z + 1, x));
         // ---- transposed one-way blend: gather over the cells q whose extrapolation reads p
-        if (habc) {
+        const int straight = habc ? w2_straight_side(z, x, g) : -1;
+        if (habc && straight >= 0) {
+            // straight side: the three cells outward of p (and the wrap partner of depth 0) with weight b(q)
+            const int jp = w2_depth(straight, z, x, g);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int jq, kk;
+                if (k < 3) { jq = jp - k; kk = k; if (jq < 0 || jq > g.bw - 1 || jq + kk > g.bw) continue; }
+                else { if (jp != 0) continue; jq = g.bw - 1; kk = 2; }
+                int zq, xq;
+                w2_at_depth(straight, jq, z, x, g, zq, xq);
+                const float wgt = CK(1, zq, xq);
+                if (wgt == 0.f) continue;
+                const float rq = CK(0, zq, xq);
+                const float lam = 2.f * rq, mu = rq * rq;
+                const float a = kk == 0 ? (2.f - lam - mu) : (kk == 1 ? (lam + 2.f * mu) : -mu);
+                acc += wgt * a * L1(f, zq, xq);
+                if (kk <= 1) {
+                    const float bt = kk == 0 ? (lam - 1.f) : -lam;
+                    acc += wgt * bt * L2(f, zq, xq);
+                }
+            }
+        } else if (habc) {
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const int jp = w2_depth(s, z, x, g);
