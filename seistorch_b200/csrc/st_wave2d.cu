@@ -1059,6 +1059,7 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
     const int warp = tid >> 5, lane = tid & 31;
     const bool zdir = kind == 1 || kind == -1;
     const bool masked = q.mx0 > 0 || q.mx1 < (1 << 30);
+    const bool xrag = q.x0 + q.ntile * q.dx + FW > g.nx;    // the tile column that crosses nx
     const int hoff = zdir ? 2 : 1;                          // rows above z0 in the `cur` box
     const CUtensorMap* mcur = zdir ? &tm.u_h2 : &tm.u_h1;
     const CUtensorMap* mprev = kind ? &tm.u_h1 : &tm.u_core;
@@ -1116,8 +1117,11 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
             const float4 D = *reinterpret_cast<const float4*>(rowc + HC + XO + 4 * lane);
             const float4 P = *reinterpret_cast<const float4*>(rowp + 4 * lane);
             float lc = __shfl_up_sync(0xffffffffu, C.w, 1), rc = __shfl_down_sync(0xffffffffu, C.x, 1);
-            if (lane == 0) lc = rowc[XO - 1];
-            if (lane == 31) rc = rowc[XO + TC];
+            {   // halo columns: broadcast shared loads + selects (no divergent branch in the hot loop)
+                const float hl = rowc[XO - 1], hr = rowc[XO + TC];
+                lc = lane == 0 ? hl : lc;
+                rc = lane == 31 ? hr : rc;
+            }
             float4 Y;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -1157,7 +1161,7 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
                     const float dmu = (a1 - a0) - (a2 - a1);
                     const float one = base + lam * dlam + mu * dmu;
                     const float y = f4get(Y, e);
-                    f4set(Y, e, x + e < g.nx ? y + f4get(bb[k], e) * (one - y) : 0.f);      // pitch padding stays zero
+                    f4set(Y, e, (!xrag || x + e < g.nx) ? y + f4get(bb[k], e) * (one - y) : 0.f);   // pitch padding stays zero
                 }
             }
             if (zok[k]) {
@@ -1853,6 +1857,7 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
     const int warp = tid >> 5, lane = tid & 31;
     const bool want_grad = a.gacc != nullptr;
     const bool masked = q.mx0 > 0 || q.mx1 < (1 << 30);
+    const bool xrag = q.x0 + q.ntile * q.dx + FW > g.nx;    // the tile column that crosses nx
     auto issue = [&](int j) {
         const int stg = j % NS, ti = j / nsh, s = j - ti * nsh;
         const int z0 = q.z0 + ti * q.dz, x0 = q.x0 + ti * q.dx;
@@ -1937,8 +1942,11 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
                 const float4 p2 = *reinterpret_cast<const float4*>(l2r + 4 * lane);
                 const float4 wU = f4mul(cp[k], lU), wC = f4mul(cp[k + 1], lC), wD = f4mul(cp[k + 2], lD);
                 float wl = __shfl_up_sync(0xffffffffu, wC.w, 1), wr = __shfl_down_sync(0xffffffffu, wC.x, 1);
-                if (lane == 0) wl = ch[k] * l1[hrow + XO - 1];
-                if (lane == 31) wr = ch[k] * l1[hrow + XO + TC];
+                {   // halo columns: broadcast shared loads + selects
+                    const float hl = l1[hrow + XO - 1], hr = l1[hrow + XO + TC];
+                    wl = lane == 0 ? ch[k] * hl : wl;
+                    wr = lane == 31 ? ch[k] * hr : wr;
+                }
                 float4 o4;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -2012,7 +2020,7 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
                         v -= f4get(X2, e);
                         v += (bze * (2.f * rze - 1.f) - pre) * f4get(p2, e);
                         v -= f4get(X3, e);
-                        f4set(o4, e, x + e < g.nx ? v : 0.f);                            // pitch padding stays zero
+                        f4set(o4, e, (!xrag || x + e < g.nx) ? v : 0.f);                 // pitch padding stays zero
                     }
                 }
                 if (z < g.nz && x < ld) {
@@ -2031,8 +2039,11 @@ __device__ __forceinline__ void adjoint_tma_tile(const W2Args& a, const W2Tma& t
                 const float4 sC = *reinterpret_cast<const float4*>(S + ro);
                 const float4 sU = *reinterpret_cast<const float4*>(S + ro - HC), sD = *reinterpret_cast<const float4*>(S + ro + HC);
                 float sl = __shfl_up_sync(0xffffffffu, sC.w, 1), sr = __shfl_down_sync(0xffffffffu, sC.x, 1);
-                if (lane == 0) sl = S[hrow + XO - 1];
-                if (lane == 31) sr = S[hrow + XO + TC];
+                {
+                    const float hl = S[hrow + XO - 1], hr = S[hrow + XO + TC];
+                    sl = lane == 0 ? hl : sl;
+                    sr = lane == 31 ? hr : sr;
+                }
                 float4 gq;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
