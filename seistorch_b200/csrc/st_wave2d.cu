@@ -80,7 +80,10 @@ template <int FL> __host__ __device__ constexpr int tma_adj_smem() {
 }
 // resident blocks per SM the TMA kernels are compiled for
 template <int FL> __host__ __device__ constexpr int tma_fwd_minb() { return (FL & ST_F_HABC) ? 3 : 4; }
-template <int FL> __host__ __device__ constexpr int tma_adj_minb() { return (FL & ST_F_HABC) ? 2 : 3; }
+#ifndef ST_TMA_ADJ_MINB_HABC
+#define ST_TMA_ADJ_MINB_HABC 2
+#endif
+template <int FL> __host__ __device__ constexpr int tma_adj_minb() { return (FL & ST_F_HABC) ? ST_TMA_ADJ_MINB_HABC : 3; }
 // flag sets with a TMA path
 template <int FL>
 __host__ __device__ constexpr bool tma_ok() { return FL == (ST_F_ISO | ST_F_PML) || FL == (ST_F_ISO | ST_F_HABC); }

@@ -1,4 +1,4 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python bench.py 2>&1 | tail -1 > gpurun_out/bench_r01c.log; cut -c1-200 gpurun_out/bench_r01c.log
-python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | cut -c1-300
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
+ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 400 --csv --log-file gpurun_out/launches_r01c.csv python bench.py --steps 1 --warmup 1 --nt 120 --no-cpu-baseline > gpurun_out/b_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:wave2d -s 300 -c 4 -f -o gpurun_out/prof_r01c_wave2d python tools/perf_step.py 8 100 > gpurun_out/ncu_full3.log 2>&1
+ls -la gpurun_out/prof_r01c_wave2d.ncu-rep gpurun_out/launches_r01c.csv
