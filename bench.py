@@ -230,15 +230,27 @@ def main():
 
     batches = [(lo, min(lo + mb, nshots)) + batch_modules(lo, min(lo + mb, nshots)) for lo in range(0, nshots, mb)]
 
+    # e2e leg: the observed data of every micro-batch travels host -> device on a copy stream while the
+    # previous micro-batch is being propagated (still inside the timed region, every step)
+    copy_stream = torch.cuda.Stream(device=dev)
+    obs_stage = torch.empty_like(obs_host, device=dev)
+    copy_done = [torch.cuda.Event() for _ in batches]
+
     def step(obs_dev, e2e=False):
         """one FWI-gradient evaluation of this rank's shots."""
         if e2e:
             vp_param.data.copy_(vp_host, non_blocking=True)
+            copy_stream.wait_stream(torch.cuda.current_stream(dev))      # the staging buffer is free again
+            with torch.cuda.stream(copy_stream):
+                for k, (lo, hi, _, _) in enumerate(batches):
+                    obs_stage[lo:hi].copy_(obs_host[lo:hi], non_blocking=True)
+                    copy_done[k].record(copy_stream)
         vp_param.grad = None
         total_loss = torch.zeros((), device=dev)
-        for lo, hi, ss, pp in batches:
+        for k, (lo, hi, ss, pp) in enumerate(batches):
             if e2e:
-                ob = obs_host[lo:hi].to(dev, non_blocking=True)
+                torch.cuda.current_stream(dev).wait_event(copy_done[k])
+                ob = obs_stage[lo:hi]
             else:
                 ob = obs_dev[lo:hi]
             syn = model(wav, None, ss, pp)

@@ -168,18 +168,22 @@ def test_mid_size_grid_against_oracle(eq):
         assert rel(getattr(model.cell.geom, k).grad.cpu().numpy(), params[k].grad.numpy()) < 1e-4, k
 
 
+@pytest.mark.parametrize("acq", ["deep", "surface"])
 @pytest.mark.parametrize("eq,multiple,nx", [("acoustic", False, 300), ("acoustic_habc", False, 300), ("acoustic_habc", True, 300),
                                             ("acoustic_habc", False, 216), ("acoustic_habc", True, 216)])
-def test_tma_path_against_oracle_and_register_path(eq, multiple, nx, monkeypatch):
+def test_tma_path_against_oracle_and_register_path(eq, multiple, nx, acq, monkeypatch):
     """The TMA-staged blocks (forced on: SEISTORCH_B200_TMA=1) against the float64 oracle and against the
     register/shuffle + tap-gather path (SEISTORCH_B200_TMA=0), 3 shots (ragged last shot group), sources
     and receivers inside TMA tiles.  Padded 250x400: frame-free + top/bottom frame tiles; padded 250x316:
     also the left/right frame tiles (one tile column per side)."""
     from oracle import cases, loop, misfit
     case = cases.make_case(eq, nz=150, nx=nx, nshots=3, nt=70, rec_step=9, multiple=multiple)
-    # put the acquisition deep enough to fall into the TMA rectangle as well as the frame rows
-    case["sources"] = [[s[0], 40.2] for s in case["sources"]]
-    case["receivers"] = [[r[0], [30] * len(r[0])] for r in case["receivers"]]
+    # "deep": acquisition rows inside the side tiles / frame-free tiles; "surface" (the bench geometry): sources and
+    # receivers just below the top frame, i.e. in the corner rows (generic corner tiles + masked TMA tiles) and in
+    # the one-shot-per-block acquisition rows
+    if acq == "deep":
+        case["sources"] = [[s[0], 40.2] for s in case["sources"]]
+        case["receivers"] = [[r[0], [30] * len(r[0])] for r in case["receivers"]]
 
     def run(mode):
         monkeypatch.setenv("SEISTORCH_B200_TMA", mode)
