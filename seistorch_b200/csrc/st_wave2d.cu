@@ -79,7 +79,10 @@ template <int FL> __host__ __device__ constexpr int tma_adj_smem() {
     return (FL & ST_F_HABC) ? (fr > in ? fr : in) : ST_TMA_ADJ_STAGES * tma_adj_stage<FL>();
 }
 // resident blocks per SM the TMA kernels are compiled for
-template <int FL> __host__ __device__ constexpr int tma_fwd_minb() { return (FL & ST_F_HABC) ? 3 : 4; }
+#ifndef ST_TMA_FWD_MINB_HABC
+#define ST_TMA_FWD_MINB_HABC 3
+#endif
+template <int FL> __host__ __device__ constexpr int tma_fwd_minb() { return (FL & ST_F_HABC) ? ST_TMA_FWD_MINB_HABC : 4; }
 #ifndef ST_TMA_ADJ_MINB_HABC
 #define ST_TMA_ADJ_MINB_HABC 2
 #endif
