@@ -259,3 +259,33 @@ def test_baseline_size_properties_cfg5_3d():
     from oracle import cases
     case = cases.make_case("acoustic", nz=200, nx=400, ny=400, nshots=2, nt=24, rec_step=8)
     _props(case, ["vp"], segment=7)
+
+
+def test_tma_path_vertical_receiver_line_and_ragged_shots(monkeypatch):
+    """TMA kernels with receivers on a vertical line (VSP-like: the acquisition spans too many rows for the
+    one-shot-per-block split, so the source / receiver epilogue runs inside the multi-shot tile blocks) and a
+    different receiver count per shot; against the register path and the float64 oracle."""
+    from oracle import cases, loop, misfit
+    case = cases.make_case("acoustic_habc", nz=150, nx=216, nshots=3, nt=70, rec_step=9)
+    zs = list(range(3, 147, 4))
+    case["receivers"] = [[[100 + 7 * k] * (len(zs) - 3 * k), zs[:len(zs) - 3 * k]] for k in range(3)]
+    case["sources"] = [[s[0], 20.0 + 30 * k] for k, s in enumerate(case["sources"])]
+
+    def run(mode):
+        monkeypatch.setenv("SEISTORCH_B200_TMA", mode)
+        cfg, model, x = _model(case)
+        syn = model(x)
+        assert [tuple(s.shape) for s in syn] == [(70, len(zs) - 3 * k, 1) for k in range(3)]
+        loss = sum((s ** 2).sum() for s in syn)
+        loss.backward()
+        from seistorch_b200 import engine
+        assert ("tma" in engine.KERNELS["adjoint"]) == (mode == "1")
+        return cat_records([s.detach().cpu().numpy() for s in syn]), model.cell.geom.vp.grad.cpu().numpy()
+
+    r_tma, g_tma = run("1")
+    r_reg, g_reg = run("0")
+    assert rel(r_tma, r_reg) < 2e-6 and rel(g_tma, g_reg) < 5e-6
+    orecs, params = loop.simulate(case, dtype=torch.float64, requires_grad=["vp"])
+    misfit.l2(orecs, [torch.zeros_like(r) for r in orecs]).backward()
+    assert rel(r_tma, cat_records([r.detach().numpy() for r in orecs])) < 1e-5
+    assert rel(g_tma, params["vp"].grad.numpy()) < 1e-4
