@@ -1050,33 +1050,23 @@ __device__ __forceinline__ void corner_tile_decode(const CornerTiles& c, const W
 // the tile touches the straight top / bottom / left / right absorbing frame: every cell gets y + b (one - y)
 // with the one-way extrapolation along the inward normal +z / -z / +x / -x (w2_habc_blend on a straight
 // side; b == 0 on the frame-free cells of the tile).  The coefficient rows stay in registers across the shots.
-template <int FL>
-__device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& tm, int nfx, int bid, int tid, unsigned char* dsm) {
+template <int FL, int KIND>
+__device__ __forceinline__ void forward_tma_tile(const W2Args& a, const W2Tma& tm, const TmaChunk& q, int tid, unsigned char* dsm,
+                                                 uint64_t* bars) {
     constexpr bool PML = (FL & ST_F_PML) != 0, HABC = (FL & ST_F_HABC) != 0;
     constexpr int NS = ST_TMA_FWD_STAGES, STAGE = tma_fwd_stage<FL>(), R0 = tma_r0<FL>();
-    __shared__ __align__(8) uint64_t bars[NS];
     const W2Geom& g = a.g;
     const int ld = g.ld;
-    const TmaChunk q = tma_block_decode(tm, g, HABC, nfx, a.B, bid);
-    if (q.ntile == 0) return;
-    const int kind = q.kind;
+    constexpr int kind = KIND;                              // block-uniform tile kind, compile-time here
     const int b_lo = q.b_lo, nsh = q.nsh;
     const int nitem = q.ntile * nsh;                        // item j = (tile j / nsh, shot j % nsh)
     const int warp = tid >> 5, lane = tid & 31;
-    const bool zdir = kind == 1 || kind == -1;
+    constexpr bool zdir = KIND == 1 || KIND == -1;
     const bool masked = q.mx0 > 0 || q.mx1 < (1 << 30);
     const bool xrag = q.x0 + q.ntile * q.dx + FW > g.nx;    // the tile column that crosses nx
-    const int hoff = zdir ? 2 : 1;                          // rows above z0 in the `cur` box
+    constexpr int hoff = zdir ? 2 : 1;                      // rows above z0 in the `cur` box
     const CUtensorMap* mcur = zdir ? &tm.u_h2 : &tm.u_h1;
     const CUtensorMap* mprev = kind ? &tm.u_h1 : &tm.u_core;
-    if (tid == 0) {
-        st_tma_prefetch_desc(mcur);
-        st_tma_prefetch_desc(mprev);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) st_mbar_init(&bars[s], 1);
-        st_mbar_init_fence();
-    }
-    __syncthreads();
     // the two boxes of an item are issued by two different warps (which = 0: cur + expect_tx, 1: prev)
     auto issue = [&](int j, int which) {
         const int stg = j % NS, ti = j / nsh, sh = j - ti * nsh;
@@ -1091,7 +1081,7 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
     if (tid == 0 || tid == 32)
         for (int j = 0; j < NS && j < nitem; ++j) issue(j, tid >> 5);
     // `prev` box geometry: core box (frame-free tiles) or 1-deep halo box (frame tiles)
-    const int ppitch = kind ? HC : TC, poff = kind ? HC + XO : 0;       // offset of (z0, x0)
+    constexpr int ppitch = KIND ? HC : TC, poff = KIND ? HC + XO : 0;   // offset of (z0, x0)
     float4 ci[2], al[2], bb[2], rr[2];
     bool zok[2];
     int z0 = q.z0, x0 = q.x0, zr = 0, x = 0;
@@ -1187,6 +1177,27 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
         if ((tid == 0 || tid == 32) && j + NS < nitem) issue(j + NS, tid >> 5);
         if (++sh == nsh) { sh = 0; z0 += q.dz; x0 += q.dx; }
     }
+}
+
+template <int FL>
+__device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& tm, int nfx, int bid, int tid, unsigned char* dsm) {
+    constexpr int NS = ST_TMA_FWD_STAGES;
+    __shared__ __align__(8) uint64_t bars[NS];
+    const TmaChunk q = tma_block_decode(tm, a.g, (FL & ST_F_HABC) != 0, nfx, a.B, bid);
+    if (q.ntile == 0) return;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) st_mbar_init(&bars[s], 1);
+        st_mbar_init_fence();
+    }
+    __syncthreads();
+    if constexpr ((FL & ST_F_HABC) != 0) {
+        if (q.kind == 1) { forward_tma_tile<FL, 1>(a, tm, q, tid, dsm, bars); return; }
+        if (q.kind == -1) { forward_tma_tile<FL, -1>(a, tm, q, tid, dsm, bars); return; }
+        if (q.kind == 2) { forward_tma_tile<FL, 2>(a, tm, q, tid, dsm, bars); return; }
+        if (q.kind == -2) { forward_tma_tile<FL, -2>(a, tm, q, tid, dsm, bars); return; }
+    }
+    forward_tma_tile<FL, 0>(a, tm, q, tid, dsm, bars);
 }
 
 #ifndef ST_FWD_MINB
