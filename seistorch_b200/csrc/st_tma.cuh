@@ -43,6 +43,12 @@ __device__ __forceinline__ void st_tma_load_3d(void* dst, const CUtensorMap* map
         "l"(reinterpret_cast<uint64_t>(map)), "r"(st_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Programmatic dependent launch (the step kernels of one time loop are launched back to back on one stream):
+// st_pdl_launch_dependents() lets the next grid start launching once every block of this one has begun,
+// st_pdl_wait() blocks until the previous grid has completed and its writes are visible.  Everything a block
+// does before st_pdl_wait() (tile decode, mbarrier init, descriptor prefetch) overlaps the previous kernel's tail.
+__device__ __forceinline__ void st_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void st_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void st_tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

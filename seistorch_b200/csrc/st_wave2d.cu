@@ -1191,6 +1191,7 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
         st_mbar_init_fence();
     }
     __syncthreads();
+    st_pdl_wait();                                          // the previous step's fields are complete from here on
     if constexpr ((FL & ST_F_HABC) != 0) {
         if (q.kind == 1) { forward_tma_tile<FL, 1>(a, tm, q, tid, dsm, bars); return; }
         if (q.kind == -1) { forward_tma_tile<FL, -1>(a, tm, q, tid, dsm, bars); return; }
@@ -1246,7 +1247,9 @@ __global__ void __launch_bounds__(NT, tma_fwd_minb<FL>()) wave2d_forward_tma_ker
     const int bid = blockIdx.x, tid = threadIdx.x;
     const CornerTiles ct = corner_tiles(tm, a.g);
     const int ncorner = ct.count * a.B;
+    st_pdl_launch_dependents();
     if (bid < ncorner) {
+        st_pdl_wait();
         if (ST_DBG_SKIP & 32) return;
         if constexpr ((FL & ST_F_HABC) != 0) {
             int tz, tx;
@@ -2162,6 +2165,7 @@ __device__ __forceinline__ void adjoint_tma_block(const W2Args& a, const W2Tma& 
         st_mbar_init_fence();
     }
     __syncthreads();
+    st_pdl_wait();                                          // the previous step's cotangents are complete from here on
     if constexpr ((FL & ST_F_HABC) != 0) {
         if (kind == 1) { adjoint_tma_tile<FL, 1>(a, tm, q, tid, dsm, bars); return; }
         if (kind == -1) { adjoint_tma_tile<FL, -1>(a, tm, q, tid, dsm, bars); return; }
@@ -2181,7 +2185,9 @@ __global__ void __launch_bounds__(NT, tma_adj_minb<FL>()) wave2d_adjoint_tma_ker
 #ifdef ST_DBG_TIMELINE
     const unsigned long long t0 = dbg_now();
 #endif
+    st_pdl_launch_dependents();
     if (bid < ncorner) {
+        st_pdl_wait();
         if (ST_DBG_SKIP & 32) return;
         if constexpr ((FL & ST_F_HABC) != 0) {
             int tz, tx;
@@ -2208,6 +2214,24 @@ template <int FL>
 int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st);
 
 #ifndef ST_W2_DISPATCH_ONLY
+// TMA kernels are launched with programmatic stream serialization (st_tma.cuh: st_pdl_*), so the prologue of step
+// i+1 overlaps the tail of step i; SEISTORCH_B200_PDL=0 falls back to ordinary launches.
+template <class K>
+static int tma_launch(K kernel, dim3 grid, int smem, cudaStream_t st, const W2Args& a, int nfx, const W2Tma& tm) {
+    static const bool pdl = [] { const char* e = getenv("SEISTORCH_B200_PDL"); return !(e && atoi(e) == 0); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, a, nfx, tm) == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+}
+
 template <int FL>
 int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
@@ -2216,8 +2240,7 @@ int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
             static const cudaError_t attr = cudaFuncSetAttribute(wave2d_forward_tma_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_fwd_smem<FL>());
             if (attr != cudaSuccess) return ST_ERR_CUDA;
             dim3 grid((unsigned)((long long)corner_tiles(tm, a.g).count * a.B + tma_blocks(tm, a.B)));
-            wave2d_forward_tma_kernel<FL><<<grid, NT, tma_fwd_smem<FL>(), st>>>(a, nfx, tm);
-            return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+            return tma_launch(wave2d_forward_tma_kernel<FL>, grid, tma_fwd_smem<FL>(), st, a, nfx, tm);
         }
     }
     const int nfast = nfx * nfz;
@@ -2239,8 +2262,7 @@ int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
             static const cudaError_t attr = cudaFuncSetAttribute(wave2d_adjoint_tma_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_adj_smem<FL>());
             if (attr != cudaSuccess) return ST_ERR_CUDA;
             dim3 grid((unsigned)((long long)corner_tiles(tm, a.g).count * a.B + tma_blocks(tm, a.B)));
-            wave2d_adjoint_tma_kernel<FL><<<grid, NT, tma_adj_smem<FL>(), st>>>(a, nfx, tm);
-            return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+            return tma_launch(wave2d_adjoint_tma_kernel<FL>, grid, tma_adj_smem<FL>(), st, a, nfx, tm);
         }
     }
     const int nfast = nfx * nfz;
