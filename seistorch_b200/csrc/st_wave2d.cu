@@ -1067,19 +1067,17 @@ __device__ __forceinline__ void forward_tma_tile(const W2Args& a, const W2Tma& t
     constexpr int hoff = zdir ? 2 : 1;                      // rows above z0 in the `cur` box
     const CUtensorMap* mcur = zdir ? &tm.u_h2 : &tm.u_h1;
     const CUtensorMap* mprev = kind ? &tm.u_h1 : &tm.u_core;
-    // the two boxes of an item are issued by two different warps (which = 0: cur + expect_tx, 1: prev)
-    auto issue = [&](int j, int which) {
+    auto issue = [&](int j) {
         const int stg = j % NS, ti = j / nsh, sh = j - ti * nsh;
         const int z0 = q.z0 + ti * q.dz, x0 = q.x0 + ti * q.dx;
         unsigned char* dst = dsm + stg * STAGE;
-        if (which == 0) {
-            st_mbar_expect_tx(&bars[stg], (zdir ? H2R : H1R) * HC * 4 + (kind ? H1R * HC * 4 : TMA_CORE_BYTES));
-            st_tma_load_3d(dst, mcur, &bars[stg], x0 - XO, z0 - hoff, tm.pl_cur + b_lo + sh);
-        } else if (kind) st_tma_load_3d(dst + R0, mprev, &bars[stg], x0 - XO, z0 - 1, tm.pl_prev + b_lo + sh);
+        st_mbar_expect_tx(&bars[stg], (zdir ? H2R : H1R) * HC * 4 + (kind ? H1R * HC * 4 : TMA_CORE_BYTES));
+        st_tma_load_3d(dst, mcur, &bars[stg], x0 - XO, z0 - hoff, tm.pl_cur + b_lo + sh);
+        if (kind) st_tma_load_3d(dst + R0, mprev, &bars[stg], x0 - XO, z0 - 1, tm.pl_prev + b_lo + sh);
         else st_tma_load_3d(dst + R0, mprev, &bars[stg], x0, z0, tm.pl_prev + b_lo + sh);
     };
-    if (tid == 0 || tid == 32)
-        for (int j = 0; j < NS && j < nitem; ++j) issue(j, tid >> 5);
+    if (tid == 0)
+        for (int j = 0; j < NS && j < nitem; ++j) issue(j);
     // `prev` box geometry: core box (frame-free tiles) or 1-deep halo box (frame tiles)
     constexpr int ppitch = KIND ? HC : TC, poff = KIND ? HC + XO : 0;   // offset of (z0, x0)
     float4 ci[2], al[2], bb[2], rr[2];
@@ -1174,7 +1172,7 @@ __device__ __forceinline__ void forward_tma_tile(const W2Args& a, const W2Tma& t
         }
         forward_tail<1>(a, b, z0, z0 + TR, x0, x0 + FW, tid, [&](int, int xx) { return xx >= q.mx0 && xx < q.mx1; });
         __syncthreads();                                   // every warp is done with this stage
-        if ((tid == 0 || tid == 32) && j + NS < nitem) issue(j + NS, tid >> 5);
+        if (tid == 0 && j + NS < nitem) issue(j + NS);
         if (++sh == nsh) { sh = 0; z0 += q.dz; x0 += q.dx; }
     }
 }
