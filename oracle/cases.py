@@ -64,6 +64,11 @@ def make_case(equation, nz=40, nx=60, nshots=2, nt=200, rec_step=3, dt=1e-3, h=1
                 models["theta"] = (15.0 + 10 * vpn).astype(np.float32)
                 inv["theta"] = True
             boundary, st, rt = "habc", ["p1"], ["p1"]
+        elif equation == "acoustic_lsrtm_habc":
+            m = np.zeros_like(vp)
+            m[1:] = (vp[1:] - vp[:-1]) / vp[1:] * 5
+            models, inv = {"vp": vp, "m": m.astype(np.float32)}, {"vp": True, "m": True}
+            boundary, st, rt = "habc", ["h1"], ["sh1"]
         elif equation in ("acoustic_vti_lsrtm_habc", "acoustic_tti_lsrtm_habc"):
             m = np.zeros_like(vp)
             m[1:] = (vp[1:] - vp[:-1]) / vp[1:] * 5

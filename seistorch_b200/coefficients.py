@@ -8,6 +8,7 @@ the coefficient algebra that the reference re-evaluates every time step:
 
   acoustic / acoustic_habc      equations2d/acoustic.py:73-86, acoustic_habc.py:206-221
   vti_habc2 / tti_habc          equations2d/vti_habc2.py:37-55, tti_habc.py:31-57
+  acoustic_lsrtm_habc           equations2d/acoustic_lsrtm_habc.py:10-30
   acoustic_{vti,tti}_lsrtm_habc equations2d/acoustic_vti_lsrtm_habc.py:33-62, ..tti..:31-68
   acoustic_fwim_habc            equations2d/acoustic_fwim_habc.py:38-60
   elastic                       equations2d/elastic.py:11-13,20-24,33-35
@@ -27,6 +28,7 @@ EQUATIONS = {
     "vti_habc2": ("wave2d", EQ_HABC),
     "tti_habc": ("wave2d", EQ_HABC | EQ_XZ),
     "acoustic_fwim_habc": ("wave2d", EQ_ISO | EQ_HABC | EQ_G1),
+    "acoustic_lsrtm_habc": ("wave2d", EQ_HABC | EQ_BORN),          # isotropic Born pair: cxx = czz
     "acoustic_vti_lsrtm_habc": ("wave2d", EQ_HABC | EQ_BORN),
     "acoustic_tti_lsrtm_habc": ("wave2d", EQ_HABC | EQ_XZ | EQ_BORN),
     "elastic": ("elastic2d", 0),
@@ -70,6 +72,10 @@ def wave2d_coefficients(equation, params, dt, h, d):
         out[3] = (1 - bd) / (1 + bd)           # alpha
     elif equation == "acoustic_habc":
         out[2] = r * r
+    elif equation == "acoustic_lsrtm_habc":    # acoustic_lsrtm_habc.py:10-30: A = vp^2 dt^2 Lap for both fields, + m A[h1]
+        out[2] = r * r
+        out[3] = r * r
+        out[7] = _f64(params[1])
     elif equation in ("vti_habc2", "acoustic_vti_lsrtm_habc"):
         eps, delta = _f64(params[1]), _f64(params[2])
         kx, kz = _kgrid(vp.shape, h, vp.device)
