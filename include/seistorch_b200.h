@@ -31,7 +31,8 @@ extern "C" {
 #define ST_EQ_PML   2   /* damped update, equations2d/acoustic.py:73-86                      */
 #define ST_EQ_HABC  4   /* one-way blend,  equations2d/acoustic_habc.py:79-101,147-221       */
 #define ST_EQ_XZ    8   /* mixed derivative, equations2d/tti_habc.py:40-57                   */
-#define ST_EQ_G1   16   /* first-derivative terms, equations2d/acoustic_fwim_habc.py:38-60   */
+#define ST_EQ_G1   16   /* first-derivative terms, equations2d/acoustic_fwim_habc.py:38-60; with cxx != czz
+                           (ST_EQ_HABC|ST_EQ_G1) the variable-density stencil of acoustic_rho_habc.py:32-57 */
 #define ST_EQ_BORN 32   /* background+scattered pair, equations2d/acoustic_*_lsrtm_habc.py   */
 /*   acoustic                 = ISO|PML          acoustic_habc            = ISO|HABC
  *   vti_habc2                = HABC             tti_habc                 = HABC|XZ

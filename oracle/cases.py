@@ -64,6 +64,9 @@ def make_case(equation, nz=40, nx=60, nshots=2, nt=200, rec_step=3, dt=1e-3, h=1
                 models["theta"] = (15.0 + 10 * vpn).astype(np.float32)
                 inv["theta"] = True
             boundary, st, rt = "habc", ["p1"], ["p1"]
+        elif equation == "acoustic_rho_habc":
+            models = {"vp": vp, "rho": (2000.0 + 400 * vpn).astype(np.float32)}
+            boundary, st, rt, inv = "habc", ["h1"], ["h1"], {"vp": True, "rho": True}
         elif equation == "acoustic_lsrtm_habc":
             m = np.zeros_like(vp)
             m[1:] = (vp[1:] - vp[:-1]) / vp[1:] * 5

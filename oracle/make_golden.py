@@ -53,7 +53,7 @@ def golden_cases():
     g = {}
     small = dict(nz=30, nx=44, nt=120)
     for eq in ["acoustic", "acoustic_habc", "elastic", "vti_habc2", "tti_habc",
-               "acoustic_vti_lsrtm_habc", "acoustic_tti_lsrtm_habc", "acoustic_fwim_habc", "acoustic_lsrtm_habc"]:
+               "acoustic_vti_lsrtm_habc", "acoustic_tti_lsrtm_habc", "acoustic_fwim_habc", "acoustic_lsrtm_habc", "acoustic_rho_habc"]:
         g[eq] = (cases.make_case(eq, **small), "l2")
     g["acoustic_multiple"] = (cases.make_case("acoustic", multiple=True, **small), "l2")
     g["acoustic_habc_multiple"] = (cases.make_case("acoustic_habc", multiple=True, **small), "l2")

@@ -121,7 +121,7 @@ def cast_module_kernels(dtype):
     names = [
         "seistorch.equations2d.acoustic", "seistorch.equations2d.acoustic_habc",
         "seistorch.equations2d.convkernel", "seistorch.equations2d.vti_habc2",
-        "seistorch.equations2d.tti_habc", "seistorch.equations2d.acoustic_vti_lsrtm_habc", "seistorch.equations2d.acoustic_lsrtm_habc",
+        "seistorch.equations2d.tti_habc", "seistorch.equations2d.acoustic_vti_lsrtm_habc", "seistorch.equations2d.acoustic_lsrtm_habc", "seistorch.equations2d.acoustic_rho_habc",
         "seistorch.equations2d.acoustic_tti_lsrtm_habc", "seistorch.equations2d.acoustic_fwim_habc",
         "seistorch.equations3d.acoustic",
     ]

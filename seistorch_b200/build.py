@@ -23,7 +23,7 @@ LIB = os.path.join(HERE, "libseistorch_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"] + os.environ.get("SEISTORCH_B200_NVCC_EXTRA", "").split()
 
-W2_FLAG_SETS = [3, 5, 4, 12, 21, 36, 44]
+W2_FLAG_SETS = [3, 5, 4, 12, 20, 21, 36, 44]
 
 
 def _nvcc():

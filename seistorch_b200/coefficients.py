@@ -9,6 +9,7 @@ the coefficient algebra that the reference re-evaluates every time step:
   acoustic / acoustic_habc      equations2d/acoustic.py:73-86, acoustic_habc.py:206-221
   vti_habc2 / tti_habc          equations2d/vti_habc2.py:37-55, tti_habc.py:31-57
   acoustic_lsrtm_habc           equations2d/acoustic_lsrtm_habc.py:10-30
+  acoustic_rho_habc             equations2d/acoustic_rho_habc.py:32-57
   acoustic_{vti,tti}_lsrtm_habc equations2d/acoustic_vti_lsrtm_habc.py:33-62, ..tti..:31-68
   acoustic_fwim_habc            equations2d/acoustic_fwim_habc.py:38-60
   elastic                       equations2d/elastic.py:11-13,20-24,33-35
@@ -29,6 +30,7 @@ EQUATIONS = {
     "tti_habc": ("wave2d", EQ_HABC | EQ_XZ),
     "acoustic_fwim_habc": ("wave2d", EQ_ISO | EQ_HABC | EQ_G1),
     "acoustic_lsrtm_habc": ("wave2d", EQ_HABC | EQ_BORN),          # isotropic Born pair: cxx = czz
+    "acoustic_rho_habc": ("wave2d", EQ_HABC | EQ_G1),              # variable density: four different neighbour weights
     "acoustic_vti_lsrtm_habc": ("wave2d", EQ_HABC | EQ_BORN),
     "acoustic_tti_lsrtm_habc": ("wave2d", EQ_HABC | EQ_XZ | EQ_BORN),
     "elastic": ("elastic2d", 0),
@@ -72,6 +74,21 @@ def wave2d_coefficients(equation, params, dt, h, d):
         out[3] = (1 - bd) / (1 + bd)           # alpha
     elif equation == "acoustic_habc":
         out[2] = r * r
+    elif equation == "acoustic_rho_habc":
+        # acoustic_rho_habc.py:32-57:  K [bxp (E-C) - bxn (C-W) + bzp (S-C) - bzn (C-N)],  K = dt^2/h^2 rho vp^2,
+        # b*p / b*n = mean of the buoyancy 1/rho with the next / previous cell (zero outside the grid)
+        #   = cxx ((E-C)+(W-C)) + ax (E-W) + czz ((N-C)+(S-C)) + az (S-N),  cxx +- ax = K bxp / K bxn, czz +- az = K bzp / K bzn
+        rho = _f64(params[1])
+        K = r * r * rho
+        bu = 1.0 / rho
+        px = F.pad(bu, (1, 1))
+        pz = F.pad(bu, (0, 0, 1, 1))
+        bxp, bxn = (bu + px[..., 2:]) / 2, (px[..., :-2] + bu) / 2
+        bzp, bzn = (bu + pz[..., 2:, :]) / 2, (pz[..., :-2, :] + bu) / 2
+        out[2] = K * (bxp + bxn) / 2
+        out[3] = K * (bzp + bzn) / 2
+        out[5] = K * (bxp - bxn) / 2
+        out[6] = K * (bzp - bzn) / 2
     elif equation == "acoustic_lsrtm_habc":    # acoustic_lsrtm_habc.py:10-30: A = vp^2 dt^2 Lap for both fields, + m A[h1]
         out[2] = r * r
         out[3] = r * r

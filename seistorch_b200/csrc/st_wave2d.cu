@@ -2295,6 +2295,7 @@ template int st_w2_launch_adj<ST_W2_INSTANCE>(const W2Args&, const W2Tma&, cudaS
         case ST_F_ISO | ST_F_HABC: return FN<ST_F_ISO | ST_F_HABC>(a, tm, st);                      \
         case ST_F_HABC: return FN<ST_F_HABC>(a, tm, st);                                            \
         case ST_F_HABC | ST_F_XZ: return FN<ST_F_HABC | ST_F_XZ>(a, tm, st);                        \
+        case ST_F_HABC | ST_F_G1: return FN<ST_F_HABC | ST_F_G1>(a, tm, st);                        \
         case ST_F_ISO | ST_F_HABC | ST_F_G1: return FN<ST_F_ISO | ST_F_HABC | ST_F_G1>(a, tm, st);  \
         case ST_F_HABC | ST_F_BORN: return FN<ST_F_HABC | ST_F_BORN>(a, tm, st);                    \
         case ST_F_HABC | ST_F_XZ | ST_F_BORN: return FN<ST_F_HABC | ST_F_XZ | ST_F_BORN>(a, tm, st);\

@@ -70,7 +70,8 @@ ST_HD void st_wrap_candidate(const W2Geom& g, int k, int& z, int& x, int& s, int
 
 // flag sets whose spatial operator fits the 9 taps (no mixed derivative, single field)
 ST_HD bool st_flags_tapped(int fl) {
-    return fl == (ST_F_ISO | ST_F_HABC) || fl == ST_F_HABC || fl == (ST_F_ISO | ST_F_HABC | ST_F_G1);
+    return fl == (ST_F_ISO | ST_F_HABC) || fl == ST_F_HABC || fl == (ST_F_ISO | ST_F_HABC | ST_F_G1) ||
+           fl == (ST_F_HABC | ST_F_G1);
 }
 
 #ifdef __CUDACC__

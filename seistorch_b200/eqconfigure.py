@@ -13,6 +13,7 @@ class Parameters:
             "acoustic_habc": ["vp"],
             "acoustic_fwim_habc": ["vp", "rx", "rz"],
             "acoustic_lsrtm_habc": ["vp", "m"],
+            "acoustic_rho_habc": ["vp", "rho"],
             "acoustic_vti_lsrtm_habc": ["vp", "epsilon", "delta", "m"],
             "acoustic_tti_lsrtm_habc": ["vp", "epsilon", "delta", "theta", "m"],
             "elastic": ["vp", "vs", "rho"],
@@ -23,7 +24,7 @@ class Parameters:
     @staticmethod
     def secondorder_equations():
         """eqconfigure.py:32-43 (restricted to the supported set)."""
-        return ["acoustic", "acoustic_habc", "vti_habc2", "acoustic_fwim_habc", "acoustic_lsrtm_habc",
+        return ["acoustic", "acoustic_habc", "vti_habc2", "acoustic_fwim_habc", "acoustic_lsrtm_habc", "acoustic_rho_habc",
                 "acoustic_vti_lsrtm_habc", "acoustic_tti_lsrtm_habc", "tti_habc"]
 
 
@@ -36,6 +37,7 @@ class Wavefield:
         "acoustic_habc": ["h1", "h2"],
         "acoustic_fwim_habc": ["h1", "h2"],
         "acoustic_lsrtm_habc": ["h1", "h2", "sh1", "sh2"],
+        "acoustic_rho_habc": ["h1", "h2"],
         "acoustic_vti_lsrtm_habc": ["p1", "p2", "sp1", "sp2"],
         "acoustic_tti_lsrtm_habc": ["p1", "p2", "sp1", "sp2"],
         "elastic": ["vx", "vz", "txx", "tzz", "txz"],

@@ -18,7 +18,7 @@ import sys
 
 _MODULES = ["cell", "rnn", "source", "probe", "checkpoint", "checkpoint_new", "type", "habc", "pml"]
 _EQ2D = ["acoustic", "acoustic_habc", "vti_habc2", "tti_habc", "acoustic_fwim_habc",
-         "acoustic_lsrtm_habc", "acoustic_vti_lsrtm_habc", "acoustic_tti_lsrtm_habc", "elastic"]
+         "acoustic_lsrtm_habc", "acoustic_rho_habc", "acoustic_vti_lsrtm_habc", "acoustic_tti_lsrtm_habc", "elastic"]
 
 
 def install(reference_package: str = "seistorch"):

@@ -70,6 +70,7 @@ static void w2_adj(const HcW2& p, const float* l1, const float* l2, const float*
         case ST_F_ISO | ST_F_HABC: FN<ST_F_ISO | ST_F_HABC>(__VA_ARGS__); break;                \
         case ST_F_HABC: FN<ST_F_HABC>(__VA_ARGS__); break;                                      \
         case ST_F_HABC | ST_F_XZ: FN<ST_F_HABC | ST_F_XZ>(__VA_ARGS__); break;                  \
+        case ST_F_HABC | ST_F_G1: FN<ST_F_HABC | ST_F_G1>(__VA_ARGS__); break;                  \
         case ST_F_ISO | ST_F_HABC | ST_F_G1: FN<ST_F_ISO | ST_F_HABC | ST_F_G1>(__VA_ARGS__); break; \
         case ST_F_HABC | ST_F_BORN: FN<ST_F_HABC | ST_F_BORN>(__VA_ARGS__); break;              \
         case ST_F_HABC | ST_F_XZ | ST_F_BORN: FN<ST_F_HABC | ST_F_XZ | ST_F_BORN>(__VA_ARGS__); break; \

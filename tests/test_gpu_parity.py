@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 REC_TOL = 1e-5
 GRAD_TOL = 1e-4
 
-ALL2D = ["acoustic", "acoustic_habc", "elastic", "vti_habc2", "tti_habc", "acoustic_lsrtm_habc", "acoustic_vti_lsrtm_habc",
+ALL2D = ["acoustic", "acoustic_habc", "elastic", "vti_habc2", "tti_habc", "acoustic_lsrtm_habc", "acoustic_rho_habc", "acoustic_vti_lsrtm_habc",
          "acoustic_tti_lsrtm_habc", "acoustic_fwim_habc", "acoustic_multiple", "acoustic_habc_multiple",
          "acoustic_habc_ragged", "elastic_l2_obs", "acoustic_envelope"]
 

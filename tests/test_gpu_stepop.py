@@ -8,7 +8,7 @@ from conftest import rel
 
 pytestmark = pytest.mark.gpu
 
-EQS = ["acoustic", "acoustic_habc", "elastic", "vti_habc2", "tti_habc", "acoustic_lsrtm_habc", "acoustic_vti_lsrtm_habc",
+EQS = ["acoustic", "acoustic_habc", "elastic", "vti_habc2", "tti_habc", "acoustic_lsrtm_habc", "acoustic_rho_habc", "acoustic_vti_lsrtm_habc",
        "acoustic_tti_lsrtm_habc", "acoustic_fwim_habc"]
 
 

@@ -7,7 +7,7 @@ import pytest
 import hostcheck_driver as hd
 from conftest import cat_records, golden_records, load_golden, rel
 
-CASES = ["acoustic", "acoustic_habc", "elastic", "vti_habc2", "tti_habc", "acoustic_lsrtm_habc", "acoustic_vti_lsrtm_habc",
+CASES = ["acoustic", "acoustic_habc", "elastic", "vti_habc2", "tti_habc", "acoustic_lsrtm_habc", "acoustic_rho_habc", "acoustic_vti_lsrtm_habc",
          "acoustic_tti_lsrtm_habc", "acoustic_fwim_habc", "acoustic_multiple", "acoustic_habc_multiple",
          "acoustic_habc_ragged"]
 

@@ -8,7 +8,7 @@ import torch
 from conftest import cat_records, golden_records, load_golden, rel
 from oracle import loop, misfit
 
-SMALL = ["acoustic", "acoustic_habc", "elastic", "vti_habc2", "tti_habc", "acoustic_lsrtm_habc", "acoustic_vti_lsrtm_habc",
+SMALL = ["acoustic", "acoustic_habc", "elastic", "vti_habc2", "tti_habc", "acoustic_lsrtm_habc", "acoustic_rho_habc", "acoustic_vti_lsrtm_habc",
          "acoustic_tti_lsrtm_habc", "acoustic_fwim_habc", "acoustic_multiple", "acoustic_habc_multiple",
          "acoustic_habc_ragged", "acoustic_envelope", "elastic_l2_obs", "acoustic3d"]
 
