@@ -57,6 +57,7 @@ if __name__ == "__main__":
         run("vti_habc2", 500, 1200, 8, 100)
         run("tti_habc", 500, 1200, 8, 100)
         run("acoustic_lsrtm_habc", 500, 1200, 8, 100)
+        run("acoustic_rho_habc", 500, 1200, 8, 100)
         run("acoustic_vti_lsrtm_habc", 500, 1200, 8, 100)
         run("acoustic_tti_lsrtm_habc", 500, 1200, 8, 100)
         run("acoustic_fwim_habc", 500, 1200, 8, 100)
