@@ -4,7 +4,7 @@
 
 Produces seistorch_b200/libseistorch_b200.so (git-ignored; ships to the GPU box with
 the gpurun snapshot).  The 2D second-order family is instantiated once per flag set in
-its own translation unit so the seven variants compile in parallel.
+its own translation unit so the eight variants compile in parallel.
 """
 from __future__ import annotations
 

@@ -1,6 +1,6 @@
 // sm_100a kernels for the 2D second-order wave-equation family:
 //   acoustic (PML), acoustic_habc, vti_habc2, tti_habc, acoustic_fwim_habc,
-//   acoustic_{vti,tti}_lsrtm_habc   -- one template, seven flag sets.
+//   acoustic_{vti,tti}_lsrtm_habc   -- one template, eight flag sets.
 //
 // One launch = one time step of every shot in the batch, with the source add and the
 // receiver gather fused in (reference: ~30-190 ATen launches per step).
