@@ -1,18 +1,29 @@
 // sm_100a kernels for the 2D second-order wave-equation family:
-//   acoustic (PML), acoustic_habc, vti_habc2, tti_habc, acoustic_fwim_habc,
-//   acoustic_{vti,tti}_lsrtm_habc   -- one template, eight flag sets.
+//   acoustic (PML), acoustic_habc, vti_habc2, tti_habc, acoustic_fwim_habc, acoustic_rho_habc,
+//   acoustic_lsrtm_habc, acoustic_{vti,tti}_lsrtm_habc   -- one template, eight flag sets.
 //
 // One launch = one time step of every shot in the batch, with the source add and the
 // receiver gather fused in (reference: ~30-190 ATen launches per step).
 //
-// Two kinds of thread blocks share a launch:
-//   * FAST blocks stream the non-frame cells: a warp owns a 128-column x 8-row tile, every
+// Two kernel families:
+//
+// (1) TMA kernels (wave2d_forward_tma_kernel / wave2d_adjoint_tma_kernel; acoustic and acoustic_habc):
+//     16 x 128 tiles, (tile, shot) items pulled through an mbarrier ring of cp.async.bulk.tensor boxes
+//     (halos and the grid edge come from the box: out-of-range elements are zero-filled), consumed as
+//     128-bit shared-memory rows with warp-shuffle x-neighbours; the straight sides of the absorbing
+//     frame in closed form (tile kinds), the four corners as generic tiles; programmatic dependent
+//     launch between time steps.  See DESIGN.md section 5.
+//
+// (2) Register kernels (wave2d_forward_kernel / wave2d_adjoint_kernel; every flag set), two kinds of
+//     thread blocks per launch:
+//   * FAST blocks stream the non-frame cells: a warp owns a 128-column x 4-row tile, every
 //     lane 4 consecutive cells; rows are loaded once as 128-bit vectors and marched through
 //     a 3-row register pipeline, left/right neighbours come from warp shuffles (plus one
 //     predicated halo load per edge lane), no shared memory.
-//   * FRAME blocks evaluate the absorbing frame (one-way blend, side ownership, wrap-around
-//     strip neighbours) cell by cell from a shared-memory tile with a 2-cell halo.
-// The two block kinds write disjoint cells; whoever stores a cell also applies the source
+//   * FRAME blocks evaluate the absorbing frame: a precomputed-tap gather (st_wave2d_band.cuh) for
+//     the single-field equations without mixed derivative, else cell by cell from a shared-memory
+//     tile with a 2-cell halo (one-way blend, side ownership, wrap-around strip neighbours).
+// Block kinds write disjoint cells; whoever stores a cell also applies the source
 // add / receiver gather for it, so no inter-block ordering is needed.
 //
 // Data layout in HBM: fields [NF][B][nz][ld] fp32, row pitch ld a multiple of 4 so that
