@@ -203,6 +203,13 @@ int st_acoustic3d_adjoint(const st_acoustic3d_problem* p, int32_t i_hi, int32_t 
  * ---------------------------------------------------------------------------------- */
 int st_misfit_l2(const float* syn, const float* obs, int64_t n, float scale,
                  double* loss, float* adj, void* stream);
+/* seistorch/loss.py:381-393 (L1Loss(reduction='sum') summed over shots); adj = scale * sign(syn - obs) */
+int st_misfit_l1(const float* syn, const float* obs, int64_t n, float scale,
+                 double* loss, float* adj, void* stream);
+/* seistorch/loss.py:52-85 ("cs"): loss += scale * (1/mean_over) * sum over traces of 1 - cosine similarity along
+ * time (eps 1e-10); mean_over = traces of one shot (the reference averages per shot, then sums the shots) */
+int st_misfit_cs(const float* syn, const float* obs, int32_t nt, int32_t ntraces, int32_t mean_over, float scale,
+                 double* loss, float* adj, void* stream);
 int st_misfit_envelope(const float* syn, const float* obs, int32_t nt, int32_t ntraces,
                        const float* hker, float scale, double* loss, float* adj,
                        float* workspace, void* stream);

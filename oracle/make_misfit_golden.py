@@ -1,0 +1,53 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product path.
+
+Golden vectors for the trace-domain misfits, generated from the REAL reference
+(seistorch/loss.py: L2 :409-421, L1 :381-393, CosineSimilarity :52-85, Envelope :178-216) on seeded random
+records with a different receiver count per shot:
+
+    python -m oracle.make_misfit_golden        # writes tests/golden/misfits.npz
+
+Stored: the records (fp32), and per misfit name the reference's loss and d loss / d syn in float64.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_shim
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "misfits.npz")
+NAMES = ["l2", "l1", "cs", "envelope"]
+SHAPES = [(64, 7, 2), (64, 5, 2), (64, 1, 2)]        # (nt, nrec, nchan) of each shot
+
+
+def main():
+    ref_shim.import_reference()
+    from seistorch.loss import Loss
+    rng = np.random.default_rng(20230503)
+    syn = [rng.standard_normal(s).astype(np.float32) for s in SHAPES]
+    obs = [(0.7 * x + 0.5 * rng.standard_normal(x.shape)).astype(np.float32) for x in syn]
+    arrs = {}
+    for k, (x, y) in enumerate(zip(syn, obs)):
+        arrs[f"syn_{k}"], arrs[f"obs_{k}"] = x, y
+    for name in NAMES:
+        xs = [torch.from_numpy(x).double().requires_grad_(True) for x in syn]
+        ys = [torch.from_numpy(y).double() for y in obs]
+        crit = Loss(name).loss(None)
+        if name == "envelope":      # loss.py:211-216 indexes a stacked [shots, nt, nrec, nchan] tensor: one shot at a time
+            loss = sum(crit(x.unsqueeze(0), y.unsqueeze(0)) for x, y in zip(xs, ys))
+        else:
+            loss = crit(xs, ys)
+        loss.backward()
+        arrs[f"{name}_loss"] = np.float64(float(loss))
+        for k, x in enumerate(xs):
+            arrs[f"{name}_grad_{k}"] = x.grad.numpy()
+        print(name, float(loss))
+    np.savez_compressed(OUT, **arrs)
+    print("wrote", OUT)
+
+
+if __name__ == "__main__":
+    main()

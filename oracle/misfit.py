@@ -4,6 +4,8 @@ L2 and envelope misfits.  Never imported by the product path.
 Follows:
   * seistorch/loss.py:409-421      L2  (MSELoss(reduction='sum') summed over shots)
   * seistorch/loss.py:178-216      Envelope (method='square')
+  * seistorch/loss.py:381-393      L1
+  * seistorch/loss.py:52-85        CosineSimilarity ("cs")
   * seistorch/transform.py:24-66   envelope / hilbert (nfft = nt, scipy convention)
 """
 from __future__ import annotations
@@ -17,6 +19,27 @@ def l2(syn, obs):
     loss = 0.0
     for x, y in zip(syn, obs):
         loss = loss + torch.sum((x - y) ** 2)
+    return loss
+
+
+def l1(syn, obs):
+    """loss.py:389-393: L1Loss(reduction='sum') summed over shots."""
+    loss = 0.0
+    for x, y in zip(syn, obs):
+        loss = loss + torch.sum(torch.abs(x - y))
+    return loss
+
+
+def cs(syn, obs):
+    """loss.py:63-85: per shot mean over traces of 1 - cosine_similarity along time (eps = 1e-10)."""
+    loss = 0.0
+    for x, y in zip(syn, obs):
+        nt = x.shape[0]
+        xr, yr = x.reshape(nt, -1), y.reshape(nt, -1)
+        nx = torch.clamp(torch.linalg.vector_norm(xr, dim=0), min=1e-10)
+        ny = torch.clamp(torch.linalg.vector_norm(yr, dim=0), min=1e-10)
+        sim = torch.sum((xr / nx) * (yr / ny), dim=0)
+        loss = loss + torch.mean(1 - sim)
     return loss
 
 

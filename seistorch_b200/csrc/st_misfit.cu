@@ -5,6 +5,10 @@
 //               convolution with the fixed kernel hker = Im ifft(one-sided filter):
 //                 E^2 = x^2 + (hker (*) x)^2,  loss = 0.5 sum (Es^2 - Eo^2)^2,
 //                 adj = 2 r x + H^T (2 r Hx),  r = Es^2 - Eo^2.
+//   L1        : seistorch/loss.py:381-393   sum |syn-obs|             adj = sign(syn-obs)
+//   CS        : seistorch/loss.py:52-85     per shot mean over traces of 1 - cos(syn_tr, obs_tr) along time
+//               (F.cosine_similarity, eps = 1e-10):  sim = <x,y> / (max(|x|,eps) max(|y|,eps)),
+//               adj = -(1/ntraces_of_the_shot) ( y/(|x||y|) - sim x/|x|^2 ).
 // Seismograms are [nt][ntraces] (ntraces = receivers x channels, fastest).
 #include <cuda_runtime.h>
 
@@ -36,6 +40,48 @@ __global__ void __launch_bounds__(256) l2_kernel(const float* __restrict__ syn, 
     }
     acc = block_sum(acc);
     if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * (double)scale);
+}
+
+__global__ void __launch_bounds__(256) l1_kernel(const float* __restrict__ syn, const float* __restrict__ obs,
+                                                 long long n, float scale, double* loss, float* adj) {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float d = syn[i] - obs[i];
+        acc += (double)fabsf(d);
+        if (adj) adj[i] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * (double)scale);
+}
+
+// one thread per trace (coalesced across traces at every time sample): three sums over time, then the adjoint source
+__global__ void __launch_bounds__(256) cs_kernel(const float* __restrict__ syn, const float* __restrict__ obs, int nt, int ntr,
+                                                 float inv_mean, float scale, double* loss, float* adj) {
+    const int tr = blockIdx.x * blockDim.x + threadIdx.x;
+    double term = 0.0;
+    if (tr < ntr) {
+        double sxy = 0.0, sxx = 0.0, syy = 0.0;
+        for (int t = 0; t < nt; ++t) {
+            const double x = syn[(long long)t * ntr + tr], y = obs[(long long)t * ntr + tr];
+            sxy += x * y; sxx += x * x; syy += y * y;
+        }
+        const double eps = 1e-10;
+        const double nx = sqrt(sxx), ny = sqrt(syy);
+        const double cx = nx > eps ? nx : eps, cy = ny > eps ? ny : eps;
+        const double sim = sxy / (cx * cy);
+        term = (1.0 - sim) * (double)inv_mean;
+        if (adj) {
+            // d sim / d x = y / (cx cy) - [|x| > eps] sim x / |x|^2
+            const double a = 1.0 / (cx * cy), bq = nx > eps ? sim / sxx : 0.0;
+            const double w = -(double)scale * (double)inv_mean;
+            for (int t = 0; t < nt; ++t) {
+                const long long i = (long long)t * ntr + tr;
+                adj[i] = (float)(w * (a * (double)obs[i] - bq * (double)syn[i]));
+            }
+        }
+    }
+    term = block_sum(term);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, term * (double)scale);
 }
 
 constexpr int CT = 32;      // tile: 32 output samples x 32 traces, 32 taps per stage
@@ -103,6 +149,23 @@ extern "C" int st_misfit_l2(const float* syn, const float* obs, int64_t n, float
     if (n == 0) return ST_OK;
     l2_kernel<<<nblocks(n), 256, 0, (cudaStream_t)stream>>>(syn, obs, n, scale, loss, adj);
     if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_l2: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}
+
+extern "C" int st_misfit_l1(const float* syn, const float* obs, int64_t n, float scale, double* loss, float* adj, void* stream) {
+    if (!syn || !obs || n < 0) { st_set_error("misfit_l1: bad arguments"); return ST_ERR_BADARG; }
+    if (n == 0) return ST_OK;
+    l1_kernel<<<nblocks(n), 256, 0, (cudaStream_t)stream>>>(syn, obs, n, scale, loss, adj);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_l1: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}
+
+extern "C" int st_misfit_cs(const float* syn, const float* obs, int32_t nt, int32_t ntraces, int32_t mean_over, float scale,
+                            double* loss, float* adj, void* stream) {
+    if (!syn || !obs || nt <= 0 || ntraces < 0 || mean_over <= 0) { st_set_error("misfit_cs: bad arguments"); return ST_ERR_BADARG; }
+    if (ntraces == 0) return ST_OK;
+    cs_kernel<<<(ntraces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, 1.f / (float)mean_over, scale, loss, adj);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_cs: launch failed"); return ST_ERR_CUDA; }
     return ST_OK;
 }
 

@@ -1,5 +1,5 @@
-"""L2 and envelope misfits with fused adjoint-source kernels -- same class surface as
-seistorch/loss.py (Loss wrapper :23-50, L2 :409-421, Envelope :178-216).
+"""L2, L1, cosine-similarity and envelope misfits with fused adjoint-source kernels -- same class surface as
+seistorch/loss.py (Loss wrapper :23-50, L2 :409-421, L1 :381-393, CosineSimilarity :52-85, Envelope :178-216).
 
 The forward value and d loss / d syn come from csrc/st_misfit.cu in one pass; inputs are
 stacked records [B, nt, nrec, nchan] (``TensorList.stack()``) or lists of per-shot
@@ -38,7 +38,7 @@ class _Misfit(torch.autograd.Function):
     """loss = misfit(syn, obs) on [nt, ntraces] data; saves d loss / d syn."""
 
     @staticmethod
-    def forward(ctx, kind, syn, obs):
+    def forward(ctx, kind, syn, obs, mean_over=1):
         _require_cuda(syn, "synthetic record")
         s = syn.detach().to(torch.float32).contiguous()
         o = obs.detach().to(device=s.device, dtype=torch.float32).contiguous()
@@ -53,6 +53,14 @@ class _Misfit(torch.autograd.Function):
             _lib.check(L.st_misfit_l2(s.data_ptr(), o.data_ptr(), s.numel(), 1.0, loss.data_ptr(), adj.data_ptr(),
                                       _stream_ptr()), "misfit_l2")
             LAUNCHES["misfit"] += 1
+        elif kind == "l1":
+            _lib.check(L.st_misfit_l1(s.data_ptr(), o.data_ptr(), s.numel(), 1.0, loss.data_ptr(), adj.data_ptr(),
+                                      _stream_ptr()), "misfit_l1")
+            LAUNCHES["misfit"] += 1
+        elif kind == "cs":
+            _lib.check(L.st_misfit_cs(s.data_ptr(), o.data_ptr(), nt, ntr, int(mean_over), 1.0, loss.data_ptr(),
+                                      adj.data_ptr(), _stream_ptr()), "misfit_cs")
+            LAUNCHES["misfit"] += 1
         else:
             ws = torch.empty(L.st_misfit_envelope_workspace(nt, ntr), dtype=torch.float32, device=s.device)
             hk = hilbert_kernel(nt, s.device)
@@ -66,7 +74,7 @@ class _Misfit(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (adj,) = ctx.saved_tensors
-        return None, (adj * g).to(ctx.dtype), None
+        return None, (adj * g).to(ctx.dtype), None, None
 
 
 def _per_shot(kind, x, y):
@@ -76,10 +84,11 @@ def _per_shot(kind, x, y):
         B, nt = x.shape[0], x.shape[1]
         xs = x.permute(1, 0, 2, 3).reshape(nt, -1)
         ys = y.permute(1, 0, 2, 3).reshape(nt, -1)
-        return _Misfit.apply(kind, xs, ys)
+        return _Misfit.apply(kind, xs, ys, xs.shape[1] // max(B, 1))      # per-shot trace count (mean of "cs")
     loss = 0.0
     for _x, _y in zip(x, y):
-        loss = loss + _Misfit.apply(kind, _x.reshape(_x.shape[0], -1), torch.as_tensor(_y).reshape(_x.shape[0], -1))
+        xs = _x.reshape(_x.shape[0], -1)
+        loss = loss + _Misfit.apply(kind, xs, torch.as_tensor(_y).reshape(_x.shape[0], -1), xs.shape[1])
     return loss
 
 
@@ -92,6 +101,29 @@ class L2(torch.nn.Module):
 
     def forward(self, x, y):
         return _per_shot("l2", x, y)
+
+
+class L1(torch.nn.Module):
+    """loss.py:381-393: sum over shots of L1Loss(reduction='sum')."""
+
+    @property
+    def name(self):
+        return "l1"
+
+    def forward(self, x, y):
+        return _per_shot("l1", x, y)
+
+
+class CosineSimilarity(torch.nn.Module):
+    """loss.py:52-85 ("cs", normalised cross-correlation): sum over shots of mean over traces of
+    1 - cosine_similarity(x_trace, y_trace) along time (eps = 1e-10)."""
+
+    @property
+    def name(self):
+        return "cs"
+
+    def forward(self, x, y):
+        return _per_shot("cs", x, y)
 
 
 class Envelope(torch.nn.Module):
@@ -125,7 +157,7 @@ class Loss:
         return self.loss(*args, **kwargs)
 
     def loss(self, cfg=None, *args, **kwargs):
-        for cls in (L2, Envelope):
+        for cls in (L2, L1, CosineSimilarity, Envelope):
             if cls().name == self.loss_name:
                 obj = cls(**kwargs)
                 obj.cfg = cfg
