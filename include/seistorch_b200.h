@@ -210,6 +210,10 @@ int st_misfit_l1(const float* syn, const float* obs, int64_t n, float scale,
  * time (eps 1e-10); mean_over = traces of one shot (the reference averages per shot, then sums the shots) */
 int st_misfit_cs(const float* syn, const float* obs, int32_t nt, int32_t ntraces, int32_t mean_over, float scale,
                  double* loss, float* adj, void* stream);
+/* seistorch/loss.py:463-501 ("nim", criterion 'l2', method 'square'): per trace the squared samples are
+ * normalised by their sum over time and integrated (cumsum); loss += scale * sum of squared differences */
+int st_misfit_nim(const float* syn, const float* obs, int32_t nt, int32_t ntraces, float scale,
+                  double* loss, float* adj, void* stream);
 int st_misfit_envelope(const float* syn, const float* obs, int32_t nt, int32_t ntraces,
                        const float* hker, float scale, double* loss, float* adj,
                        float* workspace, void* stream);

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- never imported by the product path.
 
 Golden vectors for the trace-domain misfits, generated from the REAL reference
-(seistorch/loss.py: L2 :409-421, L1 :381-393, CosineSimilarity :52-85, Envelope :178-216) on seeded random
+(seistorch/loss.py: L2 :409-421, L1 :381-393, CosineSimilarity :52-85, NormalizedIntegrationMethod :463-501, Envelope :178-216) on seeded random
 records with a different receiver count per shot:
 
     python -m oracle.make_misfit_golden        # writes tests/golden/misfits.npz
@@ -19,7 +19,7 @@ import torch
 from . import ref_shim
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "misfits.npz")
-NAMES = ["l2", "l1", "cs", "envelope"]
+NAMES = ["l2", "l1", "cs", "nim", "envelope"]
 SHAPES = [(64, 7, 2), (64, 5, 2), (64, 1, 2)]        # (nt, nrec, nchan) of each shot
 
 

@@ -6,6 +6,7 @@ Follows:
   * seistorch/loss.py:178-216      Envelope (method='square')
   * seistorch/loss.py:381-393      L1
   * seistorch/loss.py:52-85        CosineSimilarity ("cs")
+  * seistorch/loss.py:463-501      NormalizedIntegrationMethod ("nim", defaults)
   * seistorch/transform.py:24-66   envelope / hilbert (nfft = nt, scipy convention)
 """
 from __future__ import annotations
@@ -40,6 +41,18 @@ def cs(syn, obs):
         ny = torch.clamp(torch.linalg.vector_norm(yr, dim=0), min=1e-10)
         sim = torch.sum((xr / nx) * (yr / ny), dim=0)
         loss = loss + torch.mean(1 - sim)
+    return loss
+
+
+def nim(syn, obs):
+    """loss.py:476-501 with the defaults (criterion 'l2', reduction 'sum', method 'square')."""
+    loss = 0.0
+    for x, y in zip(syn, obs):
+        x, y = x ** 2, y ** 2                                  # transform.both_nonnegative(type='square')
+        x = x / torch.sum(x, dim=0, keepdim=True)
+        y = y / torch.sum(y, dim=0, keepdim=True)
+        x, y = torch.cumsum(x, dim=0), torch.cumsum(y, dim=0)
+        loss = loss + torch.sum((x - y) ** 2)
     return loss
 
 

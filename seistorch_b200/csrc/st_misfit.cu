@@ -9,6 +9,9 @@
 //   CS        : seistorch/loss.py:52-85     per shot mean over traces of 1 - cos(syn_tr, obs_tr) along time
 //               (F.cosine_similarity, eps = 1e-10):  sim = <x,y> / (max(|x|,eps) max(|y|,eps)),
 //               adj = -(1/ntraces_of_the_shot) ( y/(|x||y|) - sim x/|x|^2 ).
+//   NIM       : seistorch/loss.py:463-501 (criterion 'l2', method 'square'; Donno et al.): per trace
+//               X = x^2 / sum_t x^2,  C = cumsum_t X  (same for obs),  loss = sum (Cx - Cy)^2;
+//               adj_u = (2 x_u / Sx) (R_u - sum_s R_s X_s),  R_s = sum_{t >= s} 2 (Cx_t - Cy_t).
 // Seismograms are [nt][ntraces] (ntraces = receivers x channels, fastest).
 #include <cuda_runtime.h>
 
@@ -77,6 +80,48 @@ __global__ void __launch_bounds__(256) cs_kernel(const float* __restrict__ syn, 
             for (int t = 0; t < nt; ++t) {
                 const long long i = (long long)t * ntr + tr;
                 adj[i] = (float)(w * (a * (double)obs[i] - bq * (double)syn[i]));
+            }
+        }
+    }
+    term = block_sum(term);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, term * (double)scale);
+}
+
+// one thread per trace; four sweeps over time (sums, loss + total residual, weighted residual sum, adjoint source)
+__global__ void __launch_bounds__(256) nim_kernel(const float* __restrict__ syn, const float* __restrict__ obs, int nt, int ntr,
+                                                  float scale, double* loss, float* adj) {
+    const int tr = blockIdx.x * blockDim.x + threadIdx.x;
+    double term = 0.0;
+    if (tr < ntr) {
+        double sx = 0.0, sy = 0.0;
+        for (int t = 0; t < nt; ++t) {
+            const double x = syn[(long long)t * ntr + tr], y = obs[(long long)t * ntr + tr];
+            sx += x * x; sy += y * y;
+        }
+        double cx = 0.0, cy = 0.0, T = 0.0;
+        for (int t = 0; t < nt; ++t) {
+            const double x = syn[(long long)t * ntr + tr], y = obs[(long long)t * ntr + tr];
+            cx += x * x / sx; cy += y * y / sy;
+            const double r = cx - cy;
+            term += r * r;
+            T += 2.0 * r;
+        }
+        if (adj) {
+            double P = 0.0, G = 0.0;          // P: residual sum strictly before s;  R_s = T - P
+            cx = cy = 0.0;
+            for (int t = 0; t < nt; ++t) {
+                const double x = syn[(long long)t * ntr + tr], y = obs[(long long)t * ntr + tr];
+                G += (T - P) * (x * x / sx);
+                cx += x * x / sx; cy += y * y / sy;
+                P += 2.0 * (cx - cy);
+            }
+            P = 0.0; cx = cy = 0.0;
+            for (int t = 0; t < nt; ++t) {
+                const long long i = (long long)t * ntr + tr;
+                const double x = syn[i], y = obs[i];
+                adj[i] = (float)((double)scale * (2.0 * x / sx) * ((T - P) - G));
+                cx += x * x / sx; cy += y * y / sy;
+                P += 2.0 * (cx - cy);
             }
         }
     }
@@ -166,6 +211,15 @@ extern "C" int st_misfit_cs(const float* syn, const float* obs, int32_t nt, int3
     if (ntraces == 0) return ST_OK;
     cs_kernel<<<(ntraces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, 1.f / (float)mean_over, scale, loss, adj);
     if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_cs: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}
+
+extern "C" int st_misfit_nim(const float* syn, const float* obs, int32_t nt, int32_t ntraces, float scale, double* loss, float* adj,
+                             void* stream) {
+    if (!syn || !obs || nt <= 0 || ntraces < 0) { st_set_error("misfit_nim: bad arguments"); return ST_ERR_BADARG; }
+    if (ntraces == 0) return ST_OK;
+    nim_kernel<<<(ntraces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, scale, loss, adj);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_nim: launch failed"); return ST_ERR_CUDA; }
     return ST_OK;
 }
 

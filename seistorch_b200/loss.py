@@ -57,6 +57,10 @@ class _Misfit(torch.autograd.Function):
             _lib.check(L.st_misfit_l1(s.data_ptr(), o.data_ptr(), s.numel(), 1.0, loss.data_ptr(), adj.data_ptr(),
                                       _stream_ptr()), "misfit_l1")
             LAUNCHES["misfit"] += 1
+        elif kind == "nim":
+            _lib.check(L.st_misfit_nim(s.data_ptr(), o.data_ptr(), nt, ntr, 1.0, loss.data_ptr(), adj.data_ptr(),
+                                       _stream_ptr()), "misfit_nim")
+            LAUNCHES["misfit"] += 1
         elif kind == "cs":
             _lib.check(L.st_misfit_cs(s.data_ptr(), o.data_ptr(), nt, ntr, int(mean_over), 1.0, loss.data_ptr(),
                                       adj.data_ptr(), _stream_ptr()), "misfit_cs")
@@ -126,6 +130,23 @@ class CosineSimilarity(torch.nn.Module):
         return _per_shot("cs", x, y)
 
 
+class NormalizedIntegrationMethod(torch.nn.Module):
+    """loss.py:463-501 ("nim", Donno et al.): traces squared, normalised by their sum over time, integrated;
+    sum of squared differences.  Only the reference's defaults (criterion 'l2', reduction 'sum', method 'square')."""
+
+    def __init__(self, criterion="l2", reduction="sum", method="square"):
+        super().__init__()
+        if (criterion, reduction, method) != ("l2", "sum", "square"):
+            raise NotImplementedError("seistorch_b200: only the default 'nim' misfit (l2 / sum / square) is accelerated")
+
+    @property
+    def name(self):
+        return "nim"
+
+    def forward(self, x, y):
+        return _per_shot("nim", x, y)
+
+
 class Envelope(torch.nn.Module):
     """loss.py:178-216 with method='square' (the only working method there):
     sum over shots of 0.5 * sum((E(x)^2 - E(y)^2)^2), E = |analytic signal| along time."""
@@ -157,7 +178,7 @@ class Loss:
         return self.loss(*args, **kwargs)
 
     def loss(self, cfg=None, *args, **kwargs):
-        for cls in (L2, L1, CosineSimilarity, Envelope):
+        for cls in (L2, L1, CosineSimilarity, NormalizedIntegrationMethod, Envelope):
             if cls().name == self.loss_name:
                 obj = cls(**kwargs)
                 obj.cfg = cfg
