@@ -214,6 +214,12 @@ int st_misfit_cs(const float* syn, const float* obs, int32_t nt, int32_t ntraces
  * normalised by their sum over time and integrated (cumsum); loss += scale * sum of squared differences */
 int st_misfit_nim(const float* syn, const float* obs, int32_t nt, int32_t ntraces, float scale,
                   double* loss, float* adj, void* stream);
+/* seistorch/signal.py:49-101 (backend 'torch'): zero-phase IIR filter along time of records [nt][ntraces]:
+ * causal pass then anti-causal pass, zero initial state, double precision inside (torchaudio filtfilt,
+ * clamp=False).  b, a: HOST arrays of `ncoef` coefficients (scipy.signal.butter), work: nt*ntraces doubles.
+ * The operator is self-adjoint: apply it to the cotangent for the backward pass. */
+int st_filtfilt(const float* x, float* y, double* work, int32_t nt, int32_t ntraces, const double* b, const double* a,
+                int32_t ncoef, void* stream);
 int st_misfit_envelope(const float* syn, const float* obs, int32_t nt, int32_t ntraces,
                        const float* hker, float scale, double* loss, float* adj,
                        float* workspace, void* stream);

@@ -5,6 +5,7 @@ Golden vectors for the trace-domain misfits, generated from the REAL reference
 records with a different receiver count per shot:
 
     python -m oracle.make_misfit_golden        # writes tests/golden/misfits.npz
+    python -m oracle.make_misfit_golden filter # writes tests/golden/filter.npz (record filter, see main_filter)
 
 Stored: the records (fp32), and per misfit name the reference's loss and d loss / d syn in float64.
 """
@@ -49,5 +50,39 @@ def main():
     print("wrote", OUT)
 
 
+def main_filter():
+    """Golden vectors of the device-side record filter (seistorch/signal.py:49-101, backend='torch'):
+    tests/golden/filter.npz -- low-pass and band-pass, two shots with different receiver counts, output and the
+    gradient of a random linear functional of the output (autograd through torchaudio in the reference)."""
+    ref_shim.import_reference()
+    from seistorch.signal import SeisSignal
+    from seistorch.type import TensorList
+    rng = np.random.default_rng(20230503)
+    dt, order = 0.002, 3
+    shapes = [(300, 6, 2), (300, 3, 2)]
+    x = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    w = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    arrs = {"dt": np.float64(dt), "order": np.int64(order)}
+    for k in range(len(x)):
+        arrs[f"x_{k}"], arrs[f"w_{k}"] = x[k], w[k]
+    sig = SeisSignal({"geom": {"dt": dt}, "training": {"filter_ord": order}})
+    for tag, freqs in (("low", [30.0]), ("band", [8.0, 60.0])):
+        xs = [torch.from_numpy(v).clone().requires_grad_(True) for v in x]
+        out = sig.filter(TensorList([v * 1.0 for v in xs]), list(freqs), backend="torch")
+        loss = sum((o.double() * torch.from_numpy(wk).double()).sum() for o, wk in zip(out.data, w))
+        loss.backward()
+        arrs[f"{tag}_freqs"] = np.asarray(freqs, dtype=np.float64)
+        for k in range(len(x)):
+            arrs[f"{tag}_y_{k}"] = out.data[k].detach().numpy()
+            arrs[f"{tag}_grad_{k}"] = xs[k].grad.numpy()
+        print(tag, float(loss))
+    out_path = os.path.join(os.path.dirname(OUT), "filter.npz")
+    np.savez_compressed(out_path, **arrs)
+    print("wrote", out_path)
+
+
 if __name__ == "__main__":
-    main()
+    if "filter" in sys.argv:
+        main_filter()
+    else:
+        main()

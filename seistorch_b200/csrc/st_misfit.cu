@@ -12,6 +12,9 @@
 //   NIM       : seistorch/loss.py:463-501 (criterion 'l2', method 'square'; Donno et al.): per trace
 //               X = x^2 / sum_t x^2,  C = cumsum_t X  (same for obs),  loss = sum (Cx - Cy)^2;
 //               adj_u = (2 x_u / Sx) (R_u - sum_s R_s X_s),  R_s = sum_{t >= s} 2 (Cx_t - Cy_t).
+//   filtfilt  : seistorch/signal.py:49-101 (backend 'torch': torchaudio filtfilt in double, clamp=False, zero initial
+//               state, no padding): y = flip(lfilter(flip(lfilter(x)))).  As a matrix A^T A with A the causal IIR
+//               operator, hence self-adjoint: the cotangent of the input is filtfilt(cotangent of the output).
 // Seismograms are [nt][ntraces] (ntraces = receivers x channels, fastest).
 #include <cuda_runtime.h>
 
@@ -129,6 +132,36 @@ __global__ void __launch_bounds__(256) nim_kernel(const float* __restrict__ syn,
     if (threadIdx.x == 0 && loss) atomicAdd(loss, term * (double)scale);
 }
 
+constexpr int FILT_MAXC = 12;             // coefficients per polynomial (Butterworth band-pass of order 5 has 11)
+struct FiltCoef { double b[FILT_MAXC], a[FILT_MAXC]; int n; };
+// one thread per trace: causal pass into `work` (double), anti-causal pass into `y`; transposed direct form II
+__global__ void __launch_bounds__(128) filtfilt_kernel(const float* __restrict__ x, float* __restrict__ y, double* __restrict__ work,
+                                                       int nt, int ntr, const FiltCoef c) {
+    const int tr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tr >= ntr) return;
+    double z[FILT_MAXC];
+#pragma unroll
+    for (int k = 0; k < FILT_MAXC; ++k) z[k] = 0.0;
+    for (int t = 0; t < nt; ++t) {
+        const double v = x[(long long)t * ntr + tr];
+        const double o = c.b[0] * v + z[0];
+#pragma unroll
+        for (int k = 1; k < FILT_MAXC; ++k)
+            if (k < c.n) z[k - 1] = c.b[k] * v + (k + 1 < c.n ? z[k] : 0.0) - c.a[k] * o;
+        work[(long long)t * ntr + tr] = o;
+    }
+#pragma unroll
+    for (int k = 0; k < FILT_MAXC; ++k) z[k] = 0.0;
+    for (int t = nt - 1; t >= 0; --t) {
+        const double v = work[(long long)t * ntr + tr];
+        const double o = c.b[0] * v + z[0];
+#pragma unroll
+        for (int k = 1; k < FILT_MAXC; ++k)
+            if (k < c.n) z[k - 1] = c.b[k] * v + (k + 1 < c.n ? z[k] : 0.0) - c.a[k] * o;
+        y[(long long)t * ntr + tr] = (float)o;
+    }
+}
+
 constexpr int CT = 32;      // tile: 32 output samples x 32 traces, 32 taps per stage
 
 // out[n][tr] = sum_m k[(n-m) mod nt] x[m][tr]      (transpose == false)
@@ -220,6 +253,22 @@ extern "C" int st_misfit_nim(const float* syn, const float* obs, int32_t nt, int
     if (ntraces == 0) return ST_OK;
     nim_kernel<<<(ntraces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, scale, loss, adj);
     if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_nim: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}
+
+extern "C" int st_filtfilt(const float* x, float* y, double* work, int32_t nt, int32_t ntraces, const double* b, const double* a,
+                           int32_t ncoef, void* stream) {
+    if (!x || !y || !work || !b || !a || nt <= 0 || ntraces < 0) { st_set_error("filtfilt: bad arguments"); return ST_ERR_BADARG; }
+    if (ncoef < 1 || ncoef > FILT_MAXC || a[0] == 0.0) { st_set_error("filtfilt: 1..%d coefficients with a[0] != 0 (got %d)", FILT_MAXC, ncoef); return ST_ERR_BADARG; }
+    if (ntraces == 0) return ST_OK;
+    FiltCoef c;
+    for (int k = 0; k < FILT_MAXC; ++k) {
+        c.b[k] = k < ncoef ? b[k] / a[0] : 0.0;
+        c.a[k] = k < ncoef ? a[k] / a[0] : 0.0;
+    }
+    c.n = ncoef;
+    filtfilt_kernel<<<(ntraces + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, y, work, nt, ntraces, c);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("filtfilt: launch failed"); return ST_ERR_CUDA; }
     return ST_OK;
 }
 
