@@ -220,6 +220,10 @@ int st_misfit_nim(const float* syn, const float* obs, int32_t nt, int32_t ntrace
  * The operator is self-adjoint: apply it to the cotangent for the backward pass. */
 int st_filtfilt(const float* x, float* y, double* work, int32_t nt, int32_t ntraces, const double* b, const double* a,
                 int32_t ncoef, void* stream);
+/* seistorch/loss.py:900-955 ("w1d", method 'linear'): as nim with the samples shifted by -c instead of squared;
+ * shift: DEVICE pointer to c = 1.1 * min(min syn, min obs, 0) of the shot (computed by the caller, no host sync) */
+int st_misfit_w1d(const float* syn, const float* obs, int32_t nt, int32_t ntraces, const float* shift, float scale,
+                  double* loss, float* adj, void* stream);
 int st_misfit_envelope(const float* syn, const float* obs, int32_t nt, int32_t ntraces,
                        const float* hker, float scale, double* loss, float* adj,
                        float* workspace, void* stream);

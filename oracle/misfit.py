@@ -7,6 +7,7 @@ Follows:
   * seistorch/loss.py:381-393      L1
   * seistorch/loss.py:52-85        CosineSimilarity ("cs")
   * seistorch/loss.py:463-501      NormalizedIntegrationMethod ("nim", defaults)
+  * seistorch/loss.py:900-955      Wasserstein1d ("w1d", method 'linear')
   * seistorch/transform.py:24-66   envelope / hilbert (nfft = nt, scipy convention)
 """
 from __future__ import annotations
@@ -53,6 +54,19 @@ def nim(syn, obs):
         y = y / torch.sum(y, dim=0, keepdim=True)
         x, y = torch.cumsum(x, dim=0), torch.cumsum(y, dim=0)
         loss = loss + torch.sum((x - y) ** 2)
+    return loss
+
+
+def w1d(syn, obs):
+    """loss.py:940-955 with method 'linear' (:917-922)."""
+    loss = 0.0
+    for x, y in zip(syn, obs):
+        m = torch.min(x.detach().min(), y.detach().min())
+        m = m if m < 0 else 0
+        x, y = x - 1.1 * m, y - 1.1 * m
+        x = x / (torch.sum(x, dim=0, keepdim=True) + 1e-18)
+        y = y / (torch.sum(y, dim=0, keepdim=True) + 1e-18)
+        loss = loss + (torch.abs(torch.cumsum(x, dim=0) - torch.cumsum(y, dim=0)) ** 2).sum()
     return loss
 
 

@@ -12,6 +12,8 @@
 //   NIM       : seistorch/loss.py:463-501 (criterion 'l2', method 'square'; Donno et al.): per trace
 //               X = x^2 / sum_t x^2,  C = cumsum_t X  (same for obs),  loss = sum (Cx - Cy)^2;
 //               adj_u = (2 x_u / Sx) (R_u - sum_s R_s X_s),  R_s = sum_{t >= s} 2 (Cx_t - Cy_t).
+//   W1D       : seistorch/loss.py:900-955 (method 'linear'): the same with X = (x - c) / (sum_t (x - c) + 1e-18),
+//               c = 1.1 min(min x, min y, 0) over the shot (a constant for the gradient);  adj_u = (R_u - G) / S.
 //   filtfilt  : seistorch/signal.py:49-101 (backend 'torch': torchaudio filtfilt in double, clamp=False, zero initial
 //               state, no padding): y = flip(lfilter(flip(lfilter(x)))).  As a matrix A^T A with A the causal IIR
 //               operator, hence self-adjoint: the cotangent of the input is filtfilt(cotangent of the output).
@@ -91,20 +93,25 @@ __global__ void __launch_bounds__(256) cs_kernel(const float* __restrict__ syn, 
 }
 
 // one thread per trace; four sweeps over time (sums, loss + total residual, weighted residual sum, adjoint source)
+// MODE 0: nim (samples squared);  MODE 1: w1d (samples shifted by -c, c read from `shift`, 1e-18 added to the sums)
+template <int MODE>
 __global__ void __launch_bounds__(256) nim_kernel(const float* __restrict__ syn, const float* __restrict__ obs, int nt, int ntr,
-                                                  float scale, double* loss, float* adj) {
+                                                  const float* __restrict__ shift, float scale, double* loss, float* adj) {
     const int tr = blockIdx.x * blockDim.x + threadIdx.x;
     double term = 0.0;
+    const double c = MODE == 1 ? (double)__ldg(shift) : 0.0;
+    auto tf = [&](double v) { return MODE == 0 ? v * v : v - c; };          // the non-negative transform
     if (tr < ntr) {
         double sx = 0.0, sy = 0.0;
         for (int t = 0; t < nt; ++t) {
             const double x = syn[(long long)t * ntr + tr], y = obs[(long long)t * ntr + tr];
-            sx += x * x; sy += y * y;
+            sx += tf(x); sy += tf(y);
         }
+        if (MODE == 1) { sx += 1e-18; sy += 1e-18; }
         double cx = 0.0, cy = 0.0, T = 0.0;
         for (int t = 0; t < nt; ++t) {
             const double x = syn[(long long)t * ntr + tr], y = obs[(long long)t * ntr + tr];
-            cx += x * x / sx; cy += y * y / sy;
+            cx += tf(x) / sx; cy += tf(y) / sy;
             const double r = cx - cy;
             term += r * r;
             T += 2.0 * r;
@@ -114,16 +121,16 @@ __global__ void __launch_bounds__(256) nim_kernel(const float* __restrict__ syn,
             cx = cy = 0.0;
             for (int t = 0; t < nt; ++t) {
                 const double x = syn[(long long)t * ntr + tr], y = obs[(long long)t * ntr + tr];
-                G += (T - P) * (x * x / sx);
-                cx += x * x / sx; cy += y * y / sy;
+                G += (T - P) * (tf(x) / sx);
+                cx += tf(x) / sx; cy += tf(y) / sy;
                 P += 2.0 * (cx - cy);
             }
             P = 0.0; cx = cy = 0.0;
             for (int t = 0; t < nt; ++t) {
                 const long long i = (long long)t * ntr + tr;
                 const double x = syn[i], y = obs[i];
-                adj[i] = (float)((double)scale * (2.0 * x / sx) * ((T - P) - G));
-                cx += x * x / sx; cy += y * y / sy;
+                adj[i] = (float)((double)scale * ((MODE == 0 ? 2.0 * x : 1.0) / sx) * ((T - P) - G));
+                cx += tf(x) / sx; cy += tf(y) / sy;
                 P += 2.0 * (cx - cy);
             }
         }
@@ -251,8 +258,17 @@ extern "C" int st_misfit_nim(const float* syn, const float* obs, int32_t nt, int
                              void* stream) {
     if (!syn || !obs || nt <= 0 || ntraces < 0) { st_set_error("misfit_nim: bad arguments"); return ST_ERR_BADARG; }
     if (ntraces == 0) return ST_OK;
-    nim_kernel<<<(ntraces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, scale, loss, adj);
+    nim_kernel<0><<<(ntraces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, nullptr, scale, loss, adj);
     if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_nim: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}
+
+extern "C" int st_misfit_w1d(const float* syn, const float* obs, int32_t nt, int32_t ntraces, const float* shift, float scale,
+                             double* loss, float* adj, void* stream) {
+    if (!syn || !obs || !shift || nt <= 0 || ntraces < 0) { st_set_error("misfit_w1d: bad arguments"); return ST_ERR_BADARG; }
+    if (ntraces == 0) return ST_OK;
+    nim_kernel<1><<<(ntraces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, shift, scale, loss, adj);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_w1d: launch failed"); return ST_ERR_CUDA; }
     return ST_OK;
 }
 

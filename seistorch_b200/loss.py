@@ -61,6 +61,12 @@ class _Misfit(torch.autograd.Function):
             _lib.check(L.st_misfit_nim(s.data_ptr(), o.data_ptr(), nt, ntr, 1.0, loss.data_ptr(), adj.data_ptr(),
                                        _stream_ptr()), "misfit_nim")
             LAUNCHES["misfit"] += 1
+        elif kind == "w1d":
+            # loss.py:919-922: shift by 1.1 * min(min x, min y, 0), a constant for the gradient; stays on the device
+            shift = (1.1 * torch.minimum(s.min(), o.min()).clamp(max=0.0)).to(torch.float32).reshape(1)
+            _lib.check(L.st_misfit_w1d(s.data_ptr(), o.data_ptr(), nt, ntr, shift.data_ptr(), 1.0, loss.data_ptr(),
+                                       adj.data_ptr(), _stream_ptr()), "misfit_w1d")
+            LAUNCHES["misfit"] += 1
         elif kind == "cs":
             _lib.check(L.st_misfit_cs(s.data_ptr(), o.data_ptr(), nt, ntr, int(mean_over), 1.0, loss.data_ptr(),
                                       adj.data_ptr(), _stream_ptr()), "misfit_cs")
@@ -147,6 +153,27 @@ class NormalizedIntegrationMethod(torch.nn.Module):
         return _per_shot("nim", x, y)
 
 
+class Wasserstein1d(torch.nn.Module):
+    """loss.py:900-955 ("w1d") with the default method 'linear': traces shifted to be positive, normalised by their
+    sum over time, integrated; sum of squared differences of the two cumulative distributions.  The shift is taken
+    per shot, so stacked input is processed shot by shot."""
+
+    def __init__(self, method="linear"):
+        super().__init__()
+        if method != "linear":
+            raise NotImplementedError("seistorch_b200: only the default 'linear' w1d misfit is accelerated")
+        self.method = method
+
+    @property
+    def name(self):
+        return "w1d"
+
+    def forward(self, x, y):
+        if isinstance(x, torch.Tensor) and x.ndim == 4:
+            x, y = list(x), list(y)
+        return _per_shot("w1d", x, y)
+
+
 class Envelope(torch.nn.Module):
     """loss.py:178-216 with method='square' (the only working method there):
     sum over shots of 0.5 * sum((E(x)^2 - E(y)^2)^2), E = |analytic signal| along time."""
@@ -178,7 +205,7 @@ class Loss:
         return self.loss(*args, **kwargs)
 
     def loss(self, cfg=None, *args, **kwargs):
-        for cls in (L2, L1, CosineSimilarity, NormalizedIntegrationMethod, Envelope):
+        for cls in (L2, L1, CosineSimilarity, NormalizedIntegrationMethod, Wasserstein1d, Envelope):
             if cls().name == self.loss_name:
                 obj = cls(**kwargs)
                 obj.cfg = cfg
