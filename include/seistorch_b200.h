@@ -224,6 +224,13 @@ int st_filtfilt(const float* x, float* y, double* work, int32_t nt, int32_t ntra
  * shift: DEVICE pointer to c = 1.1 * min(min syn, min obs, 0) of the shot (computed by the caller, no host sync) */
 int st_misfit_w1d(const float* syn, const float* obs, int32_t nt, int32_t ntraces, const float* shift, float scale,
                   double* loss, float* adj, void* stream);
+/* seistorch/loss.py:395-407 ("sml1": SmoothL1Loss(reduction='sum', beta)), :126-176 ("cc": minus the zero-lag
+ * cross-correlation, - sum syn*obs), :366-379 ("integration": MSELoss(mean) of the cumulative sums along time;
+ * mean_over = samples of one shot, nt * traces of the shot) */
+int st_misfit_sml1(const float* syn, const float* obs, int64_t n, float beta, float scale, double* loss, float* adj, void* stream);
+int st_misfit_cc(const float* syn, const float* obs, int64_t n, float scale, double* loss, float* adj, void* stream);
+int st_misfit_integration(const float* syn, const float* obs, int32_t nt, int32_t ntraces, int64_t mean_over, float scale,
+                          double* loss, float* adj, void* stream);
 int st_misfit_envelope(const float* syn, const float* obs, int32_t nt, int32_t ntraces,
                        const float* hker, float scale, double* loss, float* adj,
                        float* workspace, void* stream);

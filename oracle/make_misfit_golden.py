@@ -20,7 +20,7 @@ import torch
 from . import ref_shim
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "misfits.npz")
-NAMES = ["l2", "l1", "cs", "nim", "w1d", "envelope"]
+NAMES = ["l2", "l1", "sml1", "cs", "cc", "integration", "nim", "w1d", "envelope"]
 SHAPES = [(64, 7, 2), (64, 5, 2), (64, 1, 2)]        # (nt, nrec, nchan) of each shot
 
 

@@ -70,6 +70,30 @@ def w1d(syn, obs):
     return loss
 
 
+def sml1(syn, obs):
+    """loss.py:403-407."""
+    loss = 0.0
+    for x, y in zip(syn, obs):
+        loss = loss + torch.nn.SmoothL1Loss(reduction="sum", beta=0.001)(x, y)
+    return loss
+
+
+def cc(syn, obs):
+    """loss.py:148-161: conv1d of a trace with the full-length other trace = its zero-lag cross-correlation."""
+    loss = 0.0
+    for x, y in zip(syn, obs):
+        loss = loss - torch.sum(x * y)
+    return loss
+
+
+def integration(syn, obs):
+    """loss.py:375-379 with transform.integrate (cumsum along time), MSELoss() = mean."""
+    loss = 0.0
+    for x, y in zip(syn, obs):
+        loss = loss + torch.mean((torch.cumsum(x, dim=0) - torch.cumsum(y, dim=0)) ** 2)
+    return loss
+
+
 def hilbert(data):
     """transform.py:27-66: analytic signal along dim 0 of (nt, ntraces, nchan)."""
     nt = data.shape[0]

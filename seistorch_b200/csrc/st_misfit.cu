@@ -6,6 +6,9 @@
 //                 E^2 = x^2 + (hker (*) x)^2,  loss = 0.5 sum (Es^2 - Eo^2)^2,
 //                 adj = 2 r x + H^T (2 r Hx),  r = Es^2 - Eo^2.
 //   L1        : seistorch/loss.py:381-393   sum |syn-obs|             adj = sign(syn-obs)
+//   SML1      : seistorch/loss.py:395-407   SmoothL1Loss(sum, beta = 1e-3): 0.5 d^2/beta for |d| < beta else |d| - 0.5 beta
+//   CC        : seistorch/loss.py:126-176   minus the zero-lag cross-correlation: - sum syn*obs          adj = -obs
+//   INTEGRATION: seistorch/loss.py:366-379  per shot MSELoss(mean) of the time integrals (transform.integrate = cumsum)
 //   CS        : seistorch/loss.py:52-85     per shot mean over traces of 1 - cos(syn_tr, obs_tr) along time
 //               (F.cosine_similarity, eps = 1e-10):  sim = <x,y> / (max(|x|,eps) max(|y|,eps)),
 //               adj = -(1/ntraces_of_the_shot) ( y/(|x||y|) - sim x/|x|^2 ).
@@ -50,13 +53,24 @@ __global__ void __launch_bounds__(256) l2_kernel(const float* __restrict__ syn, 
     if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * (double)scale);
 }
 
+// KIND 0: l1, 1: smooth l1 (beta = par), 2: minus zero-lag cross-correlation
+template <int KIND>
 __global__ void __launch_bounds__(256) l1_kernel(const float* __restrict__ syn, const float* __restrict__ obs,
-                                                 long long n, float scale, double* loss, float* adj) {
+                                                 long long n, float par, float scale, double* loss, float* adj) {
     double acc = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float d = syn[i] - obs[i];
-        acc += (double)fabsf(d);
-        if (adj) adj[i] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+        if (KIND == 0) {
+            acc += (double)fabsf(d);
+            if (adj) adj[i] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+        } else if (KIND == 1) {
+            const float ad = fabsf(d);
+            acc += ad < par ? 0.5 * (double)d * (double)d / (double)par : (double)ad - 0.5 * (double)par;
+            if (adj) adj[i] = scale * (ad < par ? d / par : (d > 0.f ? 1.f : -1.f));
+        } else {
+            acc -= (double)syn[i] * (double)obs[i];
+            if (adj) adj[i] = -scale * obs[i];
+        }
     }
     acc = block_sum(acc);
     if (threadIdx.x == 0 && loss) atomicAdd(loss, acc * (double)scale);
@@ -93,14 +107,15 @@ __global__ void __launch_bounds__(256) cs_kernel(const float* __restrict__ syn, 
 }
 
 // one thread per trace; four sweeps over time (sums, loss + total residual, weighted residual sum, adjoint source)
-// MODE 0: nim (samples squared);  MODE 1: w1d (samples shifted by -c, c read from `shift`, 1e-18 added to the sums)
+// MODE 0: nim (samples squared);  MODE 1: w1d (samples shifted by -c, c read from `shift`, 1e-18 added to the sums);
+// MODE 2: integration (plain cumsum, no normalisation: the caller folds the 1/N of the mean into `scale`)
 template <int MODE>
 __global__ void __launch_bounds__(256) nim_kernel(const float* __restrict__ syn, const float* __restrict__ obs, int nt, int ntr,
                                                   const float* __restrict__ shift, float scale, double* loss, float* adj) {
     const int tr = blockIdx.x * blockDim.x + threadIdx.x;
     double term = 0.0;
     const double c = MODE == 1 ? (double)__ldg(shift) : 0.0;
-    auto tf = [&](double v) { return MODE == 0 ? v * v : v - c; };          // the non-negative transform
+    auto tf = [&](double v) { return MODE == 0 ? v * v : v - c; };          // the non-negative transform (identity for MODE 2)
     if (tr < ntr) {
         double sx = 0.0, sy = 0.0;
         for (int t = 0; t < nt; ++t) {
@@ -108,6 +123,7 @@ __global__ void __launch_bounds__(256) nim_kernel(const float* __restrict__ syn,
             sx += tf(x); sy += tf(y);
         }
         if (MODE == 1) { sx += 1e-18; sy += 1e-18; }
+        if (MODE == 2) sx = sy = 1.0;
         double cx = 0.0, cy = 0.0, T = 0.0;
         for (int t = 0; t < nt; ++t) {
             const double x = syn[(long long)t * ntr + tr], y = obs[(long long)t * ntr + tr];
@@ -129,7 +145,7 @@ __global__ void __launch_bounds__(256) nim_kernel(const float* __restrict__ syn,
             for (int t = 0; t < nt; ++t) {
                 const long long i = (long long)t * ntr + tr;
                 const double x = syn[i], y = obs[i];
-                adj[i] = (float)((double)scale * ((MODE == 0 ? 2.0 * x : 1.0) / sx) * ((T - P) - G));
+                adj[i] = (float)((double)scale * ((MODE == 0 ? 2.0 * x : 1.0) / sx) * ((T - P) - (MODE == 2 ? 0.0 : G)));
                 cx += tf(x) / sx; cy += tf(y) / sy;
                 P += 2.0 * (cx - cy);
             }
@@ -240,8 +256,25 @@ extern "C" int st_misfit_l2(const float* syn, const float* obs, int64_t n, float
 extern "C" int st_misfit_l1(const float* syn, const float* obs, int64_t n, float scale, double* loss, float* adj, void* stream) {
     if (!syn || !obs || n < 0) { st_set_error("misfit_l1: bad arguments"); return ST_ERR_BADARG; }
     if (n == 0) return ST_OK;
-    l1_kernel<<<nblocks(n), 256, 0, (cudaStream_t)stream>>>(syn, obs, n, scale, loss, adj);
+    l1_kernel<0><<<nblocks(n), 256, 0, (cudaStream_t)stream>>>(syn, obs, n, 0.f, scale, loss, adj);
     if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_l1: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}
+
+extern "C" int st_misfit_sml1(const float* syn, const float* obs, int64_t n, float beta, float scale, double* loss, float* adj,
+                              void* stream) {
+    if (!syn || !obs || n < 0 || !(beta > 0.f)) { st_set_error("misfit_sml1: bad arguments"); return ST_ERR_BADARG; }
+    if (n == 0) return ST_OK;
+    l1_kernel<1><<<nblocks(n), 256, 0, (cudaStream_t)stream>>>(syn, obs, n, beta, scale, loss, adj);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_sml1: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}
+
+extern "C" int st_misfit_cc(const float* syn, const float* obs, int64_t n, float scale, double* loss, float* adj, void* stream) {
+    if (!syn || !obs || n < 0) { st_set_error("misfit_cc: bad arguments"); return ST_ERR_BADARG; }
+    if (n == 0) return ST_OK;
+    l1_kernel<2><<<nblocks(n), 256, 0, (cudaStream_t)stream>>>(syn, obs, n, 0.f, scale, loss, adj);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_cc: launch failed"); return ST_ERR_CUDA; }
     return ST_OK;
 }
 
@@ -260,6 +293,15 @@ extern "C" int st_misfit_nim(const float* syn, const float* obs, int32_t nt, int
     if (ntraces == 0) return ST_OK;
     nim_kernel<0><<<(ntraces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, nullptr, scale, loss, adj);
     if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_nim: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}
+
+extern "C" int st_misfit_integration(const float* syn, const float* obs, int32_t nt, int32_t ntraces, int64_t mean_over, float scale,
+                                     double* loss, float* adj, void* stream) {
+    if (!syn || !obs || nt <= 0 || ntraces < 0 || mean_over <= 0) { st_set_error("misfit_integration: bad arguments"); return ST_ERR_BADARG; }
+    if (ntraces == 0) return ST_OK;
+    nim_kernel<2><<<(ntraces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, nullptr, scale / (float)mean_over, loss, adj);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_integration: launch failed"); return ST_ERR_CUDA; }
     return ST_OK;
 }
 

@@ -57,6 +57,18 @@ class _Misfit(torch.autograd.Function):
             _lib.check(L.st_misfit_l1(s.data_ptr(), o.data_ptr(), s.numel(), 1.0, loss.data_ptr(), adj.data_ptr(),
                                       _stream_ptr()), "misfit_l1")
             LAUNCHES["misfit"] += 1
+        elif kind == "sml1":
+            _lib.check(L.st_misfit_sml1(s.data_ptr(), o.data_ptr(), s.numel(), 0.001, 1.0, loss.data_ptr(), adj.data_ptr(),
+                                        _stream_ptr()), "misfit_sml1")
+            LAUNCHES["misfit"] += 1
+        elif kind == "cc":
+            _lib.check(L.st_misfit_cc(s.data_ptr(), o.data_ptr(), s.numel(), 1.0, loss.data_ptr(), adj.data_ptr(),
+                                      _stream_ptr()), "misfit_cc")
+            LAUNCHES["misfit"] += 1
+        elif kind == "integration":
+            _lib.check(L.st_misfit_integration(s.data_ptr(), o.data_ptr(), nt, ntr, nt * int(mean_over), 1.0, loss.data_ptr(),
+                                               adj.data_ptr(), _stream_ptr()), "misfit_integration")
+            LAUNCHES["misfit"] += 1
         elif kind == "nim":
             _lib.check(L.st_misfit_nim(s.data_ptr(), o.data_ptr(), nt, ntr, 1.0, loss.data_ptr(), adj.data_ptr(),
                                        _stream_ptr()), "misfit_nim")
@@ -153,6 +165,39 @@ class NormalizedIntegrationMethod(torch.nn.Module):
         return _per_shot("nim", x, y)
 
 
+class SML1(torch.nn.Module):
+    """loss.py:395-407: sum over shots of SmoothL1Loss(reduction='sum', beta=0.001)."""
+
+    @property
+    def name(self):
+        return "sml1"
+
+    def forward(self, x, y):
+        return _per_shot("sml1", x, y)
+
+
+class Crosscorrelation(torch.nn.Module):
+    """loss.py:126-176 ("cc"): minus the zero-lag cross-correlation of every trace (all channels), summed."""
+
+    @property
+    def name(self):
+        return "cc"
+
+    def forward(self, x, y, win=512, step=1):
+        return _per_shot("cc", x, y)
+
+
+class Integration(torch.nn.Module):
+    """loss.py:366-379: sum over shots of MSELoss() (mean) between the time integrals (cumsum) of the records."""
+
+    @property
+    def name(self):
+        return "integration"
+
+    def forward(self, x, y):
+        return _per_shot("integration", x, y)
+
+
 class Wasserstein1d(torch.nn.Module):
     """loss.py:900-955 ("w1d") with the default method 'linear': traces shifted to be positive, normalised by their
     sum over time, integrated; sum of squared differences of the two cumulative distributions.  The shift is taken
@@ -205,7 +250,7 @@ class Loss:
         return self.loss(*args, **kwargs)
 
     def loss(self, cfg=None, *args, **kwargs):
-        for cls in (L2, L1, CosineSimilarity, NormalizedIntegrationMethod, Wasserstein1d, Envelope):
+        for cls in (L2, L1, SML1, CosineSimilarity, Crosscorrelation, Integration, NormalizedIntegrationMethod, Wasserstein1d, Envelope):
             if cls().name == self.loss_name:
                 obj = cls(**kwargs)
                 obj.cfg = cfg

@@ -10,7 +10,7 @@ import torch
 from conftest import rel
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "misfits.npz")
-NAMES = ["l2", "l1", "cs", "nim", "w1d", "envelope"]
+NAMES = ["l2", "l1", "sml1", "cs", "cc", "integration", "nim", "w1d", "envelope"]
 
 
 def _load():
@@ -22,7 +22,7 @@ def _load():
 @pytest.mark.parametrize("name", NAMES)
 def test_oracle_misfit_matches_reference(name):
     from oracle import misfit
-    fn = {"l2": misfit.l2, "l1": misfit.l1, "cs": misfit.cs, "nim": misfit.nim, "w1d": misfit.w1d, "envelope": misfit.envelope_loss}[name]
+    fn = {"l2": misfit.l2, "l1": misfit.l1, "sml1": misfit.sml1, "cc": misfit.cc, "integration": misfit.integration, "cs": misfit.cs, "nim": misfit.nim, "w1d": misfit.w1d, "envelope": misfit.envelope_loss}[name]
     z, syn, obs = _load()
     xs = [torch.from_numpy(x).double().requires_grad_(True) for x in syn]
     loss = fn(xs, [torch.from_numpy(y).double() for y in obs])
