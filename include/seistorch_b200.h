@@ -231,6 +231,13 @@ int st_misfit_sml1(const float* syn, const float* obs, int64_t n, float beta, fl
 int st_misfit_cc(const float* syn, const float* obs, int64_t n, float scale, double* loss, float* adj, void* stream);
 int st_misfit_integration(const float* syn, const float* obs, int32_t nt, int32_t ntraces, int64_t mean_over, float scale,
                           double* loss, float* adj, void* stream);
+/* seistorch/loss.py:674-728 ("traveltime") with signal.py:203-208: loss += scale * (1/mean_over) * sum over traces
+ * of tau^2, tau = soft-argmax lag of the cross-correlation of the max-normalised traces minus (nt-1).
+ * lagidx: DEVICE array [2nt-1] = (2nt-2) * linspace(0, 1, 2nt-1) in fp32 (the reference's lag axis);
+ * mean_over = traces of all shots (the reference takes one mean over shots x receivers x channels);
+ * nt <= 8500 (24 nt bytes of shared memory per block). */
+int st_misfit_traveltime(const float* syn, const float* obs, int32_t nt, int32_t ntraces, const float* lagidx,
+                         int32_t mean_over, float scale, double* loss, float* adj, void* stream);
 int st_misfit_envelope(const float* syn, const float* obs, int32_t nt, int32_t ntraces,
                        const float* hker, float scale, double* loss, float* adj,
                        float* workspace, void* stream);

@@ -46,6 +46,14 @@ def main():
         for k, x in enumerate(xs):
             arrs[f"{name}_grad_{k}"] = x.grad.numpy()
         print(name, float(loss))
+    # traveltime (loss.py:674-728) takes stacked records [shots, nt, nrec, nchan]
+    xs = torch.from_numpy(np.stack([syn[0], syn[0][::-1].copy() * 0.5 + 0.1 * obs[0]])).double().requires_grad_(True)
+    ys = torch.from_numpy(np.stack([obs[0], np.roll(obs[0], 3, axis=0)])).double()
+    loss = Loss("traveltime").loss(None)(xs, ys)
+    loss.backward()
+    arrs["tt_syn"], arrs["tt_obs"] = xs.detach().numpy().astype(np.float32), ys.numpy().astype(np.float32)
+    arrs["tt_loss"], arrs["tt_grad"] = np.float64(float(loss)), xs.grad.numpy()
+    print("traveltime", float(loss))
     np.savez_compressed(OUT, **arrs)
     print("wrote", OUT)
 

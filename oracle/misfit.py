@@ -8,6 +8,7 @@ Follows:
   * seistorch/loss.py:52-85        CosineSimilarity ("cs")
   * seistorch/loss.py:463-501      NormalizedIntegrationMethod ("nim", defaults)
   * seistorch/loss.py:900-955      Wasserstein1d ("w1d", method 'linear')
+  * seistorch/loss.py:674-728      Traveltime (+ signal.py:203-208)
   * seistorch/transform.py:24-66   envelope / hilbert (nfft = nt, scipy convention)
 """
 from __future__ import annotations
@@ -92,6 +93,22 @@ def integration(syn, obs):
     for x, y in zip(syn, obs):
         loss = loss + torch.mean((torch.cumsum(x, dim=0) - torch.cumsum(y, dim=0)) ** 2)
     return loss
+
+
+def traveltime(syn, obs):
+    """loss.py:683-728 with signal.py:203-208 (soft argmax of the cross-correlation); stacked [nb, nt, nr, nc]."""
+    x, y = torch.stack(list(syn), 0), torch.stack(list(obs), 0)
+    nb, nt, nr, nc = x.shape
+    x = x / (torch.max(torch.abs(x), dim=1, keepdim=True).values + 1e-16)
+    y = y / (torch.max(torch.abs(y), dim=1, keepdim=True).values + 1e-16)
+    x = x.permute(0, 2, 3, 1).contiguous().view(nb * nr * nc, nt)
+    y = y.permute(0, 2, 3, 1).contiguous().view(nb * nr * nc, 1, nt)
+    cc = torch.nn.functional.conv1d(x, y, padding=nt - 1, groups=nb * nr * nc).view(nb, nr, nc, -1)
+    n = cc.shape[-1]
+    p = torch.softmax(1 * cc, dim=-1)
+    idx = torch.linspace(0, 1, n)                           # fp32, as in the reference
+    tau = torch.sum((n - 1) * p * idx, dim=-1) - nt + 1
+    return (tau.view(nb, 1, nr, nc) ** 2).mean()
 
 
 def hilbert(data):

@@ -20,6 +20,9 @@
 //   filtfilt  : seistorch/signal.py:49-101 (backend 'torch': torchaudio filtfilt in double, clamp=False, zero initial
 //               state, no padding): y = flip(lfilter(flip(lfilter(x)))).  As a matrix A^T A with A the causal IIR
 //               operator, hence self-adjoint: the cotangent of the input is filtfilt(cotangent of the output).
+//   TRAVELTIME: seistorch/loss.py:674-728 + signal.py:203-208: per trace, both records normalised by their max |.|
+//               (+1e-16), full cross-correlation over the 2nt-1 lags, softmax over the lags (beta 1), expected lag
+//               index minus (nt-1) = traveltime difference tau; loss = mean over traces of tau^2.
 // Seismograms are [nt][ntraces] (ntraces = receivers x channels, fastest).
 #include <cuda_runtime.h>
 
@@ -185,6 +188,98 @@ __global__ void __launch_bounds__(128) filtfilt_kernel(const float* __restrict__
     }
 }
 
+// one block per trace; dynamic shared memory: cc[2nt-1] (double), xn[nt], yn[nt] (float).  lagidx[k] = (n-1)*linspace(0,1,n)[k]
+// exactly as the reference builds it (fp32 linspace), n = 2nt-1.
+__global__ void __launch_bounds__(256) traveltime_kernel(const float* __restrict__ syn, const float* __restrict__ obs, int nt, int ntr,
+                                                         const float* __restrict__ lagidx, float inv_mean, float scale,
+                                                         double* loss, float* adj) {
+    extern __shared__ double tsm[];
+    double* cc = tsm;
+    float* xn = reinterpret_cast<float*>(tsm + (2 * nt - 1));
+    float* yn = xn + nt;
+    __shared__ double red[33];
+    __shared__ int s_arg;
+    const int tr = blockIdx.x, tid = threadIdx.x, nl = 2 * nt - 1;
+    auto bsum = [&](double v) {                      // block-wide sum, result to every thread
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) { double t = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w]; red[32] = t; }
+        __syncthreads();
+        return red[32];
+    };
+    auto bmax = [&](double v) {
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) { double t = red[0]; for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = fmax(t, red[w]); red[32] = t; }
+        __syncthreads();
+        return red[32];
+    };
+    // normalisation by max |.| (first index attaining it, like torch.max)
+    double mx = 0.0, my = 0.0;
+    for (int t = tid; t < nt; t += blockDim.x) {
+        mx = fmax(mx, fabs((double)syn[(long long)t * ntr + tr]));
+        my = fmax(my, fabs((double)obs[(long long)t * ntr + tr]));
+    }
+    mx = bmax(mx);
+    my = bmax(my);
+    if (tid == 0) s_arg = nt;
+    __syncthreads();
+    for (int t = tid; t < nt; t += blockDim.x)
+        if (fabs((double)syn[(long long)t * ntr + tr]) == mx) atomicMin(&s_arg, t);
+    const double dx = mx + 1e-16, dy = my + 1e-16;
+    for (int t = tid; t < nt; t += blockDim.x) {
+        xn[t] = (float)((double)syn[(long long)t * ntr + tr] / dx);
+        yn[t] = (float)((double)obs[(long long)t * ntr + tr] / dy);
+    }
+    __syncthreads();
+    // cc[k] = sum_j xn[k + j - (nt-1)] yn[j]
+    double cmax = -1e300;
+    for (int k = tid; k < nl; k += blockDim.x) {
+        const int j0 = max(0, nt - 1 - k), j1 = min(nt, 2 * nt - 1 - k);
+        double acc = 0.0;
+        for (int j = j0; j < j1; ++j) acc += (double)xn[k + j - (nt - 1)] * (double)yn[j];
+        cc[k] = acc;
+        cmax = fmax(cmax, acc);
+    }
+    cmax = bmax(cmax);
+    double se = 0.0, sk = 0.0;
+    for (int k = tid; k < nl; k += blockDim.x) {
+        const double e = exp(cc[k] - cmax);
+        se += e;
+        sk += e * (double)lagidx[k];
+    }
+    se = bsum(se);
+    sk = bsum(sk);
+    const double E = sk / se, tau = E - (double)(nt - 1);
+    if (tid == 0 && loss) atomicAdd(loss, tau * tau * (double)inv_mean * (double)scale);
+    if (!adj) return;
+    // d loss / d cc[k] = (2 tau / N) p_k (idx_k - E)   (stored over cc)
+    __syncthreads();
+    for (int k = tid; k < nl; k += blockDim.x) {
+        const double p = exp(cc[k] - cmax) / se;
+        cc[k] = 2.0 * tau * (double)inv_mean * p * ((double)lagidx[k] - E);
+    }
+    __syncthreads();
+    // d / d xn[s] = sum_j gcc[s - j + nt - 1] yn[j];   through xn = x / (max|x| + eps)
+    double dot = 0.0;
+    for (int s = tid; s < nt; s += blockDim.x) {
+        double acc = 0.0;
+        for (int j = 0; j < nt; ++j) acc += cc[s - j + nt - 1] * (double)yn[j];
+        adj[(long long)s * ntr + tr] = (float)((double)scale * acc / dx);
+        dot += acc * (double)syn[(long long)s * ntr + tr];
+    }
+    dot = bsum(dot);
+    if (tid == 0 && s_arg < nt) {
+        const long long i = (long long)s_arg * ntr + tr;
+        const double sg = syn[i] > 0.f ? 1.0 : (syn[i] < 0.f ? -1.0 : 0.0);
+        adj[i] -= (float)((double)scale * sg * dot / (dx * dx));
+    }
+}
+
 constexpr int CT = 32;      // tile: 32 output samples x 32 traces, 32 taps per stage
 
 // out[n][tr] = sum_m k[(n-m) mod nt] x[m][tr]      (transpose == false)
@@ -302,6 +397,19 @@ extern "C" int st_misfit_integration(const float* syn, const float* obs, int32_t
     if (ntraces == 0) return ST_OK;
     nim_kernel<2><<<(ntraces + 255) / 256, 256, 0, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, nullptr, scale / (float)mean_over, loss, adj);
     if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_integration: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}
+
+extern "C" int st_misfit_traveltime(const float* syn, const float* obs, int32_t nt, int32_t ntraces, const float* lagidx,
+                                    int32_t mean_over, float scale, double* loss, float* adj, void* stream) {
+    if (!syn || !obs || !lagidx || nt <= 0 || ntraces < 0 || mean_over <= 0) { st_set_error("misfit_traveltime: bad arguments"); return ST_ERR_BADARG; }
+    if (ntraces == 0) return ST_OK;
+    const size_t smem = (size_t)(2 * nt - 1) * sizeof(double) + (size_t)2 * nt * sizeof(float);
+    if (smem > 200 * 1024) { st_set_error("misfit_traveltime: nt = %d needs %zu bytes of shared memory (max 200 KB)", nt, smem); return ST_ERR_UNSUPPORTED; }
+    static const cudaError_t attr = cudaFuncSetAttribute(traveltime_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (attr != cudaSuccess) { st_set_error("misfit_traveltime: cannot raise the shared-memory limit"); return ST_ERR_CUDA; }
+    traveltime_kernel<<<ntraces, 256, smem, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, lagidx, 1.f / (float)mean_over, scale, loss, adj);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_traveltime: launch failed"); return ST_ERR_CUDA; }
     return ST_OK;
 }
 

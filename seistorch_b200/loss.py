@@ -73,6 +73,12 @@ class _Misfit(torch.autograd.Function):
             _lib.check(L.st_misfit_nim(s.data_ptr(), o.data_ptr(), nt, ntr, 1.0, loss.data_ptr(), adj.data_ptr(),
                                        _stream_ptr()), "misfit_nim")
             LAUNCHES["misfit"] += 1
+        elif kind == "traveltime":
+            n = 2 * nt - 1
+            lag = ((n - 1) * torch.linspace(0, 1, n, dtype=torch.float32)).to(s.device)     # signal.py:206-207
+            _lib.check(L.st_misfit_traveltime(s.data_ptr(), o.data_ptr(), nt, ntr, lag.data_ptr(), int(mean_over), 1.0,
+                                              loss.data_ptr(), adj.data_ptr(), _stream_ptr()), "misfit_traveltime")
+            LAUNCHES["misfit"] += 1
         elif kind == "w1d":
             # loss.py:919-922: shift by 1.1 * min(min x, min y, 0), a constant for the gradient; stays on the device
             shift = (1.1 * torch.minimum(s.min(), o.min()).clamp(max=0.0)).to(torch.float32).reshape(1)
@@ -198,6 +204,24 @@ class Integration(torch.nn.Module):
         return _per_shot("integration", x, y)
 
 
+class Traveltime(torch.nn.Module):
+    """loss.py:674-728: mean over shots x receivers x channels of the squared soft-argmax lag of the cross-correlation
+    of the max-normalised traces (signal.py:203-208).  Like the reference it takes stacked records
+    [shots, nt, nrec, nchan] (a list of equally shaped records is stacked)."""
+
+    @property
+    def name(self):
+        return "traveltime"
+
+    def forward(self, x, y):
+        if not isinstance(x, torch.Tensor):
+            x, y = torch.stack(list(x), 0), torch.stack([torch.as_tensor(v) for v in y], 0)
+        nb, nt = x.shape[0], x.shape[1]
+        xs = x.permute(1, 0, 2, 3).reshape(nt, -1)
+        ys = y.to(x.device).permute(1, 0, 2, 3).reshape(nt, -1)
+        return _Misfit.apply("traveltime", xs, ys, xs.shape[1])
+
+
 class Wasserstein1d(torch.nn.Module):
     """loss.py:900-955 ("w1d") with the default method 'linear': traces shifted to be positive, normalised by their
     sum over time, integrated; sum of squared differences of the two cumulative distributions.  The shift is taken
@@ -250,7 +274,7 @@ class Loss:
         return self.loss(*args, **kwargs)
 
     def loss(self, cfg=None, *args, **kwargs):
-        for cls in (L2, L1, SML1, CosineSimilarity, Crosscorrelation, Integration, NormalizedIntegrationMethod, Wasserstein1d, Envelope):
+        for cls in (L2, L1, SML1, CosineSimilarity, Crosscorrelation, Integration, NormalizedIntegrationMethod, Wasserstein1d, Traveltime, Envelope):
             if cls().name == self.loss_name:
                 obj = cls(**kwargs)
                 obj.cfg = cfg

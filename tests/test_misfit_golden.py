@@ -49,3 +49,24 @@ def test_cuda_misfit_matches_reference(name):
     l_stack = sb.Loss(name).loss(None)(xs2, ys2)
     l_list = sb.Loss(name).loss(None)([xs2[0], xs2[1]], [ys2[0], ys2[1]])
     assert abs(float(l_stack) - float(l_list)) <= 2e-5 * abs(float(l_list))
+
+
+def test_oracle_traveltime_matches_reference():
+    from oracle import misfit
+    z = np.load(GOLD)
+    xs = torch.from_numpy(z["tt_syn"]).double().requires_grad_(True)
+    loss = misfit.traveltime(list(xs), list(torch.from_numpy(z["tt_obs"]).double()))
+    loss.backward()
+    assert abs(float(loss) - float(z["tt_loss"])) <= 1e-10 * abs(float(z["tt_loss"]))
+    assert rel(xs.grad.numpy(), z["tt_grad"]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_cuda_traveltime_matches_reference():
+    import seistorch_b200 as sb
+    z = np.load(GOLD)
+    xs = torch.from_numpy(z["tt_syn"]).cuda().requires_grad_(True)
+    loss = sb.Loss("traveltime").loss(None)(xs, torch.from_numpy(z["tt_obs"]).cuda())
+    loss.backward()
+    assert abs(float(loss) - float(z["tt_loss"])) <= 2e-5 * abs(float(z["tt_loss"]))
+    assert rel(xs.grad.cpu().numpy(), z["tt_grad"]) < 2e-5
