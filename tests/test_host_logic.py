@@ -153,3 +153,32 @@ def test_build_model_surface():
     assert model.cell.forward_func is m._time_step
     with pytest.raises(NotImplementedError):
         m._time_step_backward()
+
+
+def test_signal_host_logic_and_loss_registry():
+    """Host-side mirror of seistorch/signal.py:23-76 (filter type, Butterworth design) and of the loss registry
+    (loss.py:23-50: classes found by their `name`); no device work."""
+    import numpy as np
+    import pytest
+    from scipy import signal as sps
+    import seistorch_b200 as sb
+    from seistorch_b200.signal import SeisSignal
+    sig = SeisSignal({"geom": {"dt": 0.002}, "training": {"filter_ord": 3}})
+    assert sig.decide_filter_type(5.0) == "lowpass" and sig.decide_filter_type([5.0]) == "lowpass"
+    assert sig.decide_filter_type([3.0, 8.0]) == "bandpass" and sig.decide_filter_type("all") == "all"
+    b, a = sig.design([30.0])
+    b0, a0 = sps.butter(3, Wn=2 * 30.0 * 0.002, btype="lowpass")
+    assert np.array_equal(b, b0) and np.array_equal(a, a0)
+    b, a = sig.design([8.0, 60.0])
+    b0, a0 = sps.butter(3, Wn=[2 * 8.0 * 0.002, 2 * 60.0 * 0.002], btype="bandpass")
+    assert np.array_equal(b, b0) and np.array_equal(a, a0)
+    marker = object()
+    assert sig.filter(marker, "all") is marker
+    with pytest.raises(NotImplementedError):
+        sig.filter(marker, [30.0], backend="scipy")
+    for name in ("l2", "l1", "sml1", "cs", "cc", "integration", "nim", "w1d", "traveltime", "envelope"):
+        assert sb.Loss(name).loss(None).name == name
+    with pytest.raises(ValueError):
+        sb.Loss("sinkhorn").loss(None)
+    with pytest.raises(NotImplementedError):
+        sb.Loss("nim").loss(None, criterion="l1")
