@@ -340,6 +340,12 @@ def main():
         if os.path.exists(prof):
             try:
                 roof["traffic"] = json.load(open(prof)).get(dom.split("<")[0])
+                if roof["traffic"]:
+                    # the same launch time against the MEASURED dram bytes of one launch (ncu --set full, profiles/):
+                    # a lower bound of the real traffic -- an isolated ncu replay leaves part of the output dirty in L2
+                    t_dom = t_adj if t_adj >= t_fwd else t_fwd
+                    roof["traffic_GBps"] = roof["traffic"] / (t_dom * 1e-3) / 1e9
+                    roof["traffic_frac"] = roof["traffic_GBps"] / peak
             except Exception:
                 pass
 
