@@ -19,6 +19,69 @@ from . import ref_shim
 PARAM_KEYS = ["vp", "vs", "rho", "Q", "epsilon", "delta", "theta", "m", "rx", "rz"]
 
 
+def build_reference(case: dict, dtype: str = "float32", want_grad: bool = True,
+                    boundary_saving: bool = False, device: str = "cpu", source_encoding: bool = False):
+    """Build the reference's own model for one case through its public API
+    (seistorch/model.py:23-93 build_model + rnn.py reset_geom).  Returns (cfg, model, x)."""
+    ref_shim.import_reference()
+    from seistorch.model import build_model
+    import seistorch.checkpoint_new as ckn
+    import seistorch.checkpoint as ck
+
+    tdtype = torch.float64 if dtype == "float64" else torch.float32
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = {k: None for k in PARAM_KEYS}
+        for name, arr in case["models"].items():
+            p = os.path.join(tmp, f"{name}.npy")
+            np.save(p, np.asarray(arr, dtype=np.float64 if dtype == "float64" else np.float32))
+            paths[name] = p
+        with open(os.path.join(tmp, "sources.pkl"), "wb") as f:
+            pickle.dump(case["sources"], f)
+        with open(os.path.join(tmp, "receivers.pkl"), "wb") as f:
+            pickle.dump(case["receivers"], f)
+        inv = {k: False for k in PARAM_KEYS}
+        inv.update({k: bool(v) for k, v in case.get("invlist", {}).items()})
+        cfg = {
+            "seed": 20230503, "name": "oracle", "dtype": dtype,
+            "equation": case["equation"],
+            "training": {"implicit": {"use": False, "pretrained": None},
+                         "minibatch": True, "batch_size": len(case["sources"]),
+                         "N_epochs": 1, "lr": None, "scale_decay": 1.0,
+                         "lr_decay": 1.0, "filter_ord": 3},
+            "geom": {
+                "obsPath": None, "truePath": dict(paths), "initPath": dict(paths),
+                "sources": os.path.join(tmp, "sources.pkl"),
+                "receivers": os.path.join(tmp, "receivers.pkl"),
+                "wavelet": None, "multiple": bool(case.get("multiple", False)),
+                "boundary_saving": bool(boundary_saving),
+                "wavelet_delay": 0, "wavelet_inverse": False,
+                "source_type": list(case["source_type"]),
+                "receiver_type": list(case["receiver_type"]),
+                "invlist": inv, "inv_savePath": None, "multiscale": ["all"],
+                "dt": float(case["dt"]), "nt": int(case["nt"]), "fm": 10.0,
+                "h": float(case["h"]), "Nshots": len(case["sources"]),
+                "boundary": {"type": case["boundary"], "width": 50},
+            },
+        }
+        cfg_path = os.path.join(tmp, "cfg.yml")
+        with open(cfg_path, "w") as f:
+            yaml.safe_dump(cfg, f)
+        mode = "inversion" if want_grad else "forward"
+        cfg2, model = build_model(cfg_path, device=device, mode=mode, source_encoding=source_encoding)
+        if str(device) == "cpu":
+            ref_shim.cast_module_kernels(tdtype, device="cpu")
+        else:
+            ref_shim.cast_module_kernels(tdtype)
+        # reset class-level state of the BS checkpoint functions (SURVEY 3.4)
+        for mod in (ckn, ck):
+            mod.CheckpointFunction.counts = 0
+            mod.CheckpointFunction.wavefields = []
+        shots = list(range(len(case["sources"])))
+        model.reset_geom(shots, case["sources"], case["receivers"], cfg2)
+    x = torch.as_tensor(np.asarray(case["wavelet"]), dtype=tdtype).unsqueeze(0)
+    return cfg2, model, x
+
+
 def run_reference(case: dict, dtype: str = "float32", want_grad: bool = True,
                   boundary_saving: bool = False, loss_name: str = "l2",
                   threads: int | None = None):
@@ -31,91 +94,39 @@ def run_reference(case: dict, dtype: str = "float32", want_grad: bool = True,
     Returns dict(records=[...], loss=float, grads={name: ndarray}).
     """
     ref_shim.import_reference()
-    from seistorch.model import build_model
     from seistorch.loss import Loss
-    import seistorch.checkpoint_new as ckn
-    import seistorch.checkpoint as ck
 
     if threads:
         torch.set_num_threads(threads)
     tdtype = torch.float64 if dtype == "float64" else torch.float32
     old_default = torch.get_default_dtype()
     try:
-        with tempfile.TemporaryDirectory() as tmp:
-            paths = {k: None for k in PARAM_KEYS}
-            for name, arr in case["models"].items():
-                p = os.path.join(tmp, f"{name}.npy")
-                np.save(p, np.asarray(arr, dtype=np.float64 if dtype == "float64" else np.float32))
-                paths[name] = p
-            with open(os.path.join(tmp, "sources.pkl"), "wb") as f:
-                pickle.dump(case["sources"], f)
-            with open(os.path.join(tmp, "receivers.pkl"), "wb") as f:
-                pickle.dump(case["receivers"], f)
-            inv = {k: False for k in PARAM_KEYS}
-            inv.update({k: bool(v) for k, v in case.get("invlist", {}).items()})
-            cfg = {
-                "seed": 20230503, "name": "oracle", "dtype": dtype,
-                "equation": case["equation"],
-                "training": {"implicit": {"use": False, "pretrained": None},
-                             "minibatch": True, "batch_size": len(case["sources"]),
-                             "N_epochs": 1, "lr": None, "scale_decay": 1.0,
-                             "lr_decay": 1.0, "filter_ord": 3},
-                "geom": {
-                    "obsPath": None, "truePath": dict(paths), "initPath": dict(paths),
-                    "sources": os.path.join(tmp, "sources.pkl"),
-                    "receivers": os.path.join(tmp, "receivers.pkl"),
-                    "wavelet": None, "multiple": bool(case.get("multiple", False)),
-                    "boundary_saving": bool(boundary_saving),
-                    "wavelet_delay": 0, "wavelet_inverse": False,
-                    "source_type": list(case["source_type"]),
-                    "receiver_type": list(case["receiver_type"]),
-                    "invlist": inv, "inv_savePath": None, "multiscale": ["all"],
-                    "dt": float(case["dt"]), "nt": int(case["nt"]), "fm": 10.0,
-                    "h": float(case["h"]), "Nshots": len(case["sources"]),
-                    "boundary": {"type": case["boundary"], "width": 50},
-                },
-            }
-            cfg_path = os.path.join(tmp, "cfg.yml")
-            with open(cfg_path, "w") as f:
-                yaml.safe_dump(cfg, f)
-            mode = "inversion" if want_grad else "forward"
-            cfg2, model = build_model(cfg_path, device="cpu", mode=mode)
-            if dtype == "float64":
-                ref_shim.cast_module_kernels(torch.float64)
-            else:
-                ref_shim.cast_module_kernels(torch.float32)
-            # reset class-level state of the BS checkpoint functions (SURVEY 3.4)
-            for mod in (ckn, ck):
-                mod.CheckpointFunction.counts = 0
-                mod.CheckpointFunction.wavefields = []
-            shots = list(range(len(case["sources"])))
-            model.reset_geom(shots, case["sources"], case["receivers"], cfg2)
-            x = torch.as_tensor(np.asarray(case["wavelet"]), dtype=tdtype).unsqueeze(0)
-            if want_grad:
-                model.train()
+        cfg2, model, x = build_reference(case, dtype, want_grad, boundary_saving)
+        if want_grad:
+            model.train()
+            syn = model(x)
+        else:
+            model.eval()
+            with torch.no_grad():
                 syn = model(x)
-            else:
-                model.eval()
-                with torch.no_grad():
-                    syn = model(x)
-            out = {"records": [s.detach().numpy().copy() for s in syn]}
-            if want_grad:
-                obs = case.get("obs")
-                if obs is None:
-                    obs = [np.zeros_like(r) for r in out["records"]]
-                obs_t = [torch.as_tensor(o, dtype=tdtype) for o in obs]
-                crit = Loss(loss_name).loss(cfg2)
-                if len({tuple(t.shape) for t in syn}) == 1:
-                    loss = crit(torch.stack(list(syn), dim=0), torch.stack(obs_t, dim=0))
-                else:  # ragged shots: L2.forward zips over shots (loss.py:417-421)
-                    loss = crit(list(syn), obs_t)
-                loss.backward()
-                out["loss"] = float(loss.item())
-                out["grads"] = {}
-                for name in model.cell.geom.model_parameters:
-                    p = getattr(model.cell.geom, name)
-                    if p.grad is not None:
-                        out["grads"][name] = p.grad.detach().numpy().copy()
-            return out
+        out = {"records": [s.detach().numpy().copy() for s in syn]}
+        if want_grad:
+            obs = case.get("obs")
+            if obs is None:
+                obs = [np.zeros_like(r) for r in out["records"]]
+            obs_t = [torch.as_tensor(o, dtype=tdtype) for o in obs]
+            crit = Loss(loss_name).loss(cfg2)
+            if len({tuple(t.shape) for t in syn}) == 1:
+                loss = crit(torch.stack(list(syn), dim=0), torch.stack(obs_t, dim=0))
+            else:  # ragged shots: L2.forward zips over shots (loss.py:417-421)
+                loss = crit(list(syn), obs_t)
+            loss.backward()
+            out["loss"] = float(loss.item())
+            out["grads"] = {}
+            for name in model.cell.geom.model_parameters:
+                p = getattr(model.cell.geom, name)
+                if p.grad is not None:
+                    out["grads"][name] = p.grad.detach().numpy().copy()
+        return out
     finally:
         torch.set_default_dtype(old_default)

@@ -3,8 +3,10 @@
 Import shim for the *real* reference (GeophyAI/seistorch, mounted read-only at
 /root/reference in the authoring container).  It is used by
 ``oracle/make_golden.py`` to generate the committed fixtures under
-``tests/golden/`` and by ``tests/test_oracle_vs_reference.py`` (skipped when the
-reference tree is absent, i.e. on the GPU box).
+``tests/golden/``, by ``bench.py --impl reference`` (the CPU arm) and by the overlay tests.
+The reference is looked for at ``$SEISTORCH_REFERENCE``, then ``/root/reference`` (authoring
+container), then ``oracle/_ref`` -- the byte-for-byte copy that ``oracle/make_ref.py`` ships to
+the GPU box (git-ignored).
 
 What the shim does:
   1. stubs third-party modules the reference imports at module scope but never
@@ -23,7 +25,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SEISTORCH_REFERENCE", "/root/reference")
+def _find_reference():
+    env = os.environ.get("SEISTORCH_REFERENCE")
+    cands = [env] if env else []
+    cands += ["/root/reference", os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "seistorch")):
+            return c
+    return cands[0]
+
+
+REFERENCE_ROOT = _find_reference()
 
 _STUBS = [
     "prettytable", "segyio", "obspy", "h5py", "geomloss", "ot", "ot.utils",
@@ -113,9 +125,11 @@ def import_reference():
     return seistorch
 
 
-def cast_module_kernels(dtype):
+def cast_module_kernels(dtype, device=None):
     """Reference quirk: module-level conv kernels are created in
-    fp32 at import; cast them so the reference's own ``dtype: float64`` path runs."""
+    fp32 on "cuda" at import; cast them so the reference's own ``dtype: float64`` path runs,
+    and (``device``) re-home them so its CPU path also runs on a host that has a GPU
+    (equations3d/acoustic.py:67 never moves its kernel)."""
     import torch
 
     names = [
@@ -132,4 +146,4 @@ def cast_module_kernels(dtype):
             continue
         for k, v in list(vars(m).items()):
             if k.startswith("kernel") and isinstance(v, torch.Tensor):
-                setattr(m, k, v.to(dtype))
+                setattr(m, k, v.to(dtype) if device is None else v.to(device=device, dtype=dtype))

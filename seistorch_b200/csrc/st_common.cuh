@@ -29,3 +29,21 @@ enum : int {
 #endif
 
 void st_set_error(const char* fmt, ...);
+
+#ifdef __CUDACC__
+#include <atomic>
+// Raise the dynamic shared-memory limit of one kernel.  The attribute is per DEVICE, so it is set once per
+// (kernel, device) -- a process that drives several GPUs gets it on each of them -- and a failure is not cached.
+template <auto Kernel>
+inline cudaError_t st_set_max_smem(int bytes) {
+    static std::atomic<unsigned long long> done{0};      // bit d = set on device d (d < 64)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (dev < 64 && (done.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+    e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev < 64) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+#endif

@@ -406,8 +406,7 @@ extern "C" int st_misfit_traveltime(const float* syn, const float* obs, int32_t 
     if (ntraces == 0) return ST_OK;
     const size_t smem = (size_t)(2 * nt - 1) * sizeof(double) + (size_t)2 * nt * sizeof(float);
     if (smem > 200 * 1024) { st_set_error("misfit_traveltime: nt = %d needs %zu bytes of shared memory (max 200 KB)", nt, smem); return ST_ERR_UNSUPPORTED; }
-    static const cudaError_t attr = cudaFuncSetAttribute(traveltime_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (attr != cudaSuccess) { st_set_error("misfit_traveltime: cannot raise the shared-memory limit"); return ST_ERR_CUDA; }
+    if (st_set_max_smem<traveltime_kernel>(200 * 1024) != cudaSuccess) { st_set_error("misfit_traveltime: cannot raise the shared-memory limit"); return ST_ERR_CUDA; }
     traveltime_kernel<<<ntraces, 256, smem, (cudaStream_t)stream>>>(syn, obs, nt, ntraces, lagidx, 1.f / (float)mean_over, scale, loss, adj);
     if (cudaGetLastError() != cudaSuccess) { st_set_error("misfit_traveltime: launch failed"); return ST_ERR_CUDA; }
     return ST_OK;

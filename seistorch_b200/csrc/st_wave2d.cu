@@ -2246,8 +2246,7 @@ int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
     if constexpr (tma_ok<FL>()) {
         if (tm.enabled) {
-            static const cudaError_t attr = cudaFuncSetAttribute(wave2d_forward_tma_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_fwd_smem<FL>());
-            if (attr != cudaSuccess) return ST_ERR_CUDA;
+            if (st_set_max_smem<wave2d_forward_tma_kernel<FL>>(tma_fwd_smem<FL>()) != cudaSuccess) return ST_ERR_CUDA;
             dim3 grid((unsigned)((long long)corner_tiles(tm, a.g).count * a.B + tma_blocks(tm, a.B)));
             return tma_launch(wave2d_forward_tma_kernel<FL>, grid, tma_fwd_smem<FL>(), st, a, nfx, tm);
         }
@@ -2268,8 +2267,7 @@ int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
     if constexpr (tma_ok<FL>()) {
         if (tm.enabled) {
-            static const cudaError_t attr = cudaFuncSetAttribute(wave2d_adjoint_tma_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_adj_smem<FL>());
-            if (attr != cudaSuccess) return ST_ERR_CUDA;
+            if (st_set_max_smem<wave2d_adjoint_tma_kernel<FL>>(tma_adj_smem<FL>()) != cudaSuccess) return ST_ERR_CUDA;
             dim3 grid((unsigned)((long long)corner_tiles(tm, a.g).count * a.B + tma_blocks(tm, a.B)));
             return tma_launch(wave2d_adjoint_tma_kernel<FL>, grid, tma_adj_smem<FL>(), st, a, nfx, tm);
         }

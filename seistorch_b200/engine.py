@@ -38,6 +38,7 @@ _W2_GRAD_OF_COEF = {0: 0, 2: 1, 3: 2, 4: 3, 5: 4, 6: 5, 7: 6}
 # number of sm_100a kernel launches issued through the C ABI (bench.py reports it)
 LAUNCHES = {"forward": 0, "adjoint": 0, "misfit": 0}
 KERNELS = {"forward": None, "adjoint": None}      # kernel family of the most recent forward / adjoint call
+LAUNCHES_LAST = {"adjoint": 0, "recompute": 0}    # step launches of the most recent backward(): adjoint, recomputed forward
 
 
 def _round_up(n, m):
@@ -53,6 +54,41 @@ def _require_cuda(t: torch.Tensor, what: str):
         raise RuntimeError(f"seistorch_b200: {what} must be a CUDA tensor (no CPU fallback); got {t.device}")
 
 
+def _one_device(tensors, what: str) -> torch.device:
+    """All operands of one call must live on ONE CUDA device; returns it.  The C ABI launches on the
+    current device's context, so every entry point runs under ``torch.cuda.device(<that device>)`` --
+    the reference drivers build the model on ``cuda:{rank}`` without ever calling ``set_device``
+    (seistorch_dist.py:89-94)."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        _require_cuda(t, what)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"seistorch_b200: {what}: operands live on different devices ({dev} and {t.device})")
+    if dev is None:
+        raise RuntimeError(f"seistorch_b200: {what}: no CUDA operand")
+    return dev
+
+
+def on_device_of(argpos: int = 1):
+    """Decorator for autograd.Function.forward/backward bodies: run under the device of the first CUDA
+    tensor found at/after positional argument ``argpos`` (backward: ctx.dev)."""
+    def deco(fn):
+        def wrapped(ctx, *args):
+            dev = getattr(ctx, "dev", None)
+            if dev is None:
+                dev = _one_device([a for a in args[argpos - 1:] if isinstance(a, torch.Tensor)], fn.__qualname__)
+                ctx.dev = dev
+            with torch.cuda.device(dev):
+                return fn(ctx, *args)
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
+
+
 # ======================================================================== acquisition
 class Acquisition:
     """Device-side source / receiver index tables (int32) in the layout of
@@ -65,6 +101,9 @@ class Acquisition:
         self.ndim = len(self.shape)
         self.B = int(B)
         dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
         src_b = torch.as_tensor(src_b, dtype=torch.int64, device=dev).reshape(-1)
         src_idx = torch.as_tensor(src_idx, dtype=torch.int64, device=dev).reshape(-1, self.ndim)
         rec_b = torch.as_tensor(rec_b, dtype=torch.int64, device=dev).reshape(-1)
@@ -365,11 +404,11 @@ class _Propagate(torch.autograd.Function):
     """records[nt, R, nchan] = F(amp[nt, ns], *coefs)."""
 
     @staticmethod
+    @on_device_of(3)
     def forward(ctx, spec: Spec, acq: Acquisition, amp: torch.Tensor, *coefs: torch.Tensor):
-        dev = coefs[0].device
-        for c in coefs:
-            _require_cuda(c, "model coefficient")
-        _require_cuda(amp, "wavelet")
+        dev = ctx.dev
+        if acq.device != dev:
+            raise RuntimeError(f"seistorch_b200: acquisition tables live on {acq.device}, the model on {dev}")
         amp32 = amp.detach().to(torch.float32).contiguous()
         if tuple(amp32.shape) != (spec.nt, acq.ns):
             raise ValueError(f"amp has shape {tuple(amp32.shape)}, expected {(spec.nt, acq.ns)}")
@@ -403,7 +442,12 @@ class _Propagate(torch.autograd.Function):
         return rec
 
     @staticmethod
+    @on_device_of(1)
     def backward(ctx, grad_rec):
+        if getattr(ctx, "prob", None) is None:
+            raise RuntimeError("seistorch_b200: the wavefield history of this forward call was already consumed and "
+                               "freed by a previous backward(); a second backward / retain_graph=True is not "
+                               "supported on the whole-loop path -- call forward again")
         spec, acq, prob = ctx.spec, ctx.acq, ctx.prob
         dev = prob.u.device
         p = spec.order
@@ -417,6 +461,7 @@ class _Propagate(torch.autograd.Function):
         prob.gacc = torch.zeros(nchunk * spec.ngrad * spec.plane, dtype=torch.float32, device=dev)
         want_gamp = ctx.needs_input_grad[2]
         prob.gamp = torch.zeros((spec.nt, acq.ns), dtype=torch.float32, device=dev) if want_gamp else None
+        l0 = dict(LAUNCHES)
         for s in reversed(range(nseg)):
             a, b = s * K, min((s + 1) * K, spec.nt)
             if s == nseg - 1:
@@ -437,6 +482,8 @@ class _Propagate(torch.autograd.Function):
                 i_lo = max(a - 1, 0)
                 if i_hi >= i_lo:
                     prob.adjoint(i_hi, i_hi - i_lo + 1, slot0 + 1 + (i_hi + 1 - a))
+        LAUNCHES_LAST["adjoint"] = LAUNCHES["adjoint"] - l0["adjoint"]
+        LAUNCHES_LAST["recompute"] = LAUNCHES["forward"] - l0["forward"]
         g = prob.gacc.view(nchunk, spec.ngrad, *spec.shape[:-1], spec.ld).sum(0)[..., :spec.shape[-1]]
         grads = []
         for k in range(ctx.ncoef):

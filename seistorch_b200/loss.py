@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import LAUNCHES, _require_cuda, _stream_ptr
+from .engine import LAUNCHES, _require_cuda, _stream_ptr, on_device_of
 
 _HKER = {}
 
@@ -38,6 +38,7 @@ class _Misfit(torch.autograd.Function):
     """loss = misfit(syn, obs) on [nt, ntraces] data; saves d loss / d syn."""
 
     @staticmethod
+    @on_device_of(2)
     def forward(ctx, kind, syn, obs, mean_over=1):
         _require_cuda(syn, "synthetic record")
         s = syn.detach().to(torch.float32).contiguous()

@@ -9,7 +9,11 @@ our modules under the names it imports -- ``seistorch.equations2d.<eq>``,
 ``seistorch.source``, ``seistorch.probe``, ``seistorch.checkpoint[_new]`` -- so the drivers
 (``seistorch_dist.py``, ``fwi.py --mode forward``, ``codingfwi.py``) run unchanged on the
 sm_100a kernels.  ``seistorch.compile.force_compile`` is switched off so the step ops are
-not wrapped by torch.compile.  See INTEGRATION.md.
+not wrapped by torch.compile.  The misfit classes of ``seistorch.loss`` that have a fused
+sm_100a kernel (L2, Envelope, L1, ...) are swapped *inside* the reference's loss module, so
+``Loss(name).loss(cfg)`` (loss.py:23-50, a scan of that module's globals) returns ours and every
+other misfit stays the reference's; ``SeisSignal.filter(..., backend='torch')`` on CUDA records
+goes to ``st_filtfilt``.  See INTEGRATION.md.
 """
 from __future__ import annotations
 
@@ -21,7 +25,48 @@ _EQ2D = ["acoustic", "acoustic_habc", "vti_habc2", "tti_habc", "acoustic_fwim_ha
          "acoustic_lsrtm_habc", "acoustic_rho_habc", "acoustic_vti_lsrtm_habc", "acoustic_tti_lsrtm_habc", "elastic"]
 
 
-def install(reference_package: str = "seistorch"):
+_LOSSES = ["L2", "L1", "SML1", "Crosscorrelation", "Integration", "CosineSimilarity", "NormalizedIntegrationMethod",
+           "Wasserstein1d", "Traveltime", "Envelope"]
+
+
+def patch_losses(reference_package: str = "seistorch"):
+    """Swap the misfit classes with a fused kernel into the reference's ``seistorch.loss`` (idempotent).
+    The reference finds a misfit by scanning ``globals()`` of that module for a class whose ``name``
+    property matches (loss.py:44-50), so replacing the class objects is all it takes."""
+    from . import loss as ours
+    ref = importlib.import_module(f"{reference_package}.loss")
+    done = []
+    for cls in _LOSSES:
+        if hasattr(ref, cls) and hasattr(ours, cls):
+            setattr(ref, cls, getattr(ours, cls))
+            done.append(cls)
+    return done
+
+
+def patch_signal(reference_package: str = "seistorch"):
+    """Route ``SeisSignal.filter(TensorList on CUDA, backend='torch')`` (signal.py:49-101) to st_filtfilt;
+    every other call (numpy input, scipy backend) keeps the reference's own code."""
+    from . import signal as ours
+    ref = importlib.import_module(f"{reference_package}.signal")
+    cls = ref.SeisSignal
+    if getattr(cls.filter, "_seistorch_b200", False):
+        return False
+    orig = cls.filter
+
+    def filter(self, d, freqs, axis=0, threads=1, backend="scipy", **kwargs):
+        items = getattr(d, "data", None)
+        if backend == "torch" and items and all(hasattr(t, "is_cuda") and t.is_cuda for t in items):
+            return ours.SeisSignal.filter(self, d, freqs, axis=axis, threads=threads, backend=backend, **kwargs)
+        return orig(self, d, freqs, axis=axis, threads=threads, backend=backend, **kwargs)
+
+    filter._seistorch_b200 = True
+    cls.filter = filter
+    if not hasattr(cls, "design"):
+        cls.design = ours.SeisSignal.design
+    return True
+
+
+def install(reference_package: str = "seistorch", losses: bool = True, signal: bool = True):
     """Register our modules under the reference package's names (idempotent)."""
     pairs = [(f"{reference_package}.{m}", f"seistorch_b200.{m}") for m in _MODULES]
     pairs += [(f"{reference_package}.equations2d.{e}", f"seistorch_b200.equations2d.{e}") for e in _EQ2D]
@@ -33,4 +78,18 @@ def install(reference_package: str = "seistorch"):
         comp.force_compile = False
     except Exception:
         pass
-    return [p[0] for p in pairs]
+    names = [p[0] for p in pairs]
+    # class-level patches need the reference package itself to be importable (they are skipped, not faked,
+    # when it is not: call patch_losses() / patch_signal() later)
+    if losses:
+        try:
+            names += [f"{reference_package}.loss.{c}" for c in patch_losses(reference_package)]
+        except ImportError:
+            pass
+    if signal:
+        try:
+            if patch_signal(reference_package):
+                names.append(f"{reference_package}.signal.SeisSignal.filter")
+        except ImportError:
+            pass
+    return names

@@ -14,11 +14,12 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import _require_cuda, _stream_ptr
+from .engine import _require_cuda, _stream_ptr, on_device_of
 
 
 class _FiltFilt(torch.autograd.Function):
     @staticmethod
+    @on_device_of(1)
     def forward(ctx, x, b, a):
         _require_cuda(x, "record")
         xs = x.detach().to(torch.float32).contiguous()

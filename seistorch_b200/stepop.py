@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 
 from . import coefficients as _coef
-from .engine import Acquisition, Spec, _Problem, _pack_coefs, _require_cuda
+from .engine import Acquisition, Spec, _Problem, _pack_coefs, _require_cuda, on_device_of
 from .eqconfigure import Parameters, Wavefield
 
 
@@ -33,6 +33,7 @@ class _Step(torch.autograd.Function):
     """fields_out = step(coefs, fields_in) for one time step (no source, no receivers)."""
 
     @staticmethod
+    @on_device_of(3)
     def forward(ctx, spec: Spec, ncoef: int, *tensors):
         coefs, fields = tensors[:ncoef], tensors[ncoef:]
         for t in tensors:
@@ -65,7 +66,10 @@ class _Step(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
+    @on_device_of(1)
     def backward(ctx, *gouts):
+        if getattr(ctx, "prob", None) is None:
+            raise RuntimeError("seistorch_b200: step buffers already freed by a previous backward(); call the step again")
         spec, prob, ncoef = ctx.spec, ctx.prob, ctx.ncoef
         dev = prob.u.device
         nx, e = spec.shape[-1], spec.slot_elems
