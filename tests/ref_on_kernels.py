@@ -80,6 +80,7 @@ def run_golden(name, device="cuda", forward_only=False):
     if device == "cuda:last":            # a device that is NOT the current one (ADVICE: no set_device in the drivers)
         device = f"cuda:{torch.cuda.device_count() - 1}"
     cfg, model, x = ref_runner.build_reference(case, "float32", want_grad=not forward_only, device=device)
+    model.to(device)                                     # seistorch_dist.py:95 `model.to(rank)`, fwi.py:112 `model.to(args.dev)`
     _check_ours(model)
     from seistorch.loss import Loss                      # the reference's wrapper; classes patched by the overlay
     out = {"name": name, "device": device, "overlaid": len(names), "current_device": torch.cuda.current_device()}
