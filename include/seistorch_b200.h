@@ -121,6 +121,14 @@ int st_wave2d_prepare(const st_wave2d_problem* p, void* stream);
  * results agree to fp32 rounding. */
 int st_wave2d_uses_tma(const st_wave2d_problem* p, int32_t adjoint);
 
+/* 1 if st_wave2d_forward(p, i0, nsteps, ...) will advance all `nsteps` time steps in ONE launch of the persistent
+ * multi-timestep kernel (replaces the Python time loop rnn.py:178-205 for small grids: the acoustic PML equation on a
+ * padded grid of at most 512 columns whose rows fit one thread-block cluster -- BASELINE configs[0] is the model case;
+ * one cluster per shot keeps the wavefield on chip, halos travel through distributed shared memory, one cluster barrier
+ * per time step), else 0 (one launch per time step).  Environment SEISTORCH_B200_PERSIST=0 turns it off.  Same
+ * arithmetic as the per-step kernels: records agree bit for bit. */
+int st_wave2d_uses_persist(const st_wave2d_problem* p, int32_t nsteps);
+
 /* advance steps i0 .. i0+nsteps-1; S_{i0-2} lives in slot `slot0`, S_{i0-1} in slot0+1,
  * step i writes slot0+2+(i-i0).                                                         */
 int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream);

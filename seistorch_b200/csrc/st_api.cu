@@ -8,6 +8,7 @@
 #include "st_common.cuh"
 #include "st_wave2d.cuh"
 #include "st_wave2d_band.cuh"
+#include "st_wave2d_persist.cuh"
 #include "st_elastic2d.cuh"
 #include "st_acoustic3d.cuh"
 
@@ -125,6 +126,37 @@ extern "C" int st_wave2d_uses_tma(const st_wave2d_problem* p, int32_t adjoint) {
     return tm.enabled;
 }
 
+// SEISTORCH_B200_PERSIST: "0" = never use the persistent multi-timestep kernel, unset / "1" = whenever it applies
+static bool w2_persist_enabled() {
+    const char* e = getenv("SEISTORCH_B200_PERSIST");
+    return !(e && *e && atoi(e) == 0);
+}
+
+// Plans the persistent launch for steps [i0, i0+nsteps); false when the problem is outside its class.
+static bool w2_persist_plan(const st_wave2d_problem* p, const W2Args& a, int i0, int nsteps, int slot0, W2Persist& pp) {
+    if (!w2_persist_enabled() || nsteps < 4) return false;
+    if (st_wave2d_persist_plan(p->flags, a, pp) != ST_OK) return false;
+    pp.u = p->u;
+    pp.slot = a.cs;
+    pp.nslots = p->nslots;
+    pp.slot0 = pmod(slot0, p->nslots);
+    pp.i0 = i0;
+    pp.nsteps = nsteps;
+    pp.history = p->nslots > 3;
+    pp.probe = 1;
+    if (st_wave2d_persist_forward(a, pp, nullptr) != ST_OK) return false;      // no resident cluster of this shape
+    pp.probe = 0;
+    return true;
+}
+
+extern "C" int st_wave2d_uses_persist(const st_wave2d_problem* p, int32_t nsteps) {
+    if (w2_check(p) != ST_OK) return 0;
+    W2Args a;
+    w2_fill(p, a);
+    W2Persist pp;
+    return w2_persist_plan(p, a, 0, nsteps, 0, pp) ? 1 : 0;
+}
+
 extern "C" int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream) {
     int rc = w2_check(p);
     if (rc) return rc;
@@ -135,6 +167,16 @@ extern "C" int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t
     const int nf = (p->flags & ST_EQ_BORN) ? 2 : 1;
     const long long slot = a.cs * nf;
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        W2Persist pp;
+        if (w2_persist_plan(p, a, i0, nsteps, slot0, pp)) {
+            a.amp = p->acq.amp ? p->acq.amp + (long long)i0 * p->acq.ns : nullptr;
+            a.rec_out = (p->acq.rec_out && p->acq.R > 0) ? p->acq.rec_out + (long long)i0 * p->acq.R * p->acq.nchan : nullptr;
+            rc = st_wave2d_persist_forward(a, pp, st);
+            if (rc) { st_set_error("wave2d_forward: persistent launch failed: %s", cudaGetErrorString(cudaGetLastError())); return ST_ERR_CUDA; }
+            return ST_OK;
+        }
+    }
     W2Tma tm;
     const int planes = nf * p->B;                // field planes per slot
     rc = st_wave2d_tma_setup(p->flags, a, p->u, (long long)planes * p->nslots, nullptr, 0, false, nsteps > 0 ? w2_tma_mode() : 0, tm);

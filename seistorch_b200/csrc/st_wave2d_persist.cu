@@ -1,0 +1,314 @@
+// Persistent multi-timestep kernels for small grids (acoustic PML: equations2d/acoustic.py:73-86, the time loop of
+// rnn.py:178-205 with source.py:47-57 and probe.py:42-44 inside) -- ONE launch advances `nsteps` time steps.
+//
+// The per-step kernels are launch-latency bound on a cfg1-class grid (250 x 400 cells: 7 us per step for 2 us of
+// work).  Here one thread-block CLUSTER owns one shot for the whole time loop:
+//   * the padded domain is cut into row strips, one per CTA of the cluster (up to 16 CTAs, non-portable size);
+//   * every thread owns 4 consecutive columns of RPW rows and keeps their current / previous field values and
+//     their two coefficients in REGISTERS for all time steps; the field never goes back to HBM unless a wavefield
+//     history is requested (gradient runs) -- then it leaves as fire-and-forget 128-bit stores;
+//   * the current field is published to a double-buffered shared-memory copy once per step: x-neighbours come
+//     from warp shuffles (edge lanes read one scalar of the published copy), z-neighbours inside a thread's rows
+//     from registers, the two halo rows from the published copy -- of the neighbouring CTA through distributed
+//     shared memory (ld.shared::cluster) at the strip boundaries;
+//   * one barrier.cluster arrive/wait pair per time step is the only synchronisation; the history store and the
+//     receiver gather of the previous step sit between arrive and wait;
+//   * source add by the thread that owns the source cell (before publishing), receiver gather from the published
+//     copy by the first threads of the CTA (cached (cell, record) pairs).
+// The per-cell arithmetic is the same expression as in wave2d_forward_kernel<ISO|PML> (st_wave2d.cu,
+// forward_fast_rows), so the records agree bit for bit with the per-step kernels.
+#include <cooperative_groups.h>
+#include <cstdlib>
+#include <cstring>
+
+#include "st_wave2d.cuh"
+#include "st_wave2d_persist.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int PW = 128;                 // columns per warp (32 lanes x float4)
+constexpr int XPAD = 4;                 // zero columns left of column 0 in the published copy (keeps rows 16-byte aligned)
+constexpr int RECCAP = 2048;            // cached (cell, record) pairs per CTA
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned map_rank(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_cluster4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+
+__device__ __forceinline__ float f4e(const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void f4s(float4& v, int e, float s) { if (e == 0) v.x = s; else if (e == 1) v.y = s; else if (e == 2) v.z = s; else v.w = s; }
+
+// y = c + alpha (c - p) + ciso (((n - c) + (s - c)) + ((e - c) + (w - c)))   -- forward_fast_rows<ISO|PML>
+__device__ __forceinline__ float pml_update(float c, float p, float n, float s, float w, float e, float alpha, float ciso) {
+    const float A = ciso * (((n - c) + (s - c)) + ((e - c) + (w - c)));
+    return c + alpha * (c - p) + A;
+}
+
+template <int NW, int RPW>
+__global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(const W2Args a, const W2Persist pp) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned crank = cluster_rank();
+    const int b = blockIdx.x / pp.cs;                       // shot of this cluster
+    const W2Geom& g = a.g;
+    const int ldp = pp.ldp, rpc = pp.rpc;
+    float* pub = reinterpret_cast<float*>(dsm);             // [2][rpc][ldp] published copies
+    int* rec_cell = reinterpret_cast<int*>(pub + 2 * rpc * ldp);      // [RECCAP] float offset inside one published copy
+    int* rec_dst = rec_cell + RECCAP;                       // [RECCAP] record index * nchan
+    __shared__ int s_nrec, s_rec_lo, s_rec_hi;
+
+    const int strip = warp % pp.nstrips, rg = warp / pp.nstrips;
+    const bool active = rg < pp.nrg;
+    const int zc0 = (int)crank * rpc;                       // first row of this CTA
+    const int lr0 = rg * RPW;                               // first local row of this thread
+    const int x = strip * PW + 4 * lane;
+    const long long boff = (long long)b * a.fs;
+    const float* u = pp.u;
+
+    // ---- zero the published copies (pads stay zero for the whole run)
+    for (int i = tid; i < 2 * rpc * ldp; i += NW * 32) pub[i] = 0.f;
+
+    // ---- receivers of this CTA's rows -> cached (cell, record) pairs
+    if (tid == 0) {
+        const int zlo = min(zc0, g.nz), zhi = min(zc0 + rpc, g.nz);
+        const bool any = a.rec_out != nullptr && a.R > 0;
+        s_rec_lo = any ? a.row_start[b * g.nz + zlo] : 0;
+        s_rec_hi = any ? a.row_start[b * g.nz + zhi] : 0;
+        s_nrec = min(s_rec_hi - s_rec_lo, RECCAP);
+    }
+    __syncthreads();
+    if (a.rec_out != nullptr && s_rec_hi > s_rec_lo) {
+        const int zhi = min(zc0 + rpc, g.nz);
+        for (int z = zc0 + warp; z < zhi; z += NW) {
+            const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
+            for (int r = lo + lane; r < hi; r += 32) {
+                const int k = r - s_rec_lo;
+                if (k < RECCAP) {
+                    rec_cell[k] = (z - zc0) * ldp + XPAD + a.rec_x[r];
+                    rec_dst[k] = a.rec_orig[r] * a.nchan;
+                }
+            }
+        }
+    }
+
+    // ---- registers: coefficients and the two field states of the owned cells
+    float4 cur[RPW], prv[RPW], al[RPW], ci[RPW];
+    const float* c_ciso = a.coef[2];
+    const float* c_alpha = a.coef[3];
+    const long long slotf = pp.slot;                        // floats per state slot
+    const float* s_prev = u + slotf * (pp.slot0 % pp.nslots) + boff;
+    const float* s_cur = u + slotf * ((pp.slot0 + 1) % pp.nslots) + boff;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const int z = zc0 + lr0 + r;
+        const bool in = active && z < g.nz && x < g.ld;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        cur[r] = prv[r] = al[r] = ci[r] = zero;
+        if (in) {
+            const long long o = (long long)z * g.ld + x;
+            cur[r] = __ldg(reinterpret_cast<const float4*>(s_cur + o));
+            prv[r] = __ldg(reinterpret_cast<const float4*>(s_prev + o));
+            al[r] = __ldg(reinterpret_cast<const float4*>(c_alpha + o));
+            ci[r] = __ldg(reinterpret_cast<const float4*>(c_ciso + o));
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (x + e >= g.nx) { f4s(al[r], e, 0.f); f4s(ci[r], e, 0.f); f4s(cur[r], e, 0.f); f4s(prv[r], e, 0.f); }
+        }
+    }
+    __syncthreads();                                        // zero fill done before the first publication
+    int pb = 0;                                             // published copy that holds `cur`
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+            *reinterpret_cast<float4*>(pub + (lr0 + r) * ldp + XPAD + x) = cur[r];
+    }
+    // sources owned by this thread: found once (a thread owns a source cell or not for the whole run)
+    int my_src[2] = {-1, -1}, my_src_rc[2] = {0, 0};
+    int nmine = 0;
+    bool src_overflow = false;
+    if (active) {
+        for (int s = 0; s < a.ns; ++s) {
+            if (a.src_b[s] != b) continue;
+            const int sz = a.src_z[s] - (zc0 + lr0), sx = a.src_x[s] - x;
+            if (sz >= 0 && sz < RPW && sx >= 0 && sx < 4 && (a.src_fmask & 1)) {
+                if (nmine < 2) { my_src[nmine] = s; my_src_rc[nmine] = sz * 4 + sx; }
+                else src_overflow = true;
+                ++nmine;
+            }
+        }
+    }
+    cluster_arrive();
+    cluster_wait();
+
+    const unsigned pub_addr = smem_u32(pub);
+    const bool up_remote = lr0 == 0, dn_remote = lr0 + RPW == rpc;
+    const bool has_up = !(up_remote && crank == 0), has_dn = !(dn_remote && (int)crank == pp.cs - 1);
+    const unsigned up_rank = up_remote ? crank - 1 : crank, dn_rank = dn_remote ? crank + 1 : crank;
+    const int up_row = up_remote ? rpc - 1 : lr0 - 1, dn_row = dn_remote ? 0 : lr0 + RPW;
+    const bool edge_l = lane == 0, edge_r = lane == 31;
+
+    for (int k = 0; k < pp.nsteps; ++k) {
+        const int i = pp.i0 + k;
+        const float* A = pub + pb * rpc * ldp;
+        float* Bf = pub + (pb ^ 1) * rpc * ldp;
+        float4 y[RPW];
+        if (active) {
+            float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = up;
+            const unsigned abase = pub_addr + (unsigned)(pb * rpc * ldp) * 4u;
+            if (has_up) up = ld_cluster4(map_rank(abase + (unsigned)(up_row * ldp + XPAD + x) * 4u, up_rank));
+            if (has_dn) dn = ld_cluster4(map_rank(abase + (unsigned)(dn_row * ldp + XPAD + x) * 4u, dn_rank));
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                const float4 c = cur[r];
+                const float4 n = r == 0 ? up : cur[r - 1];
+                const float4 s = r == RPW - 1 ? dn : cur[r + 1];
+                float lc = __shfl_up_sync(0xffffffffu, c.w, 1);
+                float rc = __shfl_down_sync(0xffffffffu, c.x, 1);
+                const float* row = A + (lr0 + r) * ldp + XPAD + x;
+                if (edge_l) lc = row[-1];
+                if (edge_r) rc = row[4];
+                y[r].x = pml_update(c.x, prv[r].x, n.x, s.x, lc, c.y, al[r].x, ci[r].x);
+                y[r].y = pml_update(c.y, prv[r].y, n.y, s.y, c.x, c.z, al[r].y, ci[r].y);
+                y[r].z = pml_update(c.z, prv[r].z, n.z, s.z, c.y, c.w, al[r].z, ci[r].z);
+                y[r].w = pml_update(c.w, prv[r].w, n.w, s.w, c.z, rc, al[r].w, ci[r].w);
+            }
+            // source add (source.py:47-57: field += wavelet sample, after the update, before sampling)
+            if (nmine > 0) {
+                const float* amp = a.amp + (long long)k * a.ns;
+                if (!src_overflow) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (q < nmine) {
+                            const float v = amp[my_src[q]];
+                            const int rr = my_src_rc[q] >> 2, e = my_src_rc[q] & 3;
+#pragma unroll
+                            for (int r = 0; r < RPW; ++r)
+                                if (r == rr) f4s(y[r], e, f4e(y[r], e) + v);
+                        }
+                    }
+                } else {
+                    for (int s = 0; s < a.ns; ++s) {
+                        if (a.src_b[s] != b) continue;
+                        const int sz = a.src_z[s] - (zc0 + lr0), sx = a.src_x[s] - x;
+                        if (sz >= 0 && sz < RPW && sx >= 0 && sx < 4) {
+#pragma unroll
+                            for (int r = 0; r < RPW; ++r)
+                                if (r == sz) f4s(y[r], sx, f4e(y[r], sx) + amp[s]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RPW; ++r)
+                *reinterpret_cast<float4*>(Bf + (lr0 + r) * ldp + XPAD + x) = y[r];
+        }
+        cluster_arrive();
+        if (active) {
+            // wavefield history (gradient runs) or, on the rolling 3-slot state, the last two states only
+            const bool store = pp.history || k >= pp.nsteps - 2;
+            if (store) {
+                float* dst = pp.u + slotf * ((pp.slot0 + k + 2) % pp.nslots) + boff;
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    const int z = zc0 + lr0 + r;
+                    if (z < g.nz && x < g.ld) *reinterpret_cast<float4*>(dst + (long long)z * g.ld + x) = y[r];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) { prv[r] = cur[r]; cur[r] = y[r]; }
+        }
+        cluster_wait();
+        pb ^= 1;
+        // receiver gather of step i from the copy just published (probe.py:42-44)
+        if (a.rec_out != nullptr) {
+            float* out = a.rec_out + (long long)k * a.R * a.nchan;
+            const float* P = pub + pb * rpc * ldp;
+            for (int r = tid; r < s_nrec; r += NW * 32) {
+                const float v = P[rec_cell[r]];
+                for (int ch = 0; ch < a.nchan; ++ch) out[rec_dst[r] + ch] = v;
+            }
+            if (s_rec_hi - s_rec_lo > RECCAP) {               // more receivers than the cache holds: walk the CSR
+                const int zhi = min(zc0 + rpc, g.nz);
+                for (int z = zc0 + warp; z < zhi; z += NW) {
+                    const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
+                    for (int r = max(lo, s_rec_lo + RECCAP) + lane; r < hi; r += 32) {
+                        const float v = P[(z - zc0) * ldp + XPAD + a.rec_x[r]];
+                        for (int ch = 0; ch < a.nchan; ++ch) out[(long long)a.rec_orig[r] * a.nchan + ch] = v;
+                    }
+                }
+            }
+        }
+        (void)i;
+    }
+    // nsteps == 1 on the rolling state: S_{i-1} must also sit in its slot -- it already does (it was the input).
+    cluster_arrive();                                       // nobody leaves while a neighbour may still read its copy
+    cluster_wait();
+}
+
+template <int NW, int RPW>
+int launch_persist(const W2Args& a, W2Persist pp, cudaStream_t st) {
+    auto kern = wave2d_persist_forward_kernel<NW, RPW>;
+    const int smem = 2 * pp.rpc * pp.ldp * (int)sizeof(float) + 2 * RECCAP * (int)sizeof(int);
+    if (st_set_max_smem<wave2d_persist_forward_kernel<NW, RPW>>(smem) != cudaSuccess) return ST_ERR_CUDA;
+    if (pp.cs > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return ST_ERR_CUDA;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(a.B * pp.cs));
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pp.cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (pp.probe) {                                         // can one cluster of this shape be resident at all?
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl < 1) { cudaGetLastError(); return ST_PERSIST_NA; }
+        return ST_OK;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, a, pp) == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+}
+
+}  // namespace
+
+// Plans the decomposition; ST_PERSIST_NA when the problem is not of the class this kernel serves.
+int st_wave2d_persist_plan(int flags, const W2Args& a, W2Persist& pp) {
+    memset(&pp, 0, sizeof(pp));
+    if (flags != (ST_F_ISO | ST_F_PML)) return ST_PERSIST_NA;
+    if (a.nchan > 4 || (a.src_fmask & ~1)) return ST_PERSIST_NA;
+    const W2Geom& g = a.g;
+    const char* ev = getenv("SEISTORCH_B200_PERSIST_VARIANT");      // experiments: 0 = 16 warps x 4 rows (default), 1 = 32 warps x 2 rows
+    pp.variant = ev && *ev ? atoi(ev) : 0;
+    const int NW = pp.variant == 1 ? 32 : 16, RPW = pp.variant == 1 ? 2 : 4;
+    pp.nstrips = (g.ld + PW - 1) / PW;
+    if (pp.nstrips < 1 || pp.nstrips > NW) return ST_PERSIST_NA;
+    pp.nrg = NW / pp.nstrips;
+    pp.rpc = pp.nrg * RPW;
+    pp.cs = 0;
+    for (int cs = 1; cs <= 16; cs *= 2)
+        if (cs * pp.rpc >= g.nz) { pp.cs = cs; break; }
+    if (pp.cs == 0) return ST_PERSIST_NA;
+    pp.ldp = pp.nstrips * PW + 2 * XPAD;
+    const long long smem = 2LL * pp.rpc * pp.ldp * 4 + 2 * RECCAP * 4;
+    if (smem > 200 * 1024) return ST_PERSIST_NA;
+    return ST_OK;
+}
+
+int st_wave2d_persist_forward(const W2Args& a, const W2Persist& pp, cudaStream_t st) {
+    return pp.variant == 1 ? launch_persist<32, 2>(a, pp, st) : launch_persist<16, 4>(a, pp, st);
+}

@@ -37,8 +37,9 @@ _W2_GRAD_OF_COEF = {0: 0, 2: 1, 3: 2, 4: 3, 5: 4, 6: 5, 7: 6}
 
 # number of sm_100a kernel launches issued through the C ABI (bench.py reports it)
 LAUNCHES = {"forward": 0, "adjoint": 0, "misfit": 0}
+STEPS = {"forward": 0, "adjoint": 0}               # time steps advanced (a persistent launch advances many)
 KERNELS = {"forward": None, "adjoint": None}      # kernel family of the most recent forward / adjoint call
-LAUNCHES_LAST = {"adjoint": 0, "recompute": 0}    # step launches of the most recent backward(): adjoint, recomputed forward
+LAUNCHES_LAST = {"adjoint": 0, "recompute": 0}    # time steps of the most recent backward(): adjoint, recomputed forward
 
 
 def _round_up(n, m):
@@ -323,29 +324,37 @@ class _Problem:
         p.bchunk = self.bchunk
         self.acq.fill(p.acq, self.amp, self.gamp, s.src_fmask, s.chan_f, self.rec_out, self.rec_adj)
 
-    def _note_kernel(self, which):
-        """Record which kernel family serves this call (bench.py / tests report it)."""
+    def _note_kernel(self, which, nsteps=0):
+        """Record which kernel family serves this call (bench.py / tests report it); returns the number of
+        kernel launches the call will issue."""
+        if which == "forward" and self.spec.family == "wave2d" and \
+                _lib.lib().st_wave2d_uses_persist(C.byref(self.p), int(nsteps)):
+            KERNELS[which] = "wave2d_persist_forward_kernel"
+            return 1
         if self.spec.family == "wave2d":
             tma = bool(_lib.lib().st_wave2d_uses_tma(C.byref(self.p), 1 if which == "adjoint" else 0))
             KERNELS[which] = f"wave2d_{which}_{'tma_' if tma else ''}kernel"
         else:
             KERNELS[which] = f"{self.spec.family}_{which}_kernel"
+        return nsteps
 
     def forward(self, i0, nsteps, slot0, record=True):
         keep = self.rec_out
         if not record:
             self.rec_out = None
         self._sync_struct()
-        self._note_kernel("forward")
+        nlaunch = self._note_kernel("forward", nsteps)
         self.rec_out = keep
         _lib.check(self.fwd(C.byref(self.p), i0, nsteps, slot0 % self.nslots, _stream_ptr()), f"{self.spec.family}_forward")
-        LAUNCHES["forward"] += nsteps
+        LAUNCHES["forward"] += nlaunch
+        STEPS["forward"] += nsteps
 
     def adjoint(self, i_hi, nsteps, slot_hi):
         self._sync_struct()
-        self._note_kernel("adjoint")
+        self._note_kernel("adjoint", nsteps)
         _lib.check(self.adj(C.byref(self.p), i_hi, nsteps, slot_hi % self.nslots, _stream_ptr()), f"{self.spec.family}_adjoint")
         LAUNCHES["adjoint"] += nsteps
+        STEPS["adjoint"] += nsteps
 
     def slot_view(self, slot, count=1):
         e = self.spec.slot_elems
@@ -461,7 +470,7 @@ class _Propagate(torch.autograd.Function):
         prob.gacc = torch.zeros(nchunk * spec.ngrad * spec.plane, dtype=torch.float32, device=dev)
         want_gamp = ctx.needs_input_grad[2]
         prob.gamp = torch.zeros((spec.nt, acq.ns), dtype=torch.float32, device=dev) if want_gamp else None
-        l0 = dict(LAUNCHES)
+        l0 = dict(STEPS)
         for s in reversed(range(nseg)):
             a, b = s * K, min((s + 1) * K, spec.nt)
             if s == nseg - 1:
@@ -482,8 +491,8 @@ class _Propagate(torch.autograd.Function):
                 i_lo = max(a - 1, 0)
                 if i_hi >= i_lo:
                     prob.adjoint(i_hi, i_hi - i_lo + 1, slot0 + 1 + (i_hi + 1 - a))
-        LAUNCHES_LAST["adjoint"] = LAUNCHES["adjoint"] - l0["adjoint"]
-        LAUNCHES_LAST["recompute"] = LAUNCHES["forward"] - l0["forward"]
+        LAUNCHES_LAST["adjoint"] = STEPS["adjoint"] - l0["adjoint"]
+        LAUNCHES_LAST["recompute"] = STEPS["forward"] - l0["forward"]
         g = prob.gacc.view(nchunk, spec.ngrad, *spec.shape[:-1], spec.ld).sum(0)[..., :spec.shape[-1]]
         grads = []
         for k in range(ctx.ncoef):
