@@ -31,6 +31,7 @@ namespace {
 constexpr int PW = 128;                 // columns per warp (32 lanes x float4)
 constexpr int XPAD = 4;                 // zero columns left of column 0 in the published copy (keeps rows 16-byte aligned)
 constexpr int RECCAP = 2048;            // cached (cell, record) pairs per CTA
+constexpr int PERSIST_SMEM_MAX = 200 * 1024 + 2 * RECCAP * 4;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned map_rank(unsigned addr, unsigned rank) {
@@ -261,7 +262,8 @@ template <int NW, int RPW>
 int launch_persist(const W2Args& a, W2Persist pp, cudaStream_t st) {
     auto kern = wave2d_persist_forward_kernel<NW, RPW>;
     const int smem = 2 * pp.rpc * pp.ldp * (int)sizeof(float) + 2 * RECCAP * (int)sizeof(int);
-    if (st_set_max_smem<wave2d_persist_forward_kernel<NW, RPW>>(smem) != cudaSuccess) return ST_ERR_CUDA;
+    // the limit is raised once per device to the largest size any plan may ask for (the plan caps it at 200 KB + lists)
+    if (st_set_max_smem<wave2d_persist_forward_kernel<NW, RPW>>(PERSIST_SMEM_MAX) != cudaSuccess) return ST_ERR_CUDA;
     if (pp.cs > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return ST_ERR_CUDA;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -278,7 +280,14 @@ int launch_persist(const W2Args& a, W2Persist pp, cudaStream_t st) {
     cfg.numAttrs = 1;
     if (pp.probe) {                                         // can one cluster of this shape be resident at all?
         int ncl = 0;
-        if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl < 1) { cudaGetLastError(); return ST_PERSIST_NA; }
+        const cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+        if (e != cudaSuccess || ncl < 1) {
+            if (getenv("SEISTORCH_B200_PERSIST_DEBUG"))
+                fprintf(stderr, "[st_wave2d_persist] no resident cluster: cs=%d smem=%d threads=%d -> %s, %d clusters\n", pp.cs, smem,
+                        NW * 32, cudaGetErrorString(e), ncl);
+            cudaGetLastError();
+            return ST_PERSIST_NA;
+        }
         return ST_OK;
     }
     return cudaLaunchKernelEx(&cfg, kern, a, pp) == cudaSuccess ? ST_OK : ST_ERR_CUDA;
