@@ -129,8 +129,7 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
         }
     }
     __syncthreads();                                        // zero fill done before the first publication
-    int pb = 0;                                             // published copy that holds `cur`
-    if (active) {
+    if (active) {                                           // copy 0 holds S_{i0-1}
 #pragma unroll
         for (int r = 0; r < RPW; ++r)
             *reinterpret_cast<float4*>(pub + (lr0 + r) * ldp + XPAD + x) = cur[r];
@@ -159,101 +158,121 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
     const unsigned up_rank = up_remote ? crank - 1 : crank, dn_rank = dn_remote ? crank + 1 : crank;
     const int up_row = up_remote ? rpc - 1 : lr0 - 1, dn_row = dn_remote ? 0 : lr0 + RPW;
     const bool edge_l = lane == 0, edge_r = lane == 31;
+    // addresses of the two halo rows in either published copy (DSMEM window of the neighbour at the strip boundaries)
+    const unsigned copy_bytes = (unsigned)(rpc * ldp) * 4u;
+    const unsigned up_addr = map_rank(pub_addr + (unsigned)(up_row * ldp + XPAD + x) * 4u, up_rank);
+    const unsigned dn_addr = map_rank(pub_addr + (unsigned)(dn_row * ldp + XPAD + x) * 4u, dn_rank);
+    const int own_off = lr0 * ldp + XPAD + x;               // first owned row inside a published copy
+    int slot_w = (pp.slot0 + 2) % pp.nslots;                // slot the next state is stored to
+    float amp_next[2] = {0.f, 0.f};                         // wavelet samples of the coming step (owner thread only)
+    if (nmine > 0 && !src_overflow && pp.nsteps > 0) {
+        for (int q = 0; q < 2; ++q)
+            if (q < nmine) amp_next[q] = a.amp[my_src[q]];
+    }
 
-    for (int k = 0; k < pp.nsteps; ++k) {
-        const int i = pp.i0 + k;
-        const float* A = pub + pb * rpc * ldp;
-        float* Bf = pub + (pb ^ 1) * rpc * ldp;
-        float4 y[RPW];
+    // Receiver gather of step k from the copy that holds S_k (probe.py:42-44).  It runs in the shadow of the NEXT
+    // step's barrier (that copy is not overwritten before the barrier after that one).
+    auto gather = [&](int k, int copy) {
+        if (a.rec_out == nullptr) return;
+        float* out = a.rec_out + (long long)k * a.R * a.nchan;
+        const float* P = pub + copy * rpc * ldp;
+        for (int r = tid; r < s_nrec; r += NW * 32) {
+            const float v = P[rec_cell[r]];
+            for (int ch = 0; ch < a.nchan; ++ch) out[rec_dst[r] + ch] = v;
+        }
+        if (s_rec_hi - s_rec_lo > RECCAP) {                   // more receivers than the cache holds: walk the CSR
+            const int zhi = min(zc0 + rpc, g.nz);
+            for (int z = zc0 + warp; z < zhi; z += NW) {
+                const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
+                for (int r = max(lo, s_rec_lo + RECCAP) + lane; r < hi; r += 32) {
+                    const float v = P[(z - zc0) * ldp + XPAD + a.rec_x[r]];
+                    for (int ch = 0; ch < a.nchan; ++ch) out[(long long)a.rec_orig[r] * a.nchan + ch] = v;
+                }
+            }
+        }
+    };
+
+    // One time step: C = S_{i-1} (published in copy `pc`), P = S_{i-2}; S_i overwrites P in place (a cell's previous
+    // value is needed by that cell only) and is published to the other copy.
+    auto step = [&](float4 (&C)[RPW], float4 (&P)[RPW], int k, int pc) {
         if (active) {
             float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = up;
-            const unsigned abase = pub_addr + (unsigned)(pb * rpc * ldp) * 4u;
-            if (has_up) up = ld_cluster4(map_rank(abase + (unsigned)(up_row * ldp + XPAD + x) * 4u, up_rank));
-            if (has_dn) dn = ld_cluster4(map_rank(abase + (unsigned)(dn_row * ldp + XPAD + x) * 4u, dn_rank));
+            if (has_up) up = ld_cluster4(up_addr + pc * copy_bytes);
+            if (has_dn) dn = ld_cluster4(dn_addr + pc * copy_bytes);
+            const float* Arow = pub + pc * rpc * ldp + own_off;
 #pragma unroll
             for (int r = 0; r < RPW; ++r) {
-                const float4 c = cur[r];
-                const float4 n = r == 0 ? up : cur[r - 1];
-                const float4 s = r == RPW - 1 ? dn : cur[r + 1];
+                const float4 c = C[r];
+                const float4 n = r == 0 ? up : C[r - 1];
+                const float4 s = r == RPW - 1 ? dn : C[r + 1];
                 float lc = __shfl_up_sync(0xffffffffu, c.w, 1);
                 float rc = __shfl_down_sync(0xffffffffu, c.x, 1);
-                const float* row = A + (lr0 + r) * ldp + XPAD + x;
-                if (edge_l) lc = row[-1];
-                if (edge_r) rc = row[4];
-                y[r].x = pml_update(c.x, prv[r].x, n.x, s.x, lc, c.y, al[r].x, ci[r].x);
-                y[r].y = pml_update(c.y, prv[r].y, n.y, s.y, c.x, c.z, al[r].y, ci[r].y);
-                y[r].z = pml_update(c.z, prv[r].z, n.z, s.z, c.y, c.w, al[r].z, ci[r].z);
-                y[r].w = pml_update(c.w, prv[r].w, n.w, s.w, c.z, rc, al[r].w, ci[r].w);
+                if (edge_l) lc = Arow[r * ldp - 1];
+                if (edge_r) rc = Arow[r * ldp + 4];
+                float4 y;
+                y.x = pml_update(c.x, P[r].x, n.x, s.x, lc, c.y, al[r].x, ci[r].x);
+                y.y = pml_update(c.y, P[r].y, n.y, s.y, c.x, c.z, al[r].y, ci[r].y);
+                y.z = pml_update(c.z, P[r].z, n.z, s.z, c.y, c.w, al[r].z, ci[r].z);
+                y.w = pml_update(c.w, P[r].w, n.w, s.w, c.z, rc, al[r].w, ci[r].w);
+                P[r] = y;
             }
             // source add (source.py:47-57: field += wavelet sample, after the update, before sampling)
             if (nmine > 0) {
-                const float* amp = a.amp + (long long)k * a.ns;
                 if (!src_overflow) {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         if (q < nmine) {
-                            const float v = amp[my_src[q]];
                             const int rr = my_src_rc[q] >> 2, e = my_src_rc[q] & 3;
 #pragma unroll
                             for (int r = 0; r < RPW; ++r)
-                                if (r == rr) f4s(y[r], e, f4e(y[r], e) + v);
+                                if (r == rr) f4s(P[r], e, f4e(P[r], e) + amp_next[q]);
                         }
                     }
                 } else {
+                    const float* amp = a.amp + (long long)k * a.ns;
                     for (int s = 0; s < a.ns; ++s) {
                         if (a.src_b[s] != b) continue;
                         const int sz = a.src_z[s] - (zc0 + lr0), sx = a.src_x[s] - x;
                         if (sz >= 0 && sz < RPW && sx >= 0 && sx < 4) {
 #pragma unroll
                             for (int r = 0; r < RPW; ++r)
-                                if (r == sz) f4s(y[r], sx, f4e(y[r], sx) + amp[s]);
+                                if (r == sz) f4s(P[r], sx, f4e(P[r], sx) + amp[s]);
                         }
                     }
                 }
             }
+            float* Brow = pub + (pc ^ 1) * rpc * ldp + own_off;
 #pragma unroll
-            for (int r = 0; r < RPW; ++r)
-                *reinterpret_cast<float4*>(Bf + (lr0 + r) * ldp + XPAD + x) = y[r];
+            for (int r = 0; r < RPW; ++r) *reinterpret_cast<float4*>(Brow + r * ldp) = P[r];
         }
         cluster_arrive();
+        // ---- in the shadow of the barrier: history store, next wavelet sample, receiver gather of the previous step
         if (active) {
-            // wavefield history (gradient runs) or, on the rolling 3-slot state, the last two states only
-            const bool store = pp.history || k >= pp.nsteps - 2;
-            if (store) {
-                float* dst = pp.u + slotf * ((pp.slot0 + k + 2) % pp.nslots) + boff;
+            if (pp.history || k >= pp.nsteps - 2) {         // rolling 3-slot state: only the last two states are kept
+                float* dst = pp.u + slotf * slot_w + boff + (long long)(zc0 + lr0) * g.ld + x;
 #pragma unroll
-                for (int r = 0; r < RPW; ++r) {
-                    const int z = zc0 + lr0 + r;
-                    if (z < g.nz && x < g.ld) *reinterpret_cast<float4*>(dst + (long long)z * g.ld + x) = y[r];
-                }
+                for (int r = 0; r < RPW; ++r)
+                    if (zc0 + lr0 + r < g.nz && x < g.ld) *reinterpret_cast<float4*>(dst + (long long)r * g.ld) = P[r];
             }
-#pragma unroll
-            for (int r = 0; r < RPW; ++r) { prv[r] = cur[r]; cur[r] = y[r]; }
+            if (nmine > 0 && !src_overflow && k + 1 < pp.nsteps) {
+                const float* amp = a.amp + (long long)(k + 1) * a.ns;
+                for (int q = 0; q < 2; ++q)
+                    if (q < nmine) amp_next[q] = amp[my_src[q]];
+            }
         }
+        slot_w = slot_w + 1 == pp.nslots ? 0 : slot_w + 1;
+        if (k > 0) gather(k - 1, pc);
         cluster_wait();
-        pb ^= 1;
-        // receiver gather of step i from the copy just published (probe.py:42-44)
-        if (a.rec_out != nullptr) {
-            float* out = a.rec_out + (long long)k * a.R * a.nchan;
-            const float* P = pub + pb * rpc * ldp;
-            for (int r = tid; r < s_nrec; r += NW * 32) {
-                const float v = P[rec_cell[r]];
-                for (int ch = 0; ch < a.nchan; ++ch) out[rec_dst[r] + ch] = v;
-            }
-            if (s_rec_hi - s_rec_lo > RECCAP) {               // more receivers than the cache holds: walk the CSR
-                const int zhi = min(zc0 + rpc, g.nz);
-                for (int z = zc0 + warp; z < zhi; z += NW) {
-                    const int lo = a.row_start[b * g.nz + z], hi = a.row_start[b * g.nz + z + 1];
-                    for (int r = max(lo, s_rec_lo + RECCAP) + lane; r < hi; r += 32) {
-                        const float v = P[(z - zc0) * ldp + XPAD + a.rec_x[r]];
-                        for (int ch = 0; ch < a.nchan; ++ch) out[(long long)a.rec_orig[r] * a.nchan + ch] = v;
-                    }
-                }
-            }
-        }
-        (void)i;
+    };
+
+    int k = 0;
+    for (; k + 1 < pp.nsteps; k += 2) {
+        step(cur, prv, k, 0);                               // S_k -> prv registers, copy 1
+        step(prv, cur, k + 1, 1);                           // S_{k+1} -> cur registers, copy 0
     }
-    // nsteps == 1 on the rolling state: S_{i-1} must also sit in its slot -- it already does (it was the input).
+    int last_copy = 0;
+    if (k < pp.nsteps) { step(cur, prv, k, 0); last_copy = 1; }
+    if (pp.nsteps > 0) gather(pp.nsteps - 1, last_copy);
     cluster_arrive();                                       // nobody leaves while a neighbour may still read its copy
     cluster_wait();
 }

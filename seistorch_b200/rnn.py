@@ -37,6 +37,7 @@ class WaveRNN(torch.nn.Module):
         # engine knobs (not in the reference): see engine._history_plan
         self.history_budget_bytes = None
         self.segment = None
+        self._acq_cache = None
 
     def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True) -> Iterator[Tuple[str, Parameter]]:
         if self.cell.geom.use_implicit:
@@ -71,9 +72,11 @@ class WaveRNN(torch.nn.Module):
 
     def reset_sources(self, sources):
         self.sources = torch.nn.ModuleList(sources if isinstance(sources, list) else [sources])
+        self._acq_cache = None
 
     def reset_probes(self, probes):
         self.probes = torch.nn.ModuleList(probes if isinstance(probes, list) else [probes])
+        self._acq_cache = None
 
     def reset_geom(self, shots, src_list, rec_list, cfg):
         sources, receivers = setup_acquisition(shots, src_list, rec_list, cfg)
@@ -95,35 +98,51 @@ class WaveRNN(torch.nn.Module):
             raise NotImplementedError("seistorch_b200: source_illumination is not on the accelerated path")
         ndim = len(geom.domain_shape)
         equation = geom.equation
-        if super_source is None:
-            bidx_source, sourcekeys = self.merge_sources_with_same_keys()
-            super_source = WaveSource(bidx_source, self.second_order_equation, **sourcekeys).to(device)
-        if super_probes is None:
-            reccounts, bidx_receivers, reckeys = self.merge_receivers_with_same_keys()
-            super_probes = WaveProbe(bidx_receivers, **reckeys).to(device)
+        # The device-side index tables (validation, sort, CSR) are built once per acquisition and reused: the
+        # model's own sources / probes until reset_*() is called, a caller-supplied (super_source, super_probes)
+        # pair for as long as the same two objects are passed (they are immutable index buffers).
+        own = super_source is None and super_probes is None
+        key = (tuple(geom.domain_shape), bool(self.source_encoding), str(device))
+        cached = getattr(self, "_acq_cache", None) if own else getattr(super_probes, "_st_acq", None)
+        if cached is not None and cached[0] == key and (own or cached[1] is super_source):
+            acq, reccounts, ns = cached[2], cached[3], cached[4]
         else:
-            reccounts = super_probes.reccounts
-        super_source.source_encoding = self.source_encoding
-        super_source.second_order_equation = self.second_order_equation
+            given_source = super_source
+            if super_source is None:
+                bidx_source, sourcekeys = self.merge_sources_with_same_keys()
+                super_source = WaveSource(bidx_source, self.second_order_equation, **sourcekeys).to(device)
+            if super_probes is None:
+                reccounts, bidx_receivers, reckeys = self.merge_receivers_with_same_keys()
+                super_probes = WaveProbe(bidx_receivers, **reckeys).to(device)
+            else:
+                reccounts = super_probes.reccounts
+            super_source.source_encoding = self.source_encoding
+            super_source.second_order_equation = self.second_order_equation
 
-        ns = int(super_source.x.reshape(-1).shape[0])
-        batchsize = 1 if self.source_encoding else ns            # rnn.py:112-116
-        sx = super_source.x.reshape(-1).to(device)
-        sy = super_source.y.reshape(-1).to(device)
-        src_b = torch.zeros(ns, dtype=torch.int64, device=device) if self.source_encoding \
-            else torch.arange(ns, dtype=torch.int64, device=device)
-        rb = torch.as_tensor(super_probes.bidx, dtype=torch.int64, device=device).reshape(-1)
-        rx = super_probes.x.reshape(-1).to(device)
-        ry = super_probes.y.reshape(-1).to(device)
-        if ndim == 2:
-            src_idx = torch.stack([sy, sx], dim=1)               # smask[b, y, x]          rnn.py:164
-            rec_idx = torch.stack([ry, rx], dim=1)               # field[bidx, y, x]       probe.py:44
-        else:
-            sz = super_source.z.reshape(-1).to(device)
-            rz = super_probes.z.reshape(-1).to(device)
-            src_idx = torch.stack([sx, sz, sy], dim=1)           # smask[b, x, z, y]       rnn.py:166
-            rec_idx = torch.stack([rx, rz, ry], dim=1)           # field[bidx, x, z, y]    probe.py:48
-        acq = Acquisition(geom.domain_shape, batchsize, src_b, src_idx, rb, rec_idx, device)
+            ns = int(super_source.x.reshape(-1).shape[0])
+            batchsize = 1 if self.source_encoding else ns            # rnn.py:112-116
+            sx = super_source.x.reshape(-1).to(device)
+            sy = super_source.y.reshape(-1).to(device)
+            src_b = torch.zeros(ns, dtype=torch.int64, device=device) if self.source_encoding \
+                else torch.arange(ns, dtype=torch.int64, device=device)
+            rb = torch.as_tensor(super_probes.bidx, dtype=torch.int64, device=device).reshape(-1)
+            rx = super_probes.x.reshape(-1).to(device)
+            ry = super_probes.y.reshape(-1).to(device)
+            if ndim == 2:
+                src_idx = torch.stack([sy, sx], dim=1)               # smask[b, y, x]          rnn.py:164
+                rec_idx = torch.stack([ry, rx], dim=1)               # field[bidx, y, x]       probe.py:44
+            else:
+                sz = super_source.z.reshape(-1).to(device)
+                rz = super_probes.z.reshape(-1).to(device)
+                src_idx = torch.stack([sx, sz, sy], dim=1)           # smask[b, x, z, y]       rnn.py:166
+                rec_idx = torch.stack([rx, rz, ry], dim=1)           # field[bidx, x, z, y]    probe.py:48
+            acq = Acquisition(geom.domain_shape, batchsize, src_b, src_idx, rb, rec_idx, device)
+            reccounts = list(reccounts)
+            if own:
+                self._acq_cache = (key, None, acq, reccounts, ns)
+            elif given_source is not None:
+                super_probes._st_acq = (key, given_source, acq, reccounts, ns)
+        batchsize = acq.B
 
         # wavelet -> per-source amplitudes amp[nt, ns]
         x = x.to(device)
@@ -170,7 +189,8 @@ class WaveRNN(torch.nn.Module):
                     history_budget_bytes=self.history_budget_bytes, segment=self.segment)
         rec = propagate(spec, acq, amp, coefs)                   # [nt, sum(nrec), nchan]
 
+        if bool(torch.isnan(rec).any()):                         # type.py:41-46 (one device sync, not one per shot)
+            raise ValueError("The tensor list contains NaN values.")
         y = TensorList()
         y.data.extend(torch.split(rec, list(reccounts), dim=1))
-        y.has_nan()
         return y
