@@ -7,7 +7,7 @@
 //   * every thread owns 4 consecutive columns of RPW rows and keeps their current / previous field values and
 //     their two coefficients in REGISTERS for all time steps; the field never goes back to HBM unless a wavefield
 //     history is requested (gradient runs) -- then it leaves as fire-and-forget 128-bit stores;
-//   * the current field is published to a double-buffered shared-memory copy once per step: x-neighbours come
+//   * the current field is published to a triple-buffered shared-memory copy once per step: x-neighbours come
 //     from warp shuffles (edge lanes read one scalar of the published copy), z-neighbours inside a thread's rows
 //     from registers, the two halo rows from the published copy -- of the neighbouring CTA through distributed
 //     shared memory (ld.shared::cluster) at the strip boundaries;
@@ -31,6 +31,8 @@ namespace {
 constexpr int PW = 128;                 // columns per warp (32 lanes x float4)
 constexpr int XPAD = 4;                 // zero columns left of column 0 in the published copy (keeps rows 16-byte aligned)
 constexpr int RECCAP = 2048;            // cached (cell, record) pairs per CTA
+constexpr int NCOPY = 3;                // published copies of the field: S_i is written to copy i % 3 while S_{i-1} is being read by
+                                        // the stencil and S_{i-2} by the receiver gather that runs in the barrier shadow
 constexpr int PERSIST_SMEM_MAX = 200 * 1024 + 2 * RECCAP * 4;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
     const W2Geom& g = a.g;
     const int ldp = pp.ldp, rpc = pp.rpc;
     float* pub = reinterpret_cast<float*>(dsm);             // [2][rpc][ldp] published copies
-    int* rec_cell = reinterpret_cast<int*>(pub + 2 * rpc * ldp);      // [RECCAP] float offset inside one published copy
+    int* rec_cell = reinterpret_cast<int*>(pub + NCOPY * rpc * ldp);      // [RECCAP] float offset inside one published copy
     int* rec_dst = rec_cell + RECCAP;                       // [RECCAP] record index * nchan
     __shared__ int s_nrec, s_rec_lo, s_rec_hi;
 
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
     const float* u = pp.u;
 
     // ---- zero the published copies (pads stay zero for the whole run)
-    for (int i = tid; i < 2 * rpc * ldp; i += NW * 32) pub[i] = 0.f;
+    for (int i = tid; i < NCOPY * rpc * ldp; i += NW * 32) pub[i] = 0.f;
 
     // ---- receivers of this CTA's rows -> cached (cell, record) pairs
     if (tid == 0) {
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
     // One time step: C = S_{i-1} (published in copy `pc`), P = S_{i-2}; S_i overwrites P in place (a cell's previous
     // value is needed by that cell only) and is published to the other copy.
     auto step = [&](float4 (&C)[RPW], float4 (&P)[RPW], int k, int pc) {
+        const int pn = pc + 1 == NCOPY ? 0 : pc + 1;        // copy S_k is published to
         if (active) {
             float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = up;
             if (has_up) up = ld_cluster4(up_addr + pc * copy_bytes);
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
                     }
                 }
             }
-            float* Brow = pub + (pc ^ 1) * rpc * ldp + own_off;
+            float* Brow = pub + pn * rpc * ldp + own_off;
 #pragma unroll
             for (int r = 0; r < RPW; ++r) *reinterpret_cast<float4*>(Brow + r * ldp) = P[r];
         }
@@ -265,14 +268,15 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
         cluster_wait();
     };
 
-    int k = 0;
+    int k = 0, pc = 0;                                      // copy `pc` holds S_{k-1}
     for (; k + 1 < pp.nsteps; k += 2) {
-        step(cur, prv, k, 0);                               // S_k -> prv registers, copy 1
-        step(prv, cur, k + 1, 1);                           // S_{k+1} -> cur registers, copy 0
+        step(cur, prv, k, pc);                              // S_k -> prv registers
+        pc = pc + 1 == NCOPY ? 0 : pc + 1;
+        step(prv, cur, k + 1, pc);                          // S_{k+1} -> cur registers
+        pc = pc + 1 == NCOPY ? 0 : pc + 1;
     }
-    int last_copy = 0;
-    if (k < pp.nsteps) { step(cur, prv, k, 0); last_copy = 1; }
-    if (pp.nsteps > 0) gather(pp.nsteps - 1, last_copy);
+    if (k < pp.nsteps) { step(cur, prv, k, pc); pc = pc + 1 == NCOPY ? 0 : pc + 1; }
+    if (pp.nsteps > 0) gather(pp.nsteps - 1, pc);
     cluster_arrive();                                       // nobody leaves while a neighbour may still read its copy
     cluster_wait();
 }
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
 template <int NW, int RPW>
 int launch_persist(const W2Args& a, W2Persist pp, cudaStream_t st) {
     auto kern = wave2d_persist_forward_kernel<NW, RPW>;
-    const int smem = 2 * pp.rpc * pp.ldp * (int)sizeof(float) + 2 * RECCAP * (int)sizeof(int);
+    const int smem = NCOPY * pp.rpc * pp.ldp * (int)sizeof(float) + 2 * RECCAP * (int)sizeof(int);
     // the limit is raised once per device to the largest size any plan may ask for (the plan caps it at 200 KB + lists)
     if (st_set_max_smem<wave2d_persist_forward_kernel<NW, RPW>>(PERSIST_SMEM_MAX) != cudaSuccess) return ST_ERR_CUDA;
     if (pp.cs > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return ST_ERR_CUDA;
@@ -332,7 +336,7 @@ int st_wave2d_persist_plan(int flags, const W2Args& a, W2Persist& pp) {
         if (cs * pp.rpc >= g.nz) { pp.cs = cs; break; }
     if (pp.cs == 0) return ST_PERSIST_NA;
     pp.ldp = pp.nstrips * PW + 2 * XPAD;
-    const long long smem = 2LL * pp.rpc * pp.ldp * 4 + 2 * RECCAP * 4;
+    const long long smem = (long long)NCOPY * pp.rpc * pp.ldp * 4 + 2 * RECCAP * 4;
     if (smem > 200 * 1024) return ST_PERSIST_NA;
     return ST_OK;
 }
