@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
     const W2Geom& g = a.g;
     const int ldp = pp.ldp, rpc = pp.rpc;
     float* pub = reinterpret_cast<float*>(dsm);             // [2][rpc][ldp] published copies
-    int* rec_cell = reinterpret_cast<int*>(pub + NCOPY * rpc * ldp);      // [RECCAP] float offset inside one published copy
+    float* zrow = pub + NCOPY * rpc * ldp;                   // [ldp] zeros: the halo row of a strip at the domain edge
+    int* rec_cell = reinterpret_cast<int*>(zrow + ldp);     // [RECCAP] float offset inside one published copy
     int* rec_dst = rec_cell + RECCAP;                       // [RECCAP] record index * nchan
     __shared__ int s_nrec, s_rec_lo, s_rec_hi;
 
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
     const float* u = pp.u;
 
     // ---- zero the published copies (pads stay zero for the whole run)
-    for (int i = tid; i < NCOPY * rpc * ldp; i += NW * 32) pub[i] = 0.f;
+    for (int i = tid; i < (NCOPY * rpc + 1) * ldp; i += NW * 32) pub[i] = 0.f;
 
     // ---- receivers of this CTA's rows -> cached (cell, record) pairs
     if (tid == 0) {
@@ -161,9 +162,12 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
     const int up_row = up_remote ? rpc - 1 : lr0 - 1, dn_row = dn_remote ? 0 : lr0 + RPW;
     const bool edge_l = lane == 0, edge_r = lane == 31;
     // addresses of the two halo rows in either published copy (DSMEM window of the neighbour at the strip boundaries)
+    // (branch-free: a strip at the domain edge reads the zero row instead, with a zero copy stride)
     const unsigned copy_bytes = (unsigned)(rpc * ldp) * 4u;
-    const unsigned up_addr = map_rank(pub_addr + (unsigned)(up_row * ldp + XPAD + x) * 4u, up_rank);
-    const unsigned dn_addr = map_rank(pub_addr + (unsigned)(dn_row * ldp + XPAD + x) * 4u, dn_rank);
+    const unsigned zrow_addr = pub_addr + (unsigned)(NCOPY * rpc * ldp + XPAD + x) * 4u;
+    const unsigned up_addr = has_up ? map_rank(pub_addr + (unsigned)(up_row * ldp + XPAD + x) * 4u, up_rank) : zrow_addr;
+    const unsigned dn_addr = has_dn ? map_rank(pub_addr + (unsigned)(dn_row * ldp + XPAD + x) * 4u, dn_rank) : zrow_addr;
+    const unsigned up_stride = has_up ? copy_bytes : 0u, dn_stride = has_dn ? copy_bytes : 0u;
     const int own_off = lr0 * ldp + XPAD + x;               // first owned row inside a published copy
     int slot_w = (pp.slot0 + 2) % pp.nslots;                // slot the next state is stored to
     float amp_next[2] = {0.f, 0.f};                         // wavelet samples of the coming step (owner thread only)
@@ -199,19 +203,21 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
     auto step = [&](float4 (&C)[RPW], float4 (&P)[RPW], int k, int pc) {
         const int pn = pc + 1 == NCOPY ? 0 : pc + 1;        // copy S_k is published to
         if (active) {
-            float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = up;
-            if (has_up) up = ld_cluster4(up_addr + pc * copy_bytes);
-            if (has_dn) dn = ld_cluster4(dn_addr + pc * copy_bytes);
+            const float4 up = ld_cluster4(up_addr + pc * up_stride);
+            const float4 dn = ld_cluster4(dn_addr + pc * dn_stride);
             const float* Arow = pub + pc * rpc * ldp + own_off;
 #pragma unroll
             for (int r = 0; r < RPW; ++r) {
                 const float4 c = C[r];
                 const float4 n = r == 0 ? up : C[r - 1];
                 const float4 s = r == RPW - 1 ? dn : C[r + 1];
+                // x-neighbours: shuffle; the two edge lanes take the published value instead (loaded by every lane:
+                // no divergent branch, the whole patch stays one basic block for the scheduler)
+                const float lh = Arow[r * ldp - 1], rh = Arow[r * ldp + 4];
                 float lc = __shfl_up_sync(0xffffffffu, c.w, 1);
                 float rc = __shfl_down_sync(0xffffffffu, c.x, 1);
-                if (edge_l) lc = Arow[r * ldp - 1];
-                if (edge_r) rc = Arow[r * ldp + 4];
+                lc = edge_l ? lh : lc;
+                rc = edge_r ? rh : rc;
                 float4 y;
                 y.x = pml_update(c.x, P[r].x, n.x, s.x, lc, c.y, al[r].x, ci[r].x);
                 y.y = pml_update(c.y, P[r].y, n.y, s.y, c.x, c.z, al[r].y, ci[r].y);
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_forward_kernel(cons
 template <int NW, int RPW>
 int launch_persist(const W2Args& a, W2Persist pp, cudaStream_t st) {
     auto kern = wave2d_persist_forward_kernel<NW, RPW>;
-    const int smem = NCOPY * pp.rpc * pp.ldp * (int)sizeof(float) + 2 * RECCAP * (int)sizeof(int);
+    const int smem = (NCOPY * pp.rpc + 1) * pp.ldp * (int)sizeof(float) + 2 * RECCAP * (int)sizeof(int);
     // the limit is raised once per device to the largest size any plan may ask for (the plan caps it at 200 KB + lists)
     if (st_set_max_smem<wave2d_persist_forward_kernel<NW, RPW>>(PERSIST_SMEM_MAX) != cudaSuccess) return ST_ERR_CUDA;
     if (pp.cs > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return ST_ERR_CUDA;
@@ -336,7 +342,7 @@ int st_wave2d_persist_plan(int flags, const W2Args& a, W2Persist& pp) {
         if (cs * pp.rpc >= g.nz) { pp.cs = cs; break; }
     if (pp.cs == 0) return ST_PERSIST_NA;
     pp.ldp = pp.nstrips * PW + 2 * XPAD;
-    const long long smem = (long long)NCOPY * pp.rpc * pp.ldp * 4 + 2 * RECCAP * 4;
+    const long long smem = ((long long)NCOPY * pp.rpc + 1) * pp.ldp * 4 + 2 * RECCAP * 4;
     if (smem > 200 * 1024) return ST_PERSIST_NA;
     return ST_OK;
 }
