@@ -17,11 +17,18 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libseistorch_b200.so")
+# tuning builds: SEISTORCH_B200_VARIANT=<tag> (+ SEISTORCH_B200_NVCC_EXTRA="-D...") writes libseistorch_b200_<tag>.so next to
+# the product library; select it at run time with SEISTORCH_B200_LIB=<path>
+_TAG = os.environ.get("SEISTORCH_B200_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "libseistorch_b200" + ("_" + _TAG if _TAG else "") + ".so")
 
+_EXTRA = os.environ.get("SEISTORCH_B200_NVCC_EXTRA", "").split()
+if any("ST_DBG" in f for f in _EXTRA) and not _TAG:
+    # -DST_DBG_SKIP / -DST_DBG_TIMELINE builds skip work or add timers: never into the product library
+    raise RuntimeError("seistorch_b200.build: ST_DBG_* defines are only allowed in a tagged tuning build (SEISTORCH_B200_VARIANT=...)")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-diag-suppress", "177"] + os.environ.get("SEISTORCH_B200_NVCC_EXTRA", "").split()
+              "-Xcompiler", "-fPIC", "-diag-suppress", "177"] + _EXTRA
 
 W2_FLAG_SETS = [3, 5, 4, 12, 20, 21, 36, 44]
 

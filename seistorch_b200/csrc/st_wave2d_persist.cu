@@ -330,8 +330,8 @@ int st_wave2d_persist_plan(int flags, const W2Args& a, W2Persist& pp) {
     if (flags != (ST_F_ISO | ST_F_PML)) return ST_PERSIST_NA;
     if (a.nchan > 4 || (a.src_fmask & ~1)) return ST_PERSIST_NA;
     const W2Geom& g = a.g;
-    const char* ev = getenv("SEISTORCH_B200_PERSIST_VARIANT");      // experiments: 0 = 16 warps x 4 rows (default), 1 = 32 warps x 2 rows
-    pp.variant = ev && *ev ? atoi(ev) : 0;
+    const char* ev = getenv("SEISTORCH_B200_PERSIST_VARIANT");      // 0 = 16 warps x 4 rows per thread, 1 = 32 warps x 2 rows (default: 2-4 % faster on B200)
+    pp.variant = ev && *ev ? atoi(ev) : 1;
     const int NW = pp.variant == 1 ? 32 : 16, RPW = pp.variant == 1 ? 2 : 4;
     pp.nstrips = (g.ld + PW - 1) / PW;
     if (pp.nstrips < 1 || pp.nstrips > NW) return ST_PERSIST_NA;

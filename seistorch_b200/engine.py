@@ -232,6 +232,8 @@ def _choose_bchunk(spec: Spec) -> int:
     env = os.environ.get("SEISTORCH_B200_BCHUNK")
     if env:
         return max(1, min(int(env), spec.B))
+    if spec.family == "elastic2d":
+        return 1          # the vectorised adjoint keeps one gradient plane set per shot (st_elastic2d.cu, fast path)
     if spec.family == "acoustic3d":
         tiles = math.ceil(spec.shape[2] / 64) * math.ceil(spec.shape[1] / 8) * math.ceil(spec.shape[0] / 16)
     elif spec.family == "wave2d":
