@@ -120,21 +120,24 @@ __device__ __forceinline__ void elastic_forward_fast(const E2Args& a, int fx, in
         float vz_r = __shfl_down_sync(0xffffffffu, vzr.x, 1);
         s.xx_r = 0.f; s.xz_l = 0.f;
         const float mz0 = (!EDGE || r > 0) ? 1.f : 0.f, mz1 = (!EDGE || r < nz - 1) ? 1.f : 0.f;   // row masks of D+z / D-z
-        if (e0) {
-            const int xl = x0 - 1;
-            vx_l = L1(VX, r, xl);
-            // txz'(r, x0-1): vz_x = vz(r,x0) - vz(r,x0-1), vx_z = vx(r,x0-1) - vx(r-1,x0-1)
-            float vz_x = vzr.x - L1(VZ, r, xl), vx_z = vx_l - L1(VX, r - 1, xl);
-            if (EDGE) { vx_z *= mz0; }                                 // (x0-1 < nx-1 always: vz_x needs no mask)
-            s.xz_l = L1(CA, r, xl) * L1(TXZ, r, xl) + L1(CM, r, xl) * (vz_x + vx_z);
-        }
-        if (e31) {
-            const int xr = x0 + FW;
-            vz_r = L1(VZ, r, xr);
-            // txx'(r, x0+128): vx_x = vx(r,x0+128) - vx(r,x0+127), vz_z = vz(r+1,x0+128) - vz(r,x0+128)
-            float vx_x = L1(VX, r, xr) - vxr.w, vz_z = L1(VZ, r + 1, xr) - vz_r;
-            if (EDGE) { vz_z *= mz1; }                                 // (x0+FW > 0 always: vx_x needs no mask)
-            s.xx_r = L1(CA, r, xr) * L1(TXX, r, xr) + (L1(C2, r, xr) * vx_x + L1(CL, r, xr) * vz_z);
+        {
+            // halo cells of the two edge lanes, evaluated by every lane without a branch (broadcast loads: one sector
+            // each) so that they are issued together with the vector loads instead of as dependent load -> use chains
+            const int xl = x0 - 1, xr = x0 + FW;
+            const float hvx_l = L1(VX, r, xl), hvz_l = L1(VZ, r, xl), hvx_ul = L1(VX, r - 1, xl);
+            const float hca_l = L1(CA, r, xl), hxz_l = L1(TXZ, r, xl), hcm_l = L1(CM, r, xl);
+            const float hvz_r = L1(VZ, r, xr), hvx_r = L1(VX, r, xr), hvz_dr = L1(VZ, r + 1, xr);
+            const float hca_r = L1(CA, r, xr), hxx_r = L1(TXX, r, xr), hc2_r = L1(C2, r, xr), hcl_r = L1(CL, r, xr);
+            // txz'(r, x0-1): vz_x = vz(r,x0) - vz(r,x0-1), vx_z = vx(r,x0-1) - vx(r-1,x0-1)   (x0-1 < nx-1 always)
+            float vz_x = vzr.x - hvz_l, vx_z = hvx_l - hvx_ul;
+            if (EDGE) vx_z *= mz0;
+            s.xz_l = hca_l * hxz_l + hcm_l * (vz_x + vx_z);
+            // txx'(r, x0+128): vx_x = vx(r,x0+128) - vx(r,x0+127), vz_z = vz(r+1,x0+128) - vz(r,x0+128)   (x0+FW > 0 always)
+            float vx_x = hvx_r - vxr.w, vz_z = hvz_dr - hvz_r;
+            if (EDGE) vz_z *= mz1;
+            s.xx_r = hca_r * hxx_r + (hc2_r * vx_x + hcl_r * vz_z);
+            vx_l = e0 ? hvx_l : vx_l;
+            vz_r = e31 ? hvz_r : vz_r;
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -206,7 +209,7 @@ __host__ __device__ inline FastRange elastic_fast_range(int nz, int nx) {
 }
 
 #ifndef ST_EL_MINB
-#define ST_EL_MINB 3
+#define ST_EL_MINB 2
 #endif
 #ifndef ST_EL_FRZ
 #define ST_EL_FRZ 8
@@ -336,6 +339,7 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
 #pragma unroll
     for (int e = 0; e < 4; ++e) { mA[e] = (!EDGE || x + e > 0) ? 1.f : 0.f; mB[e] = (!EDGE || x + e < nx - 1) ? 1.f : 0.f; }
     const int xl = x0 - 1, xr = x0 + FW;                        // halo columns
+    const int xh = lane < 16 ? xl : xr;                         // the one this lane would need if it were an edge lane
     const float mA_l = (!EDGE || xl > 0) ? 1.f : 0.f;           // masks at the halo cells
     const float mB_r = (!EDGE || xr < nx - 1) ? 1.f : 0.f;
 
@@ -346,13 +350,10 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
         const float4 cb = L4(CB, r);
         w.wx = f4mul(cb, L4(LVX, r));
         w.wz = f4mul(cb, L4(LVZ, r));
-        w.hx = 0.f; w.hz = 0.f;
-        if (e0 || e31) {
-            const int xh = e0 ? xl : xr;
-            const float cbh = L1(CB, r, xh);
-            w.hx = cbh * L1(LVX, r, xh);
-            w.hz = cbh * L1(LVZ, r, xh);
-        }
+        // halo scalars without a branch: the lower half-warp looks left, the upper half right (only lanes 0 / 31 use them)
+        const float cbh = L1(CB, r, xh);
+        w.hx = cbh * L1(LVX, r, xh);
+        w.hz = cbh * L1(LVZ, r, xh);
         return w;
     };
 
@@ -390,13 +391,11 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
             f4s(o.e, e, f4g(cm, e) * le);
         }
         // halo cells of the edge lanes: e(r, x0-1) for lane 0, a(r, x0+FW) for lane 31
-        o.a_r = 0.f; o.e_l = 0.f;
-        if (e0) {
+        {
+            // (every lane evaluates both, branch-free; only lanes 0 / 31 use the result)
             // Ltxz(q), q = (r, x0-1): Wx(r-1,q) / Wx(r,q) / Wz(r,q) are the halo scalars, Wz(r, x0) is this lane's own .x
             const float le = L1(LXZ, r, xl) + (m0 * up.hx - m1 * cur.hx) + (mA_l * cur.hz - cur.wz.x);
             o.e_l = L1(CM, r, xl) * le;
-        }
-        if (e31) {
             // Ltxx(q), Ltzz(q), q = (r, x0+FW): Wx(r, x0+FW-1) is this lane's own .w
             const float lx = L1(LXX, r, xr) + (cur.wx.w - mB_r * cur.hx);
             const float lz = L1(LZZ, r, xr) + (m0 * cur.hz - m1 * dn.hz);
@@ -416,8 +415,9 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
             if (grad) {
                 float vx_l = __shfl_up_sync(0xffffffffu, svx.w, 1);
                 float vz_r = __shfl_down_sync(0xffffffffu, svz_cur.x, 1);
-                if (e0) vx_l = L1(SVX, r, xl);
-                if (e31) vz_r = L1(SVZ, r, xr);
+                const float hvx = L1(SVX, r, xl), hvz = L1(SVZ, r, xr);
+                vx_l = e0 ? hvx : vx_l;
+                vz_r = e31 ? hvz : vz_r;
                 if (st_ok) {
                     float4 g2 = *reinterpret_cast<const float4*>(gpl + ro);
                     float4 gl = *reinterpret_cast<const float4*>(gpl + plane + ro);
@@ -492,8 +492,9 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
             const float4 txx = L4(TXX, z), tzz = L4(TZZ, z), txz_dn = L4(TXZ, z + 1);
             float txx_r = __shfl_down_sync(0xffffffffu, txx.x, 1);
             float txz_l = __shfl_up_sync(0xffffffffu, txz_cur.w, 1);
-            if (e31) txx_r = L1(TXX, z, xr);
-            if (e0) txz_l = L1(TXZ, z, xl);
+            const float hxx = L1(TXX, z, xr), hxz = L1(TXZ, z, xl);
+            txx_r = e31 ? hxx : txx_r;
+            txz_l = e0 ? hxz : txz_l;
             if (st_ok) {
                 float4 gb = *reinterpret_cast<const float4*>(gpl + 3 * plane + ro);
 #pragma unroll
