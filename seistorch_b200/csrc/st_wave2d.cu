@@ -577,20 +577,23 @@ __device__ __forceinline__ bool band_block_outside_rows(const W2Args& a, const B
     return same && (hi < a.row_lo || lo > a.row_hi);
 }
 
+template <int FL>
 __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int b_lo, int b_hi, int tid) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    constexpr bool STRIPS = !(FL & ST_F_BORN);               // st_flags_stripped
     const W2Geom g = a.g;
     const BandCells bc = st_band_cells(g, g.bw);
     const int i0 = blk * NT, i = i0 + tid;
     const long long plane = (long long)g.nz * g.ld;
     const StripGeom sg = strip_geom(g, g.bw);
     auto mine = [&](int z, int x) {
-        if (z < 0 || z >= g.nz || x < 0 || x >= g.nx || !w2_in_frame(z, x, g) || in_strip(sg, g, z, x)) return false;
+        if (z < 0 || z >= g.nz || x < 0 || x >= g.nx || !w2_in_frame(z, x, g) || (STRIPS && in_strip(sg, g, z, x))) return false;
         const int e = st_band_encode(bc, z, x);
         return e >= i0 && e < i0 + NT;
     };
     int zc = -1, xc = -1;
     if (i < bc.total) st_band_decode(bc, i, zc, xc);
-    if (i < bc.total && !in_strip(sg, g, zc, xc)) {          // strip cells belong to the vectorised strip blocks
+    if (i < bc.total && !(STRIPS && in_strip(sg, g, zc, xc))) {          // strip cells belong to the vectorised strip blocks
         const int z = zc, x = xc;
         const int idx = z * g.ld + x;
         // increment form: Y = h1 + (h1 - h2) + sum_{o != 0} F1[o] (h1(p+o) - h1(p)) + F2[o] (h2(p+o) - h2(p))
@@ -613,31 +616,55 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
                 t2self -= in ? 0.f : u;
             }
         }
+        // Born pair: coupling  pre m A[p1]  into the scattered field, A = czz (N + S - 2C) + cxx (W + E - 2C) with zero
+        // padding (w2_forward_cell); kc[o-1] multiplies (p1(q+o) - p1(q)), kself the centre value for absent neighbours
+        float kc[4] = {0.f, 0.f, 0.f, 0.f}, kself = 0.f;
+        if (NF == 2) {
+            const float pm = (1.f - __ldg(a.coef[1] + idx)) * __ldg(a.coef[7] + idx);
+            const float cx = __ldg(a.coef[2] + idx), cz = __ldg(a.coef[3] + idx);
+#pragma unroll
+            for (int o = 1; o <= 4; ++o) {
+                const int zz = z + st_tap_dz(o), xx = x + st_tap_dx(o);
+                const bool in = zz >= 0 && zz < g.nz && xx >= 0 && xx < g.nx;
+                const float t = pm * (o <= 2 ? cz : cx);
+                kc[o - 1] = in ? t : 0.f;
+                kself -= in ? 0.f : t;
+            }
+        }
         for (int b = b_lo; b < b_hi; b += 2) {
             // two shots per iteration: two independent load chains in flight
             const bool two = b + 1 < b_hi;
             const long long boff0 = (long long)b * a.fs, boff1 = two ? boff0 + a.fs : boff0;
-            const float* cur0 = a.cur + boff0;
-            const float* prv0 = a.prev + boff0;
-            const float* cur1 = a.cur + boff1;
-            const float* prv1 = a.prev + boff1;
-            const float c0 = __ldg(cur0 + idx), p0 = __ldg(prv0 + idx);
-            const float c1 = __ldg(cur1 + idx), p1 = __ldg(prv1 + idx);
-            float acc0 = t1self * c0 + t2self * p0, acc1 = t1self * c1 + t2self * p1;
+            float cpl0 = 0.f, cpl1 = 0.f;                       // coupling term (computed with field 0, used by field 1)
 #pragma unroll
-            for (int o = 1; o < ST_NTAP1; ++o) {
-                // most cells use one side only: 3 of the 4 far taps and 3 of the 4 h2 taps are zero
-                if (t1[o - 1] != 0.f) {
-                    acc0 += t1[o - 1] * (__ldg(cur0 + q1[o - 1]) - c0);
-                    acc1 += t1[o - 1] * (__ldg(cur1 + q1[o - 1]) - c1);
+            for (int f = 0; f < NF; ++f) {
+                const float* cur0 = a.cur + f * a.cs + boff0;
+                const float* prv0 = a.prev + f * a.cs + boff0;
+                const float* cur1 = a.cur + f * a.cs + boff1;
+                const float* prv1 = a.prev + f * a.cs + boff1;
+                const float c0 = __ldg(cur0 + idx), p0 = __ldg(prv0 + idx);
+                const float c1 = __ldg(cur1 + idx), p1 = __ldg(prv1 + idx);
+                float acc0 = t1self * c0 + t2self * p0, acc1 = t1self * c1 + t2self * p1;
+                if (NF == 2 && f == 0) { cpl0 = kself * c0; cpl1 = kself * c1; }
+#pragma unroll
+                for (int o = 1; o < ST_NTAP1; ++o) {
+                    // most cells use one side only: 3 of the 4 far taps and 3 of the 4 h2 taps are zero
+                    const bool need = t1[o - 1] != 0.f || (NF == 2 && f == 0 && o <= 4 && kc[o - 1] != 0.f);
+                    if (need) {
+                        const float d0 = __ldg(cur0 + q1[o - 1]) - c0, d1 = __ldg(cur1 + q1[o - 1]) - c1;
+                        acc0 += t1[o - 1] * d0;
+                        acc1 += t1[o - 1] * d1;
+                        if (NF == 2 && f == 0 && o <= 4) { cpl0 += kc[o - 1] * d0; cpl1 += kc[o - 1] * d1; }
+                    }
+                    if (o < ST_NTAP2 && t2[o - 1] != 0.f) {
+                        acc0 += t2[o - 1] * (__ldg(prv0 + q1[o - 1]) - p0);
+                        acc1 += t2[o - 1] * (__ldg(prv1 + q1[o - 1]) - p1);
+                    }
                 }
-                if (o < ST_NTAP2 && t2[o - 1] != 0.f) {
-                    acc0 += t2[o - 1] * (__ldg(prv0 + q1[o - 1]) - p0);
-                    acc1 += t2[o - 1] * (__ldg(prv1 + q1[o - 1]) - p1);
-                }
+                if (NF == 2 && f == 1) { acc0 += cpl0; acc1 += cpl1; }
+                a.next[f * a.cs + boff0 + idx] = c0 + ((c0 - p0) + acc0);
+                if (two) a.next[f * a.cs + boff1 + idx] = c1 + ((c1 - p1) + acc1);
             }
-            a.next[boff0 + idx] = c0 + ((c0 - p0) + acc0);
-            if (two) a.next[boff1 + idx] = c1 + ((c1 - p1) + acc1);
         }
     }
     __syncthreads();
@@ -654,8 +681,11 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
             // implicitly carries -mu*w*h1(q) for the missing tap: replace it
             if (w != 0.f)
                 for (int b = b_lo; b < b_hi; ++b) {
-                    const long long boff = (long long)b * a.fs;
-                    a.next[boff + idx] += w * (-r * r) * (__ldg(a.cur + boff + (zw * g.ld + xw)) - __ldg(a.cur + boff + idx));
+#pragma unroll
+                    for (int fl = 0; fl < NF; ++fl) {
+                        const long long boff = fl * a.cs + (long long)b * a.fs;
+                        a.next[boff + idx] += w * (-r * r) * (__ldg(a.cur + boff + (zw * g.ld + xw)) - __ldg(a.cur + boff + idx));
+                    }
                 }
         }
     }
@@ -663,7 +693,11 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
     __syncthreads();
     for (int s = tid; s < a.ns; s += NT) {
         const int sz = a.src_z[s], sx = a.src_x[s], sb = a.src_b[s];
-        if (sb >= b_lo && sb < b_hi && mine(sz, sx) && (a.src_fmask & 1)) atomicAdd(a.next + (long long)sb * a.fs + (sz * g.ld + sx), a.amp[s]);
+        if (sb >= b_lo && sb < b_hi && mine(sz, sx)) {
+#pragma unroll
+            for (int fl = 0; fl < NF; ++fl)
+                if (a.src_fmask >> fl & 1) atomicAdd(a.next + fl * a.cs + (long long)sb * a.fs + (sz * g.ld + sx), a.amp[s]);
+        }
     }
     if (!a.rec_out) return;
     __shared__ int s_cnt, s_rows[16];
@@ -676,7 +710,8 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
                 const int rx = a.rec_x[r];
                 if (mine(z, rx)) {
                     const long long o = (long long)a.rec_orig[r] * a.nchan;
-                    for (int ch = 0; ch < a.nchan; ++ch) a.rec_out[o + ch] = a.next[(long long)b * a.fs + (z * g.ld + rx)];
+                    for (int ch = 0; ch < a.nchan; ++ch)
+                        a.rec_out[o + ch] = a.next[a.chan_f[ch] * a.cs + (long long)b * a.fs + (z * g.ld + rx)];
                 }
             }
         }
@@ -685,6 +720,8 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
 
 template <int FL>
 __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int b_lo, int b_hi, int gplane, int tid) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    constexpr bool STRIPS = !(FL & ST_F_BORN);               // st_flags_stripped
     const W2Geom g = a.g;
     const int bd = g.bw + 1;
     const BandCells bc = st_band_cells(g, bd);
@@ -694,13 +731,13 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
     auto inb = [&](int z, int x) { return z >= 0 && z < g.nz && x >= 0 && x < g.nx; };
     const StripGeom sg = strip_geom(g, bd);
     auto mine = [&](int z, int x) {
-        if (!inb(z, x) || in_strip(sg, g, z, x)) return false;
+        if (!inb(z, x) || (STRIPS && in_strip(sg, g, z, x))) return false;
         const int e = st_band_encode(bc, z, x);
         return e >= i0 && e < i0 + NT;
     };
     int zc = -1, xc = -1;
     if (i < bc.total) st_band_decode(bc, i, zc, xc);
-    if (i < bc.total && !in_strip(sg, g, zc, xc)) {          // strip cells belong to the vectorised strip blocks
+    if (i < bc.total && !(STRIPS && in_strip(sg, g, zc, xc))) {          // strip cells belong to the vectorised strip blocks
         const int z = zc, x = xc;
         const int idx = z * g.ld + x;
         // transposed taps: coefficient of L(p+o) is the tap -o of cell p+o
@@ -721,61 +758,102 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
                 m[o] = in ? 1.f : 0.f;
             }
         }
-        float gr = 0.f, gc = 0.f, gz = 0.f, gax = 0.f, gaz = 0.f;
-        // one shot: Lam_i(p) and the gradient contributions; written as a lambda so two shots can be
-        // issued back to back (two independent load chains in flight)
-        auto one_shot = [&](int b, float& accOut, float& gcOut, float& grOut, float& gzOut, float& gaxOut, float& gazOut) {
-            const long long boff = (long long)b * a.fs;
-            const float* l1 = a.lam1 + boff;
-            const float* l2 = a.lam2 + boff;
-            float acc = 0.f, lc = 0.f;
+        // Born pair: the scattered field's cotangent reaches the background field through the coupling
+        //   sp' += pre m A[p1]  =>  Lam_p(p) += sum_o K[-o](p+o) L1_s(p+o),   K[o](q) = pre(q) m(q) T[o](q), K[0] = -sum_o K[o]
+        // (T = czz for the z-neighbours, cxx for the x-neighbours; w2_adjoint_cell: leffq)
+        float gk[ST_NTAP2] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        float pm_p = 0.f, cx_p = 0.f, cz_p = 0.f;
+        if (NF == 2) {
+            cx_p = __ldg(a.coef[2] + idx); cz_p = __ldg(a.coef[3] + idx);
+            pm_p = pre * __ldg(a.coef[7] + idx);
+            gk[0] = -pm_p * (2.f * cx_p + 2.f * cz_p);
 #pragma unroll
-            for (int o = 0; o < ST_NTAP1; ++o) {
-                // zero taps (most far taps of single-side cells) are skipped; the centre value is
-                // always needed for the imaging condition
-                if (o == 0 || g1[o] != 0.f) {
-                    const float v = __ldg(l1 + q[o]);
-                    if (o == 0) lc = v;
-                    acc += g1[o] * v;
+            for (int o = 1; o < ST_NTAP2; ++o) {
+                if (m[o] != 0.f) {
+                    const int zz = z + st_tap_dz(o), xx = x + st_tap_dx(o);
+                    const float preq = w2_in_frame(zz, xx, g) ? 1.f - __ldg(a.coef[1] + q[o]) : 1.f;
+                    gk[o] = preq * __ldg(a.coef[7] + q[o]) * __ldg(a.coef[o <= 2 ? 3 : 2] + q[o]);
                 }
-                if (o < ST_NTAP2 && g2[o] != 0.f) acc += g2[o] * __ldg(l2 + q[o]);
             }
-            accOut = acc;
-            if (want_grad) {
-                const float* S1 = a.s1 + boff;
-                const float* S2 = a.s2 + boff;
-                float s[ST_NTAP2], t = 0.f;
+        }
+        float gr = 0.f, gc = 0.f, gz = 0.f, gax = 0.f, gaz = 0.f, gm = 0.f;
+        // one shot: Lam_i(p) of every field and the gradient contributions; written as a lambda so two shots can be
+        // issued back to back (two independent load chains in flight)
+        auto one_shot = [&](int b, float (&accOut)[NF], float& gcOut, float& grOut, float& gzOut, float& gaxOut, float& gazOut, float& gmOut) {
+            const long long boff = (long long)b * a.fs;
+            float lc[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) accOut[f] = 0.f;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const float* l1 = a.lam1 + f * a.cs + boff;
+                const float* l2 = a.lam2 + f * a.cs + boff;
+                float acc = 0.f;
+                lc[f] = 0.f;
 #pragma unroll
                 for (int o = 0; o < ST_NTAP1; ++o) {
-                    if (o < ST_NTAP2) {
-                        s[o] = m[o] * __ldg(S1 + q[o]);
-                        t += h1[o] * s[o];
-                        if (h2[o] != 0.f) t += h2[o] * __ldg(S2 + q[o]);
-                    } else if (h1[o] != 0.f) {
-                        t += h1[o] * __ldg(S1 + q[o]);
+                    // zero taps (most far taps of single-side cells) are skipped; the centre value is
+                    // always needed for the imaging condition
+                    const bool cpl = NF == 2 && f == 1 && o < ST_NTAP2 && gk[o] != 0.f;
+                    if (o == 0 || g1[o] != 0.f || cpl) {
+                        const float v = __ldg(l1 + q[o]);
+                        if (o == 0) lc[f] = v;
+                        acc += g1[o] * v;
+                        if (NF == 2 && f == 1 && o < ST_NTAP2) accOut[0] += gk[o] * v;
                     }
+                    if (o < ST_NTAP2 && g2[o] != 0.f) acc += g2[o] * __ldg(l2 + q[o]);
                 }
-                const float szz = (s[1] - s[0]) + (s[2] - s[0]), sxx = (s[3] - s[0]) + (s[4] - s[0]);
-                if (FL & ST_F_ISO) gcOut += pre * lc * (szz + sxx);
-                else { gcOut += pre * lc * sxx; gzOut += pre * lc * szz; }
-                if (FL & ST_F_G1) { gaxOut += pre * lc * (s[4] - s[3]); gazOut += pre * lc * (s[2] - s[1]); }
-                grOut += lc * t;
+                accOut[f] += acc;
+            }
+            if (want_grad) {
+                float A0 = 0.f;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const float* S1 = a.s1 + f * a.cs + boff;
+                    const float* S2 = a.s2 + f * a.cs + boff;
+                    float s[ST_NTAP2], t = 0.f;
+#pragma unroll
+                    for (int o = 0; o < ST_NTAP1; ++o) {
+                        if (o < ST_NTAP2) {
+                            s[o] = m[o] * __ldg(S1 + q[o]);
+                            t += h1[o] * s[o];
+                            if (h2[o] != 0.f) t += h2[o] * __ldg(S2 + q[o]);
+                        } else if (h1[o] != 0.f) {
+                            t += h1[o] * __ldg(S1 + q[o]);
+                        }
+                    }
+                    const float szz = (s[1] - s[0]) + (s[2] - s[0]), sxx = (s[3] - s[0]) + (s[4] - s[0]);
+                    float le = pre * lc[f];
+                    if (NF == 2 && f == 0) le += pm_p * lc[1];
+                    if (FL & ST_F_ISO) gcOut += le * (szz + sxx);
+                    else { gcOut += le * sxx; gzOut += le * szz; }
+                    if (FL & ST_F_G1) { gaxOut += le * (s[4] - s[3]); gazOut += le * (s[2] - s[1]); }
+                    if (NF == 2) {
+                        if (f == 0) A0 = cx_p * sxx + cz_p * szz;
+                        else gmOut += (pre * lc[1]) * A0;
+                    }
+                    grOut += lc[f] * t;
+                }
             }
         };
         for (int b = b_lo; b < b_hi; b += 2) {
-            float acc0, acc1 = 0.f, gc1 = 0.f, gr1 = 0.f, gz1 = 0.f, gax1 = 0.f, gaz1 = 0.f;
-            one_shot(b, acc0, gc, gr, gz, gax, gaz);
+            float acc0[NF], acc1[NF], gc1 = 0.f, gr1 = 0.f, gz1 = 0.f, gax1 = 0.f, gaz1 = 0.f, gm1 = 0.f;
+            one_shot(b, acc0, gc, gr, gz, gax, gaz, gm);
             const bool two = b + 1 < b_hi;
-            if (two) one_shot(b + 1, acc1, gc1, gr1, gz1, gax1, gaz1);
-            a.lam0[(long long)b * a.fs + idx] = acc0;
-            if (two) a.lam0[(long long)(b + 1) * a.fs + idx] = acc1;
-            gc += gc1; gr += gr1; gz += gz1; gax += gax1; gaz += gaz1;
+            if (two) one_shot(b + 1, acc1, gc1, gr1, gz1, gax1, gaz1, gm1);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                a.lam0[f * a.cs + (long long)b * a.fs + idx] = acc0[f];
+                if (two) a.lam0[f * a.cs + (long long)(b + 1) * a.fs + idx] = acc1[f];
+            }
+            gc += gc1; gr += gr1; gz += gz1; gax += gax1; gaz += gaz1; gm += gm1;
         }
         if (want_grad) {
             float* gb = a.gacc + (long long)gplane * 7 * plane;
             gb[plane + idx] += gc;              // slot 1: d/d ciso (ISO) or d/d cxx
             if (!(FL & ST_F_ISO)) gb[2 * plane + idx] += gz;                   // slot 2: d/d czz
             if (FL & ST_F_G1) { gb[4 * plane + idx] += gax; gb[5 * plane + idx] += gaz; }
+            if (FL & ST_F_BORN) gb[6 * plane + idx] += gm;                      // slot 6: d/d m
             if (frame) gb[idx] += gr;           // slot 0: d/d r
         }
     }
@@ -789,10 +867,13 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
         const float r = __ldg(a.coef[0] + qq), w = __ldg(a.coef[1] + qq) * f[s];
         if (w != 0.f) {
             for (int b = b_lo; b < b_hi; ++b) {
-                const long long boff = (long long)b * a.fs;
-                const float lq = __ldg(a.lam1 + boff + qq);
-                if (mine(zw, xw)) atomicAdd(a.lam0 + boff + qw, w * (-r * r) * lq);
-                if (want_grad && mine(z, x)) atomicAdd(a.gacc + (long long)gplane * 7 * plane + qq, lq * w * (-2.f * r) * __ldg(a.s1 + boff + qw));
+#pragma unroll
+                for (int fl = 0; fl < NF; ++fl) {
+                    const long long boff = fl * a.cs + (long long)b * a.fs;
+                    const float lq = __ldg(a.lam1 + boff + qq);
+                    if (mine(zw, xw)) atomicAdd(a.lam0 + boff + qw, w * (-r * r) * lq);
+                    if (want_grad && mine(z, x)) atomicAdd(a.gacc + (long long)gplane * 7 * plane + qq, lq * w * (-2.f * r) * __ldg(a.s1 + boff + qw));
+                }
             }
         }
     }
@@ -810,7 +891,7 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
                     if (mine(z, rx)) {
                         const long long o = (long long)a.rec_orig[r] * a.nchan;
                         for (int ch = 0; ch < a.nchan; ++ch)
-                            atomicAdd(a.lam0 + (long long)b * a.fs + (z * g.ld + rx), a.rec_adj[o + ch]);
+                            atomicAdd(a.lam0 + a.chan_f[ch] * a.cs + (long long)b * a.fs + (z * g.ld + rx), a.rec_adj[o + ch]);
                     }
                 }
             }
@@ -820,7 +901,13 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
         __syncthreads();
         for (int s = tid; s < a.ns; s += NT) {
             const int sz = a.src_z[s], sx = a.src_x[s], sb = a.src_b[s];
-            if (sb >= b_lo && sb < b_hi && mine(sz, sx) && (a.src_fmask & 1)) a.gamp[s] = a.lam0[(long long)sb * a.fs + (sz * g.ld + sx)];
+            if (sb >= b_lo && sb < b_hi && mine(sz, sx)) {
+                float v = 0.f;
+#pragma unroll
+                for (int fl = 0; fl < NF; ++fl)
+                    if (a.src_fmask >> fl & 1) v += a.lam0[fl * a.cs + (long long)sb * a.fs + (sz * g.ld + sx)];
+                a.gamp[s] = v;
+            }
         }
     }
 }
@@ -1223,7 +1310,7 @@ __global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W
     // they are scheduled first.  Tapped frame blocks walk all shots themselves.
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     const int ngrp = (a.B + BSH - 1) / BSH;
-    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
+    const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
     const int nframe = HABC ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
     if (bid >= nframe) {
         const int q = bid - nframe;
@@ -1232,7 +1319,7 @@ __global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W
         const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;
         const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
         if (k < nstrip) forward_strip_block(a, k, b_lo, b_hi, tid);
-        else forward_band_block(a, k - nstrip, b_lo, b_hi, tid);
+        else forward_band_block<FL>(a, k - nstrip, b_lo, b_hi, tid);
     } else {
         if constexpr (HABC) {
             int tz, tx;
@@ -1830,7 +1917,7 @@ __global__ void __launch_bounds__(NT, adj_minb<FL>()) wave2d_adjoint_kernel(cons
     if constexpr (adj_fast<FL>()) {
         const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
         const int ngrp = (a.B + BSH - 1) / BSH;
-        const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
+        const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
         const int nband = (FL & ST_F_HABC) ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
         if (bid >= nband) {
             const int q = bid - nband;
@@ -2256,7 +2343,7 @@ int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     if (!(FL & ST_F_HABC)) bt.count = 0;
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
-    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
+    const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
     dim3 grid((unsigned)((long long)nfast * a.B + (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B)));
     wave2d_forward_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
@@ -2277,7 +2364,7 @@ int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw + 1).total + NT - 1) / NT;
     long long nblocks;
-    const int nstrip = tapped ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
+    const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
     if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B) : 0);
     else nblocks = (long long)bt.nxt * bt.nzt * nchunk;
     dim3 grid((unsigned)nblocks);

@@ -68,11 +68,17 @@ ST_HD void st_wrap_candidate(const W2Geom& g, int k, int& z, int& x, int& s, int
     else { z = g.nz - 1; x = w - 1; s = 2; zw = z; xw = 0; }                        // BL diagonal end, left side
 }
 
-// flag sets whose spatial operator fits the 9 taps (no mixed derivative, single field)
+// flag sets whose spatial operator fits the 9 taps (no mixed derivative): the single-field equations, and the Born
+// pair without mixed derivative (acoustic_lsrtm_habc, acoustic_vti_lsrtm_habc) -- both of its fields take the SAME
+// taps (the one-way blend acts on each field by itself, acoustic_vti_lsrtm_habc.py:60-66), the scattered field adds
+// the coupling term  pre m A[p1]  evaluated from the coefficient planes
 ST_HD bool st_flags_tapped(int fl) {
     return fl == (ST_F_ISO | ST_F_HABC) || fl == ST_F_HABC || fl == (ST_F_ISO | ST_F_HABC | ST_F_G1) ||
-           fl == (ST_F_HABC | ST_F_G1);
+           fl == (ST_F_HABC | ST_F_G1) || fl == (ST_F_HABC | ST_F_BORN);
 }
+// ... of which the straight top / bottom strips run on the vectorised strip blocks (single-field equations only; the
+// band threads serve every frame cell of the Born pair)
+ST_HD bool st_flags_stripped(int fl) { return st_flags_tapped(fl) && !(fl & ST_F_BORN); }
 
 #ifdef __CUDACC__
 int st_wave2d_launch_prepare(int flags, const W2Args& a, cudaStream_t st);
