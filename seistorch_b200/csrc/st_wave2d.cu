@@ -58,7 +58,7 @@ constexpr int FH = FRZ * NWARP;             // rows per fast block
 #endif
 constexpr int BSH = ST_BAND_SHOTS;          // shots a band thread walks with its taps in registers
 #ifndef ST_DBG_SKIP
-#define ST_DBG_SKIP 0                       // tuning only: bit 3 = TMA blocks return at once, bit 4 = all tiles as kind 0, bit 5 = corner blocks return
+#define ST_DBG_SKIP 0                       // tuning only: bit 0 / 1 = frame / fast blocks of the register adjoint kernel return at once, bit 3 = TMA blocks return at once, bit 4 = all tiles as kind 0, bit 5 = corner blocks return
 #endif
 // ---- TMA-staged tiles (st_wave2d.cuh: W2Tma)
 constexpr int TC = ST_TMA_TC, TR = ST_TMA_TR, HC = ST_TMA_HC, H1R = ST_TMA_H1, H2R = ST_TMA_H2, XO = ST_TMA_XO;
@@ -1622,19 +1622,34 @@ __device__ __forceinline__ void adjoint_fast_rows_gen(const W2Args& a, const W2G
                 }
             }
             const int ro = z * ld + x;
+            if (clean) {
+                // the whole tile is frame-free and inside the domain: 128-bit stores and gradient read-modify-writes
+                *reinterpret_cast<float4*>(l0 + ro) = out;
+                if (want_grad) {
+                    auto rmw = [&](int slot, const float4& v) {
+                        float4* p4 = reinterpret_cast<float4*>(gb + slot * plane + ro);
+                        *p4 = f4add(*p4, v);
+                    };
+                    rmw(1, g1v);
+                    if (!ISO) rmw(2, g2v);
+                    if (XZ) rmw(3, g3v);
+                    if (G1) { rmw(4, g4v); rmw(5, g5v); }
+                }
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const bool mine = x + e < g.nx && (clean || owns(z, x + e));
-                if (mine) {
-                    l0[ro + e] = f4get(out, e);
-                    if (want_grad) {
-                        gb[plane + ro + e] += f4get(g1v, e);
-                        if (!ISO) gb[2 * plane + ro + e] += f4get(g2v, e);
-                        if (XZ) gb[3 * plane + ro + e] += f4get(g3v, e);
-                        if (G1) { gb[4 * plane + ro + e] += f4get(g4v, e); gb[5 * plane + ro + e] += f4get(g5v, e); }
+                for (int e = 0; e < 4; ++e) {
+                    const bool mine = x + e < g.nx && owns(z, x + e);
+                    if (mine) {
+                        l0[ro + e] = f4get(out, e);
+                        if (want_grad) {
+                            gb[plane + ro + e] += f4get(g1v, e);
+                            if (!ISO) gb[2 * plane + ro + e] += f4get(g2v, e);
+                            if (XZ) gb[3 * plane + ro + e] += f4get(g3v, e);
+                            if (G1) { gb[4 * plane + ro + e] += f4get(g4v, e); gb[5 * plane + ro + e] += f4get(g5v, e); }
+                        }
+                    } else if (x + e >= g.nx && x + e < ld) {
+                        l0[ro + e] = 0.f;
                     }
-                } else if (x + e >= g.nx && x + e < ld) {
-                    l0[ro + e] = 0.f;
                 }
             }
             U = C; C = D;
@@ -1747,19 +1762,34 @@ __device__ __forceinline__ void adjoint_fast_rows_born(const W2Args& a, const W2
                     }
                 }
                 const int ro = z * ld + x;
+                if (clean) {
+                    // the whole tile is frame-free and inside the domain: 128-bit stores and gradient read-modify-writes
+                    *reinterpret_cast<float4*>(l0 + ro) = out;
+                    if (want_grad) {
+                        auto rmw = [&](int slot, const float4& v) {
+                            float4* p4 = reinterpret_cast<float4*>(gb + slot * plane + ro);
+                            *p4 = f4add(*p4, v);
+                        };
+                        rmw(1, g1v);
+                        rmw(2, g2v);
+                        if (XZ) rmw(3, g3v);
+                        if (f == 0) rmw(6, g6v);
+                    }
+                } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const bool mine = x + e < g.nx && (clean || owns(z, x + e));
-                    if (mine) {
-                        l0[ro + e] = f4get(out, e);
-                        if (want_grad) {
-                            gb[plane + ro + e] += f4get(g1v, e);
-                            gb[2 * plane + ro + e] += f4get(g2v, e);
-                            if (XZ) gb[3 * plane + ro + e] += f4get(g3v, e);
-                            if (f == 0) gb[6 * plane + ro + e] += f4get(g6v, e);
+                    for (int e = 0; e < 4; ++e) {
+                        const bool mine = x + e < g.nx && owns(z, x + e);
+                        if (mine) {
+                            l0[ro + e] = f4get(out, e);
+                            if (want_grad) {
+                                gb[plane + ro + e] += f4get(g1v, e);
+                                gb[2 * plane + ro + e] += f4get(g2v, e);
+                                if (XZ) gb[3 * plane + ro + e] += f4get(g3v, e);
+                                if (f == 0) gb[6 * plane + ro + e] += f4get(g6v, e);
+                            }
+                        } else if (x + e >= g.nx && x + e < ld) {
+                            l0[ro + e] = 0.f;
                         }
-                    } else if (x + e >= g.nx && x + e < ld) {
-                        l0[ro + e] = 0.f;
                     }
                 }
                 U = C; C = D;
@@ -1919,6 +1949,8 @@ __global__ void __launch_bounds__(NT, adj_minb<FL>()) wave2d_adjoint_kernel(cons
         const int ngrp = (a.B + BSH - 1) / BSH;
         const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
         const int nband = (FL & ST_F_HABC) ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
+        if ((ST_DBG_SKIP & 1) && bid < nband) return;          // tuning builds only: frame blocks off
+        if ((ST_DBG_SKIP & 2) && bid >= nband) return;         //                     fast blocks off
         if (bid >= nband) {
             const int q = bid - nband;
             adjoint_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid, reinterpret_cast<float (*)[FRZ][FW]>(smem));
