@@ -95,9 +95,15 @@ def build_geometry(case, dtype=torch.float32):
     return names, params, d, src, bidx, rec, counts
 
 
-def simulate(case, dtype=torch.float32, requires_grad=(), wavelet=None):
+def simulate(case, dtype=torch.float32, requires_grad=(), wavelet=None, source_encoding=False):
     """rnn.py:100-216 restated.  Returns (records [list of (nt, nrec, nchan)],
-    params list).  Differentiable w.r.t. params named in requires_grad."""
+    params list).  Differentiable w.r.t. params named in requires_grad.
+
+    ``source_encoding`` (codingfwi.py:129-132,240-241; rnn.py:113,162; source.py:54-55): ONE wavefield (batch 1)
+    into which every source of the case fires with its own wavelet -- ``wavelet`` is then (nsources, nt) -- through
+    ``Y[..., y, x] += X`` (an index_put WITHOUT accumulation: of two sources in the same cell only one counts, a
+    reference quirk this restatement keeps by using the same torch indexing); the receivers are those of the first
+    shot (the driver sets the probes once, codingfwi.py:129-132)."""
     eq = oracle_key(case)
     multiple = bool(case.get("multiple", False))
     names, params, d, src, bidx, rec, counts = build_geometry(case, dtype)
@@ -105,7 +111,10 @@ def simulate(case, dtype=torch.float32, requires_grad=(), wavelet=None):
         p.requires_grad_(n in requires_grad)
     step = equations.get_step(eq, multiple)
     wf_names = equations.WAVEFIELDS[eq]
-    B = len(case["sources"])
+    B = 1 if source_encoding else len(case["sources"])
+    if source_encoding:
+        nrec0 = counts[0]
+        bidx, rec, counts = bidx[:nrec0], rec[:, :nrec0], counts[:1]
     shape = tuple(params[0].shape)
     fields = [torch.zeros((B,) + shape, dtype=dtype) for _ in wf_names]
     dt = torch.tensor(float(case["dt"]), dtype=dtype)   # cell.py:18 0-dim tensor
@@ -117,7 +126,8 @@ def simulate(case, dtype=torch.float32, requires_grad=(), wavelet=None):
     nt = int(case["nt"])
     # one-hot source mask, rnn.py:160-166
     smask = torch.zeros((B,) + shape, dtype=dtype)
-    for b in range(B):
+    st = torch.from_numpy(src)
+    for b in range(0 if source_encoding else B):
         if len(shape) == 2:
             smask[b, src[b, 1], src[b, 0]] = 1.0
         else:  # 3D layout (B, x, z, y); source keys x, y, z
@@ -127,9 +137,17 @@ def simulate(case, dtype=torch.float32, requires_grad=(), wavelet=None):
     recs = {k: [] for k in case["receiver_type"]}
     for i in range(nt):
         fields = list(step(params, fields, dt, h, d))
-        for st in case["source_type"]:
-            k = wf_names.index(st)
-            fields[k] = fields[k] + smask * x[i]
+        for stype in case["source_type"]:
+            k = wf_names.index(stype)
+            if source_encoding:                                    # source.py:54-55  Y_new[..., y, x] += dt * X, dt = 1.0
+                y_new = fields[k].clone()
+                if len(shape) == 2:
+                    y_new[..., st[:, 1], st[:, 0]] += x[:, i].view(1, -1)
+                else:
+                    raise NotImplementedError("the reference has no encoded 3D injection (source.py:59-70)")
+                fields[k] = y_new
+            else:
+                fields[k] = fields[k] + smask * x[i]
         for rtname in case["receiver_type"]:
             f = fields[wf_names.index(rtname)]
             if len(shape) == 2:

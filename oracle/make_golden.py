@@ -84,6 +84,24 @@ def main(argv):
     ref0 = run_reference(l2o, want_grad=False)
     l2o["obs"] = [(r * 0.7).astype(np.float32) for r in ref0["records"]]
     gc["elastic_l2_obs"] = (l2o, "l2")
+    # source encoding (codingfwi.py): 4 sources into one wavefield, one wavelet (random polarity / scale) per source
+    if not argv or any(a in "acoustic_habc_encoded" for a in argv):
+        from .ref_runner import run_reference_encoded
+        enc = cases.make_case("acoustic_habc", nz=30, nx=44, nt=120, nshots=4)
+        rngw = np.random.default_rng(11)
+        wavs = np.stack([np.asarray(enc["wavelet"]) * s for s in (1.0, -1.0, 0.5, -2.0)]).astype(np.float32)
+        arrs = pack_case(enc)
+        arrs["enc_wavelets"] = wavs
+        arrs["loss_name"] = np.frombuffer(b"l2", dtype=np.uint8)
+        for dt in ("float32", "float64"):
+            out = run_reference_encoded(enc, wavs, dtype=dt)
+            tag = "f32" if dt == "float32" else "f64"
+            arrs[f"{tag}_rec_0"] = out["records"][0]
+            arrs[f"{tag}_loss"] = np.float64(out["loss"])
+            for k, v in out["grads"].items():
+                arrs[f"{tag}_grad_{k}"] = v
+        np.savez_compressed(os.path.join(OUT, "acoustic_habc_encoded.npz"), **arrs)
+        print("wrote acoustic_habc_encoded", flush=True)
     for name, (case, loss) in gc.items():
         if argv and not any(a in name for a in argv):
             continue

@@ -131,3 +131,34 @@ def run_reference(case: dict, dtype: str = "float32", want_grad: bool = True,
         return out
     finally:
         torch.set_default_dtype(old_default)
+
+
+def run_reference_encoded(case: dict, wavelets, dtype: str = "float32", want_grad: bool = True, threads: int | None = None):
+    """Source-encoded run through the reference, in the call order of codingfwi.py:88,129-132,240-261: model built with
+    ``source_encoding=True``, probes set ONCE (first shot's receivers), all sources set, ``model(coding_wav)`` with one
+    wavelet per source, L2 against zeros, backward.  Returns dict(records=[one array], loss, grads)."""
+    ref_shim.import_reference()
+    from seistorch.loss import Loss
+    if threads:
+        torch.set_num_threads(threads)
+    tdtype = torch.float64 if dtype == "float64" else torch.float32
+    old_default = torch.get_default_dtype()
+    try:
+        cfg2, model, _x = build_reference(case, dtype, want_grad, False, source_encoding=True)
+        model.reset_probes(model.probes[0])
+        x = torch.as_tensor(np.asarray(wavelets), dtype=tdtype)
+        model.train() if want_grad else model.eval()
+        with torch.set_grad_enabled(want_grad):
+            syn = model(x)
+        out = {"records": [s.detach().numpy().copy() for s in syn]}
+        if want_grad:
+            crit = Loss("l2").loss(cfg2)
+            stacked = torch.stack(list(syn), dim=0)
+            loss = crit(stacked, torch.zeros_like(stacked))
+            loss.backward()
+            out["loss"] = float(loss.item())
+            out["grads"] = {n: getattr(model.cell.geom, n).grad.detach().numpy().copy()
+                            for n in model.cell.geom.model_parameters if getattr(model.cell.geom, n).grad is not None}
+        return out
+    finally:
+        torch.set_default_dtype(old_default)

@@ -64,6 +64,35 @@ def test_source_encoding_and_per_source_wavelets():
     assert rel(rec_enc, tot) < 2e-6
 
 
+def test_source_encoding_against_reference_golden_and_oracle():
+    """Encoded mode against the REAL reference (tests/golden/acoustic_habc_encoded.npz, generated through the call order of
+    codingfwi.py) -- records and the gradient w.r.t. vp -- and against the float64 oracle's encoded mode on a mid-size
+    grid with sources in different tile kinds."""
+    import seistorch_b200 as sb
+    from conftest import load_golden
+    from oracle import cases, loop, misfit
+    z, case = load_golden("acoustic_habc_encoded")
+    for c, w in ((case, z["enc_wavelets"]), (None, None)):
+        if c is None:
+            c = cases.make_case("acoustic_habc", nz=150, nx=300, nshots=5, nt=80, rec_step=7)
+            c["sources"] = [[s[0], 3.0 + 30 * k] for k, s in enumerate(c["sources"])]
+            w = np.stack([np.asarray(c["wavelet"]) * s for s in (1.0, -1.0, 0.5, -2.0, 1.5)]).astype(np.float32)
+        cfg, model = sb.model_from_case(c, device="cuda", mode="inversion", source_encoding=True)
+        model.reset_probes(model.probes[0])
+        syn = model(torch.as_tensor(w, device="cuda"))
+        assert len(syn) == 1
+        (syn[0].double() ** 2).sum().backward()
+        g = model.cell.geom.vp.grad.cpu().numpy()
+        if c is case:
+            assert rel(syn[0].detach().cpu().numpy(), z["f64_rec_0"]) < 1e-5
+            assert rel(g, z["f64_grad_vp"]) < 1e-4
+        else:
+            orecs, params = loop.simulate(c, dtype=torch.float64, requires_grad=["vp"], wavelet=torch.as_tensor(w), source_encoding=True)
+            misfit.l2(orecs, [torch.zeros_like(r) for r in orecs]).backward()
+            assert rel(syn[0].detach().cpu().numpy(), orecs[0].detach().numpy()) < 1e-5
+            assert rel(g, params["vp"].grad.numpy()) < 1e-4
+
+
 def test_empty_receivers_and_zero_wavelet():
     from oracle import cases
     case = cases.make_case("acoustic", nz=20, nx=30, nshots=2, nt=20)

@@ -68,3 +68,19 @@ def test_impulse_response_timing():
     r = recs[0].numpy()[:, :, 0]
     assert r[0, 0] == 1.0 and r[0, 1] == 0.0
     assert abs(r[1, 1] - 0.0225) < 1e-12
+
+
+def test_oracle_source_encoding_matches_reference():
+    """codingfwi.py mode (source.py:54-55, rnn.py:113,162): every source fires into ONE wavefield with its own wavelet.
+    The golden vectors come from the real reference driven like codingfwi.py:88,129-132,240-261
+    (oracle/ref_runner.run_reference_encoded); fp32 bit for bit, fp64 to rounding."""
+    z, case = load_golden("acoustic_habc_encoded")
+    w = torch.as_tensor(z["enc_wavelets"])
+    recs, _ = loop.simulate(case, dtype=torch.float32, wavelet=w, source_encoding=True)
+    assert len(recs) == 1 and np.array_equal(recs[0].numpy(), z["f32_rec_0"])
+    recs, params = loop.simulate(case, dtype=torch.float64, requires_grad=["vp"], wavelet=w, source_encoding=True)
+    assert rel(recs[0].detach().numpy(), z["f64_rec_0"]) < 1e-12
+    loss = misfit.l2(recs, [torch.zeros_like(r) for r in recs])
+    loss.backward()
+    assert abs(float(loss.detach()) - float(z["f64_loss"])) <= 1e-10 * abs(float(z["f64_loss"]))
+    assert rel(params["vp"].grad.numpy(), z["f64_grad_vp"]) < 1e-9
