@@ -182,7 +182,8 @@ int st_elastic2d_adjoint(const st_elastic2d_problem* p, int32_t i_hi, int32_t ns
  * = the reference's (B, x, z, y), n2 fastest with pitch ld.
  * coef[0] = ciso = (vp*dt/h)^2/(1+b*dt), coef[1] = alpha = (1-b*dt)/(1+b*dt), each [n0][n1][ld].
  * The adjoint state `lam` holds the SCALED cotangent w = ciso * dL/dS (the damped acoustic
- * operator is self-adjoint up to that diagonal scaling); gacc receives dL/d ciso.
+ * operator is self-adjoint up to that diagonal scaling); gacc accumulates ciso * dL/d ciso (the sum over time of
+ * w_{i+1} * lap7(S_i)): 1/ciso does not depend on time, the caller divides the plane by ciso once after the last step.
  * ---------------------------------------------------------------------------------- */
 typedef struct st_acoustic3d_problem {
     int32_t B, n0, n1, n2, ld, nt;
@@ -191,7 +192,7 @@ typedef struct st_acoustic3d_problem {
     float* u;                   /* [nslots][B][n0][n1][ld] */
     int32_t nslots;
     float* lam;                 /* [3][B][n0][n1][ld] */
-    float* gacc;                /* [nchunk][n0][n1][ld] += d loss / d ciso, or NULL */
+    float* gacc;                /* [nchunk][n0][n1][ld] += ciso * d loss / d ciso, or NULL */
     int32_t bchunk;
     st_acquisition acq;
 } st_acoustic3d_problem;

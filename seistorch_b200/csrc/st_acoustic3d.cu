@@ -8,7 +8,8 @@
 //                 Lam_i = (1+alpha) Lam_{i+1} + lap7(ciso Lam_{i+1}) - alpha Lam_{i+2}
 //             becomes  w_i = w1 + alpha (w1 - w2) + ciso * lap7(w1)  -- the forward kernel --
 //             plus the imaging condition  g_ciso += (w1/ciso) * lap7(S_i)  and receiver terms
-//             scaled by ciso.  One template serves both.
+//             scaled by ciso.  One template serves both.  The kernel accumulates  w1 * lap7(S_i)  only: 1/ciso does
+//             not depend on time, the caller divides the accumulated plane once (include/seistorch_b200.h).
 //
 // Same streaming structure as the 2D fast path: a warp owns 128 columns (n2, fastest) x RZ
 // rows (n1) of one n0-plane; rows are 128-bit vector loads marched through a 3-row register
@@ -38,12 +39,13 @@ __device__ __forceinline__ void halo3(const float4& c, const float* __restrict__
                                       const G3& g, float& left, float& right) {
     left = __shfl_up_sync(0xffffffffu, c.w, 1);
     right = __shfl_down_sync(0xffffffffu, c.x, 1);
-    if (lane == 0 || lane == 31) {
-        const int xx = lane == 0 ? x0 - 1 : x0 + FW;
-        float v = 0.f;
-        if (i1 >= 0 && i1 < g.n1 && xx >= 0 && xx < g.n2) v = __ldg(base + (i0 * g.ps + (long long)i1 * g.ld + xx));
-        if (lane == 0) left = v; else right = v;
-    }
+    // halo column of the two edge lanes, loaded by every lane (lower half-warp looks left, upper half right) so the
+    // load carries no divergent branch and is issued together with the vector loads
+    const int xx = lane < 16 ? x0 - 1 : x0 + FW;
+    float v = 0.f;
+    if (i1 >= 0 && i1 < g.n1 && xx >= 0 && xx < g.n2) v = __ldg(base + (i0 * g.ps + (long long)i1 * g.ld + xx));
+    left = lane == 0 ? v : left;
+    right = lane == 31 ? v : right;
 }
 __device__ __forceinline__ float lap7(const float4& C, const float4& U, const float4& D, const float4& F, const float4& Bk,
                                       float l, float r, int e) {
@@ -118,11 +120,8 @@ __global__ void __launch_bounds__(NT, ADJ ? 3 : 4) acoustic3d_kernel(const A3Arg
                         halo3(sC, S, i0, z, x0, lane, g, sl, sr);
                         float4 acc = gsl[k * (FW / 4)];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float ci = f4get(CI, e);
-                            const float lam = ci != 0.f ? f4get(C, e) / ci : 0.f;          // Lam_{i+1} = w1 / ciso
-                            f4set(acc, e, f4get(acc, e) + lam * lap7(sC, sU, sD, sF, sB, sl, sr, e));
-                        }
+                        for (int e = 0; e < 4; ++e)       // w1 * lap7(S_i); the time-invariant factor 1/ciso is applied once
+                            f4set(acc, e, f4get(acc, e) + f4get(C, e) * lap7(sC, sU, sD, sF, sB, sl, sr, e));   // by the caller
                         gsl[k * (FW / 4)] = acc;
                         sU = sC; sC = sD;
                     }
@@ -187,9 +186,15 @@ __global__ void __launch_bounds__(NT, ADJ ? 3 : 4) acoustic3d_kernel(const A3Arg
             if (z < zn) {
                 float* o = gb + (i0 * g.ps + (long long)z * g.ld + x);
                 const float4 acc = gsl[k * (FW / 4)];
+                if (full) {
+                    float4 v = *reinterpret_cast<float4*>(o);
+                    v.x += acc.x; v.y += acc.y; v.z += acc.z; v.w += acc.w;
+                    *reinterpret_cast<float4*>(o) = v;
+                } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (x + e < g.n2) o[e] += f4get(acc, e);
+                    for (int e = 0; e < 4; ++e)
+                        if (x + e < g.n2) o[e] += f4get(acc, e);
+                }
             }
         }
     }

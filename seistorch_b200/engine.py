@@ -508,7 +508,13 @@ class _Propagate(torch.autograd.Function):
             elif spec.family == "elastic2d":
                 grads.append(None if k == 0 else g[k - 1].to(ctx.coef_dtypes[k]))
             else:
-                grads.append(g[0].to(ctx.coef_dtypes[k]) if k == 0 else None)
+                if k == 0:
+                    # acoustic3d: the kernel accumulates ciso * dL/dciso (st_acoustic3d.cu); divide once
+                    ciso = prob.coefp[0].view(*spec.shape[:-1], spec.ld)[..., :spec.shape[-1]]
+                    g0 = torch.where(ciso != 0, g[0] / ciso, torch.zeros_like(g[0]))
+                    grads.append(g0.to(ctx.coef_dtypes[k]))
+                else:
+                    grads.append(None)
         gamp = prob.gamp.to(ctx.amp_dtype) if want_gamp else None
         # free the big buffers eagerly
         ctx.prob = None

@@ -112,7 +112,8 @@ class _Step(torch.autograd.Function):
                     gi = _W2_GRAD_OF_COEF.get(spec.coef_slots[k])
                     gcoefs.append(None if gi is None else g[gi])
                 else:
-                    gcoefs.append(g[0] if k == 0 else None)
+                    # acoustic3d: the kernel accumulates ciso * dL/dciso; divide once (st_acoustic3d.cu)
+                    gcoefs.append(g[0] * inv if (k == 0 and scale is not None) else (g[0] if k == 0 else None))
         else:
             # first order: Lam_i from Lam_{i+1} = g_out; S_i in slot 0, S_{i+1} (no source added) in slot 1
             gl = _to_slots(gouts, spec).reshape(-1)
@@ -154,7 +155,12 @@ def time_step(equation, ndim, *args, **kwargs):
     else:
         family, flags = _coef.EQUATIONS[equation]
         coefs, slots = _coef.wave2d_coefficients(equation, params, dtf, hf, d)
-        spec = Spec(family, flags, shape, B, 1, dtf, multiple=multiple, coef_slots=slots)
+        # absorbing width = depth of the one-way masks the caller built (cell.setup_habc: bottom mask is [B, bw, nx]);
+        # the whole-loop path passes geom.bwidth, the two agree by construction
+        bw = 50
+        if habcs is not None and habcs[1] is not None:
+            bw = int(habcs[1].shape[-2])
+        spec = Spec(family, flags, shape, B, 1, dtf, bw=bw, multiple=multiple, coef_slots=slots)
     return _Step.apply(spec, len(coefs), *coefs, *fields)
 
 
