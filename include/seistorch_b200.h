@@ -252,6 +252,13 @@ int st_misfit_envelope(const float* syn, const float* obs, int32_t nt, int32_t n
                        float* workspace, void* stream);
 int64_t st_misfit_envelope_workspace(int32_t nt, int32_t ntraces);
 
+/* ---- gradient post-processing ------------------------------------------------------------------------------------
+ * One pass of the reference's gradient smoothing (process.py:66-112 -> signal.py:247-319): truncated Gaussian of
+ * `2*radius+1` normalised `weights` along `axis` (0 = z / rows, 1 = x / columns) of a contiguous [nz][nx] plane with
+ * numpy 'reflect' boundaries.  in != out; radius < n along the axis. */
+int st_gaussian_smooth2d(const float* in, float* out, int32_t nz, int32_t nx, const float* weights, int32_t radius,
+                         int32_t axis, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

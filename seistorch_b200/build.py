@@ -41,7 +41,7 @@ def _units():
     units = [("st_api", "st_api.cu", []), ("st_elastic2d", "st_elastic2d.cu", []),
              ("st_acoustic3d", "st_acoustic3d.cu", []), ("st_misfit", "st_misfit.cu", []),
              ("st_wave2d_band", "st_wave2d_band.cu", []), ("st_tma", "st_tma.cu", []),
-             ("st_wave2d_persist", "st_wave2d_persist.cu", []),
+             ("st_wave2d_persist", "st_wave2d_persist.cu", []), ("st_postproc", "st_postproc.cu", []),
              ("st_wave2d_dispatch", "st_wave2d.cu", ["-DST_W2_DISPATCH_ONLY"])]
     for fl in W2_FLAG_SETS:
         units.append((f"st_wave2d_{fl}", "st_wave2d.cu", [f"-DST_W2_INSTANCE={fl}"]))

@@ -1,0 +1,54 @@
+// Gradient post-processing on the device (include/seistorch_b200.h: st_gaussian_smooth2d).
+//
+// Reference: PostProcess.smooth_gradient (seistorch/process.py:66-112) copies every parameter gradient to the host,
+// reflect-pads it with numpy, convolves it with a truncated Gaussian along z then x through conv2d on the CPU
+// (signal.py:247-319) `counts` times, and copies it back.  One pass of that filter is
+//     y(i) = sum_{j=-p..p} w[j+p] x(mirror(i+j)),   mirror = numpy 'reflect' (no edge repeat), p = radius,
+// with the normalised weights w (kernel size 2 radius + 1; the reference's even kernel size for odd radii changes the
+// array shape and cannot be assigned back to the parameter: not supported, the Python wrapper raises).
+// One thread per output element; the gradient plane (<= 8 MB at the BASELINE sizes) lives in L2.
+#include <cuda_runtime.h>
+
+#include "../../include/seistorch_b200.h"
+#include "st_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int mirror(int i, int n) {
+    // numpy.pad(mode='reflect') index map, valid for |offset| < n
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) gaussian_smooth2d_kernel(const float* __restrict__ in, float* __restrict__ out, int nz, int nx,
+                                                                 const float* __restrict__ w, int radius, int axis) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (x >= nx || z >= nz) return;
+    float acc = 0.f;
+    if (axis == 0) {
+        for (int j = -radius; j <= radius; ++j) acc += __ldg(w + j + radius) * __ldg(in + (long long)mirror(z + j, nz) * nx + x);
+    } else {
+        const float* row = in + (long long)z * nx;
+        for (int j = -radius; j <= radius; ++j) acc += __ldg(w + j + radius) * __ldg(row + mirror(x + j, nx));
+    }
+    out[(long long)z * nx + x] = acc;
+}
+
+}  // namespace
+
+extern "C" int st_gaussian_smooth2d(const float* in, float* out, int32_t nz, int32_t nx, const float* weights, int32_t radius,
+                                    int32_t axis, void* stream) {
+    if (!in || !out || !weights || nz <= 0 || nx <= 0 || radius < 0 || (axis != 0 && axis != 1) || in == out) {
+        st_set_error("gaussian_smooth2d: bad arguments");
+        return ST_ERR_BADARG;
+    }
+    if (radius >= (axis == 0 ? nz : nx)) {
+        st_set_error("gaussian_smooth2d: radius %d does not fit the axis (reflect padding needs radius < n)", radius);
+        return ST_ERR_UNSUPPORTED;
+    }
+    dim3 grid((nx + 255) / 256, nz);
+    gaussian_smooth2d_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, nz, nx, weights, radius, axis);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("gaussian_smooth2d: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}

@@ -66,7 +66,32 @@ def patch_signal(reference_package: str = "seistorch"):
     return True
 
 
-def install(reference_package: str = "seistorch", losses: bool = True, signal: bool = True):
+def patch_process(reference_package: str = "seistorch"):
+    """``PostProcess.smooth_gradient`` (process.py:66-112) stays on the device when the gradients live there (even
+    radii: the only ones the reference can assign back); anything else keeps the reference's own code."""
+    from . import process as ours
+    ref = importlib.import_module(f"{reference_package}.process")
+    cls = ref.PostProcess
+    if getattr(cls.smooth_gradient, "_seistorch_b200", False):
+        return False
+    orig = cls.smooth_gradient
+
+    def smooth_gradient(self):
+        sm = self.cfg["training"]["smooth"]
+        grads = [p.grad for p in self.model.parameters() if p.requires_grad and p.grad is not None]
+        even = all(int(r) % 2 == 0 for r in sm["radius"].values())
+        if grads and even and all(g.is_cuda and g.ndim == 2 for g in grads):
+            if getattr(self.commands, "grad_cut", False):
+                self.modelmask = self.modelmask.to(grads[0].device)
+            return ours.PostProcess.smooth_gradient(self)
+        return orig(self)
+
+    smooth_gradient._seistorch_b200 = True
+    cls.smooth_gradient = smooth_gradient
+    return True
+
+
+def install(reference_package: str = "seistorch", losses: bool = True, signal: bool = True, process: bool = True):
     """Register our modules under the reference package's names (idempotent)."""
     pairs = [(f"{reference_package}.{m}", f"seistorch_b200.{m}") for m in _MODULES]
     pairs += [(f"{reference_package}.equations2d.{e}", f"seistorch_b200.equations2d.{e}") for e in _EQ2D]
@@ -90,6 +115,12 @@ def install(reference_package: str = "seistorch", losses: bool = True, signal: b
         try:
             if patch_signal(reference_package):
                 names.append(f"{reference_package}.signal.SeisSignal.filter")
+        except ImportError:
+            pass
+    if process:
+        try:
+            if patch_process(reference_package):
+                names.append(f"{reference_package}.process.PostProcess.smooth_gradient")
         except ImportError:
             pass
     return names
