@@ -548,13 +548,54 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
 
 // ------------------------------------------------------------------------------ band (tap gather)
 // rows touched by the 256 consecutive band cells of a block -> shared list (<= 16 rows)
-__device__ __forceinline__ int band_block_rows(const BandCells& bc, int i, int tid, int* s_rows, int* s_cnt) {
+// ---- cell maps of the tap-gather blocks: which cell a thread owns, which cells the block owns
+// BandMap: the compact enumeration of the absorbing band (st_band_cells), minus the vectorised strips, NT cells per block
+struct BandMap {
+    W2Geom g; BandCells bc; StripGeom sg; bool strips, frame_only; int i0;
+    __device__ __forceinline__ bool cell(int t, int& z, int& x) const {
+        const int i = i0 + t;
+        if (t < 0 || i >= bc.total) return false;
+        st_band_decode(bc, i, z, x);
+        return !(strips && in_strip(sg, g, z, x));
+    }
+    __device__ __forceinline__ bool mine(int z, int x) const {
+        if (z < 0 || z >= g.nz || x < 0 || x >= g.nx || (frame_only && !w2_in_frame(z, x, g)) || (strips && in_strip(sg, g, z, x))) return false;
+        const int e = st_band_encode(bc, z, x);
+        return e >= i0 && e < i0 + NT;
+    }
+    // true when none of the block's cells lies in the acquisition row range (block-uniform)
+    __device__ __forceinline__ bool outside_rows(const W2Args& a) const {
+        int zf, xf, zl, xl;
+        st_band_decode(bc, i0, zf, xf);
+        st_band_decode(bc, min(i0 + NT, bc.total) - 1, zl, xl);
+        const int lo = min(zf, zl), hi = max(zf, zl);
+        // rows of a block are contiguous inside one rectangle; straddling blocks are never skipped
+        const bool same = (i0 + NT <= bc.n_top) || (i0 >= bc.n_top && i0 + NT <= bc.n_top + bc.n_bot) || (i0 >= bc.n_top + bc.n_bot);
+        return same && (hi < a.row_lo || lo > a.row_hi);
+    }
+};
+// RectMap: NT/w rows x w columns of a rectangle (the corner tiles of the TMA launches: every cell, frame or not)
+struct RectMap {
+    W2Geom g; int z0, x0, w;            // first row / column of the block's cells, columns per row
+    __device__ __forceinline__ bool cell(int t, int& z, int& x) const {
+        if (t < 0) return false;
+        z = z0 + t / w; x = x0 + t % w;
+        return z < g.nz && x < g.nx;
+    }
+    __device__ __forceinline__ bool mine(int z, int x) const {
+        return z >= z0 && z < z0 + NT / w && z < g.nz && x >= x0 && x < x0 + w && x < g.nx;
+    }
+    __device__ __forceinline__ bool outside_rows(const W2Args& a) const { return z0 + NT / w - 1 < a.row_lo || z0 > a.row_hi; }
+};
+
+// distinct rows of the block's cells (at most 16 per block), for the receiver epilogue
+template <class Map>
+__device__ __forceinline__ int tap_block_rows(const Map& map, int tid, int* s_rows, int* s_cnt) {
     if (tid == 0) *s_cnt = 0;
     __syncthreads();
-    if (i < bc.total) {
-        int z, x, zp = -1, xp;
-        st_band_decode(bc, i, z, x);
-        if (tid > 0) st_band_decode(bc, i - 1, zp, xp);
+    int z, x, zp = -1, xp;
+    if (map.cell(tid, z, x)) {
+        if (!map.cell(tid - 1, zp, xp)) zp = -1;
         if (z != zp) {
             const int k = atomicAdd(s_cnt, 1);
             if (k < 16) s_rows[k] = z;
@@ -564,36 +605,16 @@ __device__ __forceinline__ int band_block_rows(const BandCells& bc, int i, int t
     return min(*s_cnt, 16);
 }
 
-// Every thread owns ONE band cell and walks all shots with its taps held in registers, so the
+// Every thread owns ONE cell and walks all shots with its taps held in registers, so the
 // tap planes are read once per step, not once per shot.
-// true when none of the block's band cells lies in the acquisition row range (block-uniform)
-__device__ __forceinline__ bool band_block_outside_rows(const W2Args& a, const BandCells& bc, int i0) {
-    int zf, xf, zl, xl;
-    st_band_decode(bc, i0, zf, xf);
-    st_band_decode(bc, min(i0 + NT, bc.total) - 1, zl, xl);
-    const int lo = min(zf, zl), hi = max(zf, zl);
-    // rows of a block are contiguous inside one rectangle; straddling blocks are never skipped
-    const bool same = (i0 + NT <= bc.n_top) || (i0 >= bc.n_top && i0 + NT <= bc.n_top + bc.n_bot) || (i0 >= bc.n_top + bc.n_bot);
-    return same && (hi < a.row_lo || lo > a.row_hi);
-}
-
-template <int FL>
-__device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int b_lo, int b_hi, int tid) {
+template <int FL, class Map>
+__device__ __forceinline__ void forward_tap_block(const W2Args& a, const Map& map, int b_lo, int b_hi, int tid) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
-    constexpr bool STRIPS = !(FL & ST_F_BORN);               // st_flags_stripped
     const W2Geom g = a.g;
-    const BandCells bc = st_band_cells(g, g.bw);
-    const int i0 = blk * NT, i = i0 + tid;
     const long long plane = (long long)g.nz * g.ld;
-    const StripGeom sg = strip_geom(g, g.bw);
-    auto mine = [&](int z, int x) {
-        if (z < 0 || z >= g.nz || x < 0 || x >= g.nx || !w2_in_frame(z, x, g) || (STRIPS && in_strip(sg, g, z, x))) return false;
-        const int e = st_band_encode(bc, z, x);
-        return e >= i0 && e < i0 + NT;
-    };
+    auto mine = [&](int z, int x) { return map.mine(z, x); };
     int zc = -1, xc = -1;
-    if (i < bc.total) st_band_decode(bc, i, zc, xc);
-    if (i < bc.total && !(STRIPS && in_strip(sg, g, zc, xc))) {          // strip cells belong to the vectorised strip blocks
+    if (map.cell(tid, zc, xc)) {
         const int z = zc, x = xc;
         const int idx = z * g.ld + x;
         // increment form: Y = h1 + (h1 - h2) + sum_{o != 0} F1[o] (h1(p+o) - h1(p)) + F2[o] (h2(p+o) - h2(p))
@@ -689,7 +710,7 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
                 }
         }
     }
-    if (band_block_outside_rows(a, bc, i0)) return;
+    if (map.outside_rows(a)) return;
     __syncthreads();
     for (int s = tid; s < a.ns; s += NT) {
         const int sz = a.src_z[s], sx = a.src_x[s], sb = a.src_b[s];
@@ -701,7 +722,7 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
     }
     if (!a.rec_out) return;
     __shared__ int s_cnt, s_rows[16];
-    const int cnt = band_block_rows(bc, i, tid, s_rows, &s_cnt);
+    const int cnt = tap_block_rows(map, tid, s_rows, &s_cnt);
     for (int k = 0; k < cnt; ++k) {
         const int z = s_rows[k];
         for (int b = b_lo; b < b_hi; ++b) {
@@ -719,25 +740,21 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
 }
 
 template <int FL>
-__device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int b_lo, int b_hi, int gplane, int tid) {
+__device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int b_lo, int b_hi, int tid) {
+    const BandMap map{a.g, st_band_cells(a.g, a.g.bw), strip_geom(a.g, a.g.bw), st_flags_stripped(FL), true, blk * NT};
+    forward_tap_block<FL>(a, map, b_lo, b_hi, tid);
+}
+
+template <int FL, class Map>
+__device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& map, int b_lo, int b_hi, int gplane, int tid) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
-    constexpr bool STRIPS = !(FL & ST_F_BORN);               // st_flags_stripped
     const W2Geom g = a.g;
-    const int bd = g.bw + 1;
-    const BandCells bc = st_band_cells(g, bd);
-    const int i0 = blk * NT, i = i0 + tid;
     const long long plane = (long long)g.nz * g.ld;
     const bool want_grad = a.gacc != nullptr;
     auto inb = [&](int z, int x) { return z >= 0 && z < g.nz && x >= 0 && x < g.nx; };
-    const StripGeom sg = strip_geom(g, bd);
-    auto mine = [&](int z, int x) {
-        if (!inb(z, x) || (STRIPS && in_strip(sg, g, z, x))) return false;
-        const int e = st_band_encode(bc, z, x);
-        return e >= i0 && e < i0 + NT;
-    };
+    auto mine = [&](int z, int x) { return map.mine(z, x); };
     int zc = -1, xc = -1;
-    if (i < bc.total) st_band_decode(bc, i, zc, xc);
-    if (i < bc.total && !(STRIPS && in_strip(sg, g, zc, xc))) {          // strip cells belong to the vectorised strip blocks
+    if (map.cell(tid, zc, xc)) {
         const int z = zc, x = xc;
         const int idx = z * g.ld + x;
         // transposed taps: coefficient of L(p+o) is the tap -o of cell p+o
@@ -877,11 +894,11 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
             }
         }
     }
-    if (band_block_outside_rows(a, bc, i0)) return;
+    if (map.outside_rows(a)) return;
     __syncthreads();
     if (a.rec_adj) {
         __shared__ int s_cnt, s_rows[16];
-        const int cnt = band_block_rows(bc, i, tid, s_rows, &s_cnt);
+        const int cnt = tap_block_rows(map, tid, s_rows, &s_cnt);
         for (int k = 0; k < cnt; ++k) {
             const int z = s_rows[k];
             for (int b = b_lo; b < b_hi; ++b) {
@@ -912,6 +929,12 @@ __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int
     }
 }
 
+
+template <int FL>
+__device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int b_lo, int b_hi, int gplane, int tid) {
+    const BandMap map{a.g, st_band_cells(a.g, a.g.bw + 1), strip_geom(a.g, a.g.bw + 1), st_flags_stripped(FL), false, blk * NT};
+    adjoint_tap_block<FL>(a, map, b_lo, b_hi, gplane, tid);
+}
 
 // ------------------------------------------------------------------------------ forward
 // rows of one warp tile.  SAFE: every load of the tile (rows z0-1..z0+FRZ, columns x0-1..x0+FW)
@@ -1137,6 +1160,14 @@ __host__ __device__ inline CornerTiles corner_tiles(const W2Tma& tm, const W2Geo
     c.count = (c.rt + c.rb) * 2;
     return c;
 }
+// blocks that serve the corner tiles of one launch.  With the precomputed frame taps (acoustic_habc: always, see
+// st_wave2d_prepare) a corner tile is cut into TX*TZ/NT blocks of NT cells, one cell per thread, each walking a group of
+// up to BSH shots with its taps in registers (forward_tap_block / adjoint_tap_block on a RectMap); without taps one
+// generic per-cell block per (tile, shot).
+constexpr int CORNER_SUB = TX * TZ / NT;                    // tap blocks per corner tile (4 rows x 64 columns each)
+__host__ __device__ inline int corner_block_count(const CornerTiles& c, int B, bool tapped) {
+    return tapped ? c.count * CORNER_SUB * ((B + BSH - 1) / BSH) : c.count * B;
+}
 __device__ __forceinline__ void corner_tile_decode(const CornerTiles& c, const W2Tma& tm, const W2Geom& g, int i, int& tz, int& xoff) {
     const int ri = i >> 1;
     tz = ri < c.rt ? ri : tm.sr1 * TR / TZ + (ri - c.rt);
@@ -1342,16 +1373,24 @@ __global__ void __launch_bounds__(NT, tma_fwd_minb<FL>()) wave2d_forward_tma_ker
     extern __shared__ __align__(128) unsigned char dsm[];
     const int bid = blockIdx.x, tid = threadIdx.x;
     const CornerTiles ct = corner_tiles(tm, a.g);
-    const int ncorner = ct.count * a.B;
+    const bool ctap = st_flags_tapped(FL) && a.taps != nullptr;
+    const int ncorner = corner_block_count(ct, a.B, ctap);
     st_pdl_launch_dependents();
     if (bid < ncorner) {
         st_pdl_wait();
         if (ST_DBG_SKIP & 32) return;
         if constexpr ((FL & ST_F_HABC) != 0) {
             int tz, tx;
-            const int b = bid / ct.count;
-            corner_tile_decode(ct, tm, a.g, bid - b * ct.count, tz, tx);
-            forward_frame_block<FL, true, ST_CORNER_UNROLL>(a, tz, 0, b, tid, reinterpret_cast<float (*)[SH][SW]>(dsm), tx);
+            if (ctap) {
+                const int per = ct.count * CORNER_SUB, grp = bid / per, r = bid - grp * per;
+                corner_tile_decode(ct, tm, a.g, r / CORNER_SUB, tz, tx);
+                const RectMap map{a.g, tz * TZ + (r % CORNER_SUB) * (NT / TX), tx, TX};
+                forward_tap_block<FL>(a, map, grp * BSH, min(grp * BSH + BSH, a.B), tid);
+            } else {
+                const int b = bid / ct.count;
+                corner_tile_decode(ct, tm, a.g, bid - b * ct.count, tz, tx);
+                forward_frame_block<FL, true, ST_CORNER_UNROLL>(a, tz, 0, b, tid, reinterpret_cast<float (*)[SH][SW]>(dsm), tx);
+            }
         }
         return;
     }
@@ -2309,7 +2348,8 @@ __global__ void __launch_bounds__(NT, tma_adj_minb<FL>()) wave2d_adjoint_tma_ker
     extern __shared__ __align__(128) unsigned char dsm[];
     const int bid = blockIdx.x, tid = threadIdx.x;
     const CornerTiles ct = corner_tiles(tm, a.g);
-    const int ncorner = ct.count * a.B;
+    const bool ctap = st_flags_tapped(FL) && a.taps != nullptr;
+    const int ncorner = corner_block_count(ct, a.B, ctap);
 #ifdef ST_DBG_TIMELINE
     const unsigned long long t0 = dbg_now();
 #endif
@@ -2319,11 +2359,19 @@ __global__ void __launch_bounds__(NT, tma_adj_minb<FL>()) wave2d_adjoint_tma_ker
         if (ST_DBG_SKIP & 32) return;
         if constexpr ((FL & ST_F_HABC) != 0) {
             int tz, tx;
-            const int b = bid / ct.count;
-            corner_tile_decode(ct, tm, a.g, bid - b * ct.count, tz, tx);
-            float* smem = reinterpret_cast<float*>(dsm);
-            adjoint_general_block<FL, ST_CORNER_UNROLL>(a, tz, 0, b, b + 1, b, tid, -1, reinterpret_cast<float (*)[SH][SW]>(smem),
-                                      reinterpret_cast<float (*)[SH][SW]>(smem + SH * SW), tx);
+            if (ctap) {
+                // gradient plane = shot-group id (fewer than B planes; the TMA blocks own other cells of it)
+                const int per = ct.count * CORNER_SUB, grp = bid / per, r = bid - grp * per;
+                corner_tile_decode(ct, tm, a.g, r / CORNER_SUB, tz, tx);
+                const RectMap map{a.g, tz * TZ + (r % CORNER_SUB) * (NT / TX), tx, TX};
+                adjoint_tap_block<FL>(a, map, grp * BSH, min(grp * BSH + BSH, a.B), grp, tid);
+            } else {
+                const int b = bid / ct.count;
+                corner_tile_decode(ct, tm, a.g, bid - b * ct.count, tz, tx);
+                float* smem = reinterpret_cast<float*>(dsm);
+                adjoint_general_block<FL, ST_CORNER_UNROLL>(a, tz, 0, b, b + 1, b, tid, -1, reinterpret_cast<float (*)[SH][SW]>(smem),
+                                          reinterpret_cast<float (*)[SH][SW]>(smem + SH * SW), tx);
+            }
         }
     } else {
         if (ST_DBG_SKIP & 8) return;
@@ -2366,7 +2414,8 @@ int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     if constexpr (tma_ok<FL>()) {
         if (tm.enabled) {
             if (st_set_max_smem<wave2d_forward_tma_kernel<FL>>(tma_fwd_smem<FL>()) != cudaSuccess) return ST_ERR_CUDA;
-            dim3 grid((unsigned)((long long)corner_tiles(tm, a.g).count * a.B + tma_blocks(tm, a.B)));
+            const bool ctap = st_flags_tapped(FL) && a.taps != nullptr;
+            dim3 grid((unsigned)((long long)corner_block_count(corner_tiles(tm, a.g), a.B, ctap) + tma_blocks(tm, a.B)));
             return tma_launch(wave2d_forward_tma_kernel<FL>, grid, tma_fwd_smem<FL>(), st, a, nfx, tm);
         }
     }
@@ -2387,7 +2436,8 @@ int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     if constexpr (tma_ok<FL>()) {
         if (tm.enabled) {
             if (st_set_max_smem<wave2d_adjoint_tma_kernel<FL>>(tma_adj_smem<FL>()) != cudaSuccess) return ST_ERR_CUDA;
-            dim3 grid((unsigned)((long long)corner_tiles(tm, a.g).count * a.B + tma_blocks(tm, a.B)));
+            const bool ctap = st_flags_tapped(FL) && a.taps != nullptr;
+            dim3 grid((unsigned)((long long)corner_block_count(corner_tiles(tm, a.g), a.B, ctap) + tma_blocks(tm, a.B)));
             return tma_launch(wave2d_adjoint_tma_kernel<FL>, grid, tma_adj_smem<FL>(), st, a, nfx, tm);
         }
     }
