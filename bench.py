@@ -609,23 +609,25 @@ def main():
                                          "note": "no_grad: 3 rolling state slots, nothing kept"}}
         dom, ach, t_dom = k_fwd, w["fwd_bytes"] * fd, t_mod
         if gradient:
-            syn = model(wav, None, ss, pp)                             # untimed pass: history buffer allocation, plans
-            crit(torch.stack(list(syn), 0), obs_host[lo:hi].to(dev)).backward()
-            del syn
-            torch.cuda.synchronize()
-            ev[2].record()
-            syn = model(wav, None, ss, pp)                             # the forward of the timed step: writes the history
-            ev[3].record()
-            loss = crit(torch.stack(list(syn), 0), obs_host[lo:hi].to(dev))
-            torch.cuda.synchronize()
-            ev[4].record()
-            loss.backward()
-            ev[5].record()
-            torch.cuda.synchronize()
-            t_fwd = ev[2].elapsed_time(ev[3]) / nt
+            ob0 = obs_host[lo:hi].to(dev)
+            t_fwd, t_bwd = 1e30, 1e30
+            for rep in range(3):                                       # pass 0 is untimed (history buffer allocation, plans);
+                torch.cuda.synchronize()                               # best of the next two: one launch sequence each
+                ev[2].record()
+                syn = model(wav, None, ss, pp)                         # the forward of the timed step: writes the history
+                ev[3].record()
+                loss = crit(torch.stack(list(syn), 0), ob0)
+                torch.cuda.synchronize()
+                ev[4].record()
+                loss.backward()
+                ev[5].record()
+                torch.cuda.synchronize()
+                if rep > 0:
+                    t_fwd = min(t_fwd, ev[2].elapsed_time(ev[3]) / nt)
+                    t_bwd = min(t_bwd, ev[4].elapsed_time(ev[5]))
+                del syn, loss
             nadj = max(engine.LAUNCHES_LAST.get("adjoint", nt), 1)
             nrec = engine.LAUNCHES_LAST.get("recompute", 0)
-            t_bwd = ev[4].elapsed_time(ev[5])
             t_adj = (t_bwd - nrec * t_fwd) / nadj                      # recomputed forward steps (checkpoints) taken out
             fwd_gbs = w["fwd_bytes"] * B * npts / (t_fwd * 1e-3) / 1e9
             adj_gbs = w["adj_bytes"] * B * npts / (t_adj * 1e-3) / 1e9

@@ -79,6 +79,19 @@ struct StressRow { float4 xx, zz, xz; float xx_r, xz_l; };
 // the four one-sided differences that the reference zeroes at the edges (equations2d/utils.py:3-48: D+ is 0 at index
 // 0, D- is 0 at the last index) are multiplied by 0/1 masks; nothing else differs, so the interior tiles (EDGE =
 // false) skip all of it.
+#ifndef ST_EL_STORE
+#define ST_EL_STORE 0                       // tuning: 1 = streaming (evict-first) stores of the new state, 2 = write-through
+#endif
+__device__ __forceinline__ void st4(float* p, const float4& v) {
+#if ST_EL_STORE == 1
+    __stcs(reinterpret_cast<float4*>(p), v);
+#elif ST_EL_STORE == 2
+    __stwt(reinterpret_cast<float4*>(p), v);
+#else
+    *reinterpret_cast<float4*>(p) = v;
+#endif
+}
+
 template <bool EDGE>
 __device__ __forceinline__ void elastic_forward_fast(const E2Args& a, int fx, int fz, int b, int tid) {
     const int ld = a.ld, nz = a.nz, nx = a.nx;
@@ -165,9 +178,9 @@ __device__ __forceinline__ void elastic_forward_fast(const E2Args& a, int fx, in
         const StressRow sn = stress(z + 1, vxm, vx0, vz0, vz1);
         const bool st_ok = !EDGE || (z < nz && x < ld);       // pad columns [nx, ld) come out as exact zeros (zero coefficients)
         if (st_ok) {
-            *reinterpret_cast<float4*>(nxt + 2 * cs + ro) = sc.xx;
-            *reinterpret_cast<float4*>(nxt + 3 * cs + ro) = sc.zz;
-            *reinterpret_cast<float4*>(nxt + 4 * cs + ro) = sc.xz;
+            st4(nxt + 2 * cs + ro, sc.xx);
+            st4(nxt + 3 * cs + ro, sc.zz);
+            st4(nxt + 4 * cs + ro, sc.xz);
         }
         const float mz0 = (!EDGE || z > 0) ? 1.f : 0.f, mz1 = (!EDGE || z < nz - 1) ? 1.f : 0.f;
         float txx_r = __shfl_down_sync(0xffffffffu, sc.xx.x, 1);
@@ -187,8 +200,8 @@ __device__ __forceinline__ void elastic_forward_fast(const E2Args& a, int fx, in
             f4s(nvz, e, f4g(ca, e) * f4g(vz_old, e) + f4g(cb, e) * (txz_x + tzz_z));
         }
         if (st_ok) {
-            *reinterpret_cast<float4*>(nxt + ro) = nvx;
-            *reinterpret_cast<float4*>(nxt + cs + ro) = nvz;
+            st4(nxt + ro, nvx);
+            st4(nxt + cs + ro, nvz);
         }
         tzz_prev = sc.zz;
         sc = sn;
