@@ -304,6 +304,9 @@ __device__ __forceinline__ void elastic_adjoint_tail(const E2Args& a, int b, int
 #ifndef ST_EL_AFRZ
 #define ST_EL_AFRZ 4
 #endif
+#ifndef ST_EL_PF
+#define ST_EL_PF 0                          // tuning: 1 = L2 prefetch of the warp's rows before the marching loop (adjoint)
+#endif
 #ifndef ST_EL_AMINB
 #define ST_EL_AMINB 2
 #endif
@@ -458,6 +461,22 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
         return o;
     };
 
+#if ST_EL_PF
+    // pull every row this warp will stream into L2 up front (one prefetch per 128-byte line): the marching loop below is
+    // latency-bound at 16 warps per SM, an L2 hit costs a third of a DRAM miss
+    {
+        auto pf = [&](const float* base, int r) {
+            if ((lane & 7) == 0 && r >= 0 && r < nz && x < ld) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (r * ld + x)));
+        };
+        for (int r = z0 - 2; r <= z0 + AFRZ + 1; ++r) { pf(LVX, r); pf(LVZ, r); }
+        for (int r = z0 - 1; r <= z0 + AFRZ; ++r) { pf(LXX, r); pf(LZZ, r); pf(LXZ, r); }
+        if (grad) {
+            for (int r = z0 - 2; r <= z0 + AFRZ + 1; ++r) { pf(SVX, r); pf(SVZ, r); }
+            for (int r = z0 - 1; r <= z0 + AFRZ; ++r) { pf(TXX, r); pf(TZZ, r); pf(TXZ, r); }
+            for (int r = z0; r < z0 + AFRZ; ++r) { pf(gpl, r); pf(gpl + plane, r); pf(gpl + 2 * plane, r); pf(gpl + 3 * plane, r); }
+        }
+    }
+#endif
     // ---- prologue: W rows z0-2 .. z0, stage A of rows z0-1 (b only is used) and z0
     WRow w_up = load_w(z0 - 2), w_cur = load_w(z0 - 1), w_dn = load_w(z0);
     if (grad) { svx_up = L4(SVX, z0 - 2); svz_cur = L4(SVZ, z0 - 1); }
