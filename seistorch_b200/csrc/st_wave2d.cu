@@ -610,6 +610,9 @@ __device__ __forceinline__ int tap_block_rows(const Map& map, int tid, int* s_ro
 template <int FL, class Map>
 __device__ __forceinline__ void forward_tap_block(const W2Args& a, const Map& map, int b_lo, int b_hi, int tid) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    constexpr bool XZ = (FL & ST_F_XZ) != 0;
+    constexpr int NT1 = XZ ? ST_NTAP1 : ST_NTAP1C;           // taps of h1 this equation uses (13 with the mixed derivative)
+    constexpr int NK = XZ ? ST_NTAP1 : ST_NTAP2;             // taps of the Born coupling stencil (cross, + diagonals for XZ)
     const W2Geom g = a.g;
     const long long plane = (long long)g.nz * g.ld;
     auto mine = [&](int z, int x) { return map.mine(z, x); };
@@ -621,10 +624,10 @@ __device__ __forceinline__ void forward_tap_block(const W2Args& a, const Map& ma
         // (the taps of h1 sum to 2 and those of h2 to -1 exactly, DESIGN.md "numerics")
         // taps that fall outside the domain read zero: t (0 - c) is folded into a self coefficient so
         // every load below is unconditional (index clamped to the cell itself)
-        float t1[ST_NTAP1 - 1], t2[ST_NTAP2 - 1], t1self = 0.f, t2self = 0.f;
-        int q1[ST_NTAP1 - 1];
+        float t1[NT1 - 1], t2[ST_NTAP2 - 1], t1self = 0.f, t2self = 0.f;
+        int q1[NT1 - 1];
 #pragma unroll
-        for (int o = 1; o < ST_NTAP1; ++o) {
+        for (int o = 1; o < NT1; ++o) {
             const int zz = z + st_tap_dz(o), xx = x + st_tap_dx(o);
             const bool in = zz >= 0 && zz < g.nz && xx >= 0 && xx < g.nx;
             q1[o - 1] = in ? zz * g.ld + xx : idx;
@@ -639,15 +642,19 @@ __device__ __forceinline__ void forward_tap_block(const W2Args& a, const Map& ma
         }
         // Born pair: coupling  pre m A[p1]  into the scattered field, A = czz (N + S - 2C) + cxx (W + E - 2C) with zero
         // padding (w2_forward_cell); kc[o-1] multiplies (p1(q+o) - p1(q)), kself the centre value for absent neighbours
-        float kc[4] = {0.f, 0.f, 0.f, 0.f}, kself = 0.f;
+        float kc[NK - 1], kself = 0.f;
+#pragma unroll
+        for (int o = 1; o < NK; ++o) kc[o - 1] = 0.f;
         if (NF == 2) {
             const float pm = (1.f - __ldg(a.coef[1] + idx)) * __ldg(a.coef[7] + idx);
             const float cx = __ldg(a.coef[2] + idx), cz = __ldg(a.coef[3] + idx);
+            const float cxz = XZ ? __ldg(a.coef[4] + idx) : 0.f;
 #pragma unroll
-            for (int o = 1; o <= 4; ++o) {
+            for (int o = 1; o < NK; ++o) {
+                if (o >= ST_NTAP2 && o < ST_NTAP1C) continue;            // the far taps are not part of the stencil
                 const int zz = z + st_tap_dz(o), xx = x + st_tap_dx(o);
                 const bool in = zz >= 0 && zz < g.nz && xx >= 0 && xx < g.nx;
-                const float t = pm * (o <= 2 ? cz : cx);
+                const float t = pm * (o <= 2 ? cz : o <= 4 ? cx : cxz * st_tap_xz_sign(o));
                 kc[o - 1] = in ? t : 0.f;
                 kself -= in ? 0.f : t;
             }
@@ -668,14 +675,15 @@ __device__ __forceinline__ void forward_tap_block(const W2Args& a, const Map& ma
                 float acc0 = t1self * c0 + t2self * p0, acc1 = t1self * c1 + t2self * p1;
                 if (NF == 2 && f == 0) { cpl0 = kself * c0; cpl1 = kself * c1; }
 #pragma unroll
-                for (int o = 1; o < ST_NTAP1; ++o) {
+                for (int o = 1; o < NT1; ++o) {
                     // most cells use one side only: 3 of the 4 far taps and 3 of the 4 h2 taps are zero
-                    const bool need = t1[o - 1] != 0.f || (NF == 2 && f == 0 && o <= 4 && kc[o - 1] != 0.f);
+                    const bool kcpl = NF == 2 && f == 0 && o < NK && kc[o < NK ? o - 1 : 0] != 0.f;
+                    const bool need = t1[o - 1] != 0.f || kcpl;
                     if (need) {
                         const float d0 = __ldg(cur0 + q1[o - 1]) - c0, d1 = __ldg(cur1 + q1[o - 1]) - c1;
                         acc0 += t1[o - 1] * d0;
                         acc1 += t1[o - 1] * d1;
-                        if (NF == 2 && f == 0 && o <= 4) { cpl0 += kc[o - 1] * d0; cpl1 += kc[o - 1] * d1; }
+                        if (NF == 2 && f == 0 && o < NK) { cpl0 += kc[o < NK ? o - 1 : 0] * d0; cpl1 += kc[o < NK ? o - 1 : 0] * d1; }
                     }
                     if (o < ST_NTAP2 && t2[o - 1] != 0.f) {
                         acc0 += t2[o - 1] * (__ldg(prv0 + q1[o - 1]) - p0);
@@ -748,6 +756,9 @@ __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int
 template <int FL, class Map>
 __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& map, int b_lo, int b_hi, int gplane, int tid) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    constexpr bool XZ = (FL & ST_F_XZ) != 0;
+    constexpr int NT1 = XZ ? ST_NTAP1 : ST_NTAP1C;           // taps of h1 this equation uses (13 with the mixed derivative)
+    constexpr int NK = XZ ? ST_NTAP1 : ST_NTAP2;             // taps of the spatial stencil (cross, + diagonals for XZ)
     const W2Geom g = a.g;
     const long long plane = (long long)g.nz * g.ld;
     const bool want_grad = a.gacc != nullptr;
@@ -758,45 +769,54 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
         const int z = zc, x = xc;
         const int idx = z * g.ld + x;
         // transposed taps: coefficient of L(p+o) is the tap -o of cell p+o
-        float g1[ST_NTAP1], g2[ST_NTAP2], h1[ST_NTAP1], h2[ST_NTAP2], m[ST_NTAP2];
-        int q[ST_NTAP1];
+        float g1[NT1], g2[ST_NTAP2], h1[ST_NTAP1C], h2[ST_NTAP2], m[NT1];
+        int q[NT1];
         const bool frame = w2_in_frame(z, x, g);
         const float pre = frame ? 1.f - __ldg(a.coef[1] + idx) : 1.f;
 #pragma unroll
-        for (int o = 0; o < ST_NTAP1; ++o) {
+        for (int o = 0; o < NT1; ++o) {
             const int zz = z + st_tap_dz(o), xx = x + st_tap_dx(o);
             const bool in = inb(zz, xx);
             q[o] = in ? zz * g.ld + xx : idx;                 // clamped: every load below is unconditional
             g1[o] = in ? __ldg(a.taps + st_tap_neg(o) * plane + q[o]) : 0.f;
-            h1[o] = (want_grad && frame && in) ? __ldg(a.taps + (ST_NTAP1 + ST_NTAP2 + o) * plane + idx) : 0.f;
+            m[o] = in ? 1.f : 0.f;
+            if (o < ST_NTAP1C) h1[o] = (want_grad && frame && in) ? __ldg(a.taps + (ST_NTAP1 + ST_NTAP2 + o) * plane + idx) : 0.f;
             if (o < ST_NTAP2) {
                 g2[o] = in ? __ldg(a.taps + (ST_NTAP1 + st_tap_neg(o)) * plane + q[o]) : 0.f;
                 h2[o] = (want_grad && frame && in) ? __ldg(a.taps + (2 * ST_NTAP1 + ST_NTAP2 + o) * plane + idx) : 0.f;
-                m[o] = in ? 1.f : 0.f;
             }
         }
         // Born pair: the scattered field's cotangent reaches the background field through the coupling
         //   sp' += pre m A[p1]  =>  Lam_p(p) += sum_o K[-o](p+o) L1_s(p+o),   K[o](q) = pre(q) m(q) T[o](q), K[0] = -sum_o K[o]
-        // (T = czz for the z-neighbours, cxx for the x-neighbours; w2_adjoint_cell: leffq)
-        float gk[ST_NTAP2] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        float pm_p = 0.f, cx_p = 0.f, cz_p = 0.f;
-        if (NF == 2) {
-            cx_p = __ldg(a.coef[2] + idx); cz_p = __ldg(a.coef[3] + idx);
-            pm_p = pre * __ldg(a.coef[7] + idx);
-            gk[0] = -pm_p * (2.f * cx_p + 2.f * cz_p);
+        // (T = czz for the z-neighbours, cxx for the x-neighbours, +-cxz for the diagonal ones; w2_adjoint_cell: leffq)
+        float gk[NK];
 #pragma unroll
-            for (int o = 1; o < ST_NTAP2; ++o) {
+        for (int o = 0; o < NK; ++o) gk[o] = 0.f;
+        float pm_p = 0.f, cx_p = 0.f, cz_p = 0.f, cxz_p = 0.f;
+        if (NF == 2 || XZ) {
+            cx_p = __ldg(a.coef[2] + idx); cz_p = __ldg(a.coef[3] + idx);
+            if (XZ) cxz_p = __ldg(a.coef[4] + idx);
+        }
+        if (NF == 2) {
+            pm_p = pre * __ldg(a.coef[7] + idx);
+            gk[0] = -pm_p * (2.f * cx_p + 2.f * cz_p);      // (the four diagonal taps sum to zero)
+#pragma unroll
+            for (int o = 1; o < NK; ++o) {
+                if (o >= ST_NTAP2 && o < ST_NTAP1C) continue;            // far taps: not part of the stencil
                 if (m[o] != 0.f) {
                     const int zz = z + st_tap_dz(o), xx = x + st_tap_dx(o);
                     const float preq = w2_in_frame(zz, xx, g) ? 1.f - __ldg(a.coef[1] + q[o]) : 1.f;
-                    gk[o] = preq * __ldg(a.coef[7] + q[o]) * __ldg(a.coef[o <= 2 ? 3 : 2] + q[o]);
+                    const float tq = o <= 2 ? __ldg(a.coef[3] + q[o]) : o <= 4 ? __ldg(a.coef[2] + q[o])
+                                                                                 : st_tap_xz_sign(o) * __ldg(a.coef[4] + q[o]);
+                    gk[o] = preq * __ldg(a.coef[7] + q[o]) * tq;
                 }
             }
         }
-        float gr = 0.f, gc = 0.f, gz = 0.f, gax = 0.f, gaz = 0.f, gm = 0.f;
+        float gr = 0.f, gc = 0.f, gz = 0.f, gax = 0.f, gaz = 0.f, gm = 0.f, gxz = 0.f;
         // one shot: Lam_i(p) of every field and the gradient contributions; written as a lambda so two shots can be
         // issued back to back (two independent load chains in flight)
-        auto one_shot = [&](int b, float (&accOut)[NF], float& gcOut, float& grOut, float& gzOut, float& gaxOut, float& gazOut, float& gmOut) {
+        auto one_shot = [&](int b, float (&accOut)[NF], float& gcOut, float& grOut, float& gzOut, float& gaxOut, float& gazOut,
+                            float& gmOut, float& gxzOut) {
             const long long boff = (long long)b * a.fs;
             float lc[NF];
 #pragma unroll
@@ -808,15 +828,15 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
                 float acc = 0.f;
                 lc[f] = 0.f;
 #pragma unroll
-                for (int o = 0; o < ST_NTAP1; ++o) {
+                for (int o = 0; o < NT1; ++o) {
                     // zero taps (most far taps of single-side cells) are skipped; the centre value is
                     // always needed for the imaging condition
-                    const bool cpl = NF == 2 && f == 1 && o < ST_NTAP2 && gk[o] != 0.f;
+                    const bool cpl = NF == 2 && f == 1 && o < NK && gk[o < NK ? o : 0] != 0.f;
                     if (o == 0 || g1[o] != 0.f || cpl) {
                         const float v = __ldg(l1 + q[o]);
                         if (o == 0) lc[f] = v;
                         acc += g1[o] * v;
-                        if (NF == 2 && f == 1 && o < ST_NTAP2) accOut[0] += gk[o] * v;
+                        if (NF == 2 && f == 1 && o < NK) accOut[0] += gk[o < NK ? o : 0] * v;
                     }
                     if (o < ST_NTAP2 && g2[o] != 0.f) acc += g2[o] * __ldg(l2 + q[o]);
                 }
@@ -830,7 +850,7 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
                     const float* S2 = a.s2 + f * a.cs + boff;
                     float s[ST_NTAP2], t = 0.f;
 #pragma unroll
-                    for (int o = 0; o < ST_NTAP1; ++o) {
+                    for (int o = 0; o < ST_NTAP1C; ++o) {
                         if (o < ST_NTAP2) {
                             s[o] = m[o] * __ldg(S1 + q[o]);
                             t += h1[o] * s[o];
@@ -840,13 +860,20 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
                         }
                     }
                     const float szz = (s[1] - s[0]) + (s[2] - s[0]), sxx = (s[3] - s[0]) + (s[4] - s[0]);
+                    float cross = 0.f;
+                    if (XZ) {       // (SE - SW) - (NE - NW), zero outside the domain
+                        const float nw = m[XZ ? 9 : 0] * __ldg(S1 + q[XZ ? 9 : 0]), ne = m[XZ ? 10 : 0] * __ldg(S1 + q[XZ ? 10 : 0]);
+                        const float sw = m[XZ ? 11 : 0] * __ldg(S1 + q[XZ ? 11 : 0]), se = m[XZ ? 12 : 0] * __ldg(S1 + q[XZ ? 12 : 0]);
+                        cross = (se - sw) - (ne - nw);
+                    }
                     float le = pre * lc[f];
                     if (NF == 2 && f == 0) le += pm_p * lc[1];
                     if (FL & ST_F_ISO) gcOut += le * (szz + sxx);
                     else { gcOut += le * sxx; gzOut += le * szz; }
+                    if (XZ) gxzOut += le * cross;
                     if (FL & ST_F_G1) { gaxOut += le * (s[4] - s[3]); gazOut += le * (s[2] - s[1]); }
                     if (NF == 2) {
-                        if (f == 0) A0 = cx_p * sxx + cz_p * szz;
+                        if (f == 0) A0 = cx_p * sxx + cz_p * szz + cxz_p * cross;
                         else gmOut += (pre * lc[1]) * A0;
                     }
                     grOut += lc[f] * t;
@@ -854,21 +881,22 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
             }
         };
         for (int b = b_lo; b < b_hi; b += 2) {
-            float acc0[NF], acc1[NF], gc1 = 0.f, gr1 = 0.f, gz1 = 0.f, gax1 = 0.f, gaz1 = 0.f, gm1 = 0.f;
-            one_shot(b, acc0, gc, gr, gz, gax, gaz, gm);
+            float acc0[NF], acc1[NF], gc1 = 0.f, gr1 = 0.f, gz1 = 0.f, gax1 = 0.f, gaz1 = 0.f, gm1 = 0.f, gxz1 = 0.f;
+            one_shot(b, acc0, gc, gr, gz, gax, gaz, gm, gxz);
             const bool two = b + 1 < b_hi;
-            if (two) one_shot(b + 1, acc1, gc1, gr1, gz1, gax1, gaz1, gm1);
+            if (two) one_shot(b + 1, acc1, gc1, gr1, gz1, gax1, gaz1, gm1, gxz1);
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 a.lam0[f * a.cs + (long long)b * a.fs + idx] = acc0[f];
                 if (two) a.lam0[f * a.cs + (long long)(b + 1) * a.fs + idx] = acc1[f];
             }
-            gc += gc1; gr += gr1; gz += gz1; gax += gax1; gaz += gaz1; gm += gm1;
+            gc += gc1; gr += gr1; gz += gz1; gax += gax1; gaz += gaz1; gm += gm1; gxz += gxz1;
         }
         if (want_grad) {
             float* gb = a.gacc + (long long)gplane * 7 * plane;
             gb[plane + idx] += gc;              // slot 1: d/d ciso (ISO) or d/d cxx
             if (!(FL & ST_F_ISO)) gb[2 * plane + idx] += gz;                   // slot 2: d/d czz
+            if (XZ) gb[3 * plane + idx] += gxz;                                 // slot 3: d/d cxz
             if (FL & ST_F_G1) { gb[4 * plane + idx] += gax; gb[5 * plane + idx] += gaz; }
             if (FL & ST_F_BORN) gb[6 * plane + idx] += gm;                      // slot 6: d/d m
             if (frame) gb[idx] += gr;           // slot 0: d/d r

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) wave2d_prepare_kernel(const W2Args a, int
     const float cx = a.coef[2][idx];
     const float cz = (flags & ST_F_ISO) ? cx : a.coef[3][idx];
     const float ax = (flags & ST_F_G1) ? a.coef[5][idx] : 0.f, az = (flags & ST_F_G1) ? a.coef[6][idx] : 0.f;
+    const float cxz = (flags & ST_F_XZ) ? a.coef[4][idx] : 0.f;
     float F1[ST_NTAP1], F2[ST_NTAP2], H1[ST_NTAP1], H2[ST_NTAP2];
 #pragma unroll
     for (int o = 0; o < ST_NTAP1; ++o) F1[o] = H1[o] = 0.f;
@@ -30,6 +31,9 @@ __global__ void __launch_bounds__(256) wave2d_prepare_kernel(const W2Args a, int
     F1[3] = pre * (cx - ax);      // W = (z, x-1)
     F1[4] = pre * (cx + ax);      // E
     F2[0] = -pre;
+    // + cxz ((SE - SW) - (NE - NW))   (tti_habc.py:40-57; zero planes for the other equations)
+#pragma unroll
+    for (int o = ST_NTAP1C; o < ST_NTAP1; ++o) F1[o] = pre * cxz * st_tap_xz_sign(o);
     if (frame) {
         float f[4];
         w2_side_weights(z, x, g, f);

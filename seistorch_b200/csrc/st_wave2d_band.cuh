@@ -16,12 +16,18 @@
 #pragma once
 #include "st_wave2d.cuh"
 
-constexpr int ST_NTAP1 = 9, ST_NTAP2 = 5;
+// plane layout: F1[ST_NTAP1], F2[ST_NTAP2], H1[ST_NTAP1], H2[ST_NTAP2].  The first ST_NTAP1C (= 9) taps of h1 form the cross
+// {0, +-z, +-x, +-2z, +-2x}; taps 9..12 are the four diagonal neighbours of the mixed derivative (TTI: ST_F_XZ), zero planes
+// for the other equations (whose kernels loop over the first 9 only).
+constexpr int ST_NTAP1 = 13, ST_NTAP1C = 9, ST_NTAP2 = 5;
 constexpr int ST_TAP_PLANES = 2 * (ST_NTAP1 + ST_NTAP2);      // F1, F2, H1, H2
 // tap offsets (dz, dx): 0:(0,0) 1:(-1,0) 2:(+1,0) 3:(0,-1) 4:(0,+1) 5:(-2,0) 6:(+2,0) 7:(0,-2) 8:(0,+2)
-ST_HD int st_tap_dz(int o) { return o == 1 ? -1 : o == 2 ? 1 : o == 5 ? -2 : o == 6 ? 2 : 0; }
-ST_HD int st_tap_dx(int o) { return o == 3 ? -1 : o == 4 ? 1 : o == 7 ? -2 : o == 8 ? 2 : 0; }
-ST_HD int st_tap_neg(int o) { return o == 0 ? 0 : ((o - 1) ^ 1) + 1; }      // index of -offset
+//                       9:(-1,-1) 10:(-1,+1) 11:(+1,-1) 12:(+1,+1)
+ST_HD int st_tap_dz(int o) { return o == 1 ? -1 : o == 2 ? 1 : o == 5 ? -2 : o == 6 ? 2 : (o == 9 || o == 10) ? -1 : (o == 11 || o == 12) ? 1 : 0; }
+ST_HD int st_tap_dx(int o) { return o == 3 ? -1 : o == 4 ? 1 : o == 7 ? -2 : o == 8 ? 2 : (o == 9 || o == 11) ? -1 : (o == 10 || o == 12) ? 1 : 0; }
+ST_HD int st_tap_neg(int o) { return o == 0 ? 0 : o >= 9 ? 21 - o : ((o - 1) ^ 1) + 1; }      // index of -offset
+// sign of the mixed-derivative stencil  cxz ((SE - SW) - (NE - NW))  at diagonal tap o (9..12)
+ST_HD float st_tap_xz_sign(int o) { return (o == 9 || o == 12) ? 1.f : -1.f; }
 // tap index of k steps along the inward normal of side s (0 top, 1 bottom, 2 left, 3 right)
 ST_HD int st_tap_normal(int s, int k) { return (k == 1 ? 0 : 4) + (s == 0 ? 2 : s == 1 ? 1 : s == 2 ? 4 : 3); }
 
@@ -68,17 +74,18 @@ ST_HD void st_wrap_candidate(const W2Geom& g, int k, int& z, int& x, int& s, int
     else { z = g.nz - 1; x = w - 1; s = 2; zw = z; xw = 0; }                        // BL diagonal end, left side
 }
 
-// flag sets whose spatial operator fits the 9 taps (no mixed derivative): the single-field equations, and the Born
-// pair without mixed derivative (acoustic_lsrtm_habc, acoustic_vti_lsrtm_habc) -- both of its fields take the SAME
+// flag sets whose frame runs on the taps: the single-field equations (9 taps; 13 with the mixed derivative of tti_habc), and
+// the Born pairs (acoustic_lsrtm_habc, acoustic_{vti,tti}_lsrtm_habc) -- both of its fields take the SAME
 // taps (the one-way blend acts on each field by itself, acoustic_vti_lsrtm_habc.py:60-66), the scattered field adds
 // the coupling term  pre m A[p1]  evaluated from the coefficient planes
 ST_HD bool st_flags_tapped(int fl) {
     return fl == (ST_F_ISO | ST_F_HABC) || fl == ST_F_HABC || fl == (ST_F_ISO | ST_F_HABC | ST_F_G1) ||
-           fl == (ST_F_HABC | ST_F_G1) || fl == (ST_F_HABC | ST_F_BORN);
+           fl == (ST_F_HABC | ST_F_G1) || fl == (ST_F_HABC | ST_F_BORN) || fl == (ST_F_HABC | ST_F_XZ) ||
+           fl == (ST_F_HABC | ST_F_XZ | ST_F_BORN);
 }
-// ... of which the straight top / bottom strips run on the vectorised strip blocks (single-field equations only; the
-// band threads serve every frame cell of the Born pair)
-ST_HD bool st_flags_stripped(int fl) { return st_flags_tapped(fl) && !(fl & ST_F_BORN); }
+// ... of which the straight top / bottom strips run on the vectorised strip blocks (single-field equations without mixed
+// derivative only; the band threads serve every frame cell of the others)
+ST_HD bool st_flags_stripped(int fl) { return st_flags_tapped(fl) && !(fl & (ST_F_BORN | ST_F_XZ)); }
 
 #ifdef __CUDACC__
 int st_wave2d_launch_prepare(int flags, const W2Args& a, cudaStream_t st);
