@@ -50,6 +50,9 @@ constexpr int FW = 128;                     // columns per warp (32 lanes x floa
 #ifndef ST_ADJ_MINB
 #define ST_ADJ_MINB 3
 #endif
+#ifndef ST_ADJ_MINB_BORN
+#define ST_ADJ_MINB_BORN 2                  // blocks / SM of the Born-pair adjoint (3 was measured: see DESIGN.md)
+#endif
 constexpr int FRZ = ST_FRZ;                 // rows per warp
 constexpr int NWARP = NT / 32;
 constexpr int FH = FRZ * NWARP;             // rows per fast block
@@ -1999,7 +2002,7 @@ __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, i
 
 // resident blocks per SM the register adjoint is compiled for (the Born pairs carry two fields: 128 registers)
 template <int FL>
-__host__ __device__ constexpr int adj_minb() { return (FL & ST_F_BORN) ? 2 : ST_ADJ_MINB; }
+__host__ __device__ constexpr int adj_minb() { return (FL & ST_F_BORN) ? ST_ADJ_MINB_BORN : ST_ADJ_MINB; }
 
 template <int FL>
 __global__ void __launch_bounds__(NT, adj_minb<FL>()) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
