@@ -554,6 +554,7 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
 // ---- cell maps of the tap-gather blocks: which cell a thread owns, which cells the block owns
 // BandMap: the compact enumeration of the absorbing band (st_band_cells), minus the vectorised strips, NT cells per block
 struct BandMap {
+    static constexpr bool dense = false;    // most band cells use one side only: zero taps are skipped (saves loads)
     W2Geom g; BandCells bc; StripGeom sg; bool strips, frame_only; int i0;
     __device__ __forceinline__ bool cell(int t, int& z, int& x) const {
         const int i = i0 + t;
@@ -579,6 +580,10 @@ struct BandMap {
 };
 // RectMap: NT/w rows x w columns of a rectangle (the corner tiles of the TMA launches: every cell, frame or not)
 struct RectMap {
+    // corner cells carry taps of two sides: every tap is loaded unconditionally, so the loads of one shot are issued
+    // together instead of as a chain of branch-guarded load -> use round trips (measured on the TMA forward: the chained
+    // version made the corner blocks the critical path of the launch)
+    static constexpr bool dense = true;
     W2Geom g; int z0, x0, w;            // first row / column of the block's cells, columns per row
     __device__ __forceinline__ bool cell(int t, int& z, int& x) const {
         if (t < 0) return false;
@@ -681,14 +686,14 @@ __device__ __forceinline__ void forward_tap_block(const W2Args& a, const Map& ma
                 for (int o = 1; o < NT1; ++o) {
                     // most cells use one side only: 3 of the 4 far taps and 3 of the 4 h2 taps are zero
                     const bool kcpl = NF == 2 && f == 0 && o < NK && kc[o < NK ? o - 1 : 0] != 0.f;
-                    const bool need = t1[o - 1] != 0.f || kcpl;
+                    const bool need = Map::dense || t1[o - 1] != 0.f || kcpl;
                     if (need) {
                         const float d0 = __ldg(cur0 + q1[o - 1]) - c0, d1 = __ldg(cur1 + q1[o - 1]) - c1;
                         acc0 += t1[o - 1] * d0;
                         acc1 += t1[o - 1] * d1;
                         if (NF == 2 && f == 0 && o < NK) { cpl0 += kc[o < NK ? o - 1 : 0] * d0; cpl1 += kc[o < NK ? o - 1 : 0] * d1; }
                     }
-                    if (o < ST_NTAP2 && t2[o - 1] != 0.f) {
+                    if (o < ST_NTAP2 && (Map::dense || t2[o < ST_NTAP2 ? o - 1 : 0] != 0.f)) {
                         acc0 += t2[o - 1] * (__ldg(prv0 + q1[o - 1]) - p0);
                         acc1 += t2[o - 1] * (__ldg(prv1 + q1[o - 1]) - p1);
                     }
@@ -835,13 +840,13 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
                     // zero taps (most far taps of single-side cells) are skipped; the centre value is
                     // always needed for the imaging condition
                     const bool cpl = NF == 2 && f == 1 && o < NK && gk[o < NK ? o : 0] != 0.f;
-                    if (o == 0 || g1[o] != 0.f || cpl) {
+                    if (o == 0 || Map::dense || g1[o] != 0.f || cpl) {
                         const float v = __ldg(l1 + q[o]);
                         if (o == 0) lc[f] = v;
                         acc += g1[o] * v;
                         if (NF == 2 && f == 1 && o < NK) accOut[0] += gk[o < NK ? o : 0] * v;
                     }
-                    if (o < ST_NTAP2 && g2[o] != 0.f) acc += g2[o] * __ldg(l2 + q[o]);
+                    if (o < ST_NTAP2 && (Map::dense || g2[o < ST_NTAP2 ? o : 0] != 0.f)) acc += g2[o < ST_NTAP2 ? o : 0] * __ldg(l2 + q[o]);
                 }
                 accOut[f] += acc;
             }
@@ -857,8 +862,8 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
                         if (o < ST_NTAP2) {
                             s[o] = m[o] * __ldg(S1 + q[o]);
                             t += h1[o] * s[o];
-                            if (h2[o] != 0.f) t += h2[o] * __ldg(S2 + q[o]);
-                        } else if (h1[o] != 0.f) {
+                            if (Map::dense || h2[o] != 0.f) t += h2[o] * __ldg(S2 + q[o]);
+                        } else if (Map::dense || h1[o] != 0.f) {
                             t += h1[o] * __ldg(S1 + q[o]);
                         }
                     }
@@ -1195,6 +1200,13 @@ __host__ __device__ inline CornerTiles corner_tiles(const W2Tma& tm, const W2Geo
 // st_wave2d_prepare) a corner tile is cut into TX*TZ/NT blocks of NT cells, one cell per thread, each walking a group of
 // up to BSH shots with its taps in registers (forward_tap_block / adjoint_tap_block on a RectMap); without taps one
 // generic per-cell block per (tile, shot).
+// The ADJOINT TMA kernel runs its corner tiles on tap blocks (74.6 -> 69.9 us per 8-shot launch at the BASELINE size).  The
+// FORWARD kernel keeps the generic per-cell corner tiles, one shot per block: a tap block walks all 8 shots of its group,
+// and the one that holds the acquisition row then scans 8 x 1151 receivers in its epilogue -- longer than the whole 38 us
+// forward launch (measured: 46 us with tap corners), while it hides inside the 70 us adjoint launch.
+#ifndef ST_CORNER_TAP_FWD
+#define ST_CORNER_TAP_FWD 0
+#endif
 constexpr int CORNER_SUB = TX * TZ / NT;                    // tap blocks per corner tile (4 rows x 64 columns each)
 __host__ __device__ inline int corner_block_count(const CornerTiles& c, int B, bool tapped) {
     return tapped ? c.count * CORNER_SUB * ((B + BSH - 1) / BSH) : c.count * B;
@@ -1404,7 +1416,7 @@ __global__ void __launch_bounds__(NT, tma_fwd_minb<FL>()) wave2d_forward_tma_ker
     extern __shared__ __align__(128) unsigned char dsm[];
     const int bid = blockIdx.x, tid = threadIdx.x;
     const CornerTiles ct = corner_tiles(tm, a.g);
-    const bool ctap = st_flags_tapped(FL) && a.taps != nullptr;
+    const bool ctap = ST_CORNER_TAP_FWD && st_flags_tapped(FL) && a.taps != nullptr;
     const int ncorner = corner_block_count(ct, a.B, ctap);
     st_pdl_launch_dependents();
     if (bid < ncorner) {
@@ -2445,7 +2457,7 @@ int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     if constexpr (tma_ok<FL>()) {
         if (tm.enabled) {
             if (st_set_max_smem<wave2d_forward_tma_kernel<FL>>(tma_fwd_smem<FL>()) != cudaSuccess) return ST_ERR_CUDA;
-            const bool ctap = st_flags_tapped(FL) && a.taps != nullptr;
+            const bool ctap = ST_CORNER_TAP_FWD && st_flags_tapped(FL) && a.taps != nullptr;
             dim3 grid((unsigned)((long long)corner_block_count(corner_tiles(tm, a.g), a.B, ctap) + tma_blocks(tm, a.B)));
             return tma_launch(wave2d_forward_tma_kernel<FL>, grid, tma_fwd_smem<FL>(), st, a, nfx, tm);
         }
