@@ -45,8 +45,8 @@ constexpr int NTX = 64, NTY = 4, RPT = TZ / NTY;
 // ---- fast tiles
 constexpr int FW = 128;                     // columns per warp (32 lanes x float4)
 #ifndef ST_FRZ
-#define ST_FRZ 4
-#endif
+#define ST_FRZ 2                            // rows per warp of the fast (register / shuffle) tiles.  2 beats 4 and 8 on every adjoint
+#endif                                      // (more, smaller blocks: the kernels are latency-bound; measured)
 #ifndef ST_ADJ_MINB
 #define ST_ADJ_MINB 3
 #endif
