@@ -237,7 +237,7 @@ def _choose_bchunk(spec: Spec) -> int:
     if spec.family == "acoustic3d":
         tiles = math.ceil(spec.shape[2] / 64) * math.ceil(spec.shape[1] / 8) * math.ceil(spec.shape[0] / 16)
     elif spec.family == "wave2d":
-        tiles = math.ceil(spec.shape[1] / 128) * math.ceil(spec.shape[0] / 16)     # fast tiles (256 threads: 8 warps x 2 rows)
+        tiles = math.ceil(spec.shape[1] / 128) * math.ceil(spec.shape[0] / 32)     # pairs of fast tiles (tuned on B200: SEISTORCH_B200_BCHUNK sweep)
     else:
         tiles = math.ceil(spec.shape[1] / 64) * math.ceil(spec.shape[0] / 32)
     best = 1
