@@ -21,7 +21,10 @@ namespace {
 
 constexpr int NT = 256, NWARP = NT / 32;
 constexpr int FW = 128;         // columns per warp
-constexpr int RZ = 4;           // rows per warp
+#ifndef ST_A3_RZ
+#define ST_A3_RZ 4
+#endif
+constexpr int RZ = ST_A3_RZ;    // rows per warp
 constexpr int FH = RZ * NWARP;  // rows per block
 
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }

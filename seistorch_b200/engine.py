@@ -62,15 +62,14 @@ def _one_device(tensors, what: str) -> torch.device:
     (seistorch_dist.py:89-94)."""
     dev = None
     for t in tensors:
-        if t is None:
+        if t is None or not t.is_cuda:          # host operands (e.g. observed data still on the CPU) are moved by the op itself
             continue
-        _require_cuda(t, what)
         if dev is None:
             dev = t.device
         elif t.device != dev:
             raise RuntimeError(f"seistorch_b200: {what}: operands live on different devices ({dev} and {t.device})")
     if dev is None:
-        raise RuntimeError(f"seistorch_b200: {what}: no CUDA operand")
+        raise RuntimeError(f"seistorch_b200: {what}: no CUDA operand (no CPU fallback)")
     return dev
 
 

@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, "gpurun_out", "r02")
+SRCS = [os.path.join(ROOT, "gpurun_out", d) for d in ("r02", "r02b", "r02c")]     # later passes override earlier captures
 KEYS = {
     "gpu__time_duration.sum": "duration_us",
     "dram__bytes_read.sum": "dram_read_MB",
@@ -36,6 +36,7 @@ WORK = {
     "cfg3_adj": ("cfg3", "elastic2d_adjoint_kernel", 4 * 500 * 1100, 96),
     "cfg4_fwd": ("cfg4", "wave2d_forward_kernel", 12 * 600 * 1300, 44),
     "cfg4_adj": ("cfg4", "wave2d_adjoint_kernel", 12 * 600 * 1300, 76),
+    "cfg4tti_adj": ("cfg4_tti", "wave2d_adjoint_kernel", 12 * 600 * 1300, 80),
     "cfg5_fwd": ("cfg5", "acoustic3d_forward_kernel", 500 * 300 * 500, 20),
     "cfg5_adj": ("cfg5", "acoustic3d_adjoint_kernel", 500 * 300 * 500, 32),
 }
@@ -65,10 +66,14 @@ def raw(path):
 
 def main():
     rows, traffic = [], {}
-    for path in sorted(glob.glob(os.path.join(SRC, "*.ncu-rep"))):
-        tag = os.path.basename(path)[:-8]
+    latest = {}
+    for src in SRCS:
+        for path in sorted(glob.glob(os.path.join(src, "*.ncu-rep"))):
+            latest[os.path.basename(path)[:-8]] = path
+    for tag, path in sorted(latest.items()):
         r = raw(path)
         r["capture"] = tag
+        r["pass"] = os.path.basename(os.path.dirname(path))
         if tag in WORK:
             cfg, key, cells, bpc = WORK[tag]
             r["cells"] = cells
@@ -87,7 +92,7 @@ def main():
         json.dump(traffic, f, indent=1, sort_keys=True)
     with open(os.path.join(ROOT, "profiles", "ncu_r02_raw.json"), "w") as f:
         json.dump(rows, f, indent=1)
-    cols = ["capture", "duration_us", "Gpts_per_s", "dram_read_MB", "dram_write_MB", "dram_B_per_cell", "algorithmic_B_per_cell",
+    cols = ["capture", "pass", "duration_us", "Gpts_per_s", "dram_read_MB", "dram_write_MB", "dram_B_per_cell", "algorithmic_B_per_cell",
             "dram_TBps", "issue_active_pct", "warps_active_pct", "regs", "grid", "waves", "stall_long_sb", "stall_barrier",
             "stall_membar", "l2_hit_pct"]
     lines = ["| " + " | ".join(cols) + " |", "|" + "---|" * len(cols)]
