@@ -128,6 +128,10 @@ int st_wave2d_uses_tma(const st_wave2d_problem* p, int32_t adjoint);
  * per time step), else 0 (one launch per time step).  Environment SEISTORCH_B200_PERSIST=0 turns it off.  Same
  * arithmetic as the per-step kernels: records agree bit for bit. */
 int st_wave2d_uses_persist(const st_wave2d_problem* p, int32_t nsteps);
+/* the same question for st_wave2d_adjoint(p, i_hi, nsteps, ...): the adjoint twin keeps the two cotangents and the
+ * gradient accumulator of every cell in registers for the whole loop (checkpoint_new.py:146-217 / autograd through
+ * rnn.py:178-205) and reads S_i from the wavefield history one step ahead of its use; gacc needs one plane set per shot. */
+int st_wave2d_adjoint_uses_persist(const st_wave2d_problem* p, int32_t nsteps);
 
 /* advance steps i0 .. i0+nsteps-1; S_{i0-2} lives in slot `slot0`, S_{i0-1} in slot0+1,
  * step i writes slot0+2+(i-i0).                                                         */

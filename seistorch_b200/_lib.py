@@ -79,7 +79,7 @@ class StAcoustic3dProblem(C.Structure):
 # every symbol include/seistorch_b200.h declares
 EXPORTS = [
     "st_version", "st_last_error",
-    "st_wave2d_taps_floats", "st_wave2d_prepare", "st_wave2d_uses_tma", "st_wave2d_uses_persist",
+    "st_wave2d_taps_floats", "st_wave2d_prepare", "st_wave2d_uses_tma", "st_wave2d_uses_persist", "st_wave2d_adjoint_uses_persist",
     "st_wave2d_forward", "st_wave2d_adjoint",
     "st_acoustic2d_forward", "st_acoustic2d_adjoint",
     "st_acoustic2d_habc_forward", "st_acoustic2d_habc_adjoint",
@@ -117,6 +117,8 @@ def lib():
     L.st_wave2d_uses_tma.argtypes = [C.c_void_p, C.c_int32]
     L.st_wave2d_uses_persist.restype = C.c_int
     L.st_wave2d_uses_persist.argtypes = [C.c_void_p, C.c_int32]
+    L.st_wave2d_adjoint_uses_persist.restype = C.c_int
+    L.st_wave2d_adjoint_uses_persist.argtypes = [C.c_void_p, C.c_int32]
     for name in EXPORTS:
         if not (name.endswith("_forward") or name.endswith("_adjoint")):
             continue

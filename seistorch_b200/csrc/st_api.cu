@@ -133,10 +133,13 @@ static bool w2_persist_enabled() {
 }
 
 // Plans the persistent launch for steps [i0, i0+nsteps); false when the problem is outside its class.
-static bool w2_persist_plan(const st_wave2d_problem* p, const W2Args& a, int i0, int nsteps, int slot0, W2Persist& pp) {
+static bool w2_persist_plan(const st_wave2d_problem* p, const W2Args& a, int i0, int nsteps, int slot0, W2Persist& pp,
+                            bool adjoint = false) {
     if (!w2_persist_enabled() || nsteps < 4) return false;
-    if (st_wave2d_persist_plan(p->flags, a, pp) != ST_OK) return false;
+    if (adjoint && p->lam == nullptr) return false;
+    if (st_wave2d_persist_plan(p->flags, a, adjoint, pp) != ST_OK) return false;
     pp.u = p->u;
+    pp.lam = adjoint ? p->lam : nullptr;
     pp.slot = a.cs;
     pp.nslots = p->nslots;
     pp.slot0 = pmod(slot0, p->nslots);
@@ -144,7 +147,8 @@ static bool w2_persist_plan(const st_wave2d_problem* p, const W2Args& a, int i0,
     pp.nsteps = nsteps;
     pp.history = p->nslots > 3;
     pp.probe = 1;
-    if (st_wave2d_persist_forward(a, pp, nullptr) != ST_OK) return false;      // no resident cluster of this shape
+    if ((adjoint ? st_wave2d_persist_adjoint(a, pp, nullptr) : st_wave2d_persist_forward(a, pp, nullptr)) != ST_OK)
+        return false;                                                           // no resident cluster of this shape
     pp.probe = 0;
     return true;
 }
@@ -155,6 +159,15 @@ extern "C" int st_wave2d_uses_persist(const st_wave2d_problem* p, int32_t nsteps
     w2_fill(p, a);
     W2Persist pp;
     return w2_persist_plan(p, a, 0, nsteps, 0, pp) ? 1 : 0;
+}
+
+extern "C" int st_wave2d_adjoint_uses_persist(const st_wave2d_problem* p, int32_t nsteps) {
+    if (w2_check(p) != ST_OK) return 0;
+    W2Args a;
+    w2_fill(p, a);
+    a.gacc = p->gacc;
+    W2Persist pp;
+    return w2_persist_plan(p, a, 0, nsteps, 0, pp, true) ? 1 : 0;
 }
 
 extern "C" int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t nsteps, int32_t slot0, void* stream) {
@@ -207,6 +220,16 @@ extern "C" int st_wave2d_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32
     const long long slot = a.cs * nf;
     cudaStream_t st = (cudaStream_t)stream;
     a.gacc = p->gacc;
+    {
+        W2Persist pp;
+        if (w2_persist_plan(p, a, i_hi, nsteps, slot_hi, pp, true)) {
+            a.rec_adj = (p->acq.rec_adj && p->acq.R > 0) ? p->acq.rec_adj + (long long)i_hi * p->acq.R * p->acq.nchan : nullptr;
+            a.gamp = p->acq.gamp ? p->acq.gamp + (long long)i_hi * p->acq.ns : nullptr;
+            rc = st_wave2d_persist_adjoint(a, pp, st);
+            if (rc) { st_set_error("wave2d_adjoint: persistent launch failed: %s", cudaGetErrorString(cudaGetLastError())); return ST_ERR_CUDA; }
+            return ST_OK;
+        }
+    }
     W2Tma tm;
     const int planes = nf * p->B;
     rc = st_wave2d_tma_setup(p->flags, a, p->u, (long long)planes * p->nslots, p->lam, 3LL * planes, true, nsteps > 0 ? w2_tma_mode() : 0, tm);

@@ -332,6 +332,10 @@ class _Problem:
                 _lib.lib().st_wave2d_uses_persist(C.byref(self.p), int(nsteps)):
             KERNELS[which] = "wave2d_persist_forward_kernel"
             return 1
+        if which == "adjoint" and self.spec.family == "wave2d" and \
+                _lib.lib().st_wave2d_adjoint_uses_persist(C.byref(self.p), int(nsteps)):
+            KERNELS[which] = "wave2d_persist_adjoint_kernel"
+            return 1
         if self.spec.family == "wave2d":
             tma = bool(_lib.lib().st_wave2d_uses_tma(C.byref(self.p), 1 if which == "adjoint" else 0))
             KERNELS[which] = f"wave2d_{which}_{'tma_' if tma else ''}kernel"
@@ -352,9 +356,9 @@ class _Problem:
 
     def adjoint(self, i_hi, nsteps, slot_hi):
         self._sync_struct()
-        self._note_kernel("adjoint", nsteps)
+        nlaunch = self._note_kernel("adjoint", nsteps)
         _lib.check(self.adj(C.byref(self.p), i_hi, nsteps, slot_hi % self.nslots, _stream_ptr()), f"{self.spec.family}_adjoint")
-        LAUNCHES["adjoint"] += nsteps
+        LAUNCHES["adjoint"] += nlaunch
         STEPS["adjoint"] += nsteps
 
     def slot_view(self, slot, count=1):
