@@ -413,18 +413,25 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_adjoint_kernel(cons
     struct SRows { float4 c[RPW], up, dn; float l[RPW], r[RPW]; };
     const int zt = zc0 + lr0;                               // first owned row (global)
     const int xl = strip * PW - 1, xr = strip * PW + PW;
-    auto load_s = [&](int k) {                              // history slot of S_{i_hi - k}
+    // (offsets and validity of the ten loads are fixed for the whole loop: computed once)
+    const long long o_own = (long long)zt * g.ld + x;
+    const bool v_up = active && zt - 1 >= 0 && zt - 1 < g.nz && x < g.ld, v_dn = active && zt + RPW < g.nz && x < g.ld;
+    const bool v_l = active && xl >= 0, v_r = active && xr < g.nx;
+    int hslot = ((pp.slot0 % pp.nslots) + pp.nslots) % pp.nslots;      // history slot of the NEXT S to load (walks down, wraps)
+    auto load_s = [&](int) {
         SRows q;
-        const float* S = pp.u + slotf * (((pp.slot0 - k) % pp.nslots + pp.nslots) % pp.nslots) + boff;
-        auto row4 = [&](int z) { return (active && z >= 0 && z < g.nz && x < g.ld) ? __ldg(reinterpret_cast<const float4*>(S + (long long)z * g.ld + x)) : zero; };
-        auto at = [&](int z, int xx) { return (active && z >= 0 && z < g.nz && xx >= 0 && xx < g.nx) ? __ldg(S + (long long)z * g.ld + xx) : 0.f; };
-        q.up = row4(zt - 1);
-        q.dn = row4(zt + RPW);
+        const float* S = pp.u + slotf * hslot + boff + o_own;
+        hslot = hslot == 0 ? pp.nslots - 1 : hslot - 1;
+        q.up = v_up ? __ldg(reinterpret_cast<const float4*>(S - g.ld)) : zero;
+        q.dn = v_dn ? __ldg(reinterpret_cast<const float4*>(S + RPW * g.ld)) : zero;
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) { q.c[r] = row4(zt + r); q.l[r] = at(zt + r, xl); q.r[r] = at(zt + r, xr); }
+        for (int r = 0; r < RPW; ++r) {
+            q.c[r] = in[r] ? __ldg(reinterpret_cast<const float4*>(S + r * g.ld)) : zero;
+            q.l[r] = (v_l && zt + r < g.nz) ? __ldg(S + r * g.ld + (xl - x)) : 0.f;
+            q.r[r] = (v_r && zt + r < g.nz) ? __ldg(S + r * g.ld + (xr - x)) : 0.f;
+        }
         return q;
     };
-    // receiver cotangent this thread will stage next step (threads 0 .. nrec-1; one record per thread and step)
     const int ncached = min(nrec, RECCAP);
     auto load_rec = [&](int k) {                            // the first cached record of this thread, one step ahead
         float v = 0.f;
@@ -470,12 +477,14 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_adjoint_kernel(cons
             const float4 up = ld_cluster4(up_addr + pc * up_stride);
             const float4 dn = ld_cluster4(dn_addr + pc * dn_stride);
             const float* Arow = pub + pc * rpc * ldp + own_off;
-            auto wrow = [&](int r) { return make_float4(ci[r].x * L1[r].x, ci[r].y * L1[r].y, ci[r].z * L1[r].z, ci[r].w * L1[r].w); };
+            float4 w[RPW];
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) w[r] = make_float4(ci[r].x * L1[r].x, ci[r].y * L1[r].y, ci[r].z * L1[r].z, ci[r].w * L1[r].w);
 #pragma unroll
             for (int r = 0; r < RPW; ++r) {
-                const float4 c = wrow(r);
-                const float4 n = r == 0 ? up : wrow(r > 0 ? r - 1 : 0);
-                const float4 s = r == RPW - 1 ? dn : wrow(r < RPW - 1 ? r + 1 : r);
+                const float4 c = w[r];
+                const float4 n = r == 0 ? up : w[r > 0 ? r - 1 : 0];
+                const float4 s = r == RPW - 1 ? dn : w[r < RPW - 1 ? r + 1 : r];
                 const float lh = Arow[r * ldp - 1], rh = Arow[r * ldp + 4];
                 float wl = __shfl_up_sync(0xffffffffu, c.w, 1);
                 float wr = __shfl_down_sync(0xffffffffu, c.x, 1);
@@ -634,10 +643,11 @@ int st_wave2d_persist_plan(int flags, const W2Args& a, bool adjoint, W2Persist& 
     if (a.nchan > 4 || (a.src_fmask & ~1)) return ST_PERSIST_NA;
     const W2Geom& g = a.g;
     // thread shape: 0 = 16 warps x 4 rows per thread (128 registers), 1 = 32 warps x 2 rows (64 registers).  The forward
-    // kernel is 2-4 % faster with 1; the adjoint keeps five register arrays per row and needs the 128 registers of 0.
+    // kernel is 2-4 % faster with 1; the adjoint keeps five register arrays per row: 8 warps x 8 rows (255 registers, no spills).
     const char* ev = getenv("SEISTORCH_B200_PERSIST_VARIANT");
-    pp.variant = adjoint ? 0 : (ev && *ev ? atoi(ev) : 1);
-    const int NW = pp.variant == 1 ? 32 : 16, RPW = pp.variant == 1 ? 2 : 4;
+    const char* eva = getenv("SEISTORCH_B200_PERSIST_ADJ_VARIANT");     // adjoint: 0 = 16 x 4, 2 = 8 warps x 8 rows (default: no spills)
+    pp.variant = adjoint ? (eva && *eva ? atoi(eva) : 2) : (ev && *ev ? atoi(ev) : 1);
+    const int NW = pp.variant == 1 ? 32 : pp.variant == 2 ? 8 : 16, RPW = pp.variant == 1 ? 2 : pp.variant == 2 ? 8 : 4;
     pp.nstrips = (g.ld + PW - 1) / PW;
     if (pp.nstrips < 1 || pp.nstrips > NW) return ST_PERSIST_NA;
     pp.nrg = NW / pp.nstrips;
@@ -656,5 +666,5 @@ int st_wave2d_persist_forward(const W2Args& a, const W2Persist& pp, cudaStream_t
 }
 
 int st_wave2d_persist_adjoint(const W2Args& a, const W2Persist& pp, cudaStream_t st) {
-    return launch_persist<true, 16, 4>(a, pp, st);
+    return pp.variant == 2 ? launch_persist<true, 8, 8>(a, pp, st) : launch_persist<true, 16, 4>(a, pp, st);
 }
