@@ -21,8 +21,17 @@ def test_reference_build_model_uses_overlay(tmp_path):
     for k in list(saved):
         del sys.modules[k]
     try:
+        sys.path.insert(0, ref_shim.REFERENCE_ROOT)
         names = ov.install()
         assert "seistorch.equations2d.acoustic_habc" in names
+        # class-level patches inside the reference's own modules: fused misfits, device filter, device smoothing
+        assert {"seistorch.loss.L2", "seistorch.loss.Envelope", "seistorch.signal.SeisSignal.filter",
+                "seistorch.process.PostProcess.smooth_gradient"} <= set(names)
+        import seistorch.loss as rl
+        import seistorch_b200.loss as ol
+        crit = rl.Loss("l2").loss({})
+        assert type(crit) is ol.L2 and type(rl.Loss("envelope").loss({})) is ol.Envelope
+        assert type(rl.Loss("phase").loss({})).__module__ == "seistorch.loss"      # not accelerated: stays the reference's
         sys.path.insert(0, ref_shim.REFERENCE_ROOT)
         from seistorch.model import build_model          # the reference's builder
         import seistorch.compile as sc
