@@ -362,6 +362,9 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_adjoint_kernel(cons
         L1[r] = L2[r] = al[r] = ci[r] = gacc[r] = zero;
         if (in[r]) {
             const long long o = (long long)z * g.ld + x;
+            // the accumulator starts from the plane's running value and is written back at the end: the sum over time
+            // steps is then associated the same way however the loop is cut into launches (checkpoint segments)
+            if (a.gacc != nullptr) gacc[r] = *reinterpret_cast<const float4*>(a.gacc + ((long long)b * 7 + 1) * ((long long)g.nz * g.ld) + o);
             L1[r] = __ldg(reinterpret_cast<const float4*>(p1 + o));
             L2[r] = __ldg(reinterpret_cast<const float4*>(p2 + o));
             al[r] = __ldg(reinterpret_cast<const float4*>(a.coef[3] + o));
@@ -578,19 +581,12 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_adjoint_kernel(cons
         }
         if (k < pp.nsteps) step(L1, L2, k, pc);
     }
-    // ---- the gradient plane of this shot: one read-modify-write for the whole time loop
+    // ---- the gradient plane of this shot: read once at the start, written once here
     if (a.gacc != nullptr) {
         float* gb = a.gacc + ((long long)b * 7 + 1) * ((long long)g.nz * g.ld) + (long long)zt * g.ld + x;     // slot 1: d/d ciso
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
-            if (in[r]) {
-                float4* gp = reinterpret_cast<float4*>(gb + (long long)r * g.ld);
-                float4 v = *gp;
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (x + e < g.nx) f4s(v, e, f4e(v, e) + f4e(gacc[r], e));
-                *gp = v;
-            }
+            if (in[r]) *reinterpret_cast<float4*>(gb + (long long)r * g.ld) = gacc[r];      // (cells past nx: zero + zero)
         }
     }
     cluster_arrive();

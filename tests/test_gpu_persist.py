@@ -69,8 +69,10 @@ def test_gradient_runs_history_segments_and_oracle(nz, nx, nshots, monkeypatch):
     # registers over the whole loop (the per-step kernels add one step at a time to the plane): rounding only
     assert all(np.array_equal(a, b) for a, b in zip(r1, r0))
     assert rel(g1, g0) < 2e-6 and rel(w1, w0) < 2e-6 and np.abs(w0).max() > 0
+    # K-step checkpoints + recomputation through the persistent kernels: bit for bit the stored-history result (the
+    # twin's gradient accumulator continues from the plane's running value)
     r2, g2, n2 = _run(case, monkeypatch, True, segment=41)
-    assert all(np.array_equal(a, b) for a, b in zip(r2, r0)) and rel(g2, g0) < 2e-6 and rel(_run.wavelet_grad, w0) < 2e-6
+    assert all(np.array_equal(a, b) for a, b in zip(r2, r1)) and np.array_equal(g2, g1) and np.array_equal(_run.wavelet_grad, w1)
     orecs, params = loop.simulate(case, dtype=torch.float64, requires_grad=["vp"])
     misfit.l2(orecs, [torch.zeros_like(r) for r in orecs]).backward()
     assert rel(cat_records(r1), cat_records([r.detach().numpy() for r in orecs])) < 1e-5
