@@ -50,6 +50,18 @@ __device__ __forceinline__ float4 ld_cluster4(unsigned addr) {
     asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+// loads the compiler may not move: issued where they are written (between the barrier's arrive and wait), so the data
+// travels while the barrier completes instead of being sunk to the first use in the next step
+__device__ __forceinline__ float4 ldg4_pinned(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ldg1_pinned(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -423,15 +435,22 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_adjoint_kernel(cons
     int hslot = ((pp.slot0 % pp.nslots) + pp.nslots) % pp.nslots;      // history slot of the NEXT S to load (walks down, wraps)
     auto load_s = [&](int) {
         SRows q;
+#if defined(ST_PADJ_DBG) && (ST_PADJ_DBG & 1)
+        q.up = q.dn = zero;
+        for (int r = 0; r < RPW; ++r) { q.c[r] = zero; q.l[r] = q.r[r] = 0.f; }
+        return q;
+#endif
         const float* S = pp.u + slotf * hslot + boff + o_own;
         hslot = hslot == 0 ? pp.nslots - 1 : hslot - 1;
-        q.up = v_up ? __ldg(reinterpret_cast<const float4*>(S - g.ld)) : zero;
-        q.dn = v_dn ? __ldg(reinterpret_cast<const float4*>(S + RPW * g.ld)) : zero;
+        q.up = q.dn = zero;
+        if (v_up) q.up = ldg4_pinned(S - g.ld);
+        if (v_dn) q.dn = ldg4_pinned(S + RPW * g.ld);
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
-            q.c[r] = in[r] ? __ldg(reinterpret_cast<const float4*>(S + r * g.ld)) : zero;
-            q.l[r] = (v_l && zt + r < g.nz) ? __ldg(S + r * g.ld + (xl - x)) : 0.f;
-            q.r[r] = (v_r && zt + r < g.nz) ? __ldg(S + r * g.ld + (xr - x)) : 0.f;
+            q.c[r] = zero; q.l[r] = 0.f; q.r[r] = 0.f;
+            if (in[r]) q.c[r] = ldg4_pinned(S + r * g.ld);
+            if (v_l && zt + r < g.nz) q.l[r] = ldg1_pinned(S + r * g.ld + (xl - x));
+            if (v_r && zt + r < g.nz) q.r[r] = ldg1_pinned(S + r * g.ld + (xr - x));
         }
         return q;
     };
@@ -464,6 +483,8 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_adjoint_kernel(cons
             }
         }
     };
+    // (An L2 prefetch of the history rows 6 steps ahead was measured and changed nothing: the twin is not waiting for
+    // HBM but for its own dependent arithmetic -- two Laplacians per cell at 2-4 warps per scheduler.)
     SRows Sn = load_s(0);
     float rec_next = load_rec(0);
     int slot_w = ((i_hi % 3) + 3) % 3;                      // ring slot Lam_i is stored to
@@ -511,7 +532,9 @@ __global__ void __launch_bounds__(NW * 32, 1) wave2d_persist_adjoint_kernel(cons
                     const float scc = f4e(sc, e);
                     const float swv = e == 0 ? sl : f4e(sc, e - 1), sev = e == 3 ? sr : f4e(sc, e + 1);
                     const float laps = ((f4e(sn, e) - scc) + (f4e(ss, e) - scc)) + ((sev - scc) + (swv - scc));
+#if !(defined(ST_PADJ_DBG) && (ST_PADJ_DBG & 2))
                     f4s(gacc[r], e, f4e(gacc[r], e) + l1c * laps);
+#endif
                 }
             }
             if (nrec > 0) {                                   // + d loss / d record_i, then clear the staging rows
@@ -639,10 +662,11 @@ int st_wave2d_persist_plan(int flags, const W2Args& a, bool adjoint, W2Persist& 
     if (a.nchan > 4 || (a.src_fmask & ~1)) return ST_PERSIST_NA;
     const W2Geom& g = a.g;
     // thread shape: 0 = 16 warps x 4 rows per thread (128 registers), 1 = 32 warps x 2 rows (64 registers).  The forward
-    // kernel is 2-4 % faster with 1; the adjoint keeps five register arrays per row: 8 warps x 8 rows (255 registers, no spills).
+    // kernel is 2-4 % faster with 1; the adjoint keeps five register arrays per row: 16 x 4 (a few spills) measured 5 % faster
+    // than 8 warps x 8 rows (255 registers, no spills).
     const char* ev = getenv("SEISTORCH_B200_PERSIST_VARIANT");
-    const char* eva = getenv("SEISTORCH_B200_PERSIST_ADJ_VARIANT");     // adjoint: 0 = 16 x 4, 2 = 8 warps x 8 rows (default: no spills)
-    pp.variant = adjoint ? (eva && *eva ? atoi(eva) : 2) : (ev && *ev ? atoi(ev) : 1);
+    const char* eva = getenv("SEISTORCH_B200_PERSIST_ADJ_VARIANT");     // adjoint: 0 = 16 x 4 (default), 2 = 8 warps x 8 rows
+    pp.variant = adjoint ? (eva && *eva ? atoi(eva) : 0) : (ev && *ev ? atoi(ev) : 1);
     const int NW = pp.variant == 1 ? 32 : pp.variant == 2 ? 8 : 16, RPW = pp.variant == 1 ? 2 : pp.variant == 2 ? 8 : 4;
     pp.nstrips = (g.ld + PW - 1) / PW;
     if (pp.nstrips < 1 || pp.nstrips > NW) return ST_PERSIST_NA;
