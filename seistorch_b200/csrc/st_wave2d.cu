@@ -2015,15 +2015,28 @@ __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, i
 // resident blocks per SM the register adjoint is compiled for (the Born pairs carry two fields: 128 registers)
 template <int FL>
 __host__ __device__ constexpr int adj_minb() { return (FL & ST_F_BORN) ? ST_ADJ_MINB_BORN : ST_ADJ_MINB; }
-
+#ifndef ST_ADJ_SPLIT
+#define ST_ADJ_SPLIT 0                      // 1: frame blocks and fast blocks of the register adjoint in two launches (tuning;
+                                            // measured on B200 with 2 / 3 / 4 resident fast blocks per SM: no gain -- the fast
+                                            // rows of the Born / TTI equations need ~100 registers themselves)
+#endif
+#ifndef ST_ADJ_MINB_FAST
+#define ST_ADJ_MINB_FAST 3                  // resident blocks per SM the fast-only launch is compiled for
+#endif
 template <int FL>
-__global__ void __launch_bounds__(NT, adj_minb<FL>()) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
+__host__ __device__ constexpr bool adj_split() { return ST_ADJ_SPLIT != 0 && (FL & (ST_F_BORN | ST_F_XZ | ST_F_G1)) != 0; }
+
+// PART: 0 = frame blocks and fast blocks in one launch; 1 = frame blocks only, 2 = fast blocks only (two launches: the
+// register allocation of a kernel is the maximum over its code paths, and the tap / generic frame code of the Born and
+// TTI equations needs far more registers than their fast rows -- see st_w2_launch_adj)
+template <int FL, int PART = 0>
+__global__ void __launch_bounds__(NT, PART == 2 ? ST_ADJ_MINB_FAST : adj_minb<FL>()) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
-    constexpr bool NEED_GEN = !adj_fast<FL>() || (FL & ST_F_HABC);
+    constexpr bool NEED_GEN = PART != 2 && (!adj_fast<FL>() || (FL & ST_F_HABC));
     constexpr int GEN_FLOATS = NEED_GEN ? 2 * NF * SH * SW : 1;
     constexpr int FAST_FLOATS = adj_iso_only<FL>() ? NWARP * FRZ * FW : 1;
     __shared__ __align__(16) float smem[GEN_FLOATS > FAST_FLOATS ? GEN_FLOATS : FAST_FLOATS];
-    const int bid = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     // grid.x = [band blocks: one per (tile, shot)] ++ [fast blocks: one per (fast tile, shot chunk)]
     // for the fast-path equations, else one general block per (tile, shot chunk).
     if constexpr (adj_fast<FL>()) {
@@ -2031,11 +2044,16 @@ __global__ void __launch_bounds__(NT, adj_minb<FL>()) wave2d_adjoint_kernel(cons
         const int ngrp = (a.B + BSH - 1) / BSH;
         const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
         const int nband = (FL & ST_F_HABC) ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
+        const int bid = PART == 2 ? blockIdx.x + nband : blockIdx.x;     // a fast-only launch enumerates the fast blocks from 0
         if ((ST_DBG_SKIP & 1) && bid < nband) return;          // tuning builds only: frame blocks off
         if ((ST_DBG_SKIP & 2) && bid >= nband) return;         //                     fast blocks off
         if (bid >= nband) {
-            const int q = bid - nband;
-            adjoint_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid, reinterpret_cast<float (*)[FRZ][FW]>(smem));
+            if constexpr (PART != 1) {
+                const int q = bid - nband;
+                adjoint_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid, reinterpret_cast<float (*)[FRZ][FW]>(smem));
+            }
+        } else if constexpr (PART == 2) {
+            return;
         } else if (tapped) {
             const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;     // gradient plane = group id (< B planes exist)
             const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
@@ -2052,6 +2070,7 @@ __global__ void __launch_bounds__(NT, adj_minb<FL>()) wave2d_adjoint_kernel(cons
             }
         }
     } else {
+        const int bid = blockIdx.x;
         const int ntile = bt.nxt * bt.nzt;
         const int chunk = bid / ntile, t = bid - chunk * ntile;
         const int tz = t / bt.nxt, tx = t - tz * bt.nxt;
@@ -2492,6 +2511,14 @@ int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
     if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B) : 0);
     else nblocks = (long long)bt.nxt * bt.nzt * nchunk;
+    if constexpr (adj_fast<FL>() && (FL & ST_F_HABC) && adj_split<FL>()) {
+        // two launches: the frame blocks (tap gather, needs the registers) and the fast blocks (compiled for more resident
+        // blocks per SM); they write disjoint cells and read the same inputs
+        const long long nband = nblocks - (long long)nfast * nchunk;
+        if (nband > 0) wave2d_adjoint_kernel<FL, 1><<<dim3((unsigned)nband), NT, 0, st>>>(a, nfx, nfast, bt);
+        wave2d_adjoint_kernel<FL, 2><<<dim3((unsigned)((long long)nfast * nchunk)), NT, 0, st>>>(a, nfx, nfast, bt);
+        return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+    }
     dim3 grid((unsigned)nblocks);
     wave2d_adjoint_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
     return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
