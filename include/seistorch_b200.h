@@ -263,6 +263,13 @@ int64_t st_misfit_envelope_workspace(int32_t nt, int32_t ntraces);
 int st_gaussian_smooth2d(const float* in, float* out, int32_t nz, int32_t nx, const float* weights, int32_t radius,
                          int32_t axis, void* stream);
 
+/* Source illumination (rnn.py:127-128,204-205: `precondition += sum_shots field[source_type]^2` every time step), read back
+ * from the wavefield history of a gradient run: out[fs] += sum over `count` consecutive slots starting at `slot_first`
+ * (mod nslots) and over the B shot planes of  u[slot * slot_stride + chan_offset + b * fs + cell]^2.
+ * All strides in floats and multiples of 4; out is one pitched plane ([nz][ld] / [n0][n1][ld]). */
+int st_illumination(const float* u, int64_t slot_stride, int32_t nslots, int32_t slot_first, int32_t count,
+                    int64_t chan_offset, int32_t B, int64_t fs, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

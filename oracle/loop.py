@@ -95,7 +95,7 @@ def build_geometry(case, dtype=torch.float32):
     return names, params, d, src, bidx, rec, counts
 
 
-def simulate(case, dtype=torch.float32, requires_grad=(), wavelet=None, source_encoding=False):
+def simulate(case, dtype=torch.float32, requires_grad=(), wavelet=None, source_encoding=False, illumination=None):
     """rnn.py:100-216 restated.  Returns (records [list of (nt, nrec, nchan)],
     params list).  Differentiable w.r.t. params named in requires_grad.
 
@@ -103,7 +103,10 @@ def simulate(case, dtype=torch.float32, requires_grad=(), wavelet=None, source_e
     into which every source of the case fires with its own wavelet -- ``wavelet`` is then (nsources, nt) -- through
     ``Y[..., y, x] += X`` (an index_put WITHOUT accumulation: of two sources in the same cell only one counts, a
     reference quirk this restatement keeps by using the same torch indexing); the receivers are those of the first
-    shot (the driver sets the probes once, codingfwi.py:129-132)."""
+    shot (the driver sets the probes once, codingfwi.py:129-132).
+
+    ``illumination``: a list; the source illumination of rnn.py:127-128,204-205 (sum over time steps and shots of the
+    squared field of the LAST source type, after the source was added) is appended to it."""
     eq = oracle_key(case)
     multiple = bool(case.get("multiple", False))
     names, params, d, src, bidx, rec, counts = build_geometry(case, dtype)
@@ -135,6 +138,7 @@ def simulate(case, dtype=torch.float32, requires_grad=(), wavelet=None, source_e
     bt = torch.from_numpy(bidx)
     rt = [torch.from_numpy(r) for r in rec]
     recs = {k: [] for k in case["receiver_type"]}
+    precondition = torch.zeros(shape, dtype=dtype)
     for i in range(nt):
         fields = list(step(params, fields, dt, h, d))
         for stype in case["source_type"]:
@@ -148,11 +152,15 @@ def simulate(case, dtype=torch.float32, requires_grad=(), wavelet=None, source_e
                 fields[k] = y_new
             else:
                 fields[k] = fields[k] + smask * x[i]
+        if illumination is not None:
+            precondition = precondition + torch.sum(fields[wf_names.index(case["source_type"][-1])].detach() ** 2, 0)
         for rtname in case["receiver_type"]:
             f = fields[wf_names.index(rtname)]
             if len(shape) == 2:
                 recs[rtname].append(f[bt, rt[1], rt[0]])           # probe.py:44  x[bidx, y, x]
             else:
                 recs[rtname].append(f[bt, rt[0], rt[2], rt[1]])    # probe.py:48  x[bidx, x, z, y]
+    if illumination is not None:
+        illumination.append(precondition)
     stacked = torch.stack([torch.stack(recs[k], dim=0) for k in recs], dim=2)
     return list(torch.split(stacked, counts, dim=1)), dict(zip(names, params))

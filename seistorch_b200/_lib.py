@@ -86,7 +86,7 @@ EXPORTS = [
     "st_qp2d_forward", "st_qp2d_adjoint", "st_fwim2d_forward", "st_fwim2d_adjoint",
     "st_elastic2d_forward", "st_elastic2d_adjoint",
     "st_acoustic3d_forward", "st_acoustic3d_adjoint",
-    "st_misfit_l2", "st_misfit_l1", "st_misfit_cs", "st_misfit_nim", "st_misfit_w1d", "st_misfit_traveltime", "st_misfit_sml1", "st_misfit_cc", "st_misfit_integration", "st_filtfilt", "st_misfit_envelope", "st_misfit_envelope_workspace", "st_gaussian_smooth2d",
+    "st_misfit_l2", "st_misfit_l1", "st_misfit_cs", "st_misfit_nim", "st_misfit_w1d", "st_misfit_traveltime", "st_misfit_sml1", "st_misfit_cc", "st_misfit_integration", "st_filtfilt", "st_misfit_envelope", "st_misfit_envelope_workspace", "st_gaussian_smooth2d", "st_illumination",
 ]
 
 _lib = None
@@ -151,6 +151,9 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.st_gaussian_smooth2d.restype = C.c_int
     L.st_gaussian_smooth2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.st_illumination.restype = C.c_int
+    L.st_illumination.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int64,
+                                  C.c_void_p, C.c_void_p]
     L.st_misfit_envelope_workspace.restype = C.c_int64
     L.st_misfit_envelope_workspace.argtypes = [C.c_int32, C.c_int32]
     _lib = L

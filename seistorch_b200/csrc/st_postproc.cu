@@ -35,7 +35,41 @@ __global__ void __launch_bounds__(256) gaussian_smooth2d_kernel(const float* __r
     out[(long long)z * nx + x] = acc;
 }
 
+// source illumination (rnn.py:127-128,204-205): out(cell) += sum over time steps and shots of field^2, read back from
+// the wavefield history the gradient run keeps anyway.  One thread per 4 consecutive cells (128-bit loads).
+__global__ void __launch_bounds__(256) illumination_kernel(const float* __restrict__ u, long long slot_stride, int nslots, int slot_first,
+                                                            int count, long long chan_offset, int B, long long fs, long long n4,
+                                                            float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 acc = reinterpret_cast<float4*>(out)[i];
+    int slot = slot_first % nslots;
+    for (int k = 0; k < count; ++k) {
+        const float* base = u + slot_stride * slot + chan_offset;
+        for (int b = 0; b < B; ++b) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(base + b * fs) + i);      // streaming: read once
+            acc.x += v.x * v.x; acc.y += v.y * v.y; acc.z += v.z * v.z; acc.w += v.w * v.w;
+        }
+        slot = slot + 1 == nslots ? 0 : slot + 1;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+}
+
 }  // namespace
+
+extern "C" int st_illumination(const float* u, int64_t slot_stride, int32_t nslots, int32_t slot_first, int32_t count,
+                               int64_t chan_offset, int32_t B, int64_t fs, float* out, void* stream) {
+    if (!u || !out || nslots <= 0 || count < 0 || B <= 0 || fs <= 0 || fs % 4 != 0 || slot_stride % 4 != 0 || chan_offset % 4 != 0) {
+        st_set_error("illumination: bad arguments (planes must be multiples of 4 floats)");
+        return ST_ERR_BADARG;
+    }
+    if (count == 0) return ST_OK;
+    const long long n4 = fs / 4;
+    illumination_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(u, slot_stride, nslots, slot_first, count,
+                                                                                         chan_offset, B, fs, n4, out);
+    if (cudaGetLastError() != cudaSuccess) { st_set_error("illumination: launch failed"); return ST_ERR_CUDA; }
+    return ST_OK;
+}
 
 extern "C" int st_gaussian_smooth2d(const float* in, float* out, int32_t nz, int32_t nx, const float* weights, int32_t radius,
                                     int32_t axis, void* stream) {

@@ -188,6 +188,8 @@ class Spec:
     src_fmask: int = 1
     chan_f: tuple = (0,)
     coef_slots: tuple = ()          # for wave2d: slot index (0..7) of every coefficient tensor passed
+    illum_chan: Optional[int] = None               # source illumination: field channel whose squares are summed (rnn.py:204-205)
+    illum_plane: Optional[torch.Tensor] = None     # ... into this zeroed pitched plane, during backward()
     history_budget_bytes: Optional[int] = None     # None: derive from free memory
     segment: Optional[int] = None                  # force a checkpoint segment length (tests)
 
@@ -431,6 +433,11 @@ class _Propagate(torch.autograd.Function):
         rec = torch.zeros((spec.nt, acq.R, nchan), dtype=torch.float32, device=dev)
         need_grad = any(ctx.needs_input_grad[2:])
         p = spec.order
+        ctx.illum = spec.illum_plane if spec.illum_chan is not None else None
+        if ctx.illum is not None and not need_grad:
+            raise NotImplementedError("seistorch_b200: source illumination is accumulated from the wavefield history of a "
+                                      "gradient run (mode 'inversion' with a parameter that requires grad); a forward-only "
+                                      "run keeps no history")
         if not need_grad:
             prob = _Problem(spec, coefp, acq, amp32, p + 1)
             prob.rec_out = rec
@@ -487,6 +494,14 @@ class _Propagate(torch.autograd.Function):
                 if p == 2:
                     prob.slot_view(1, 1).copy_(c1)
                 prob.forward(a, b - a, 0, record=False)
+            if ctx.illum is not None:
+                # S_i, i = a .. b-1, sit in slots slot0 + p + (i - a): add their squares (all shots) to the illumination
+                with torch.cuda.device(dev):
+                    _lib.check(_lib.lib().st_illumination(
+                        prob.u.data_ptr(), spec.slot_elems, prob.nslots, (slot0 + p) % prob.nslots, b - a,
+                        int(spec.illum_chan) * spec.B * spec.plane, spec.B, spec.plane, ctx.illum.data_ptr(), _stream_ptr()),
+                        "illumination")
+                LAUNCHES["misfit"] += 1
             if p == 2:
                 # Lam_i for i = b-1 .. a ; S_i sits in slot slot0 + 2 + (i - a)
                 prob.adjoint(b - 1, b - a, slot0 + 2 + (b - 1 - a))
@@ -525,5 +540,6 @@ class _Propagate(torch.autograd.Function):
 
 
 def propagate(spec: Spec, acq: Acquisition, amp: torch.Tensor, coefs: Sequence[torch.Tensor]) -> torch.Tensor:
-    """Run nt steps; returns seismograms [nt, R, nchan] (differentiable w.r.t. amp, coefs)."""
+    """Run nt steps; returns seismograms [nt, R, nchan] (differentiable w.r.t. amp, coefs).  With ``spec.illum_chan`` /
+    ``spec.illum_plane`` set, backward() also adds the source illumination to that plane (from the wavefield history)."""
     return _Propagate.apply(spec, acq, amp, *coefs)

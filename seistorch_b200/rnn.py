@@ -94,8 +94,6 @@ class WaveRNN(torch.nn.Module):
         if device.type != "cuda":
             raise RuntimeError("seistorch_b200: WaveRNN runs on CUDA devices only (no CPU fallback); "
                                f"geom.device = {geom.device}")
-        if self.source_illumination:
-            raise NotImplementedError("seistorch_b200: source_illumination is not on the accelerated path")
         ndim = len(geom.domain_shape)
         equation = geom.equation
         # The device-side index tables (validation, sort, CSR) are built once per acquisition and reused: the
@@ -187,6 +185,14 @@ class WaveRNN(torch.nn.Module):
                     bw=int(geom.bwidth), multiple=bool(geom.multiple), src_fmask=fmask,
                     chan_f=tuple(chan[n] for n in geom.receiver_type), coef_slots=slots,
                     history_budget_bytes=self.history_budget_bytes, segment=self.segment)
+        if self.source_illumination:
+            # rnn.py:127-128,204-205: precondition = sum over time and shots of field[last source_type]^2, reset at every
+            # forward call.  Here it is filled during backward() from the wavefield history (the drivers use it after
+            # loss.backward(): seistorch_dist.py:258,279-280).
+            spec.illum_chan = chan[list(geom.source_type)[-1]]
+            illum = torch.zeros(tuple(geom.domain_shape[:-1]) + (spec.ld,), dtype=torch.float32, device=device)
+            spec.illum_plane = illum
+            self.precondition = illum[..., :geom.domain_shape[-1]]
         rec = propagate(spec, acq, amp, coefs)                   # [nt, sum(nrec), nchan]
 
         if bool(torch.isnan(rec).any()):                         # type.py:41-46 (one device sync, not one per shot)

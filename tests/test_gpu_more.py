@@ -93,6 +93,34 @@ def test_source_encoding_against_reference_golden_and_oracle():
             assert rel(g, params["vp"].grad.numpy()) < 1e-4
 
 
+@pytest.mark.parametrize("eq,seg", [("acoustic_habc", None), ("acoustic_habc", 23), ("elastic", None), ("acoustic", None)])
+def test_source_illumination_from_the_history(eq, seg):
+    """rnn.py:127-128,204-205 + process.py:115-118: precondition = sum over time and shots of field[source_type]^2, used to
+    scale the gradient.  Filled during backward() from the wavefield history (whole history or K-step segments; through the
+    persistent kernels for the small acoustic grid); against the float64 oracle."""
+    import seistorch_b200 as sb
+    from seistorch_b200.process import PostProcess
+    from types import SimpleNamespace
+    from oracle import cases, loop
+    case = cases.make_case(eq, nz=40, nx=64, nshots=2, nt=90)
+    cfg, model = sb.model_from_case(case, device="cuda", mode="inversion")
+    model.source_illumination = True
+    model.segment = seg
+    x = torch.as_tensor(np.asarray(case["wavelet"]), device="cuda").unsqueeze(0)
+    syn = model(x)
+    assert float(model.precondition.abs().max()) == 0.0          # reset at every forward call, filled by backward()
+    sum((s ** 2).sum() for s in syn).backward()
+    ill = []
+    loop.simulate(case, dtype=torch.float64, illumination=ill)
+    assert rel(model.precondition.cpu().numpy(), ill[0].numpy()) < 1e-5
+    g0 = model.cell.geom.vp.grad.clone()
+    PostProcess(model, cfg, SimpleNamespace(grad_cut=False)).precondition()
+    assert torch.allclose(model.cell.geom.vp.grad * model.precondition, g0, rtol=1e-5, atol=0)
+    with pytest.raises(NotImplementedError):
+        with torch.no_grad():
+            model(x)
+
+
 def test_empty_receivers_and_zero_wavelet():
     from oracle import cases
     case = cases.make_case("acoustic", nz=20, nx=30, nshots=2, nt=20)
