@@ -115,7 +115,8 @@ def test_source_illumination_from_the_history(eq, seg):
     assert rel(model.precondition.cpu().numpy(), ill[0].numpy()) < 1e-5
     g0 = model.cell.geom.vp.grad.clone()
     PostProcess(model, cfg, SimpleNamespace(grad_cut=False)).precondition()
-    assert torch.allclose(model.cell.geom.vp.grad * model.precondition, g0, rtol=1e-5, atol=0)
+    lit = model.precondition > 0                                # cells the wavefield never reached divide 0 by 0, as in the reference
+    assert bool(lit.any()) and torch.allclose((model.cell.geom.vp.grad * model.precondition)[lit], g0[lit], rtol=1e-5, atol=0)
     with pytest.raises(NotImplementedError):
         with torch.no_grad():
             model(x)
