@@ -172,7 +172,6 @@ def run_dist(work):
     """runpy the reference's seistorch_dist.py byte for byte, as __main__, under torchrun."""
     from oracle import ref_shim
     setup_overlay()
-    import matplotlib                                   # noqa: F401 (stub)
     script = os.path.join(ref_shim.REFERENCE_ROOT, "seistorch_dist.py")
     sys.argv = [script, os.path.join(work, "config.yml"), "--opt", "adam", "--loss", "vp=l2", "--lr", "vp=10.0",
                 "--mode", "inversion", "--save-path", os.path.join(work, "results"), "--use-cuda"]
@@ -183,7 +182,7 @@ def expected_dist_gradient(world):
     """What the driver must have saved in grad_vp_nosm_0.pt: per rank the sum over its shots of the gradient of
     L2(filter(syn), filter(obs)), then DDP's mean over ranks -- from the float64 oracle."""
     import torch
-    from oracle import loop, misfit, sigproc
+    from oracle import loop, sigproc
     case, true = dist_case()
     obs, _ = loop.simulate(true, dtype=torch.float32)
     b, a = sigproc.butter(3, [8.0], float(case["dt"]))
