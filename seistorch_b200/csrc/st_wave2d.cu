@@ -1376,6 +1376,8 @@ __device__ __forceinline__ void forward_tma_block(const W2Args& a, const W2Tma& 
 #endif
 template <int FL>
 __global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
+    st_pdl_launch_dependents();                             // (no-ops unless launched with programmatic stream serialization)
+    st_pdl_wait();
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     constexpr bool HABC = (FL & ST_F_HABC) != 0;
     __shared__ float s1[HABC ? NF : 1][HABC ? SH : 1][SW];
@@ -2031,6 +2033,8 @@ __host__ __device__ constexpr bool adj_split() { return ST_ADJ_SPLIT != 0 && (FL
 // TTI equations needs far more registers than their fast rows -- see st_w2_launch_adj)
 template <int FL, int PART = 0>
 __global__ void __launch_bounds__(NT, PART == 2 ? ST_ADJ_MINB_FAST : adj_minb<FL>()) wave2d_adjoint_kernel(const W2Args a, int nfx, int nfast, BandTiles bt) {
+    st_pdl_launch_dependents();
+    st_pdl_wait();
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     constexpr bool NEED_GEN = PART != 2 && (!adj_fast<FL>() || (FL & ST_F_HABC));
     constexpr int GEN_FLOATS = NEED_GEN ? 2 * NF * SH * SW : 1;
@@ -2470,6 +2474,25 @@ static int tma_launch(K kernel, dim3 grid, int smem, cudaStream_t st, const W2Ar
     return cudaLaunchKernelEx(&cfg, kernel, a, nfx, tm) == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
 
+// register kernels: launched with programmatic stream serialization too (SEISTORCH_B200_PDL=0 turns it off).  Every block
+// executes launch_dependents + wait first thing, so the launch processing and block scheduling of step i+1 overlap step i
+// -- what matters on small grids, where a step is a few microseconds and the GPU is mostly empty.
+template <class K, class... Args>
+static int pdl_launch(K kernel, dim3 grid, cudaStream_t st, Args... args) {
+    static const bool pdl = [] { const char* e = getenv("SEISTORCH_B200_PDL"); return !(e && atoi(e) == 0); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...) == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+}
+
 template <int FL>
 int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     const int nfx = (a.g.nx + FW - 1) / FW, nfz = (a.g.nz + FH - 1) / FH;
@@ -2488,8 +2511,7 @@ int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
     const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
     dim3 grid((unsigned)((long long)nfast * a.B + (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B)));
-    wave2d_forward_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
-    return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+    return pdl_launch(wave2d_forward_kernel<FL>, grid, st, a, nfx, nfast, bt);
 }
 template <int FL>
 int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
@@ -2515,13 +2537,11 @@ int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
         // two launches: the frame blocks (tap gather, needs the registers) and the fast blocks (compiled for more resident
         // blocks per SM); they write disjoint cells and read the same inputs
         const long long nband = nblocks - (long long)nfast * nchunk;
-        if (nband > 0) wave2d_adjoint_kernel<FL, 1><<<dim3((unsigned)nband), NT, 0, st>>>(a, nfx, nfast, bt);
-        wave2d_adjoint_kernel<FL, 2><<<dim3((unsigned)((long long)nfast * nchunk)), NT, 0, st>>>(a, nfx, nfast, bt);
-        return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+        if (nband > 0 && pdl_launch(wave2d_adjoint_kernel<FL, 1>, dim3((unsigned)nband), st, a, nfx, nfast, bt) != ST_OK) return ST_ERR_CUDA;
+        return pdl_launch(wave2d_adjoint_kernel<FL, 2>, dim3((unsigned)((long long)nfast * nchunk)), st, a, nfx, nfast, bt);
     }
     dim3 grid((unsigned)nblocks);
-    wave2d_adjoint_kernel<FL><<<grid, NT, 0, st>>>(a, nfx, nfast, bt);
-    return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+    return pdl_launch(wave2d_adjoint_kernel<FL, 0>, grid, st, a, nfx, nfast, bt);
 }
 #if defined(ST_DBG_TIMELINE) && defined(ST_W2_INSTANCE)
 #if ST_W2_INSTANCE == 5
