@@ -59,6 +59,8 @@ __device__ __forceinline__ float lap7(const float4& C, const float4& U, const fl
 
 template <bool ADJ>
 __global__ void __launch_bounds__(NT, ADJ ? 3 : 4) acoustic3d_kernel(const A3Args a, int nfx, int nfz) {
+    st_pdl_launch_dependents();                             // (no-ops unless launched with programmatic stream serialization)
+    st_pdl_wait();
     __shared__ __align__(16) float gsm[ADJ ? NWARP * RZ * FW : 4];
     __shared__ int s_cnt, s_rows[FH];
     const G3 g{a.n0, a.n1, a.n2, a.ld, a.ps};
@@ -219,14 +221,12 @@ __global__ void __launch_bounds__(NT, ADJ ? 3 : 4) acoustic3d_kernel(const A3Arg
 int st_acoustic3d_launch_forward(const A3Args& a, cudaStream_t st) {
     const int nfx = (a.n2 + FW - 1) / FW, nfz = (a.n1 + FH - 1) / FH;
     dim3 grid(a.n0 * nfx * nfz, a.B);
-    acoustic3d_kernel<false><<<grid, NT, 0, st>>>(a, nfx, nfz);
-    return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+    return st_pdl_launch(acoustic3d_kernel<false>, grid, dim3(NT), 0, st, a, nfx, nfz) == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
 
 int st_acoustic3d_launch_adjoint(const A3Args& a, cudaStream_t st) {
     const int nfx = (a.n2 + FW - 1) / FW, nfz = (a.n1 + FH - 1) / FH;
     const int nchunk = (a.B + a.bchunk - 1) / a.bchunk;
     dim3 grid(a.n0 * nfx * nfz, nchunk);
-    acoustic3d_kernel<true><<<grid, NT, 0, st>>>(a, nfx, nfz);
-    return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+    return st_pdl_launch(acoustic3d_kernel<true>, grid, dim3(NT), 0, st, a, nfx, nfz) == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }

@@ -32,6 +32,30 @@ void st_set_error(const char* fmt, ...);
 
 #ifdef __CUDACC__
 #include <atomic>
+#include <cstdlib>
+// Programmatic dependent launch (the step kernels of one time loop are launched back to back on one stream):
+// st_pdl_launch_dependents() lets the next grid start launching once every block of this one has begun,
+// st_pdl_wait() blocks until the previous grid has completed and its writes are visible.  Everything a block
+// does before st_pdl_wait() (tile decode, mbarrier init, descriptor prefetch) overlaps the previous kernel's tail; on small
+// grids the launch processing and block scheduling of step i+1 overlap step i.  No-ops in a plain launch.
+__device__ __forceinline__ void st_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void st_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// launch with programmatic stream serialization (SEISTORCH_B200_PDL=0 turns it off)
+template <class K, class... Args>
+inline cudaError_t st_pdl_launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool pdl = [] { const char* e = getenv("SEISTORCH_B200_PDL"); return !(e && atoi(e) == 0); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 // Raise the dynamic shared-memory limit of one kernel.  The attribute is per DEVICE, so it is set once per
 // (kernel, device) -- a process that drives several GPUs gets it on each of them -- and a failure is not cached.
 template <auto Kernel>

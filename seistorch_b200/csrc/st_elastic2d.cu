@@ -230,6 +230,8 @@ __host__ __device__ inline FastRange elastic_fast_range(int nz, int nx) {
 // grid = (fast tiles, shots): every 128 x 64 tile runs the register / shuffle path; tiles that touch the domain
 // boundary take the masked variant.
 __global__ void __launch_bounds__(NT, ST_EL_MINB) elastic2d_forward_kernel(const E2Args a, int nfx) {
+    st_pdl_launch_dependents();                             // (no-ops unless launched with programmatic stream serialization)
+    st_pdl_wait();
     const int tid = threadIdx.x, b = blockIdx.y;
     const FastRange fr = elastic_fast_range(a.nz, a.nx);
     const int fz = blockIdx.x / nfx, fx = blockIdx.x - fz * nfx;
@@ -707,6 +709,8 @@ __global__ void __launch_bounds__(NT) elastic2d_adjoint_kernel(const E2Args a) {
 
 // grid = (tiles of 128 x AFH cells, shots); tiles touching the domain boundary take the masked variant
 __global__ void __launch_bounds__(NT, ST_EL_AMINB) elastic2d_adjoint_fast_kernel(const E2Args a, int nfx) {
+    st_pdl_launch_dependents();
+    st_pdl_wait();
     const int tid = threadIdx.x, b = blockIdx.y;
     const int fz = blockIdx.x / nfx, fx = blockIdx.x - fz * nfx;
     const int x0 = fx * FW, z0 = fz * AFH;
@@ -722,8 +726,7 @@ __global__ void __launch_bounds__(NT, ST_EL_AMINB) elastic2d_adjoint_fast_kernel
 int st_elastic2d_launch_forward(const E2Args& a, cudaStream_t st) {
     const int nfx = (a.nx + FW - 1) / FW, nfz = (a.nz + FH - 1) / FH;
     dim3 grid(nfx * nfz, a.B);
-    elastic2d_forward_kernel<<<grid, NT, 0, st>>>(a, nfx);
-    return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+    return st_pdl_launch(elastic2d_forward_kernel, grid, dim3(NT), 0, st, a, nfx) == cudaSuccess ? ST_OK : ST_ERR_CUDA;
 }
 
 int st_elastic2d_launch_adjoint(const E2Args& a, cudaStream_t st) {
@@ -733,8 +736,7 @@ int st_elastic2d_launch_adjoint(const E2Args& a, cudaStream_t st) {
     if (fast_on && a.lam1 != nullptr && a.bchunk == 1 && !(a.gacc && a.amp && (a.src_fmask & 0x1c))) {
         const int nfx = (a.nx + FW - 1) / FW, nfz = (a.nz + AFH - 1) / AFH;
         dim3 grid(nfx * nfz, a.B);
-        elastic2d_adjoint_fast_kernel<<<grid, NT, 0, st>>>(a, nfx);
-        return cudaGetLastError() == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+        return st_pdl_launch(elastic2d_adjoint_fast_kernel, grid, dim3(NT), 0, st, a, nfx) == cudaSuccess ? ST_OK : ST_ERR_CUDA;
     }
     const int nchunk = (a.B + a.bchunk - 1) / a.bchunk;
     dim3 grid((a.nx + TX - 1) / TX, (a.nz + TZ - 1) / TZ, nchunk), block(NTX, NTY);

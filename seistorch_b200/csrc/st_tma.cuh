@@ -8,6 +8,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "st_common.cuh"
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -43,12 +45,7 @@ __device__ __forceinline__ void st_tma_load_3d(void* dst, const CUtensorMap* map
         "l"(reinterpret_cast<uint64_t>(map)), "r"(st_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// Programmatic dependent launch (the step kernels of one time loop are launched back to back on one stream):
-// st_pdl_launch_dependents() lets the next grid start launching once every block of this one has begun,
-// st_pdl_wait() blocks until the previous grid has completed and its writes are visible.  Everything a block
-// does before st_pdl_wait() (tile decode, mbarrier init, descriptor prefetch) overlaps the previous kernel's tail.
-__device__ __forceinline__ void st_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void st_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// (programmatic dependent launch helpers st_pdl_*: st_common.cuh)
 __device__ __forceinline__ void st_tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
