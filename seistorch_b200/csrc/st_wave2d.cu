@@ -57,9 +57,13 @@ constexpr int FRZ = ST_FRZ;                 // rows per warp
 constexpr int NWARP = NT / 32;
 constexpr int FH = FRZ * NWARP;             // rows per fast block
 #ifndef ST_BAND_SHOTS
-#define ST_BAND_SHOTS 8
+#define ST_BAND_SHOTS 12
 #endif
-constexpr int BSH = ST_BAND_SHOTS;          // shots a band thread walks with its taps in registers
+constexpr int BSH = ST_BAND_SHOTS;          // most shots a band thread walks with its taps in registers (B200, 12 shots 600x1300,
+                                            // adjoint of the VTI Born pair: groups of 4 / 6 / 8+4 / 12 shots: 282 / 267 / 268 / 251 us)
+// the shots of a launch are split into equal groups of at most BSH
+__host__ __device__ __forceinline__ int band_groups(int B) { return (B + BSH - 1) / BSH; }
+__host__ __device__ __forceinline__ int band_group_shots(int B) { const int n = band_groups(B); return (B + n - 1) / n; }
 #ifndef ST_DBG_SKIP
 #define ST_DBG_SKIP 0                       // tuning only: bit 0 / 1 = frame / fast blocks of the register adjoint kernel return at once, bit 3 = TMA blocks return at once, bit 4 = all tiles as kind 0, bit 5 = corner blocks return
 #endif
@@ -552,9 +556,15 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
 // ------------------------------------------------------------------------------ band (tap gather)
 // rows touched by the 256 consecutive band cells of a block -> shared list (<= 16 rows)
 // ---- cell maps of the tap-gather blocks: which cell a thread owns, which cells the block owns
+#ifndef ST_BAND_DENSE
+#define ST_BAND_DENSE 0
+#endif
+#ifndef ST_BAND_DENSE_BORN
+#define ST_BAND_DENSE_BORN 1
+#endif
 // BandMap: the compact enumeration of the absorbing band (st_band_cells), minus the vectorised strips, NT cells per block
 struct BandMap {
-    static constexpr bool dense = false;    // most band cells use one side only: zero taps are skipped (saves loads)
+    static constexpr bool dense = ST_BAND_DENSE != 0;    // false: zero taps (most band cells use one side only) are skipped
     W2Geom g; BandCells bc; StripGeom sg; bool strips, frame_only; int i0;
     __device__ __forceinline__ bool cell(int t, int& z, int& x) const {
         const int i = i0 + t;
@@ -767,6 +777,9 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
     constexpr bool XZ = (FL & ST_F_XZ) != 0;
     constexpr int NT1 = XZ ? ST_NTAP1 : ST_NTAP1C;           // taps of h1 this equation uses (13 with the mixed derivative)
     constexpr int NK = XZ ? ST_NTAP1 : ST_NTAP2;             // taps of the spatial stencil (cross, + diagonals for XZ)
+    // zero taps: skipped by the single-field equations (saves loads); the Born pairs load every tap unconditionally -- their
+    // guard needs the tap AND the coupling weight, and the guarded version issues 3x the instructions (B200: 268 -> 224 us)
+    constexpr bool DENSE = Map::dense || (ST_BAND_DENSE_BORN != 0 && NF == 2);
     const W2Geom g = a.g;
     const long long plane = (long long)g.nz * g.ld;
     const bool want_grad = a.gacc != nullptr;
@@ -840,13 +853,13 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
                     // zero taps (most far taps of single-side cells) are skipped; the centre value is
                     // always needed for the imaging condition
                     const bool cpl = NF == 2 && f == 1 && o < NK && gk[o < NK ? o : 0] != 0.f;
-                    if (o == 0 || Map::dense || g1[o] != 0.f || cpl) {
+                    if (o == 0 || DENSE || g1[o] != 0.f || cpl) {
                         const float v = __ldg(l1 + q[o]);
                         if (o == 0) lc[f] = v;
                         acc += g1[o] * v;
                         if (NF == 2 && f == 1 && o < NK) accOut[0] += gk[o < NK ? o : 0] * v;
                     }
-                    if (o < ST_NTAP2 && (Map::dense || g2[o < ST_NTAP2 ? o : 0] != 0.f)) acc += g2[o < ST_NTAP2 ? o : 0] * __ldg(l2 + q[o]);
+                    if (o < ST_NTAP2 && (DENSE || g2[o < ST_NTAP2 ? o : 0] != 0.f)) acc += g2[o < ST_NTAP2 ? o : 0] * __ldg(l2 + q[o]);
                 }
                 accOut[f] += acc;
             }
@@ -862,8 +875,8 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
                         if (o < ST_NTAP2) {
                             s[o] = m[o] * __ldg(S1 + q[o]);
                             t += h1[o] * s[o];
-                            if (Map::dense || h2[o] != 0.f) t += h2[o] * __ldg(S2 + q[o]);
-                        } else if (Map::dense || h1[o] != 0.f) {
+                            if (DENSE || h2[o] != 0.f) t += h2[o] * __ldg(S2 + q[o]);
+                        } else if (DENSE || h1[o] != 0.f) {
                             t += h1[o] * __ldg(S1 + q[o]);
                         }
                     }
@@ -1209,7 +1222,7 @@ __host__ __device__ inline CornerTiles corner_tiles(const W2Tma& tm, const W2Geo
 #endif
 constexpr int CORNER_SUB = TX * TZ / NT;                    // tap blocks per corner tile (4 rows x 64 columns each)
 __host__ __device__ inline int corner_block_count(const CornerTiles& c, int B, bool tapped) {
-    return tapped ? c.count * CORNER_SUB * ((B + BSH - 1) / BSH) : c.count * B;
+    return tapped ? c.count * CORNER_SUB * band_groups(B) : c.count * B;
 }
 __device__ __forceinline__ void corner_tile_decode(const CornerTiles& c, const W2Tma& tm, const W2Geom& g, int i, int& tz, int& xoff) {
     const int ri = i >> 1;
@@ -1385,7 +1398,7 @@ __global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W
     // grid.x = [frame blocks] ++ [fast blocks x shots]; the (slower) frame blocks get the low ids so
     // they are scheduled first.  Tapped frame blocks walk all shots themselves.
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
-    const int ngrp = (a.B + BSH - 1) / BSH;
+    const int ngrp = band_groups(a.B), gsh = band_group_shots(a.B);
     const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
     const int nframe = HABC ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
     if (bid >= nframe) {
@@ -1393,7 +1406,7 @@ __global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W
         forward_fast_block<FL>(a, q % nfast, nfx, q / nfast, tid);
     } else if (tapped) {
         const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;
-        const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
+        const int b_lo = grp * gsh, b_hi = min(b_lo + gsh, a.B);
         if (k < nstrip) forward_strip_block(a, k, b_lo, b_hi, tid);
         else forward_band_block<FL>(a, k - nstrip, b_lo, b_hi, tid);
     } else {
@@ -1430,7 +1443,7 @@ __global__ void __launch_bounds__(NT, tma_fwd_minb<FL>()) wave2d_forward_tma_ker
                 const int per = ct.count * CORNER_SUB, grp = bid / per, r = bid - grp * per;
                 corner_tile_decode(ct, tm, a.g, r / CORNER_SUB, tz, tx);
                 const RectMap map{a.g, tz * TZ + (r % CORNER_SUB) * (NT / TX), tx, TX};
-                forward_tap_block<FL>(a, map, grp * BSH, min(grp * BSH + BSH, a.B), tid);
+                forward_tap_block<FL>(a, map, grp * band_group_shots(a.B), min((grp + 1) * band_group_shots(a.B), a.B), tid);
             } else {
                 const int b = bid / ct.count;
                 corner_tile_decode(ct, tm, a.g, bid - b * ct.count, tz, tx);
@@ -1607,6 +1620,19 @@ __device__ __forceinline__ void adjoint_fast_rows(const W2Args& a, const W2Geom&
 }
 
 
+#ifndef ST_GEN_SMEM_GRAD
+#define ST_GEN_SMEM_GRAD 1                  // 0: the single-field non-ISO equations add their gradients straight to the global plane
+#endif
+constexpr int GPL4 = NWARP * FRZ * FW / 4;      // float4s per shared-memory gradient plane of a fast block
+// position of gradient slot `slot` among the slots the flag set uses (= its shared-memory plane), and their number
+template <int FL>
+__host__ __device__ constexpr int adj_gslot_index(int slot) {
+    int n = 0;
+    for (int q = 1; q < slot; ++q) if (grad_used<FL>(q)) ++n;
+    return n;
+}
+template <int FL>
+__host__ __device__ constexpr int adj_smem_planes() { return adj_gslot_index<FL>(7); }
 // Single-field, non-Born flag sets (vti_habc2, tti_habc, acoustic_fwim_habc): interior cells
 //   Lam_i = 2 L1 - L2 + dxx(cxx L1) + dzz(czz L1) + dxz^T(cxz L1) - dx(ax L1) - dz(az L1)
 // evaluated on rows of the coefficient-times-cotangent products, which are formed once per row
@@ -1614,7 +1640,8 @@ __device__ __forceinline__ void adjoint_fast_rows(const W2Args& a, const W2Geom&
 // (imaging condition) are added straight to the block's gradient plane.
 template <int FL, class Own>
 __device__ __forceinline__ void adjoint_fast_rows_gen(const W2Args& a, const W2Geom& g, int b, int chunk, int x0, int z0,
-                                                      int zn, int lane, bool clean, bool want_grad, Own owns) {
+                                                      int zn, int lane, bool clean, bool want_grad, Own owns,
+                                                      float4* gsl = nullptr) {       // gsl: shared-memory gradient planes
     constexpr bool ISO = (FL & ST_F_ISO) != 0, XZ = (FL & ST_F_XZ) != 0, G1 = (FL & ST_F_G1) != 0;
     const int x = x0 + 4 * lane;
     const int ld = g.ld;
@@ -1706,7 +1733,26 @@ __device__ __forceinline__ void adjoint_fast_rows_gen(const W2Args& a, const W2G
                 }
             }
             const int ro = z * ld + x;
-            if (clean) {
+            if (gsl != nullptr) {
+                // gradient partial sums of the block's shots in shared memory; cells the block does not own are never flushed
+                if (want_grad) {
+                    float4* p4 = gsl + k * (FW / 4);
+                    auto add = [&](int slot_index, const float4& v) { p4[slot_index * GPL4] = f4add(p4[slot_index * GPL4], v); };
+                    add(adj_gslot_index<FL>(1), g1v);
+                    if (!ISO) add(adj_gslot_index<FL>(2), g2v);
+                    if (XZ) add(adj_gslot_index<FL>(3), g3v);
+                    if (G1) { add(adj_gslot_index<FL>(4), g4v); add(adj_gslot_index<FL>(5), g5v); }
+                }
+                if (clean) {
+                    *reinterpret_cast<float4*>(l0 + ro) = out;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (x + e < g.nx && owns(z, x + e)) l0[ro + e] = f4get(out, e);
+                        else if (x + e >= g.nx && x + e < ld) l0[ro + e] = 0.f;
+                    }
+                }
+            } else if (clean) {
                 // the whole tile is frame-free and inside the domain: 128-bit stores and gradient read-modify-writes
                 *reinterpret_cast<float4*>(l0 + ro) = out;
                 if (want_grad) {
@@ -1749,7 +1795,8 @@ __device__ __forceinline__ void adjoint_fast_rows_gen(const W2Args& a, const W2G
 // Same row-marching register pipeline as adjoint_fast_rows_gen, one field after the other.
 template <int FL, class Own>
 __device__ __forceinline__ void adjoint_fast_rows_born(const W2Args& a, const W2Geom& g, int b, int chunk, int x0, int z0,
-                                                       int zn, int lane, bool clean, bool want_grad, Own owns) {
+                                                       int zn, int lane, bool clean, bool want_grad, Own owns,
+                                                       float4* gsl = nullptr) {      // gsl: shared-memory gradient planes
     constexpr bool XZ = (FL & ST_F_XZ) != 0;
     const int x = x0 + 4 * lane;
     const int ld = g.ld;
@@ -1846,7 +1893,25 @@ __device__ __forceinline__ void adjoint_fast_rows_born(const W2Args& a, const W2
                     }
                 }
                 const int ro = z * ld + x;
-                if (clean) {
+                if (gsl != nullptr) {
+                    // gradient partial sums of the block's shots in shared memory; cells the block does not own are never flushed
+                    if (want_grad) {
+                        float4* p4 = gsl + k * (FW / 4);
+                        p4[0] = f4add(p4[0], g1v);
+                        p4[GPL4] = f4add(p4[GPL4], g2v);
+                        if (XZ) p4[2 * GPL4] = f4add(p4[2 * GPL4], g3v);
+                        if (f == 0) p4[(XZ ? 3 : 2) * GPL4] = f4add(p4[(XZ ? 3 : 2) * GPL4], g6v);
+                    }
+                    if (clean) {
+                        *reinterpret_cast<float4*>(l0 + ro) = out;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (x + e < g.nx && owns(z, x + e)) l0[ro + e] = f4get(out, e);
+                            else if (x + e >= g.nx && x + e < ld) l0[ro + e] = 0.f;
+                        }
+                    }
+                } else if (clean) {
                     // the whole tile is frame-free and inside the domain: 128-bit stores and gradient read-modify-writes
                     *reinterpret_cast<float4*>(l0 + ro) = out;
                     if (want_grad) {
@@ -1883,10 +1948,170 @@ __device__ __forceinline__ void adjoint_fast_rows_born(const W2Args& a, const W2
     }
 }
 
+// Born pairs, BOTH fields in one pass over the rows (default; ST_BORN_FUSED=0 keeps the field-after-field version above for
+// A/B timing): one load of cxx, czz (cxz), m and of the scattered cotangent serves the two fields, the loads of a row are
+// all independent (one memory round trip per row instead of one per field and gradient plane), and the gradient partial
+// sums of the block's shots live in shared memory (planes cxx, czz, [cxz,] m; flushed once per `bchunk` shots).
+#ifndef ST_BORN_FUSED
+#define ST_BORN_FUSED 2                     // 0: field after field, global gradient RMW (round-2 first version); 1: fused rows for
+#endif                                      // the VTI pair, field after field + shared-memory gradients for the TTI pair; 2: fused
+                                            // rows for both (B200, 12 shots 600x1300: VTI 393 / 275 / 276 us, TTI 496 / 439 / 386 us)
+template <int FL, class Own>
+__device__ __forceinline__ void adjoint_fast_rows_born2(const W2Args& a, const W2Geom& g, int b, int x0, int z0, int zn,
+                                                        int lane, bool clean, bool want_grad, float4* gsl, Own owns) {
+    constexpr bool XZ = (FL & ST_F_XZ) != 0;
+    const int x = x0 + 4 * lane;
+    const int ld = g.ld;
+    const long long boff = (long long)b * a.fs;
+    const float* __restrict__ l1b = a.lam1 + boff;             // cotangent of the background field
+    const float* __restrict__ l1s = a.lam1 + a.cs + boff;      // ... of the scattered field
+    const float* __restrict__ S0 = a.s1 + boff;
+    const float* __restrict__ S1 = a.s1 + a.cs + boff;
+    const float* __restrict__ cxx = a.coef[2];
+    const float* __restrict__ czz = a.coef[3];
+    const float* __restrict__ cxz = a.coef[4];
+    const float* __restrict__ mm = a.coef[7];
+    const int xh = lane == 0 ? x0 - 1 : x0 + FW;               // halo column (every lane issues the same predicated loads;
+    const bool xhin = xh >= 0 && xh < g.nx;                    //  lanes 1..30 read lane 31's column and drop it)
+    struct Row {
+        float4 le0, le1, r0;                   // effective cotangents le0 = L1(0) + m L1(1), le1 = L1(1); raw L1(0)
+        float4 a0, a1, b0, b1, c0, c1;         // cxx*le, czz*le, cxz*le
+        float4 s0, s1;                         // S_i rows of the two fields
+        float a0l, a0r, a1l, a1r, c0l, c0r, c1l, c1r, s0l, s0r, s1l, s1r;
+    };
+    auto edges = [&](const float4& v, float h, float& l, float& r) {
+        l = __shfl_up_sync(0xffffffffu, v.w, 1);
+        r = __shfl_down_sync(0xffffffffu, v.x, 1);
+        l = lane == 0 ? h : l;
+        r = lane == 31 ? h : r;
+    };
+    auto load_row = [&](int z) {
+        Row q;
+        q.r0 = ldrow(l1b, z, x, g);
+        q.le1 = ldrow(l1s, z, x, g);
+        q.le0 = f4fma(ldrow(mm, z, x, g), q.le1, q.r0);
+        const float4 ca = ldrow(cxx, z, x, g);
+        const float4 cb = ldrow(czz, z, x, g);
+        const float4 cc = XZ ? ldrow(cxz, z, x, g) : f4zero();
+        q.a0 = f4mul(ca, q.le0); q.a1 = f4mul(ca, q.le1);
+        q.b0 = f4mul(cb, q.le0); q.b1 = f4mul(cb, q.le1);
+        q.c0 = f4mul(cc, q.le0); q.c1 = f4mul(cc, q.le1);
+        q.s0 = want_grad ? ldrow(S0, z, x, g) : f4zero();
+        q.s1 = want_grad ? ldrow(S1, z, x, g) : f4zero();
+        // halo column
+        const bool in = xhin && z >= 0 && z < g.nz;
+        const int o = z * ld + xh;
+        const float h1 = in ? __ldg(l1s + o) : 0.f;
+        const float h0 = in ? fmaf(__ldg(mm + o), h1, __ldg(l1b + o)) : 0.f;
+        const float hca = in ? __ldg(cxx + o) : 0.f;
+        const float hcc = (XZ && in) ? __ldg(cxz + o) : 0.f;
+        const float hs0 = (want_grad && in) ? __ldg(S0 + o) : 0.f;
+        const float hs1 = (want_grad && in) ? __ldg(S1 + o) : 0.f;
+        edges(q.a0, hca * h0, q.a0l, q.a0r);
+        edges(q.a1, hca * h1, q.a1l, q.a1r);
+        edges(q.c0, hcc * h0, q.c0l, q.c0r);
+        edges(q.c1, hcc * h1, q.c1l, q.c1r);
+        edges(q.s0, hs0, q.s0l, q.s0r);
+        edges(q.s1, hs1, q.s1l, q.s1r);
+        return q;
+    };
+    Row U = load_row(z0 - 1), C = load_row(z0), D;
+#pragma unroll
+    for (int k = 0; k < FRZ; ++k) {
+        const int z = z0 + k;
+        if (z < zn) {
+            D = load_row(z + 1);
+            const float4 p20 = ldrow(a.lam2 + boff, z, x, g);
+            const float4 p21 = ldrow(a.lam2 + a.cs + boff, z, x, g);
+            float4 out0, out1, g1v = f4zero(), g2v = f4zero(), g3v = f4zero(), g6v = f4zero();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                auto field = [&](const float4& raw, const float4& p2, const float4& ca_, float al, float ar,
+                                 const float4& ub, const float4& cb_, const float4& db,
+                                 const float4& uc, float ucl, float ucr, const float4& dc, float dcl, float dcr) {
+                    const float ac = f4get(ca_, e);
+                    const float aw = e == 0 ? al : f4get(ca_, e - 1), ae = e == 3 ? ar : f4get(ca_, e + 1);
+                    float acc = 2.f * f4get(raw, e) - f4get(p2, e);
+                    acc += ((ae - ac) + (aw - ac));                                              // dxx of cxx*le
+                    acc += ((f4get(ub, e) - f4get(cb_, e)) + (f4get(db, e) - f4get(cb_, e)));    // dzz of czz*le
+                    if (XZ) {
+                        const float uw = e == 0 ? ucl : f4get(uc, e - 1), ue = e == 3 ? ucr : f4get(uc, e + 1);
+                        const float dw = e == 0 ? dcl : f4get(dc, e - 1), de = e == 3 ? dcr : f4get(dc, e + 1);
+                        acc += (uw - ue) - (dw - de);
+                    }
+                    return acc;
+                };
+                f4set(out0, e, field(C.r0, p20, C.a0, C.a0l, C.a0r, U.b0, C.b0, D.b0, U.c0, U.c0l, U.c0r, D.c0, D.c0l, D.c0r));
+                f4set(out1, e, field(C.le1, p21, C.a1, C.a1l, C.a1r, U.b1, C.b1, D.b1, U.c1, U.c1l, U.c1r, D.c1, D.c1l, D.c1r));
+                if (want_grad) {
+                    auto second = [&](const float4& su, const float4& sc_, const float4& sd, float scl, float scr,
+                                      float sul, float sur, float sdl, float sdr, float& sxx, float& szz, float& cross) {
+                        const float sc = f4get(sc_, e);
+                        const float sw_ = e == 0 ? scl : f4get(sc_, e - 1), se_ = e == 3 ? scr : f4get(sc_, e + 1);
+                        sxx = (se_ - sc) + (sw_ - sc);
+                        szz = (f4get(su, e) - sc) + (f4get(sd, e) - sc);
+                        cross = 0.f;
+                        if (XZ) {
+                            const float nw = e == 0 ? sul : f4get(su, e - 1), ne = e == 3 ? sur : f4get(su, e + 1);
+                            const float sw2 = e == 0 ? sdl : f4get(sd, e - 1), se2 = e == 3 ? sdr : f4get(sd, e + 1);
+                            cross = (se2 - sw2) - (ne - nw);
+                        }
+                    };
+                    float sxx0, szz0, cr0, sxx1, szz1, cr1;
+                    second(U.s0, C.s0, D.s0, C.s0l, C.s0r, U.s0l, U.s0r, D.s0l, D.s0r, sxx0, szz0, cr0);
+                    second(U.s1, C.s1, D.s1, C.s1l, C.s1r, U.s1l, U.s1r, D.s1l, D.s1r, sxx1, szz1, cr1);
+                    const float le0 = f4get(C.le0, e), le1 = f4get(C.le1, e);
+                    f4set(g1v, e, fmaf(le0, sxx0, le1 * sxx1));
+                    f4set(g2v, e, fmaf(le0, szz0, le1 * szz1));
+                    if (XZ) f4set(g3v, e, fmaf(le0, cr0, le1 * cr1));
+                    // g_m += L1(1) A[S_0] = (cxx L1(1)) dxx S_0 + (czz L1(1)) dzz S_0 + (cxz L1(1)) dxz S_0: the products are at hand
+                    f4set(g6v, e, f4get(C.a1, e) * sxx0 + f4get(C.b1, e) * szz0 + (XZ ? f4get(C.c1, e) * cr0 : 0.f));
+                }
+            }
+            const int ro = z * ld + x;
+            float* o0 = a.lam0 + boff + ro;
+            float* o1 = a.lam0 + a.cs + boff + ro;
+            if (clean) {
+                *reinterpret_cast<float4*>(o0) = out0;
+                *reinterpret_cast<float4*>(o1) = out1;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (x + e < g.nx && owns(z, x + e)) { o0[e] = f4get(out0, e); o1[e] = f4get(out1, e); }
+                    else if (x + e >= g.nx && x + e < ld) { o0[e] = 0.f; o1[e] = 0.f; }
+                }
+            }
+            if (want_grad) {                   // cells this block does not own are never flushed (adjoint_fast_block)
+                float4* p4 = gsl + k * (FW / 4);
+                p4[0] = f4add(p4[0], g1v);
+                p4[GPL4] = f4add(p4[GPL4], g2v);
+                if (XZ) p4[2 * GPL4] = f4add(p4[2 * GPL4], g3v);
+                p4[(XZ ? 3 : 2) * GPL4] = f4add(p4[(XZ ? 3 : 2) * GPL4], g6v);
+            }
+            U = C; C = D;
+        }
+    }
+}
+
+// The fast blocks keep the gradient partial sums of their shots in shared memory: one plane per coefficient gradient the
+// flag set has (slots 1..6 of the gradient accumulator; slot 0, d/d r, belongs to the frame blocks), flushed once per chunk.
+template <int FL>
+__host__ __device__ constexpr bool adj_smem_grad() {
+    return adj_iso_only<FL>() || ((FL & ST_F_BORN) ? ST_BORN_FUSED != 0 : ST_GEN_SMEM_GRAD != 0);
+}
+template <int FL>
+__host__ __device__ constexpr int adj_smem_slot(int i) {       // i-th gradient slot in use
+    int n = 0;
+    for (int q = 1; q <= 6; ++q)
+        if (grad_used<FL>(q)) { if (n == i) return q; ++n; }
+    return 1;
+}
+
 template <int FL>
 __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int nfx, int chunk, int tid,
                                                    float (*gsm)[FRZ][FW]) {
     constexpr bool HABC = (FL & ST_F_HABC) != 0;
+    constexpr int NGS = adj_smem_planes<FL>();
     const W2Geom g = a.g;
     const int warp = tid >> 5, lane = tid & 31;
     const int fz = bid / nfx, fx = bid - fz * nfx;
@@ -1906,10 +2131,12 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
     }
     const bool safe = z0 >= 1 && z0 + FRZ + 1 <= g.nz && x0 >= 1 && x0 + FW + 1 <= g.nx;
     auto owns = [&](int z, int xx) { return !HABC || edge_depth(z, xx, g) >= band; };
-    float4* gsl = reinterpret_cast<float4*>(&gsm[warp][0][4 * lane]);      // stride FW/4 float4 per row
-    if (want_grad && adj_iso_only<FL>()) {
+    float4* gsl = reinterpret_cast<float4*>(&gsm[warp][0][4 * lane]);      // stride FW/4 float4 per row, GPL4 per plane
+    if (want_grad && adj_smem_grad<FL>()) {
 #pragma unroll
-        for (int k = 0; k < FRZ; ++k) gsl[k * (FW / 4)] = f4zero();
+        for (int q = 0; q < NGS; ++q)
+#pragma unroll
+            for (int k = 0; k < FRZ; ++k) gsl[q * GPL4 + k * (FW / 4)] = f4zero();
     }
     const int b_lo = chunk * a.bchunk, b_hi = min(b_lo + a.bchunk, a.B);
     for (int b = b_lo; b < b_hi; ++b) {
@@ -1917,29 +2144,36 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
             if constexpr (adj_iso_only<FL>()) {
                 if (safe) adjoint_fast_rows<FL, true>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
                 else adjoint_fast_rows<FL, false>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
+            } else if constexpr ((FL & ST_F_BORN) != 0) {
+                if constexpr (ST_BORN_FUSED == 2 || (ST_BORN_FUSED == 1 && !(FL & ST_F_XZ)))
+                    adjoint_fast_rows_born2<FL>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
+                else adjoint_fast_rows_born<FL>(a, g, b, chunk, x0, z0, zn, lane, clean, want_grad, owns, ST_BORN_FUSED ? gsl : nullptr);
             } else {
-                if constexpr ((FL & ST_F_BORN) != 0) adjoint_fast_rows_born<FL>(a, g, b, chunk, x0, z0, zn, lane, clean, want_grad, owns);
-                else adjoint_fast_rows_gen<FL>(a, g, b, chunk, x0, z0, zn, lane, clean, want_grad, owns);
+                adjoint_fast_rows_gen<FL>(a, g, b, chunk, x0, z0, zn, lane, clean, want_grad, owns, adj_smem_grad<FL>() ? gsl : nullptr);
             }
         }
         adjoint_tail<(FL & ST_F_BORN) ? 2 : 1>(a, b, zb0, zb0 + FH, x0, x0 + FW, tid, owns);
     }
-    if (want_grad && adj_iso_only<FL>() && rows && x < g.ld) {
-        float* gb = a.gacc + ((long long)chunk * 7 + 1) * ((long long)g.nz * g.ld);       // slot 1: d/d ciso
+    if (want_grad && adj_smem_grad<FL>() && rows && x < g.ld) {
+        const long long plane = (long long)g.nz * g.ld;
 #pragma unroll
-        for (int k = 0; k < FRZ; ++k) {
-            const int z = z0 + k;
-            if (z < zn) {
-                float* o = gb + (z * g.ld + x);
-                const float4 acc = gsl[k * (FW / 4)];
-                if (clean) {
-                    float4 v = *reinterpret_cast<float4*>(o);
-                    v.x += acc.x; v.y += acc.y; v.z += acc.z; v.w += acc.w;
-                    *reinterpret_cast<float4*>(o) = v;
-                } else {
+        for (int q = 0; q < NGS; ++q) {
+            float* gb = a.gacc + ((long long)chunk * 7 + adj_smem_slot<FL>(q)) * plane;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (x + e < g.nx && owns(z, x + e)) o[e] += f4get(acc, e);
+            for (int k = 0; k < FRZ; ++k) {
+                const int z = z0 + k;
+                if (z < zn) {
+                    float* o = gb + (z * g.ld + x);
+                    const float4 acc = gsl[q * GPL4 + k * (FW / 4)];
+                    if (clean) {
+                        float4 v = *reinterpret_cast<float4*>(o);
+                        v.x += acc.x; v.y += acc.y; v.z += acc.z; v.w += acc.w;
+                        *reinterpret_cast<float4*>(o) = v;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (x + e < g.nx && owns(z, x + e)) o[e] += f4get(acc, e);
+                    }
                 }
             }
         }
@@ -2038,14 +2272,14 @@ __global__ void __launch_bounds__(NT, PART == 2 ? ST_ADJ_MINB_FAST : adj_minb<FL
     constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
     constexpr bool NEED_GEN = PART != 2 && (!adj_fast<FL>() || (FL & ST_F_HABC));
     constexpr int GEN_FLOATS = NEED_GEN ? 2 * NF * SH * SW : 1;
-    constexpr int FAST_FLOATS = adj_iso_only<FL>() ? NWARP * FRZ * FW : 1;
+    constexpr int FAST_FLOATS = adj_smem_grad<FL>() ? adj_smem_planes<FL>() * NWARP * FRZ * FW : 1;
     __shared__ __align__(16) float smem[GEN_FLOATS > FAST_FLOATS ? GEN_FLOATS : FAST_FLOATS];
     const int tid = threadIdx.x;
     // grid.x = [band blocks: one per (tile, shot)] ++ [fast blocks: one per (fast tile, shot chunk)]
     // for the fast-path equations, else one general block per (tile, shot chunk).
     if constexpr (adj_fast<FL>()) {
         const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
-        const int ngrp = (a.B + BSH - 1) / BSH;
+        const int ngrp = band_groups(a.B), gsh = band_group_shots(a.B);
         const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
         const int nband = (FL & ST_F_HABC) ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
         const int bid = PART == 2 ? blockIdx.x + nband : blockIdx.x;     // a fast-only launch enumerates the fast blocks from 0
@@ -2060,7 +2294,7 @@ __global__ void __launch_bounds__(NT, PART == 2 ? ST_ADJ_MINB_FAST : adj_minb<FL
             return;
         } else if (tapped) {
             const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;     // gradient plane = group id (< B planes exist)
-            const int b_lo = grp * BSH, b_hi = min(b_lo + BSH, a.B);
+            const int b_lo = grp * gsh, b_hi = min(b_lo + gsh, a.B);
             if (k < nstrip) adjoint_strip_block<FL>(a, k, b_lo, b_hi, grp, tid);
             else adjoint_band_block<FL>(a, k - nstrip, b_lo, b_hi, grp, tid);
         } else {
@@ -2430,7 +2664,7 @@ __global__ void __launch_bounds__(NT, tma_adj_minb<FL>()) wave2d_adjoint_tma_ker
                 const int per = ct.count * CORNER_SUB, grp = bid / per, r = bid - grp * per;
                 corner_tile_decode(ct, tm, a.g, r / CORNER_SUB, tz, tx);
                 const RectMap map{a.g, tz * TZ + (r % CORNER_SUB) * (NT / TX), tx, TX};
-                adjoint_tap_block<FL>(a, map, grp * BSH, min(grp * BSH + BSH, a.B), grp, tid);
+                adjoint_tap_block<FL>(a, map, grp * band_group_shots(a.B), min((grp + 1) * band_group_shots(a.B), a.B), grp, tid);
             } else {
                 const int b = bid / ct.count;
                 corner_tile_decode(ct, tm, a.g, bid - b * ct.count, tz, tx);
@@ -2500,7 +2734,7 @@ int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
     const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
-    dim3 grid((unsigned)((long long)nfast * a.B + (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B)));
+    dim3 grid((unsigned)((long long)nfast * a.B + (long long)(bt.count + nstrip) * (tapped ? band_groups(a.B) : a.B)));
     return pdl_launch(wave2d_forward_kernel<FL>, grid, st, a, nfx, nfast, bt);
 }
 template <int FL>
@@ -2521,7 +2755,7 @@ int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw + 1).total + NT - 1) / NT;
     long long nblocks;
     const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
-    if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)(bt.count + nstrip) * (tapped ? (a.B + BSH - 1) / BSH : a.B) : 0);
+    if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)(bt.count + nstrip) * (tapped ? band_groups(a.B) : a.B) : 0);
     else nblocks = (long long)bt.nxt * bt.nzt * nchunk;
     if constexpr (adj_fast<FL>() && (FL & ST_F_HABC) && adj_split<FL>()) {
         // two launches: the frame blocks (tap gather, needs the registers) and the fast blocks (compiled for more resident
