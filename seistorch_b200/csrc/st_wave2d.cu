@@ -50,6 +50,9 @@ constexpr int FW = 128;                     // columns per warp (32 lanes x floa
 #ifndef ST_ADJ_MINB
 #define ST_ADJ_MINB 3
 #endif
+#ifndef ST_ADJ_MINB_XZ
+#define ST_ADJ_MINB_XZ 3                    // blocks / SM of the tti_habc adjoint
+#endif
 #ifndef ST_ADJ_MINB_BORN
 #define ST_ADJ_MINB_BORN 2                  // blocks / SM of the Born-pair adjoint (3 was measured: see DESIGN.md)
 #endif
@@ -275,6 +278,12 @@ __device__ __forceinline__ float4 ldrow(const float* __restrict__ base, int z, i
     if (z < 0 || z >= g.nz || x >= g.ld) return f4zero();
     return __ldg(reinterpret_cast<const float4*>(base + (z * g.ld + x)));
 }
+// SAFE: the caller knows the row is inside the domain (tiles away from the domain edge): no bounds predicate
+template <bool SAFE>
+__device__ __forceinline__ float4 ldrow_s(const float* __restrict__ base, int z, int x, const W2Geom& g) {
+    if (SAFE) return __ldg(reinterpret_cast<const float4*>(base + (z * g.ld + x)));
+    return ldrow(base, z, x, g);
+}
 // left / right neighbours of the lane's 4 cells: shuffles + predicated halo loads at the warp edges
 __device__ __forceinline__ void row_halo(const float4& c, const float* __restrict__ base, int z, int x0, int lane,
                                          const W2Geom& g, float& left, float& right) {
@@ -433,8 +442,15 @@ __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, in
     }
 }
 
+// Adjoint of the straight strips.  Besides the single-field cross (round 1) it serves the mixed derivative of tti_habc
+// (the four diagonal transposed taps) and the Born pairs without mixed derivative (both fields through the same taps; the
+// scattered cotangent reaches the background one through  K = pre m T,  T = czz / cxx of the z / x neighbours, held as
+// rows in registers like the taps).  The TTI Born pair would need ~120 registers of row constants and stays on the band threads.
 template <int FL>
 __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, int b_lo, int b_hi, int gplane, int tid) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    constexpr bool XZ = (FL & ST_F_XZ) != 0;
+    static_assert(!(XZ && NF == 2), "strip blocks: no TTI Born pair");
     const W2Geom g = a.g;
     const StripGeom t = strip_geom(g, g.bw + 1);
     const int warp = tid >> 5, lane = tid & 31;
@@ -448,9 +464,18 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
     const bool active = x < t.xe;
     const long long plane = (long long)g.nz * g.ld;
     const bool want_grad = a.gacc != nullptr;
-    const bool frame = top ? z < g.bw : z >= g.nz - g.bw;       // the deepest band row is not a frame row
+    auto frame_row = [&](int zq) { return (!g.multiple && zq < g.bw) || zq >= g.nz - g.bw; };
+    const bool frame = frame_row(z);                            // the deepest band row is not a frame row
     const float* F1 = a.taps;
     const float* F2 = a.taps + ST_NTAP1 * plane;
+    // x-1 / x+4 neighbours of a row that may lie outside the domain in z
+    auto lr = [&](const float4& c, const float* p, int zq, float& left, float& right) {
+        left = __shfl_up_sync(0xffffffffu, c.w, 1);
+        right = __shfl_down_sync(0xffffffffu, c.x, 1);
+        const bool zin = zq >= 0 && zq < g.nz;
+        if (lane == 0) left = zin ? __ldg(p + (zq * g.ld + x0c - 1)) : 0.f;
+        if (lane == 31) right = (zin && x0c + FW < g.nx) ? __ldg(p + (zq * g.ld + x0c + FW)) : 0.f;
+    };
     // transposed taps: coefficient of L(p+o) is tap -o of cell p+o
     const float4 G0 = strip_row(F1, z, x, g);
     const float4 Gm = strip_row(F1 + 2 * plane, z - 1, x, g), Gp = strip_row(F1 + 1 * plane, z + 1, x, g);
@@ -462,70 +487,146 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
     const float4 Gl = f4shl(A4, al);                  // F1[+x](z, x-1): the left neighbour reads us through its +x tap
     const float4 Gr = f4shr(B4, br);                  // F1[-x](z, x+1)
     const float4 K0 = strip_row(F2, z, x, g), Km = strip_row(F2 + 2 * plane, z - 1, x, g), Kp = strip_row(F2 + 1 * plane, z + 1, x, g);
+    // mixed derivative: the diagonal neighbours read us through their opposite diagonal tap (st_tap_neg: 9 <-> 12, 10 <-> 11)
+    float4 Gnw = f4zero(), Gne = f4zero(), Gsw = f4zero(), Gse = f4zero();
+    if (XZ) {
+        float l_, r_;
+        const float4 t12 = strip_row(F1 + 12 * plane, z - 1, x, g);
+        lr(t12, F1 + 12 * plane, z - 1, l_, r_); Gnw = f4shl(t12, l_);
+        const float4 t11 = strip_row(F1 + 11 * plane, z - 1, x, g);
+        lr(t11, F1 + 11 * plane, z - 1, l_, r_); Gne = f4shr(t11, r_);
+        const float4 t10 = strip_row(F1 + 10 * plane, z + 1, x, g);
+        lr(t10, F1 + 10 * plane, z + 1, l_, r_); Gsw = f4shl(t10, l_);
+        const float4 t9 = strip_row(F1 + 9 * plane, z + 1, x, g);
+        lr(t9, F1 + 9 * plane, z + 1, l_, r_); Gse = f4shr(t9, r_);
+    }
     float4 pre = make_float4(1.f, 1.f, 1.f, 1.f);
     if (frame) { const float4 bb = strip_row(a.coef[1], z, x, g); pre = make_float4(1.f - bb.x, 1.f - bb.y, 1.f - bb.z, 1.f - bb.w); }
+    // Born coupling rows  K[-o](p+o) = (pre m T)(p+o)  and  K[0](p) = -(pre m)(p) (2 cxx + 2 czz)(p)
+    float4 Czm = f4zero(), Czp = f4zero(), Cxl = f4zero(), Cxr = f4zero(), C0 = f4zero(), pm = f4zero(), cxr = f4zero(), czr = f4zero();
+    if (NF == 2) {
+        auto pm_row = [&](int zq) {                   // (pre m)(zq, x..x+3)
+            float4 v = strip_row(a.coef[7], zq, x, g);
+            if (frame_row(zq)) {
+                const float4 bb = strip_row(a.coef[1], zq, x, g);
+                v = make_float4(v.x * (1.f - bb.x), v.y * (1.f - bb.y), v.z * (1.f - bb.z), v.w * (1.f - bb.w));
+            }
+            return v;
+        };
+        pm = pm_row(z);
+        cxr = strip_row(a.coef[2], z, x, g); czr = strip_row(a.coef[3], z, x, g);
+        Czm = f4mul(pm_row(z - 1), strip_row(a.coef[3], z - 1, x, g));
+        Czp = f4mul(pm_row(z + 1), strip_row(a.coef[3], z + 1, x, g));
+        const float4 px = f4mul(pm, cxr);
+        float pl_ = __shfl_up_sync(0xffffffffu, px.w, 1), pr_ = __shfl_down_sync(0xffffffffu, px.x, 1);
+        if (lane == 0 || lane == 31) {
+            const int xq = lane == 0 ? x0c - 1 : x0c + FW;
+            float v = 0.f;
+            if (xq < g.nx) {
+                const int o = z * g.ld + xq;
+                v = __ldg(a.coef[7] + o) * __ldg(a.coef[2] + o) * (frame ? 1.f - __ldg(a.coef[1] + o) : 1.f);
+            }
+            if (lane == 0) pl_ = v; else pr_ = v;
+        }
+        Cxl = f4shl(px, pl_); Cxr = f4shr(px, pr_);
+        C0 = make_float4(-pm.x * (2.f * cxr.x + 2.f * czr.x), -pm.y * (2.f * cxr.y + 2.f * czr.y),
+                         -pm.z * (2.f * cxr.z + 2.f * czr.z), -pm.w * (2.f * cxr.w + 2.f * czr.w));
+    }
     const int on1 = top ? 2 : 1, on2 = top ? 6 : 5;
     const float* H1 = a.taps + (ST_NTAP1 + ST_NTAP2) * plane;
     const float* H2 = a.taps + (2 * ST_NTAP1 + ST_NTAP2) * plane;
-    float4 gc = f4zero(), gr = f4zero(), gz = f4zero(), gax = f4zero(), gaz = f4zero();
+    float4 gc = f4zero(), gr = f4zero(), gz = f4zero(), gax = f4zero(), gaz = f4zero(), gxz = f4zero(), gm = f4zero();
     for (int b = b_lo; b < b_hi; ++b) {
-        const long long boff = (long long)b * a.fs;
-        const float* l1 = a.lam1 + boff;
-        const float* l2 = a.lam2 + boff;
-        const float4 L0 = strip_row(l1, z, x, g);
-        float ll, lr;
-        strip_lr(L0, l1, z, x0c, lane, g, ll, lr);
-        float4 acc = f4mul(G0, L0);
-        acc = f4fma(Gm, strip_row(l1, z - 1, x, g), acc);
-        acc = f4fma(Gp, strip_row(l1, z + 1, x, g), acc);
-        acc = f4fma(Gmm, strip_row(l1, z - 2, x, g), acc);
-        acc = f4fma(Gpp, strip_row(l1, z + 2, x, g), acc);
-        acc = f4fma(Gl, f4shl(L0, ll), acc);
-        acc = f4fma(Gr, f4shr(L0, lr), acc);
-        acc = f4fma(K0, strip_row(l2, z, x, g), acc);
-        acc = f4fma(Km, strip_row(l2, z - 1, x, g), acc);
-        acc = f4fma(Kp, strip_row(l2, z + 1, x, g), acc);
-        if (active) *reinterpret_cast<float4*>(a.lam0 + boff + (z * g.ld + x)) = acc;
+        float4 Lc[NF], sxx0 = f4zero(), szz0 = f4zero();
+#pragma unroll
+        for (int f = NF - 1; f >= 0; --f) {             // the scattered field first: its cotangent rows feed the background one
+            const long long boff = f * a.cs + (long long)b * a.fs;
+            const float* l1 = a.lam1 + boff;
+            const float* l2 = a.lam2 + boff;
+            const float4 L0 = strip_row(l1, z, x, g), Lm = strip_row(l1, z - 1, x, g), Lp = strip_row(l1, z + 1, x, g);
+            Lc[f] = L0;
+            float ll, lr_;
+            strip_lr(L0, l1, z, x0c, lane, g, ll, lr_);
+            float4 acc = f4mul(G0, L0);
+            acc = f4fma(Gm, Lm, acc);
+            acc = f4fma(Gp, Lp, acc);
+            acc = f4fma(Gmm, strip_row(l1, z - 2, x, g), acc);
+            acc = f4fma(Gpp, strip_row(l1, z + 2, x, g), acc);
+            acc = f4fma(Gl, f4shl(L0, ll), acc);
+            acc = f4fma(Gr, f4shr(L0, lr_), acc);
+            acc = f4fma(K0, strip_row(l2, z, x, g), acc);
+            acc = f4fma(Km, strip_row(l2, z - 1, x, g), acc);
+            acc = f4fma(Kp, strip_row(l2, z + 1, x, g), acc);
+            if (XZ) {
+                float ml, mr, pl2, pr2;
+                lr(Lm, l1, z - 1, ml, mr);
+                lr(Lp, l1, z + 1, pl2, pr2);
+                acc = f4fma(Gnw, f4shl(Lm, ml), acc);
+                acc = f4fma(Gne, f4shr(Lm, mr), acc);
+                acc = f4fma(Gsw, f4shl(Lp, pl2), acc);
+                acc = f4fma(Gse, f4shr(Lp, pr2), acc);
+            }
+            if (NF == 2 && f == 1) {
+                // coupling into the background cotangent (stored with it below): held in Cacc until f == 0
+                float4 c = f4mul(C0, L0);
+                c = f4fma(Czm, Lm, c);
+                c = f4fma(Czp, Lp, c);
+                c = f4fma(Cxl, f4shl(L0, ll), c);
+                c = f4fma(Cxr, f4shr(L0, lr_), c);
+                sxx0 = c;                               // (register reuse: sxx0 is overwritten when the gradients are formed)
+            }
+            if (NF == 2 && f == 0) acc = f4add(acc, sxx0);
+            if (active) *reinterpret_cast<float4*>(a.lam0 + boff + (z * g.ld + x)) = acc;
+        }
         if (want_grad) {
-            const float* S1 = a.s1 + boff;
-            const float4 s0 = strip_row(S1, z, x, g), sm = strip_row(S1, z - 1, x, g), sp = strip_row(S1, z + 1, x, g);
-            float sl, sr;
-            strip_lr(s0, S1, z, x0c, lane, g, sl, sr);
-            const float4 sw4 = f4shl(s0, sl), se4 = f4shr(s0, sr);
-            const float4 szz = f4add(f4sub(sm, s0), f4sub(sp, s0)), sxx = f4add(f4sub(sw4, s0), f4sub(se4, s0));
-            const float4 pl = f4mul(pre, L0);
-            if (FL & ST_F_ISO) gc = f4fma(pl, f4add(szz, sxx), gc);
-            else { gc = f4fma(pl, sxx, gc); gz = f4fma(pl, szz, gz); }
-            if (FL & ST_F_G1) { gax = f4fma(pl, f4sub(se4, sw4), gax); gaz = f4fma(pl, f4sub(sp, sm), gaz); }
-            if (frame) {
-                const float* S2 = a.s2 + boff;
-                const float4 sn = top ? sp : sm;
-                float4 tt = f4mul(strip_row(H1, z, x, g), s0);
-                tt = f4fma(strip_row(H1 + on1 * plane, z, x, g), sn, tt);
-                tt = f4fma(strip_row(H1 + on2 * plane, z, x, g), strip_row(S1, z + 2 * n, x, g), tt);
-                tt = f4fma(strip_row(H2, z, x, g), strip_row(S2, z, x, g), tt);
-                tt = f4fma(strip_row(H2 + on1 * plane, z, x, g), strip_row(S2, z + n, x, g), tt);
-                gr = f4fma(L0, tt, gr);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const long long boff = f * a.cs + (long long)b * a.fs;
+                const float* S1 = a.s1 + boff;
+                const float4 s0 = strip_row(S1, z, x, g), sm = strip_row(S1, z - 1, x, g), sp = strip_row(S1, z + 1, x, g);
+                float sl, sr;
+                strip_lr(s0, S1, z, x0c, lane, g, sl, sr);
+                const float4 sw4 = f4shl(s0, sl), se4 = f4shr(s0, sr);
+                const float4 szz = f4add(f4sub(sm, s0), f4sub(sp, s0)), sxx = f4add(f4sub(sw4, s0), f4sub(se4, s0));
+                float4 pl = f4mul(pre, Lc[f]);                                   // effective cotangent of this field
+                if (NF == 2 && f == 0) { pl = f4fma(pm, Lc[NF - 1], pl); sxx0 = sxx; szz0 = szz; }
+                if (FL & ST_F_ISO) gc = f4fma(pl, f4add(szz, sxx), gc);
+                else { gc = f4fma(pl, sxx, gc); gz = f4fma(pl, szz, gz); }
+                if (FL & ST_F_G1) { gax = f4fma(pl, f4sub(se4, sw4), gax); gaz = f4fma(pl, f4sub(sp, sm), gaz); }
+                if (XZ) {                                                        // (SE - SW) - (NE - NW)
+                    float ml, mr, pl2, pr2;
+                    lr(sm, S1, z - 1, ml, mr);
+                    lr(sp, S1, z + 1, pl2, pr2);
+                    const float4 cross = f4sub(f4sub(f4shr(sp, pr2), f4shl(sp, pl2)), f4sub(f4shr(sm, mr), f4shl(sm, ml)));
+                    gxz = f4fma(pl, cross, gxz);
+                }
+                if (NF == 2 && f == 1)                                           // g_m += (pre L1_s) A[S_background]
+                    gm = f4fma(f4mul(pre, Lc[NF - 1]), f4fma(cxr, sxx0, f4mul(czr, szz0)), gm);
+                if (frame) {
+                    const float* S2 = a.s2 + boff;
+                    const float4 sn = top ? sp : sm;
+                    float4 tt = f4mul(strip_row(H1, z, x, g), s0);
+                    tt = f4fma(strip_row(H1 + on1 * plane, z, x, g), sn, tt);
+                    tt = f4fma(strip_row(H1 + on2 * plane, z, x, g), strip_row(S1, z + 2 * n, x, g), tt);
+                    tt = f4fma(strip_row(H2, z, x, g), strip_row(S2, z, x, g), tt);
+                    tt = f4fma(strip_row(H2 + on1 * plane, z, x, g), strip_row(S2, z + n, x, g), tt);
+                    gr = f4fma(Lc[f], tt, gr);
+                }
             }
         }
     }
     if (want_grad && active) {
         float* gb = a.gacc + (long long)gplane * 7 * plane + (z * g.ld + x);
-        float4 v = *reinterpret_cast<float4*>(gb + plane);
-        *reinterpret_cast<float4*>(gb + plane) = f4add(v, gc);                  // slot 1: d/d ciso (ISO) or d/d cxx
-        if (!(FL & ST_F_ISO)) {
-            float4 u = *reinterpret_cast<float4*>(gb + 2 * plane);
-            *reinterpret_cast<float4*>(gb + 2 * plane) = f4add(u, gz);          // slot 2: d/d czz
-        }
-        if (FL & ST_F_G1) {
-            float4 u4 = *reinterpret_cast<float4*>(gb + 4 * plane), u5 = *reinterpret_cast<float4*>(gb + 5 * plane);
-            *reinterpret_cast<float4*>(gb + 4 * plane) = f4add(u4, gax);
-            *reinterpret_cast<float4*>(gb + 5 * plane) = f4add(u5, gaz);
-        }
-        if (frame) {
-            float4 w = *reinterpret_cast<float4*>(gb);
-            *reinterpret_cast<float4*>(gb) = f4add(w, gr);                      // slot 0: d/d r
-        }
+        auto rmw = [&](int slot, const float4& v) {
+            float4* p4 = reinterpret_cast<float4*>(gb + slot * plane);
+            *p4 = f4add(*p4, v);
+        };
+        rmw(1, gc);                                       // slot 1: d/d ciso (ISO) or d/d cxx
+        if (!(FL & ST_F_ISO)) rmw(2, gz);                 // slot 2: d/d czz
+        if (XZ) rmw(3, gxz);                              // slot 3: d/d cxz
+        if (FL & ST_F_G1) { rmw(4, gax); rmw(5, gaz); }
+        if (NF == 2) rmw(6, gm);                          // slot 6: d/d m
+        if (frame) rmw(0, gr);                            // slot 0: d/d r
     }
     if (z < a.row_lo || z > a.row_hi) return;
     __syncwarp();
@@ -538,7 +639,7 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
                 if (rx >= x0c && rx < xhi) {
                     const long long o = (long long)a.rec_orig[r] * a.nchan;
                     for (int ch = 0; ch < a.nchan; ++ch)
-                        atomicAdd(a.lam0 + (long long)b * a.fs + (z * g.ld + rx), a.rec_adj[o + ch]);
+                        atomicAdd(a.lam0 + a.chan_f[ch] * a.cs + (long long)b * a.fs + (z * g.ld + rx), a.rec_adj[o + ch]);
                 }
             }
         }
@@ -547,8 +648,13 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
         __syncwarp();
         for (int s = lane; s < a.ns; s += 32) {
             const int sb = a.src_b[s], sx = a.src_x[s];
-            if (a.src_z[s] == z && sx >= x0c && sx < xhi && sb >= b_lo && sb < b_hi && (a.src_fmask & 1))
-                a.gamp[s] = a.lam0[(long long)sb * a.fs + (z * g.ld + sx)];
+            if (a.src_z[s] == z && sx >= x0c && sx < xhi && sb >= b_lo && sb < b_hi) {
+                float v = 0.f;
+#pragma unroll
+                for (int f = 0; f < NF; ++f)
+                    if (a.src_fmask >> f & 1) v += a.lam0[f * a.cs + (long long)sb * a.fs + (z * g.ld + sx)];
+                if (NF == 2 || (a.src_fmask & 1)) a.gamp[s] = v;
+            }
         }
     }
 }
@@ -556,6 +662,9 @@ __device__ __forceinline__ void adjoint_strip_block(const W2Args& a, int blk, in
 // ------------------------------------------------------------------------------ band (tap gather)
 // rows touched by the 256 consecutive band cells of a block -> shared list (<= 16 rows)
 // ---- cell maps of the tap-gather blocks: which cell a thread owns, which cells the block owns
+#ifndef ST_TAP_INFLIGHT
+#define ST_TAP_INFLIGHT 2                  // shots a band thread of the adjoint has in flight
+#endif
 #ifndef ST_BAND_DENSE
 #define ST_BAND_DENSE 0
 #endif
@@ -901,17 +1010,25 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
                 }
             }
         };
-        for (int b = b_lo; b < b_hi; b += 2) {
-            float acc0[NF], acc1[NF], gc1 = 0.f, gr1 = 0.f, gz1 = 0.f, gax1 = 0.f, gaz1 = 0.f, gm1 = 0.f, gxz1 = 0.f;
-            one_shot(b, acc0, gc, gr, gz, gax, gaz, gm, gxz);
-            const bool two = b + 1 < b_hi;
-            if (two) one_shot(b + 1, acc1, gc1, gr1, gz1, gax1, gaz1, gm1, gxz1);
+        // NIF shots are issued back to back (independent load chains in flight); their gradient sums are kept apart and
+        // added in shot order
+        constexpr int NIF = ST_TAP_INFLIGHT;
+        for (int b = b_lo; b < b_hi; b += NIF) {
+            float accs[NIF][NF], gs[NIF][7];
 #pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                a.lam0[f * a.cs + (long long)b * a.fs + idx] = acc0[f];
-                if (two) a.lam0[f * a.cs + (long long)(b + 1) * a.fs + idx] = acc1[f];
+            for (int i = 0; i < NIF; ++i) {
+#pragma unroll
+                for (int q = 0; q < 7; ++q) gs[i][q] = 0.f;
+                if (i == 0 || b + i < b_hi) one_shot(b + i, accs[i], gs[i][0], gs[i][1], gs[i][2], gs[i][3], gs[i][4], gs[i][5], gs[i][6]);
             }
-            gc += gc1; gr += gr1; gz += gz1; gax += gax1; gaz += gaz1; gm += gm1; gxz += gxz1;
+#pragma unroll
+            for (int i = 0; i < NIF; ++i) {
+                if (i == 0 || b + i < b_hi) {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) a.lam0[f * a.cs + (long long)(b + i) * a.fs + idx] = accs[i][f];
+                }
+                gc += gs[i][0]; gr += gs[i][1]; gz += gs[i][2]; gax += gs[i][3]; gaz += gs[i][4]; gm += gs[i][5]; gxz += gs[i][6];
+            }
         }
         if (want_grad) {
             float* gb = a.gacc + (long long)gplane * 7 * plane;
@@ -981,7 +1098,7 @@ __device__ __forceinline__ void adjoint_tap_block(const W2Args& a, const Map& ma
 
 template <int FL>
 __device__ __forceinline__ void adjoint_band_block(const W2Args& a, int blk, int b_lo, int b_hi, int gplane, int tid) {
-    const BandMap map{a.g, st_band_cells(a.g, a.g.bw + 1), strip_geom(a.g, a.g.bw + 1), st_flags_stripped(FL), false, blk * NT};
+    const BandMap map{a.g, st_band_cells(a.g, a.g.bw + 1), strip_geom(a.g, a.g.bw + 1), st_flags_stripped_adj(FL), false, blk * NT};
     adjoint_tap_block<FL>(a, map, b_lo, b_hi, gplane, tid);
 }
 
@@ -1638,7 +1755,7 @@ __host__ __device__ constexpr int adj_smem_planes() { return adj_gslot_index<FL>
 // evaluated on rows of the coefficient-times-cotangent products, which are formed once per row
 // when it is loaded and marched through 3-row register pipelines; coefficient gradients
 // (imaging condition) are added straight to the block's gradient plane.
-template <int FL, class Own>
+template <int FL, bool SAFE, class Own>
 __device__ __forceinline__ void adjoint_fast_rows_gen(const W2Args& a, const W2Geom& g, int b, int chunk, int x0, int z0,
                                                       int zn, int lane, bool clean, bool want_grad, Own owns,
                                                       float4* gsl = nullptr) {       // gsl: shared-memory gradient planes
@@ -1657,12 +1774,12 @@ __device__ __forceinline__ void adjoint_fast_rows_gen(const W2Args& a, const W2G
     struct Prod { float4 l, a, b, c, d; float al, ar, cl, cr, dl, dr; };
     auto load_prod = [&](int z) {
         Prod p;
-        p.l = ldrow(l1, z, x, g);
-        const float4 ca = ldrow(a.coef[2], z, x, g);
+        p.l = ldrow_s<SAFE>(l1, z, x, g);
+        const float4 ca = ldrow_s<SAFE>(a.coef[2], z, x, g);
         p.a = f4mul(ca, p.l);
-        p.b = ISO ? p.a : f4mul(ldrow(a.coef[3], z, x, g), p.l);
-        p.c = XZ ? f4mul(ldrow(a.coef[4], z, x, g), p.l) : (G1 ? f4mul(ldrow(a.coef[6], z, x, g), p.l) : f4zero());
-        p.d = G1 ? f4mul(ldrow(a.coef[5], z, x, g), p.l) : f4zero();
+        p.b = ISO ? p.a : f4mul(ldrow_s<SAFE>(a.coef[3], z, x, g), p.l);
+        p.c = XZ ? f4mul(ldrow_s<SAFE>(a.coef[4], z, x, g), p.l) : (G1 ? f4mul(ldrow_s<SAFE>(a.coef[6], z, x, g), p.l) : f4zero());
+        p.d = G1 ? f4mul(ldrow_s<SAFE>(a.coef[5], z, x, g), p.l) : f4zero();
         // x-neighbours of the products (shuffles; the warp's edge lanes read coefficient and cotangent)
         p.al = __shfl_up_sync(0xffffffffu, p.a.w, 1); p.ar = __shfl_down_sync(0xffffffffu, p.a.x, 1);
         p.cl = p.cr = p.dl = p.dr = 0.f;
@@ -1670,7 +1787,7 @@ __device__ __forceinline__ void adjoint_fast_rows_gen(const W2Args& a, const W2G
         if (G1) { p.dl = __shfl_up_sync(0xffffffffu, p.d.w, 1); p.dr = __shfl_down_sync(0xffffffffu, p.d.x, 1); }
         if (edge) {
             float va = 0.f, vc = 0.f, vd = 0.f;
-            if (z >= 0 && z < g.nz && xh >= 0 && xh < g.nx) {
+            if (SAFE || (z >= 0 && z < g.nz && xh >= 0 && xh < g.nx)) {
                 const int o = z * ld + xh;
                 const float lv = __ldg(l1 + o);
                 va = __ldg(a.coef[2] + o) * lv;
@@ -1684,7 +1801,7 @@ __device__ __forceinline__ void adjoint_fast_rows_gen(const W2Args& a, const W2G
     struct SRow { float4 s; float l, r; };
     auto load_s = [&](int z) {
         SRow q;
-        q.s = ldrow(S, z, x, g);
+        q.s = ldrow_s<SAFE>(S, z, x, g);
         row_halo(q.s, S, z, x0, lane, g, q.l, q.r);
         return q;
     };
@@ -1696,7 +1813,7 @@ __device__ __forceinline__ void adjoint_fast_rows_gen(const W2Args& a, const W2G
         const int z = z0 + k;
         if (z < zn) {
             D = load_prod(z + 1);
-            const float4 p2 = ldrow(l2, z, x, g);
+            const float4 p2 = ldrow_s<SAFE>(l2, z, x, g);
             if (want_grad) sD = load_s(z + 1);
             float4 out, g1v = f4zero(), g2v = f4zero(), g3v = f4zero(), g4v = f4zero(), g5v = f4zero();
 #pragma unroll
@@ -1956,7 +2073,7 @@ __device__ __forceinline__ void adjoint_fast_rows_born(const W2Args& a, const W2
 #define ST_BORN_FUSED 2                     // 0: field after field, global gradient RMW (round-2 first version); 1: fused rows for
 #endif                                      // the VTI pair, field after field + shared-memory gradients for the TTI pair; 2: fused
                                             // rows for both (B200, 12 shots 600x1300: VTI 393 / 275 / 276 us, TTI 496 / 439 / 386 us)
-template <int FL, class Own>
+template <int FL, bool SAFE, class Own>
 __device__ __forceinline__ void adjoint_fast_rows_born2(const W2Args& a, const W2Geom& g, int b, int x0, int z0, int zn,
                                                         int lane, bool clean, bool want_grad, float4* gsl, Own owns) {
     constexpr bool XZ = (FL & ST_F_XZ) != 0;
@@ -1987,19 +2104,19 @@ __device__ __forceinline__ void adjoint_fast_rows_born2(const W2Args& a, const W
     };
     auto load_row = [&](int z) {
         Row q;
-        q.r0 = ldrow(l1b, z, x, g);
-        q.le1 = ldrow(l1s, z, x, g);
-        q.le0 = f4fma(ldrow(mm, z, x, g), q.le1, q.r0);
-        const float4 ca = ldrow(cxx, z, x, g);
-        const float4 cb = ldrow(czz, z, x, g);
-        const float4 cc = XZ ? ldrow(cxz, z, x, g) : f4zero();
+        q.r0 = ldrow_s<SAFE>(l1b, z, x, g);
+        q.le1 = ldrow_s<SAFE>(l1s, z, x, g);
+        q.le0 = f4fma(ldrow_s<SAFE>(mm, z, x, g), q.le1, q.r0);
+        const float4 ca = ldrow_s<SAFE>(cxx, z, x, g);
+        const float4 cb = ldrow_s<SAFE>(czz, z, x, g);
+        const float4 cc = XZ ? ldrow_s<SAFE>(cxz, z, x, g) : f4zero();
         q.a0 = f4mul(ca, q.le0); q.a1 = f4mul(ca, q.le1);
         q.b0 = f4mul(cb, q.le0); q.b1 = f4mul(cb, q.le1);
         q.c0 = f4mul(cc, q.le0); q.c1 = f4mul(cc, q.le1);
-        q.s0 = want_grad ? ldrow(S0, z, x, g) : f4zero();
-        q.s1 = want_grad ? ldrow(S1, z, x, g) : f4zero();
+        q.s0 = want_grad ? ldrow_s<SAFE>(S0, z, x, g) : f4zero();
+        q.s1 = want_grad ? ldrow_s<SAFE>(S1, z, x, g) : f4zero();
         // halo column
-        const bool in = xhin && z >= 0 && z < g.nz;
+        const bool in = SAFE || (xhin && z >= 0 && z < g.nz);
         const int o = z * ld + xh;
         const float h1 = in ? __ldg(l1s + o) : 0.f;
         const float h0 = in ? fmaf(__ldg(mm + o), h1, __ldg(l1b + o)) : 0.f;
@@ -2021,8 +2138,8 @@ __device__ __forceinline__ void adjoint_fast_rows_born2(const W2Args& a, const W
         const int z = z0 + k;
         if (z < zn) {
             D = load_row(z + 1);
-            const float4 p20 = ldrow(a.lam2 + boff, z, x, g);
-            const float4 p21 = ldrow(a.lam2 + a.cs + boff, z, x, g);
+            const float4 p20 = ldrow_s<SAFE>(a.lam2 + boff, z, x, g);
+            const float4 p21 = ldrow_s<SAFE>(a.lam2 + a.cs + boff, z, x, g);
             float4 out0, out1, g1v = f4zero(), g2v = f4zero(), g3v = f4zero(), g6v = f4zero();
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -2146,10 +2263,16 @@ __device__ __forceinline__ void adjoint_fast_block(const W2Args& a, int bid, int
                 else adjoint_fast_rows<FL, false>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
             } else if constexpr ((FL & ST_F_BORN) != 0) {
                 if constexpr (ST_BORN_FUSED == 2 || (ST_BORN_FUSED == 1 && !(FL & ST_F_XZ)))
-                    adjoint_fast_rows_born2<FL>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
+                {
+                    // frame-free tiles of an HABC grid lie at least bw + 1 cells inside the domain: unchecked loads
+                    if (clean && safe) adjoint_fast_rows_born2<FL, true>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
+                    else adjoint_fast_rows_born2<FL, false>(a, g, b, x0, z0, zn, lane, clean, want_grad, gsl, owns);
+                }
                 else adjoint_fast_rows_born<FL>(a, g, b, chunk, x0, z0, zn, lane, clean, want_grad, owns, ST_BORN_FUSED ? gsl : nullptr);
             } else {
-                adjoint_fast_rows_gen<FL>(a, g, b, chunk, x0, z0, zn, lane, clean, want_grad, owns, adj_smem_grad<FL>() ? gsl : nullptr);
+                // (an unchecked-load instantiation for the frame-free tiles was measured: two copies of the rows at 80 registers
+                //  spill more and run 5-8 % slower; the Born pairs, at 128 registers, gain 2-3 % from theirs)
+                adjoint_fast_rows_gen<FL, false>(a, g, b, chunk, x0, z0, zn, lane, clean, want_grad, owns, adj_smem_grad<FL>() ? gsl : nullptr);
             }
         }
         adjoint_tail<(FL & ST_F_BORN) ? 2 : 1>(a, b, zb0, zb0 + FH, x0, x0 + FW, tid, owns);
@@ -2250,7 +2373,7 @@ __device__ __forceinline__ void adjoint_general_block(const W2Args& a, int tz, i
 
 // resident blocks per SM the register adjoint is compiled for (the Born pairs carry two fields: 128 registers)
 template <int FL>
-__host__ __device__ constexpr int adj_minb() { return (FL & ST_F_BORN) ? ST_ADJ_MINB_BORN : ST_ADJ_MINB; }
+__host__ __device__ constexpr int adj_minb() { return (FL & ST_F_BORN) ? ST_ADJ_MINB_BORN : (FL & ST_F_XZ) ? ST_ADJ_MINB_XZ : ST_ADJ_MINB; }
 #ifndef ST_ADJ_SPLIT
 #define ST_ADJ_SPLIT 0                      // 1: frame blocks and fast blocks of the register adjoint in two launches (tuning;
                                             // measured on B200 with 2 / 3 / 4 resident fast blocks per SM: no gain -- the fast
@@ -2280,7 +2403,7 @@ __global__ void __launch_bounds__(NT, PART == 2 ? ST_ADJ_MINB_FAST : adj_minb<FL
     if constexpr (adj_fast<FL>()) {
         const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
         const int ngrp = band_groups(a.B), gsh = band_group_shots(a.B);
-        const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
+        const int nstrip = (tapped && st_flags_stripped_adj(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
         const int nband = (FL & ST_F_HABC) ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
         const int bid = PART == 2 ? blockIdx.x + nband : blockIdx.x;     // a fast-only launch enumerates the fast blocks from 0
         if ((ST_DBG_SKIP & 1) && bid < nband) return;          // tuning builds only: frame blocks off
@@ -2295,8 +2418,12 @@ __global__ void __launch_bounds__(NT, PART == 2 ? ST_ADJ_MINB_FAST : adj_minb<FL
         } else if (tapped) {
             const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;     // gradient plane = group id (< B planes exist)
             const int b_lo = grp * gsh, b_hi = min(b_lo + gsh, a.B);
-            if (k < nstrip) adjoint_strip_block<FL>(a, k, b_lo, b_hi, grp, tid);
-            else adjoint_band_block<FL>(a, k - nstrip, b_lo, b_hi, grp, tid);
+            if constexpr (st_flags_stripped_adj(FL)) {
+                if (k < nstrip) adjoint_strip_block<FL>(a, k, b_lo, b_hi, grp, tid);
+                else adjoint_band_block<FL>(a, k - nstrip, b_lo, b_hi, grp, tid);
+            } else {
+                adjoint_band_block<FL>(a, k, b_lo, b_hi, grp, tid);
+            }
         } else {
             if constexpr (NEED_GEN) {
                 int tz, tx;
@@ -2754,7 +2881,7 @@ int st_w2_launch_adj(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw + 1).total + NT - 1) / NT;
     long long nblocks;
-    const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
+    const int nstrip = (tapped && st_flags_stripped_adj(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw + 1)) : 0;
     if (adj_fast<FL>()) nblocks = (long long)nfast * nchunk + ((FL & ST_F_HABC) ? (long long)(bt.count + nstrip) * (tapped ? band_groups(a.B) : a.B) : 0);
     else nblocks = (long long)bt.nxt * bt.nzt * nchunk;
     if constexpr (adj_fast<FL>() && (FL & ST_F_HABC) && adj_split<FL>()) {

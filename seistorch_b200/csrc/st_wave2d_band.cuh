@@ -78,14 +78,21 @@ ST_HD void st_wrap_candidate(const W2Geom& g, int k, int& z, int& x, int& s, int
 // the Born pairs (acoustic_lsrtm_habc, acoustic_{vti,tti}_lsrtm_habc) -- both of its fields take the SAME
 // taps (the one-way blend acts on each field by itself, acoustic_vti_lsrtm_habc.py:60-66), the scattered field adds
 // the coupling term  pre m A[p1]  evaluated from the coefficient planes
-ST_HD bool st_flags_tapped(int fl) {
+ST_HD constexpr bool st_flags_tapped(int fl) {
     return fl == (ST_F_ISO | ST_F_HABC) || fl == ST_F_HABC || fl == (ST_F_ISO | ST_F_HABC | ST_F_G1) ||
            fl == (ST_F_HABC | ST_F_G1) || fl == (ST_F_HABC | ST_F_BORN) || fl == (ST_F_HABC | ST_F_XZ) ||
            fl == (ST_F_HABC | ST_F_XZ | ST_F_BORN);
 }
 // ... of which the straight top / bottom strips run on the vectorised strip blocks (single-field equations without mixed
 // derivative only; the band threads serve every frame cell of the others)
-ST_HD bool st_flags_stripped(int fl) { return st_flags_tapped(fl) && !(fl & (ST_F_BORN | ST_F_XZ)); }
+ST_HD constexpr bool st_flags_stripped(int fl) { return st_flags_tapped(fl) && !(fl & (ST_F_BORN | ST_F_XZ)); }
+// the adjoint strip blocks also serve the mixed derivative and the Born pairs without it (all but the TTI Born pair)
+#ifndef ST_STRIP_ADJ_ALL
+#define ST_STRIP_ADJ_ALL 1
+#endif
+ST_HD constexpr bool st_flags_stripped_adj(int fl) {
+    return ST_STRIP_ADJ_ALL ? st_flags_tapped(fl) && !((fl & ST_F_BORN) && (fl & ST_F_XZ)) : st_flags_stripped(fl);
+}
 
 #ifdef __CUDACC__
 int st_wave2d_launch_prepare(int flags, const W2Args& a, cudaStream_t st);

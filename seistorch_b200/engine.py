@@ -243,7 +243,9 @@ def _choose_bchunk(spec: Spec) -> int:
         tiles = math.ceil(spec.shape[1] / 64) * math.ceil(spec.shape[0] / 32)
     best = 1
     for c in range(1, spec.B + 1):
-        if spec.B % c == 0 and tiles * (spec.B // c) >= 888:      # >= 2 waves of 3 blocks/SM on 148 SMs
+        # >= 2 waves of 3 blocks/SM on 148 SMs; the wave2d fast blocks keep their gradient sums in shared memory across the
+        # chunk, so longer chunks pay (B200 sweep, 12 shots 600x1300: chunks of 2 / 4 / 6 shots: 207 / 197 / 193 us Born, 197 / 188 / 208 us tti_habc)
+        if spec.B % c == 0 and tiles * (spec.B // c) >= (600 if spec.family == "wave2d" else 888):
             best = c
     return best
 
