@@ -200,6 +200,9 @@ def workload_config(n, name="cfg2", shots=None, nt=None):
 
 
 # ----------------------------------------------------------------------------- clocks
+STEP_MS = {}          # per-step device times of the last timed() legs (reported as `step_ms`)
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -209,6 +212,8 @@ class ClockSampler:
         self.rows, self.proc, self.gpu = [], None, gpu_index
 
     def start(self):
+        if os.environ.get("SEISTORCH_B200_BENCH_NO_SAMPLER"):        # diagnostics only: is the polling itself visible in the step times?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
@@ -557,21 +562,34 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps + 1)]     # one event per step boundary, no sync
         l0 = dict(engine.LAUNCHES)
-        e0.record()
-        for _ in range(nsteps):
+        m0 = torch.cuda.memory_stats(dev)
+        marks[0].record()
+        for i in range(nsteps):
             out = step(obs_dev, e2e)
-        e1.record()
+            marks[i + 1].record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([marks[0].elapsed_time(marks[-1])], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         launches = sum(engine.LAUNCHES[k] - l0[k] for k in l0)
+        STEP_MS["e2e" if e2e else "device"] = [round(marks[i].elapsed_time(marks[i + 1]), 3) for i in range(nsteps)]
+        m1 = torch.cuda.memory_stats(dev)
+        # cudaMalloc calls / allocator cache flushes inside the timed region (0 / 0 in steady state: the engine keeps its history buffer)
+        STEP_MS[("e2e" if e2e else "device") + "_cudamallocs"] = int(m1.get("num_device_alloc", 0) - m0.get("num_device_alloc", 0))
+        STEP_MS[("e2e" if e2e else "device") + "_alloc_retries"] = int(m1.get("num_alloc_retries", 0) - m0.get("num_alloc_retries", 0))
         return float(ms.item()), launches, out
 
+    # the set-up above leaves millions of long-lived Python objects (acquisition lists, the CPU arm's modules); a full
+    # garbage-collection pass over them inside the timed region stalls the launching thread for tens of ms right after the
+    # forward's NaN check has drained the launch queue.  Park them in the permanent generation (nothing is skipped: the
+    # collector keeps running on the objects the steps create).
+    import gc
+    gc.collect()
+    gc.freeze()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -675,7 +693,7 @@ def main():
         line = {"metric": metric_name(name), "value": value, "unit": "shots/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(world, name, nshots, nt), "microbatch_shots": mb,
+                "config": workload_config(world, name, nshots, nt), "microbatch_shots": mb, "step_ms": dict(STEP_MS),
                 "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
                 "fd_gpts_per_s": fd, "loss": float(last) if not isinstance(last, float) else last}

@@ -12,5 +12,6 @@ from .cell import WaveCell  # noqa: F401
 from .rnn import WaveRNN  # noqa: F401
 from .loss import Loss, L2, L1, SML1, Crosscorrelation, Integration, CosineSimilarity, NormalizedIntegrationMethod, Wasserstein1d, Traveltime, Envelope  # noqa: F401
 from .model import build_model, model_from_case  # noqa: F401
+from .engine import release_buffers  # noqa: F401
 
 __version__ = "0.1.0"

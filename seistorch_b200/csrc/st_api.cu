@@ -11,6 +11,7 @@
 #include "st_wave2d_persist.cuh"
 #include "st_elastic2d.cuh"
 #include "st_acoustic3d.cuh"
+#include "st_graph.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -33,6 +34,11 @@ static inline int pmod(int a, int n) { int r = a % n; return r < 0 ? r + n : r; 
 
 extern "C" int st_version(void) { return ST_ABI_VERSION; }
 extern "C" const char* st_last_error(void) { return g_err; }
+// time loops run as plain launches / captured into a graph / replayed from one (st_graph.cuh), since process start
+extern "C" void st_graph_counters(int64_t* out3) {
+    std::lock_guard<std::mutex> lock(st_graph_mutex());
+    out3[0] = st_graph_stats().plain; out3[1] = st_graph_stats().captured; out3[2] = st_graph_stats().replayed;
+}
 
 static int check_acq(const st_acquisition& q, int nfields) {
     ST_REQUIRE(q.ns >= 0 && q.R >= 0, "acquisition: negative counts");
@@ -194,6 +200,7 @@ extern "C" int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t
     const int planes = nf * p->B;                // field planes per slot
     rc = st_wave2d_tma_setup(p->flags, a, p->u, (long long)planes * p->nslots, nullptr, 0, false, nsteps > 0 ? w2_tma_mode() : 0, tm);
     if (rc) return rc;
+    auto loop = [&]() -> int {
     for (int k = 0; k < nsteps; ++k) {
         const int i = i0 + k;
         tm.pl_prev = planes * pmod(slot0 + k, p->nslots);
@@ -203,10 +210,12 @@ extern "C" int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t
         a.next = p->u + slot * pmod(slot0 + k + 2, p->nslots);
         a.amp = p->acq.amp ? p->acq.amp + (long long)i * p->acq.ns : nullptr;
         a.rec_out = (p->acq.rec_out && p->acq.R > 0) ? p->acq.rec_out + (long long)i * p->acq.R * p->acq.nchan : nullptr;
-        rc = st_wave2d_launch_forward(p->flags, a, tm, st);
+        const int rc = st_wave2d_launch_forward(p->flags, a, tm, st);
         if (rc) { if (rc == ST_ERR_CUDA) st_set_error("wave2d_forward: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
     }
     return ST_OK;
+    };
+    return st_run_steps(p, sizeof(*p), 0 + 16 * (w2_tma_mode() + 1), i0, nsteps, slot0, st, loop);       // plain loop, or its CUDA-graph replay (st_graph.cuh)
 }
 
 extern "C" int st_wave2d_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32_t nsteps, int32_t slot_hi, void* stream) {
@@ -234,6 +243,7 @@ extern "C" int st_wave2d_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32
     const int planes = nf * p->B;
     rc = st_wave2d_tma_setup(p->flags, a, p->u, (long long)planes * p->nslots, p->lam, 3LL * planes, true, nsteps > 0 ? w2_tma_mode() : 0, tm);
     if (rc) return rc;
+    auto loop = [&]() -> int {
     for (int k = 0; k < nsteps; ++k) {
         const int i = i_hi - k;
         tm.pl_l1 = planes * pmod(i + 1, 3);
@@ -247,10 +257,12 @@ extern "C" int st_wave2d_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32
         a.s2 = p->u + slot * pmod(slot_hi - k - 1, p->nslots);
         a.rec_adj = (p->acq.rec_adj && p->acq.R > 0) ? p->acq.rec_adj + (long long)i * p->acq.R * p->acq.nchan : nullptr;
         a.gamp = p->acq.gamp ? p->acq.gamp + (long long)i * p->acq.ns : nullptr;
-        rc = st_wave2d_launch_adjoint(p->flags, a, tm, st);
+        const int rc = st_wave2d_launch_adjoint(p->flags, a, tm, st);
         if (rc) { if (rc == ST_ERR_CUDA) st_set_error("wave2d_adjoint: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
     }
     return ST_OK;
+    };
+    return st_run_steps(p, sizeof(*p), 1 + 16 * (w2_tma_mode() + 1), i_hi, nsteps, slot_hi, st, loop);   // (the kernel family is part of the key)
 }
 
 #define ST_ALIAS(NAME, COND, WHAT)                                                                                    \
@@ -300,16 +312,19 @@ extern "C" int st_elastic2d_forward(const st_elastic2d_problem* p, int32_t i0, i
     e2_fill(p, a);
     const long long slot = a.cs * 5;
     cudaStream_t st = (cudaStream_t)stream;
+    auto loop = [&]() -> int {
     for (int k = 0; k < nsteps; ++k) {
         const int i = i0 + k;
         a.cur = p->u + slot * pmod(slot0 + k, p->nslots);
         a.next = p->u + slot * pmod(slot0 + k + 1, p->nslots);
         a.amp = p->acq.amp ? p->acq.amp + (long long)i * p->acq.ns : nullptr;
         a.rec_out = (p->acq.rec_out && p->acq.R > 0) ? p->acq.rec_out + (long long)i * p->acq.R * p->acq.nchan : nullptr;
-        rc = st_elastic2d_launch_forward(a, st);
+        const int rc = st_elastic2d_launch_forward(a, st);
         if (rc) { st_set_error("elastic2d_forward: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
     }
     return ST_OK;
+    };
+    return st_run_steps(p, sizeof(*p), 2, i0, nsteps, slot0, st, loop);
 }
 
 extern "C" int st_elastic2d_adjoint(const st_elastic2d_problem* p, int32_t i_hi, int32_t nsteps, int32_t slot_hi1, void* stream) {
@@ -322,6 +337,7 @@ extern "C" int st_elastic2d_adjoint(const st_elastic2d_problem* p, int32_t i_hi,
     const long long slot = a.cs * 5;
     cudaStream_t st = (cudaStream_t)stream;
     a.gacc = p->gacc;
+    auto loop = [&]() -> int {
     for (int k = 0; k < nsteps; ++k) {
         const int i = i_hi - k;
         a.lam0 = p->lam + slot * pmod(i, 2);
@@ -331,10 +347,12 @@ extern "C" int st_elastic2d_adjoint(const st_elastic2d_problem* p, int32_t i_hi,
         a.rec_adj = (p->acq.rec_adj && p->acq.R > 0 && i >= 0) ? p->acq.rec_adj + (long long)i * p->acq.R * p->acq.nchan : nullptr;
         a.amp = (p->acq.amp && i + 1 < p->nt) ? p->acq.amp + (long long)(i + 1) * p->acq.ns : nullptr;   // injected into S_{i+1}
         a.gamp = (p->acq.gamp && i >= 0) ? p->acq.gamp + (long long)i * p->acq.ns : nullptr;
-        rc = st_elastic2d_launch_adjoint(a, st);
+        const int rc = st_elastic2d_launch_adjoint(a, st);
         if (rc) { st_set_error("elastic2d_adjoint: launch failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
     }
     return ST_OK;
+    };
+    return st_run_steps(p, sizeof(*p), 3, i_hi, nsteps, slot_hi1, st, loop);
 }
 
 // ===================================================================== acoustic3d

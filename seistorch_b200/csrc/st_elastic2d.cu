@@ -313,6 +313,8 @@ __device__ __forceinline__ void elastic_adjoint_tail(const E2Args& a, int b, int
 #define ST_EL_AMINB 2
 #endif
 constexpr int AFRZ = ST_EL_AFRZ, AFH = AFRZ * (NT / 32);
+constexpr int AGP = (NT / 32) * AFRZ * 32;          // float4s per shared-memory gradient plane of an adjoint block
+constexpr int ADJ_FAST_SMEM = 4 * AGP * 16;         // c2, cl, cm, cb
 
 __device__ __forceinline__ float4 f4mul(const float4& a, const float4& b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 __device__ __forceinline__ float4 f4z() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -320,7 +322,9 @@ __device__ __forceinline__ float4 f4z() { return make_float4(0.f, 0.f, 0.f, 0.f)
 struct AdjRow { float4 a, b, e; float a_r, e_l; };       // stage-A products of one row (+ halo columns x0+FW / x0-1)
 
 template <bool EDGE>
-__device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, int fz, int b, int tid, float* __restrict__ gpl) {
+__device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, int fz, int b, int tid, bool grad_on, float4* __restrict__ gs) {
+    // gs: this lane's float4 of the block's shared-memory gradient planes (row stride 32, plane stride AGP float4s); the
+    // partial sums of the block's shots stay there and are flushed once per chunk (elastic2d_adjoint_fast_kernel)
     const int ld = a.ld, nz = a.nz, nx = a.nx;
     const int warp = tid >> 5, lane = tid & 31;
     const int x0 = fx * FW, zb0 = fz * AFH, z0 = zb0 + warp * AFRZ;
@@ -343,8 +347,7 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
     const float* CM = a.coef[3];
     const float* CB = a.coef[4];
     const bool e0 = lane == 0, e31 = lane == 31;
-    const bool grad = gpl != nullptr;
-    const long long plane = (long long)nz * ld;
+    const bool grad = grad_on;
     auto L4 = [&](const float* p, int r) {
         if (EDGE && (r < 0 || r >= nz || x >= ld)) return f4z();
         return __ldg(reinterpret_cast<const float4*>(p + (r * ld + x)));
@@ -437,9 +440,8 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
                 vx_l = e0 ? hvx : vx_l;
                 vz_r = e31 ? hvz : vz_r;
                 if (st_ok) {
-                    float4 g2 = *reinterpret_cast<const float4*>(gpl + ro);
-                    float4 gl = *reinterpret_cast<const float4*>(gpl + plane + ro);
-                    float4 gm = *reinterpret_cast<const float4*>(gpl + 2 * plane + ro);
+                    float4* gp = gs + (r - z0) * 32;
+                    float4 g2 = gp[0], gl = gp[AGP], gm = gp[2 * AGP];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         float vx_x = f4g(svx, e) - (e == 0 ? vx_l : f4g(svx, e - 1));
@@ -452,9 +454,7 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
                         f4s(gl, e, f4g(gl, e) + (lx * vz_z + lz * vx_x));
                         f4s(gm, e, f4g(gm, e) + le * (vz_x + vx_z));
                     }
-                    *reinterpret_cast<float4*>(gpl + ro) = g2;
-                    *reinterpret_cast<float4*>(gpl + plane + ro) = gl;
-                    *reinterpret_cast<float4*>(gpl + 2 * plane + ro) = gm;
+                    gp[0] = g2; gp[AGP] = gl; gp[2 * AGP] = gm;
                 }
             }
         }
@@ -475,7 +475,6 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
         if (grad) {
             for (int r = z0 - 2; r <= z0 + AFRZ + 1; ++r) { pf(SVX, r); pf(SVZ, r); }
             for (int r = z0 - 1; r <= z0 + AFRZ; ++r) { pf(TXX, r); pf(TZZ, r); pf(TXZ, r); }
-            for (int r = z0; r < z0 + AFRZ; ++r) { pf(gpl, r); pf(gpl + plane, r); pf(gpl + 2 * plane, r); pf(gpl + 3 * plane, r); }
         }
     }
 #endif
@@ -530,7 +529,7 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
             txx_r = e31 ? hxx : txx_r;
             txz_l = e0 ? hxz : txz_l;
             if (st_ok) {
-                float4 gb = *reinterpret_cast<const float4*>(gpl + 3 * plane + ro);
+                float4 gb = gs[3 * AGP + k * 32];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     float txx_x = (e == 3 ? txx_r : f4g(txx, e + 1)) - f4g(txx, e);
@@ -540,7 +539,7 @@ __device__ __forceinline__ void elastic_adjoint_fast(const E2Args& a, int fx, in
                     if (EDGE) { txx_x *= mB[e]; txz_z *= m1; tzz_z *= m0; txz_x *= mA[e]; }
                     f4s(gb, e, f4g(gb, e) + (f4g(lvx, e) * (txx_x + txz_z) + f4g(lvz, e) * (txz_x + tzz_z)));
                 }
-                *reinterpret_cast<float4*>(gpl + 3 * plane + ro) = gb;
+                gs[3 * AGP + k * 32] = gb;
             }
             tzz_prev = tzz;
             txz_cur = txz_dn;
@@ -707,18 +706,48 @@ __global__ void __launch_bounds__(NT) elastic2d_adjoint_kernel(const E2Args a) {
     }
 }
 
-// grid = (tiles of 128 x AFH cells, shots); tiles touching the domain boundary take the masked variant
+// grid = (tiles of 128 x AFH cells, shot chunks); tiles touching the domain boundary take the masked variant.  A block walks
+// the shots of its chunk with the gradient partial sums of its cells in shared memory and read-modify-writes the chunk's
+// gradient planes once (every cell has one owner: deterministic, no atomics).
 __global__ void __launch_bounds__(NT, ST_EL_AMINB) elastic2d_adjoint_fast_kernel(const E2Args a, int nfx) {
     st_pdl_launch_dependents();
     st_pdl_wait();
-    const int tid = threadIdx.x, b = blockIdx.y;
+    extern __shared__ __align__(16) float4 el_gsm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, chunk = blockIdx.y;
     const int fz = blockIdx.x / nfx, fx = blockIdx.x - fz * nfx;
     const int x0 = fx * FW, z0 = fz * AFH;
-    float* gpl = a.gacc ? a.gacc + (long long)b * 4 * a.nz * a.ld : nullptr;     // one set of 4 planes per shot (bchunk == 1)
+    const bool grad = a.gacc != nullptr;
+    float4* gs = el_gsm + warp * AFRZ * 32 + lane;
+    if (grad) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int k = 0; k < AFRZ; ++k) gs[q * AGP + k * 32] = f4z();
+    }
     const bool inner = z0 >= 3 && z0 + AFH + 3 <= a.nz && x0 >= 2 && x0 + FW + 2 <= a.nx;
-    if (inner) elastic_adjoint_fast<false>(a, fx, fz, b, tid, gpl);
-    else elastic_adjoint_fast<true>(a, fx, fz, b, tid, gpl);
-    elastic_adjoint_tail(a, b, z0, z0 + AFH, x0, x0 + FW, tid);
+    const int b_lo = chunk * a.bchunk, b_hi = min(b_lo + a.bchunk, a.B);
+    for (int b = b_lo; b < b_hi; ++b) {
+        if (inner) elastic_adjoint_fast<false>(a, fx, fz, b, tid, grad, gs);
+        else elastic_adjoint_fast<true>(a, fx, fz, b, tid, grad, gs);
+        elastic_adjoint_tail(a, b, z0, z0 + AFH, x0, x0 + FW, tid);
+    }
+    if (grad) {
+        const long long plane = (long long)a.nz * a.ld;
+        float* gpl = a.gacc + (long long)chunk * 4 * plane;       // one set of 4 planes per chunk
+        const int x = x0 + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < AFRZ; ++k) {
+            const int z = z0 + warp * AFRZ + k;
+            if (z < a.nz && x < a.ld) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4* p4 = reinterpret_cast<float4*>(gpl + q * plane + (z * a.ld + x));
+                    const float4 v = *p4, w = gs[q * AGP + k * 32];
+                    *p4 = make_float4(v.x + w.x, v.y + w.y, v.z + w.z, v.w + w.w);
+                }
+            }
+        }
+    }
 }
 
 }  // namespace
@@ -733,10 +762,11 @@ int st_elastic2d_launch_adjoint(const E2Args& a, cudaStream_t st) {
     // fast path: Lam_{i+1} live, one gradient plane set per shot, no stress-type sources (their injected samples would
     // have to be taken out of S_{i+1} for the cb gradient: the generic kernel does that)
     static const bool fast_on = !(getenv("SEISTORCH_B200_EL_ADJ_FAST") && atoi(getenv("SEISTORCH_B200_EL_ADJ_FAST")) == 0);
-    if (fast_on && a.lam1 != nullptr && a.bchunk == 1 && !(a.gacc && a.amp && (a.src_fmask & 0x1c))) {
+    if (fast_on && a.lam1 != nullptr && !(a.gacc && a.amp && (a.src_fmask & 0x1c))) {
         const int nfx = (a.nx + FW - 1) / FW, nfz = (a.nz + AFH - 1) / AFH;
-        dim3 grid(nfx * nfz, a.B);
-        return st_pdl_launch(elastic2d_adjoint_fast_kernel, grid, dim3(NT), 0, st, a, nfx) == cudaSuccess ? ST_OK : ST_ERR_CUDA;
+        dim3 grid(nfx * nfz, (a.B + a.bchunk - 1) / a.bchunk);
+        if (st_set_max_smem<elastic2d_adjoint_fast_kernel>(ADJ_FAST_SMEM) != cudaSuccess) return ST_ERR_CUDA;
+        return st_pdl_launch(elastic2d_adjoint_fast_kernel, grid, dim3(NT), ADJ_FAST_SMEM, st, a, nfx) == cudaSuccess ? ST_OK : ST_ERR_CUDA;
     }
     const int nchunk = (a.B + a.bchunk - 1) / a.bchunk;
     dim3 grid((a.nx + TX - 1) / TX, (a.nz + TZ - 1) / TZ, nchunk), block(NTX, NTY);

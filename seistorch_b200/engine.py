@@ -234,7 +234,15 @@ def _choose_bchunk(spec: Spec) -> int:
     if env:
         return max(1, min(int(env), spec.B))
     if spec.family == "elastic2d":
-        return 1          # the vectorised adjoint keeps one gradient plane set per shot (st_elastic2d.cu, fast path)
+        # the vectorised adjoint keeps the gradient sums of a chunk's shots in shared memory (st_elastic2d.cu, fast path):
+        # the longest chunk that still fills one wave of 2 blocks / SM (B200, 500x1100: 4 shots 73 -> 63 us with chunks of 2,
+        # 97 us with one chunk of 4; 8 shots 137 -> 112 us with chunks of 4)
+        tiles = math.ceil(spec.shape[1] / 128) * math.ceil(spec.shape[0] / 32)
+        best = 1
+        for c in range(1, spec.B + 1):
+            if spec.B % c == 0 and tiles * (spec.B // c) >= 280:
+                best = c
+        return best
     if spec.family == "acoustic3d":
         tiles = math.ceil(spec.shape[2] / 64) * math.ceil(spec.shape[1] / 8) * math.ceil(spec.shape[0] / 16)
     elif spec.family == "wave2d":
@@ -400,7 +408,7 @@ def _history_plan(spec: Spec, dev) -> tuple:
         else:
             free, _total = torch.cuda.mem_get_info(dev)
             # blocks cached by torch's allocator (e.g. the previous call's history) are reusable
-            free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+            free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev) + _pooled_bytes(dev)
             reserve = (spec.nlam + 2) * slot_bytes + spec.ngrad * spec.plane * 4 * spec.B + (1 << 30)
             budget = int(0.85 * free) - reserve
     nslots_max = max(budget // slot_bytes, p + 2)
@@ -416,6 +424,50 @@ def _history_plan(spec: Spec, dev) -> tuple:
             f"seistorch_b200: wavefield history does not fit: one state slot is {slot_bytes / 2**20:.1f} MiB and "
             f"the budget allows {nslots_max} slots; reduce the number of shots per call")
     return best, math.ceil(nt / best)
+
+
+# ---- wavefield-history buffers are kept across calls -------------------------------------------------------------------
+# A gradient call stores nt (or K) states of all shots: 100+ GB on the BASELINE grids.  Handing that block back to torch's
+# caching allocator after every backward() lets later small allocations carve pieces out of it; the next forward then finds
+# no block of its size, the allocator frees its whole cache (a device sync) and cudaMallocs again -- sporadic 30-500 ms
+# stalls per step, measured on B200.  The engine therefore keeps ONE idle history buffer per (device, stream) and reuses it
+# when it is large enough.  `release_buffers()` returns the memory; SEISTORCH_B200_HISTORY_POOL=0 turns the pool off.
+_HISTORY_POOL: dict = {}
+
+
+def _pool_on() -> bool:
+    return os.environ.get("SEISTORCH_B200_HISTORY_POOL", "1") != "0"
+
+
+def _pool_key(dev):
+    return (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _pooled_bytes(dev) -> int:
+    buf = _HISTORY_POOL.get(_pool_key(dev))
+    return 0 if buf is None else buf.numel() * 4
+
+
+def _take_history(nelem: int, dev) -> torch.Tensor:
+    buf = _HISTORY_POOL.pop(_pool_key(dev), None) if _pool_on() else None
+    if buf is not None and buf.numel() >= nelem:
+        return buf
+    del buf                                   # too small: give it back before asking for a bigger one
+    return torch.empty(nelem, dtype=torch.float32, device=dev)
+
+
+def _give_history(buf: torch.Tensor) -> None:
+    if not _pool_on() or buf is None:
+        return
+    key = _pool_key(buf.device)
+    cur = _HISTORY_POOL.get(key)
+    if cur is None or cur.numel() < buf.numel():
+        _HISTORY_POOL[key] = buf
+
+
+def release_buffers() -> None:
+    """Drop the idle wavefield-history buffers the engine keeps between calls (returns the memory to torch)."""
+    _HISTORY_POOL.clear()
 
 
 class _Propagate(torch.autograd.Function):
@@ -446,7 +498,9 @@ class _Propagate(torch.autograd.Function):
             prob.forward(0, spec.nt, 0)
             return rec
         K, nseg = _history_plan(spec, dev)
-        prob = _Problem(spec, coefp, acq, amp32, K + p)
+        u = _take_history((K + p) * spec.slot_elems, dev)
+        u[:(p + 1) * spec.slot_elems].zero_()            # initial state; every later slot is written in full by the kernels
+        prob = _Problem(spec, coefp, acq, amp32, K + p, u=u)
         prob.rec_out = rec
         ckpts = []
         slot0_last = 0
@@ -536,7 +590,9 @@ class _Propagate(torch.autograd.Function):
                 else:
                     grads.append(None)
         gamp = prob.gamp.to(ctx.amp_dtype) if want_gamp else None
-        # free the big buffers eagerly
+        # the history goes back to the engine's pool (next call), everything else is freed eagerly
+        _give_history(prob.u)
+        prob.u = None
         ctx.prob = None
         return (None, None, gamp, *grads)
 

@@ -1,9 +1,8 @@
-# A/B timing of tuning builds of the register adjoint (tools only; not part of the product path)
+# A/B timing of tuning builds / settings of the adjoint kernels (tools only; not part of the product path)
 mkdir -p gpurun_out/r02d
-for v in "" nif3 nif4; do
-  if [ -n "$v" ]; then export SEISTORCH_B200_LIB=$PWD/seistorch_b200/libseistorch_b200_$v.so; else unset SEISTORCH_B200_LIB; fi
-  echo "== variant '$v'"
-  for eq in acoustic_vti_lsrtm_habc acoustic_tti_lsrtm_habc tti_habc vti_habc2 acoustic_fwim_habc; do
-    timeout 300 python tools/perf_kernels.py $eq 500 1200 12 100
-  done
-done 2>&1 | tee gpurun_out/r02d/born_ab9.log
+timeout 900 python -m pytest tests -m gpu -x -q -k "elastic or golden or cfg3" 2>&1 | tail -3
+for c in 1 2 4; do
+  echo "== elastic bchunk $c"
+  SEISTORCH_B200_BCHUNK=$c timeout 300 python tools/perf_kernels.py elastic 400 1000 4 200
+  SEISTORCH_B200_BCHUNK=$c timeout 300 python tools/perf_kernels.py elastic 400 1000 8 200
+done 2>&1 | tee gpurun_out/r02d/el_ab1.log

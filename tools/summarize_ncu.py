@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRCS = [os.path.join(ROOT, "gpurun_out", d) for d in ("r02", "r02b", "r02c")]     # later passes override earlier captures
+SRCS = [os.path.join(ROOT, "gpurun_out", d) for d in ("r02", "r02b", "r02c", "r02d")]     # later passes override earlier captures
 KEYS = {
     "gpu__time_duration.sum": "duration_us",
     "dram__bytes_read.sum": "dram_read_MB",
