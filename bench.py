@@ -694,6 +694,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(world, name, nshots, nt), "microbatch_shots": mb, "step_ms": dict(STEP_MS),
+                "ms_per_step_median": float(np.median(STEP_MS["device"])) if STEP_MS.get("device") else None,
+                "graph": dict(zip(("plain_loops", "captured", "replayed"), sb._lib.graph_counters())),
                 "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
                 "fd_gpts_per_s": fd, "loss": float(last) if not isinstance(last, float) else last}

@@ -47,9 +47,10 @@ int st_version(void);
 const char* st_last_error(void);
 /* The time loops of st_*_forward / st_*_adjoint (one launch per step, as the reference's python loop rnn.py:118-190 issues
  * its ~100 torch launches per step) are replayed as ONE CUDA graph when the identical call -- same problem struct bytes,
- * same step range, same stream -- is made again (csrc/st_graph.cuh; SEISTORCH_B200_GRAPH=0 turns it off).
+ * same step range, same stream -- is made again (csrc/st_graph.cuh; opt-in: SEISTORCH_B200_GRAPH=1).
  * out3 = {calls run as plain launch loops, calls captured into a graph, calls replayed from a graph} since process start. */
 void st_graph_counters(int64_t* out3);
+const char* st_graph_last_failure(void);      /* why the last capture attempt fell back to the plain loop ("" if none did) */
 
 /* ------------------------------------------------------------------------------------
  * Acquisition shared by all propagators.

@@ -78,7 +78,7 @@ class StAcoustic3dProblem(C.Structure):
 
 # every symbol include/seistorch_b200.h declares
 EXPORTS = [
-    "st_version", "st_last_error", "st_graph_counters",
+    "st_version", "st_last_error", "st_graph_counters", "st_graph_last_failure",
     "st_wave2d_taps_floats", "st_wave2d_prepare", "st_wave2d_uses_tma", "st_wave2d_uses_persist", "st_wave2d_adjoint_uses_persist",
     "st_wave2d_forward", "st_wave2d_adjoint",
     "st_acoustic2d_forward", "st_acoustic2d_adjoint",
@@ -108,6 +108,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     L.st_version.restype = C.c_int
     L.st_last_error.restype = C.c_char_p
+    L.st_graph_last_failure.restype = C.c_char_p
     L.st_graph_counters.restype = None
     L.st_graph_counters.argtypes = [C.POINTER(C.c_int64)]
     step_args = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
@@ -178,3 +179,7 @@ def graph_counters():
     out = (C.c_int64 * 3)()
     lib().st_graph_counters(out)
     return tuple(int(v) for v in out)
+
+
+def graph_last_failure() -> str:
+    return lib().st_graph_last_failure().decode(errors="replace")

@@ -39,6 +39,7 @@ extern "C" void st_graph_counters(int64_t* out3) {
     std::lock_guard<std::mutex> lock(st_graph_mutex());
     out3[0] = st_graph_stats().plain; out3[1] = st_graph_stats().captured; out3[2] = st_graph_stats().replayed;
 }
+extern "C" const char* st_graph_last_failure(void) { return st_graph_failure(); }
 
 static int check_acq(const st_acquisition& q, int nfields) {
     ST_REQUIRE(q.ns >= 0 && q.R >= 0, "acquisition: negative counts");
@@ -200,7 +201,7 @@ extern "C" int st_wave2d_forward(const st_wave2d_problem* p, int32_t i0, int32_t
     const int planes = nf * p->B;                // field planes per slot
     rc = st_wave2d_tma_setup(p->flags, a, p->u, (long long)planes * p->nslots, nullptr, 0, false, nsteps > 0 ? w2_tma_mode() : 0, tm);
     if (rc) return rc;
-    auto loop = [&]() -> int {
+    auto loop = [&](cudaStream_t st) -> int {
     for (int k = 0; k < nsteps; ++k) {
         const int i = i0 + k;
         tm.pl_prev = planes * pmod(slot0 + k, p->nslots);
@@ -243,7 +244,7 @@ extern "C" int st_wave2d_adjoint(const st_wave2d_problem* p, int32_t i_hi, int32
     const int planes = nf * p->B;
     rc = st_wave2d_tma_setup(p->flags, a, p->u, (long long)planes * p->nslots, p->lam, 3LL * planes, true, nsteps > 0 ? w2_tma_mode() : 0, tm);
     if (rc) return rc;
-    auto loop = [&]() -> int {
+    auto loop = [&](cudaStream_t st) -> int {
     for (int k = 0; k < nsteps; ++k) {
         const int i = i_hi - k;
         tm.pl_l1 = planes * pmod(i + 1, 3);
@@ -312,7 +313,7 @@ extern "C" int st_elastic2d_forward(const st_elastic2d_problem* p, int32_t i0, i
     e2_fill(p, a);
     const long long slot = a.cs * 5;
     cudaStream_t st = (cudaStream_t)stream;
-    auto loop = [&]() -> int {
+    auto loop = [&](cudaStream_t st) -> int {
     for (int k = 0; k < nsteps; ++k) {
         const int i = i0 + k;
         a.cur = p->u + slot * pmod(slot0 + k, p->nslots);
@@ -337,7 +338,7 @@ extern "C" int st_elastic2d_adjoint(const st_elastic2d_problem* p, int32_t i_hi,
     const long long slot = a.cs * 5;
     cudaStream_t st = (cudaStream_t)stream;
     a.gacc = p->gacc;
-    auto loop = [&]() -> int {
+    auto loop = [&](cudaStream_t st) -> int {
     for (int k = 0; k < nsteps; ++k) {
         const int i = i_hi - k;
         a.lam0 = p->lam + slot * pmod(i, 2);

@@ -36,6 +36,7 @@ def _iterate(eq, n_iter, **kw):
 ])
 def test_replayed_time_loops_are_bit_identical(eq, kw, monkeypatch):
     from seistorch_b200 import _lib
+    monkeypatch.setenv("SEISTORCH_B200_GRAPH", "1")          # opt-in (csrc/st_graph.cuh)
     monkeypatch.setenv("SEISTORCH_B200_PERSIST", "0")        # the persistent kernels are one launch already
     if eq == "acoustic_habc":
         monkeypatch.setenv("SEISTORCH_B200_TMA", "1")        # small grid: ask for the TMA kernels explicitly
@@ -45,7 +46,7 @@ def test_replayed_time_loops_are_bit_identical(eq, kw, monkeypatch):
     plain, captured, replayed = (b - a for a, b in zip(c0, c1))
     # torch's caching allocator hands out the same addresses from the second iteration on: forward and adjoint loop are each
     # captured once and replayed afterwards
-    assert captured >= 2 and replayed >= 2, (plain, captured, replayed)
+    assert captured >= 2 and replayed >= 2, (plain, captured, replayed, _lib.graph_last_failure())
     r0, g0 = outs[0]
     assert max(np.abs(r).max() for r in r0) > 0 and max(np.abs(g).max() for g in g0) > 0
     for r, g in outs[1:]:
@@ -53,8 +54,9 @@ def test_replayed_time_loops_are_bit_identical(eq, kw, monkeypatch):
         assert all(np.array_equal(a, b) for a, b in zip(g, g0))
 
 
-def test_short_loops_and_one_off_calls_stay_plain():
+def test_short_loops_and_one_off_calls_stay_plain(monkeypatch):
     from seistorch_b200 import _lib
+    monkeypatch.setenv("SEISTORCH_B200_GRAPH", "1")
     c0 = _lib.graph_counters()
     _iterate("acoustic_habc", 3, nz=60, nx=130, nshots=2, nt=40, rec_step=2)       # fewer steps than the graph threshold
     c1 = _lib.graph_counters()
@@ -62,3 +64,6 @@ def test_short_loops_and_one_off_calls_stay_plain():
     _iterate("acoustic_habc", 1, nz=60, nx=130, nshots=2, nt=70, rec_step=2)       # seen once: plain loop, nothing captured
     c2 = _lib.graph_counters()
     assert c2[1] == c1[1] and c2[2] == c1[2] and c2[0] - c1[0] == 2
+    monkeypatch.setenv("SEISTORCH_B200_GRAPH", "0")          # default: the mechanism is off, nothing is even counted
+    _iterate("acoustic_habc", 3, nz=60, nx=130, nshots=2, nt=70, rec_step=2)
+    assert _lib.graph_counters() == c2
