@@ -50,3 +50,19 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"] == json.loads(json.dumps(__import__("bench").workload_config(1, "cfg1")))
+
+
+def test_adjoint_chunk_rule(monkeypatch):
+    """engine._choose_bchunk: shots one adjoint block walks with its gradient sums on chip -- the longest divisor of B that
+    keeps enough blocks in flight (wave2d: >= 600 fast blocks; elastic2d: >= 280 tiles of 128 x 32, one wave of 2 blocks / SM)."""
+    from types import SimpleNamespace as NS
+    from seistorch_b200 import engine
+    monkeypatch.delenv("SEISTORCH_B200_BCHUNK", raising=False)
+    assert engine._choose_bchunk(NS(family="wave2d", B=12, shape=(600, 1300))) == 4        # cfg4: 209 tile pairs x 3 chunks
+    assert engine._choose_bchunk(NS(family="wave2d", B=8, shape=(851, 2401))) == 4         # cfg2 grid on the register path
+    assert engine._choose_bchunk(NS(family="wave2d", B=1, shape=(250, 400))) == 1
+    assert engine._choose_bchunk(NS(family="elastic2d", B=4, shape=(500, 1100))) == 2      # cfg3: 144 tiles x 2 chunks
+    assert engine._choose_bchunk(NS(family="elastic2d", B=8, shape=(500, 1100))) == 4
+    assert engine._choose_bchunk(NS(family="elastic2d", B=2, shape=(90, 150))) == 1
+    monkeypatch.setenv("SEISTORCH_B200_BCHUNK", "3")
+    assert engine._choose_bchunk(NS(family="elastic2d", B=2, shape=(90, 150))) == 2        # clamped to B
