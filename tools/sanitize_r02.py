@@ -29,6 +29,13 @@ run("elastic", nz=150, nx=300, nshots=2, nt=4)                       # interior 
 for eq in ("acoustic_habc", "vti_habc2", "tti_habc", "acoustic_fwim_habc", "acoustic_rho_habc", "acoustic_lsrtm_habc",
            "acoustic_vti_lsrtm_habc", "acoustic_tti_lsrtm_habc"):
     run(eq, nz=33, nx=61, nshots=3, nt=5)
+# second pass of round 2: frame-free tiles (unchecked-load rows of the Born pairs), strips of the tti / Born adjoints next to
+# clean tiles, multi-shot chunks with shared-memory gradient sums (wave2d and elastic)
+os.environ["SEISTORCH_B200_BCHUNK"] = "2"
+for eq in ("acoustic_vti_lsrtm_habc", "acoustic_tti_lsrtm_habc", "tti_habc", "acoustic_fwim_habc"):
+    run(eq, nz=60, nx=300, nshots=4, nt=4)
+run("elastic", nz=150, nx=300, nshots=4, nt=4)
+os.environ.pop("SEISTORCH_B200_BCHUNK")
 os.environ["SEISTORCH_B200_TMA"] = "1"
 run("acoustic_habc", nz=150, nx=216, nshots=3, nt=5)                 # TMA kernels, tap-gather corner tiles (adjoint)
 run("acoustic", nz=150, nx=300, nshots=3, nt=5)
