@@ -383,7 +383,12 @@ __device__ __forceinline__ float4 f4mul(const float4& a, const float4& b) { retu
 __device__ __forceinline__ float4 f4shl(const float4& c, float left) { return make_float4(left, c.x, c.y, c.z); }
 __device__ __forceinline__ float4 f4shr(const float4& c, float right) { return make_float4(c.y, c.z, c.w, right); }
 
+// FL only selects the extras: the four diagonal taps of the mixed derivative (XZ) and the second field + coupling
+// pre m A[p1] of the Born pairs; the single-field cross is the round-1 code.
+template <int FL>
 __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, int b_lo, int b_hi, int tid) {
+    constexpr int NF = (FL & ST_F_BORN) ? 2 : 1;
+    constexpr bool XZ = (FL & ST_F_XZ) != 0;
     const W2Geom g = a.g;
     const StripGeom t = strip_geom(g, g.bw);
     const int warp = tid >> 5, lane = tid & 31;
@@ -397,27 +402,74 @@ __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, in
     const bool active = x < t.xe;
     const long long plane = (long long)g.nz * g.ld;
     const int on1 = top ? 2 : 1, on2 = top ? 6 : 5;
+    // x-1 / x+4 neighbours of a row that may lie outside the domain in z
+    auto lr = [&](const float4& c, const float* p, int zq, float& left, float& right) {
+        left = __shfl_up_sync(0xffffffffu, c.w, 1);
+        right = __shfl_down_sync(0xffffffffu, c.x, 1);
+        const bool zin = zq >= 0 && zq < g.nz;
+        if (lane == 0) left = zin ? __ldg(p + (zq * g.ld + x0c - 1)) : 0.f;
+        if (lane == 31) right = (zin && x0c + FW < g.nx) ? __ldg(p + (zq * g.ld + x0c + FW)) : 0.f;
+    };
     // forward taps of this cell (increment form, st_wave2d_band.cuh)
     const float4 Tm = strip_row(a.taps + 1 * plane, z, x, g), Tp = strip_row(a.taps + 2 * plane, z, x, g);
     const float4 Tl = strip_row(a.taps + 3 * plane, z, x, g), Tr = strip_row(a.taps + 4 * plane, z, x, g);
     const float4 Tf = strip_row(a.taps + on2 * plane, z, x, g);
     const float4 T2 = strip_row(a.taps + (ST_NTAP1 + on1) * plane, z, x, g);
+    float4 Tnw = f4zero(), Tne = f4zero(), Tsw = f4zero(), Tse = f4zero();
+    if (XZ) {
+        Tnw = strip_row(a.taps + 9 * plane, z, x, g); Tne = strip_row(a.taps + 10 * plane, z, x, g);
+        Tsw = strip_row(a.taps + 11 * plane, z, x, g); Tse = strip_row(a.taps + 12 * plane, z, x, g);
+    }
+    // Born coupling  pre m A[p1]:  kz (N + S - 2C) + kx (W + E - 2C) + kxz ((SE - SW) - (NE - NW))  (every strip row is a frame row)
+    float4 kx = f4zero(), kz = f4zero(), kxz = f4zero();
+    if (NF == 2) {
+        const float4 bb = strip_row(a.coef[1], z, x, g), mm = strip_row(a.coef[7], z, x, g);
+        const float4 pm = make_float4((1.f - bb.x) * mm.x, (1.f - bb.y) * mm.y, (1.f - bb.z) * mm.z, (1.f - bb.w) * mm.w);
+        kx = f4mul(pm, strip_row(a.coef[2], z, x, g));
+        kz = f4mul(pm, strip_row(a.coef[3], z, x, g));
+        if (XZ) kxz = f4mul(pm, strip_row(a.coef[4], z, x, g));
+    }
     for (int b = b_lo; b < b_hi; ++b) {
-        const long long boff = (long long)b * a.fs;
-        const float* cur = a.cur + boff;
-        const float* prv = a.prev + boff;
-        const float4 C = strip_row(cur, z, x, g), Um = strip_row(cur, z - 1, x, g), Up = strip_row(cur, z + 1, x, g);
-        const float4 Uf = strip_row(cur, z + 2 * n, x, g);
-        const float4 P = strip_row(prv, z, x, g), Pn = strip_row(prv, z + n, x, g);
-        float l, r;
-        strip_lr(C, cur, z, x0c, lane, g, l, r);
-        float4 acc = f4mul(Tm, f4sub(Um, C));
-        acc = f4fma(Tp, f4sub(Up, C), acc);
-        acc = f4fma(Tl, f4sub(f4shl(C, l), C), acc);
-        acc = f4fma(Tr, f4sub(f4shr(C, r), C), acc);
-        acc = f4fma(Tf, f4sub(Uf, C), acc);
-        acc = f4fma(T2, f4sub(Pn, P), acc);
-        if (active) *reinterpret_cast<float4*>(a.next + boff + (z * g.ld + x)) = f4add(C, f4add(f4sub(C, P), acc));
+        float4 cpl = f4zero();
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const long long boff = f * a.cs + (long long)b * a.fs;
+            const float* cur = a.cur + boff;
+            const float* prv = a.prev + boff;
+            const float4 C = strip_row(cur, z, x, g), Um = strip_row(cur, z - 1, x, g), Up = strip_row(cur, z + 1, x, g);
+            const float4 Uf = strip_row(cur, z + 2 * n, x, g);
+            const float4 P = strip_row(prv, z, x, g), Pn = strip_row(prv, z + n, x, g);
+            float l, r;
+            strip_lr(C, cur, z, x0c, lane, g, l, r);
+            const float4 dN = f4sub(Um, C), dS = f4sub(Up, C), dW = f4sub(f4shl(C, l), C), dE = f4sub(f4shr(C, r), C);
+            float4 acc = f4mul(Tm, dN);
+            acc = f4fma(Tp, dS, acc);
+            acc = f4fma(Tl, dW, acc);
+            acc = f4fma(Tr, dE, acc);
+            acc = f4fma(Tf, f4sub(Uf, C), acc);
+            acc = f4fma(T2, f4sub(Pn, P), acc);
+            float4 dNW = f4zero(), dNE = f4zero(), dSW = f4zero(), dSE = f4zero();
+            if (XZ) {
+                float ml, mr, pl, pr;
+                lr(Um, cur, z - 1, ml, mr);
+                lr(Up, cur, z + 1, pl, pr);
+                dNW = f4sub(f4shl(Um, ml), C); dNE = f4sub(f4shr(Um, mr), C);
+                dSW = f4sub(f4shl(Up, pl), C); dSE = f4sub(f4shr(Up, pr), C);
+                acc = f4fma(Tnw, dNW, acc);
+                acc = f4fma(Tne, dNE, acc);
+                acc = f4fma(Tsw, dSW, acc);
+                acc = f4fma(Tse, dSE, acc);
+            }
+            if (NF == 2 && f == 0) {
+                cpl = f4mul(kz, dN);
+                cpl = f4fma(kz, dS, cpl);
+                cpl = f4fma(kx, dW, cpl);
+                cpl = f4fma(kx, dE, cpl);
+                if (XZ) cpl = f4fma(kxz, f4sub(f4add(dNW, dSE), f4add(dNE, dSW)), cpl);
+            }
+            if (NF == 2 && f == 1) acc = f4add(acc, cpl);
+            if (active) *reinterpret_cast<float4*>(a.next + boff + (z * g.ld + x)) = f4add(C, f4add(f4sub(C, P), acc));
+        }
     }
     // sources / receivers inside this warp's cells (ordering only needs the warp's own stores)
     if (z < a.row_lo || z > a.row_hi) return;
@@ -425,8 +477,11 @@ __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, in
     const int xhi = min(x0c + FW, t.xe);
     for (int s = lane; s < a.ns; s += 32) {
         const int sb = a.src_b[s], sx = a.src_x[s];
-        if (a.src_z[s] == z && sx >= x0c && sx < xhi && sb >= b_lo && sb < b_hi && (a.src_fmask & 1))
-            atomicAdd(a.next + (long long)sb * a.fs + (z * g.ld + sx), a.amp[s]);
+        if (a.src_z[s] == z && sx >= x0c && sx < xhi && sb >= b_lo && sb < b_hi) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+                if (a.src_fmask >> f & 1) atomicAdd(a.next + f * a.cs + (long long)sb * a.fs + (z * g.ld + sx), a.amp[s]);
+        }
     }
     if (!a.rec_out) return;
     __syncwarp();
@@ -436,7 +491,8 @@ __device__ __forceinline__ void forward_strip_block(const W2Args& a, int blk, in
             const int rx = a.rec_x[r];
             if (rx >= x0c && rx < xhi) {
                 const long long o = (long long)a.rec_orig[r] * a.nchan;
-                for (int ch = 0; ch < a.nchan; ++ch) a.rec_out[o + ch] = a.next[(long long)b * a.fs + (z * g.ld + rx)];
+                for (int ch = 0; ch < a.nchan; ++ch)
+                    a.rec_out[o + ch] = a.next[a.chan_f[ch] * a.cs + (long long)b * a.fs + (z * g.ld + rx)];
             }
         }
     }
@@ -876,7 +932,7 @@ __device__ __forceinline__ void forward_tap_block(const W2Args& a, const Map& ma
 
 template <int FL>
 __device__ __forceinline__ void forward_band_block(const W2Args& a, int blk, int b_lo, int b_hi, int tid) {
-    const BandMap map{a.g, st_band_cells(a.g, a.g.bw), strip_geom(a.g, a.g.bw), st_flags_stripped(FL), true, blk * NT};
+    const BandMap map{a.g, st_band_cells(a.g, a.g.bw), strip_geom(a.g, a.g.bw), st_flags_stripped_fwd(FL), true, blk * NT};
     forward_tap_block<FL>(a, map, b_lo, b_hi, tid);
 }
 
@@ -1516,7 +1572,7 @@ __global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W
     // they are scheduled first.  Tapped frame blocks walk all shots themselves.
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     const int ngrp = band_groups(a.B), gsh = band_group_shots(a.B);
-    const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
+    const int nstrip = (tapped && st_flags_stripped_fwd(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
     const int nframe = HABC ? (bt.count + nstrip) * (tapped ? ngrp : a.B) : 0;
     if (bid >= nframe) {
         const int q = bid - nframe;
@@ -1524,7 +1580,7 @@ __global__ void __launch_bounds__(NT, ST_FWD_MINB) wave2d_forward_kernel(const W
     } else if (tapped) {
         const int per = bt.count + nstrip, grp = bid / per, k = bid - grp * per;
         const int b_lo = grp * gsh, b_hi = min(b_lo + gsh, a.B);
-        if (k < nstrip) forward_strip_block(a, k, b_lo, b_hi, tid);
+        if (k < nstrip) forward_strip_block<FL>(a, k, b_lo, b_hi, tid);
         else forward_band_block<FL>(a, k - nstrip, b_lo, b_hi, tid);
     } else {
         if constexpr (HABC) {
@@ -2860,7 +2916,7 @@ int st_w2_launch_fwd(const W2Args& a, const W2Tma& tm, cudaStream_t st) {
     if (!(FL & ST_F_HABC)) bt.count = 0;
     const bool tapped = st_flags_tapped(FL) && a.taps != nullptr;
     if (tapped) bt.count = (st_band_cells(a.g, a.g.bw).total + NT - 1) / NT;
-    const int nstrip = (tapped && st_flags_stripped(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
+    const int nstrip = (tapped && st_flags_stripped_fwd(FL)) ? strip_blocks(strip_geom(a.g, a.g.bw)) : 0;
     dim3 grid((unsigned)((long long)nfast * a.B + (long long)(bt.count + nstrip) * (tapped ? band_groups(a.B) : a.B)));
     return pdl_launch(wave2d_forward_kernel<FL>, grid, st, a, nfx, nfast, bt);
 }

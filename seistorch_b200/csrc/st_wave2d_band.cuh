@@ -86,6 +86,11 @@ ST_HD constexpr bool st_flags_tapped(int fl) {
 // ... of which the straight top / bottom strips run on the vectorised strip blocks (single-field equations without mixed
 // derivative only; the band threads serve every frame cell of the others)
 ST_HD constexpr bool st_flags_stripped(int fl) { return st_flags_tapped(fl) && !(fl & (ST_F_BORN | ST_F_XZ)); }
+// the forward strip blocks serve every tapped flag set (the mixed derivative and the Born pairs included)
+#ifndef ST_STRIP_FWD_ALL
+#define ST_STRIP_FWD_ALL 1
+#endif
+ST_HD constexpr bool st_flags_stripped_fwd(int fl) { return ST_STRIP_FWD_ALL ? st_flags_tapped(fl) : st_flags_stripped(fl); }
 // the adjoint strip blocks also serve the mixed derivative and the Born pairs without it (all but the TTI Born pair)
 #ifndef ST_STRIP_ADJ_ALL
 #define ST_STRIP_ADJ_ALL 1
