@@ -467,6 +467,7 @@ def main():
             parity = parity_check(name, dev, mb)
         except Exception as e:                                         # pragma: no cover
             parity = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+        sb.release_buffers()                                           # the check's (small) history buffer is not the workload's
 
     # ---- set-up (untimed): observed data = forward modelling of the true model with our path
     total_shots = nshots * world if name != "cfg1" else 1
