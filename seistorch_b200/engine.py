@@ -20,8 +20,8 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
-from dataclasses import dataclass, field
-from typing import List, Optional, Sequence
+from dataclasses import dataclass
+from typing import Optional, Sequence
 
 import torch
 

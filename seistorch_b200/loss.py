@@ -7,7 +7,6 @@ records, like the reference.
 """
 from __future__ import annotations
 
-import ctypes as C
 
 import numpy as np
 import torch

@@ -5,7 +5,6 @@ signal.py:247-319); here the truncated-Gaussian passes run in csrc/st_postproc.c
 ``cut_gradient`` / ``precondition`` are element-wise products the reference already does on the device."""
 from __future__ import annotations
 
-import ctypes as C
 
 import numpy as np
 import torch
